@@ -1,0 +1,163 @@
+/*
+ * sparse_b200.h -- C ABI of the B200 (sm_100a) neural-sparse encoding hot path.
+ *
+ * Every entry point replaces one PyTorch-op cluster of the reference
+ * (zhichao-aws/opensearch-sparse-model-tuning-sample); the reference location each one stands in
+ * for is cited per function as file:line relative to the reference root.
+ *
+ * Conventions (all functions):
+ *   - plain C types only: raw DEVICE pointers, sizes, and a cudaStream_t passed as void*;
+ *   - the caller owns every buffer (inputs, outputs, workspace); nothing is allocated inside;
+ *   - launches are asynchronous on `stream`; no host synchronisation happens inside;
+ *   - re-entrant, no global mutable state apart from a thread-local last-error string;
+ *   - return value: SB200_OK (0) or an SB200_ERR_* code; sb200_last_error() describes the failure.
+ *   - matrices are dense row-major; "bf16" is the raw 16-bit bfloat16 pattern.
+ */
+#ifndef SPARSE_B200_H_
+#define SPARSE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SB200_ABI_VERSION 1
+
+enum {
+    SB200_OK = 0,
+    SB200_ERR_ARG = 1,         /* bad shape / null pointer / unsupported size */
+    SB200_ERR_CUDA = 2,        /* a CUDA runtime/driver call failed */
+    SB200_ERR_WORKSPACE = 3    /* workspace too small */
+};
+
+/* flags for the sparse head */
+enum {
+    SB200_HEAD_L0 = 1          /* second log1p ("use_l0", sparse_encoders.py:113-114) */
+};
+
+/* loss modes for sb200_score_loss_* (scripts/train/loss.py:110 LOSS_CLS_MAP) */
+enum {
+    SB200_LOSS_INFONCE = 0,    /* loss.py:80-107 */
+    SB200_LOSS_KLDIV = 1,      /* loss.py:18-43  */
+    SB200_LOSS_MARGINMSE = 2   /* loss.py:46-77  */
+};
+
+typedef void* sb200_stream_t;  /* cudaStream_t */
+
+int sb200_abi_version(void);
+const char* sb200_last_error(void);
+/* Number of kernels this library has launched in the calling process (for bench.py's gpu_launches). */
+unsigned long long sb200_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * (1) Fused sparse head forward.   Replaces sparse_encoders.py:108-114 (MLM decoder GEMM inside
+ *     self.backbone + `output * mask` + torch.max(dim=1) + log1p(relu) [+ log1p]) and
+ *     bi_encoder_wrapper.py:29-33.
+ *
+ *   hidden  bf16 [B, L, H]   output of the MLM head transform (input of the vocab decoder)
+ *   W       bf16 [V, H]      decoder weight (tied word embeddings)
+ *   bias    f32  [V]         decoder bias (may be NULL)
+ *   mask    [B, L] attention mask, element size mask_elem_bytes in {1, 4, 8}; non-zero = real token
+ *   rep     f32  [B, V]  out: log1p(relu(max_l(logit*mask)))  (log1p applied twice with SB200_HEAD_L0)
+ *   xmax    f32  [B, V]  out (nullable): the pooled pre-activation value max_l(logit*mask)
+ *   argmax  i32  [B, V]  out (nullable): sequence position of that maximum (lowest l on ties, the
+ *                        first masked position when the maximum is the 0 of a masked slot)
+ *   H % 8 == 0, 1 <= L <= 4096, V >= 1.  Logits never touch HBM.
+ * ------------------------------------------------------------------------------------------- */
+size_t sb200_head_fwd_workspace_bytes(int B, int L);
+int sb200_head_fwd(const void* hidden, const void* W, const float* bias, const void* mask, int mask_elem_bytes,
+                   int B, int L, int H, int V, int flags, float* rep, float* xmax, int32_t* argmax,
+                   void* workspace, size_t workspace_bytes, sb200_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (2) Sparse head backward.   Replaces the autograd backward of sparse_encoders.py:108-114
+ *     (dense dlogits + two dense GEMMs) with a gather/scatter over the B*V winning positions.
+ *
+ *   d_rep   f32 [B, V]   gradient w.r.t. rep
+ *   xmax, argmax         as saved by sb200_head_fwd
+ *   d_hidden f32 [B, L, H] out (fully written)       dW f32 [V, H] out (fully written)
+ *   dbias   f32 [V] out (nullable)
+ * ------------------------------------------------------------------------------------------- */
+size_t sb200_head_bwd_workspace_bytes(int B, int L, int H, int V);
+int sb200_head_bwd(const float* d_rep, const float* xmax, const int32_t* argmax, const void* hidden, const void* W,
+                   int B, int L, int H, int V, int flags, float* d_hidden, float* dW, float* dbias,
+                   void* workspace, size_t workspace_bytes, sb200_stream_t stream);
+
+/* (2b) Row pruning, in place: rep[b,v] *= (rep[b,v] > ratio * max_v rep[b,:]).  sparse_encoders.py:115-119 */
+int sb200_prune_rows(float* rep, int B, int V, float ratio, sb200_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (3) Inf-free IDF query encoding.   Replaces sparse_encoders.py:121-127.
+ *   ids      i64 [Nq, Lq]   token ids (attention mask is ignored, as in the reference)
+ *   idf      f32 [V]        idf_vector parameter
+ *   special  i32 [n_special] token ids forced to zero
+ *   q        f32 [Nq, V]    out: relu(idf[v]) where v occurs in row and is not special, else 0
+ * Bit-exact with the reference.  Ids outside [0, V) are an error in the reference (index error);
+ * here they are ignored and counted in *bad_ids (device i32, nullable).
+ * ------------------------------------------------------------------------------------------- */
+int sb200_idf_query(const int64_t* ids, const float* idf, const int32_t* special, int n_special, int Nq, int Lq, int V,
+                    float* q, int32_t* bad_ids, sb200_stream_t stream);
+/* d_idf[v] = sum_b d_q[b,v] * [q[b,v] > 0]   (gradient of the above w.r.t. idf; idf_requires_grad) */
+int sb200_idf_query_bwd(const float* d_q, const float* q, int Nq, int V, float* d_idf, sb200_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (4) FLOPS / L0-thresholded FLOPS regulariser.   Replaces trainer.py:61-73 (flops_value).
+ *   rep      f32 [N*G, V] viewed as [N, G, V]
+ *   threshold < 0: plain FLOPS  sum_{g,v} (mean_n |rep|)^2
+ *   threshold >= 0: only rows with nnz(row) > threshold contribute to the mean (mean still over N)
+ *   colsum   f32 [G, V]  out: sum_n rowmask*|rep|  (saved for backward)
+ *   rowmask  f32 [N*G]   out: 1/0 row mask (all ones when threshold < 0)
+ *   value    f32 [1]     out
+ *   stats    f32 [4]     out (nullable): total nnz, sum of positive entries, max entry, unused
+ * Backward: d_rep[n,g,v] (+)= gscale * 2*colsum[g,v]/N^2 * sign(rep) * rowmask   (gscale read on device)
+ * ------------------------------------------------------------------------------------------- */
+int sb200_flops_fwd(const float* rep, int N, int G, int V, float threshold, float* colsum, float* rowmask,
+                    float* value, float* stats, sb200_stream_t stream);
+int sb200_flops_bwd(const float* rep, const float* colsum, const float* rowmask, const float* gscale, int N, int G,
+                    int V, int row_begin, int row_end, int accumulate, float* d_rep, sb200_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (5) Query x doc score matrix.   Replaces the matmul/bmm of loss.py:30-37, 62-68, 92-101 and
+ *     bi_encoder_wrapper.py:124-131.   S[i,j] = sum_v q[i,v] * d[j,v], fp32 accumulate.
+ *   in_batch != 0: S is [Nq, Nd] (all pairs).  in_batch == 0: S is [Nq, G], G = Nd/Nq, query i
+ *   against its own docs i*G .. i*G+G-1.
+ * ------------------------------------------------------------------------------------------- */
+size_t sb200_scores_workspace_bytes(int Nq, int Nd, int V, int in_batch);
+int sb200_scores_fwd(const float* q, const float* d, int Nq, int Nd, int V, int in_batch, float* S, void* workspace,
+                     size_t workspace_bytes, sb200_stream_t stream);
+/* d_q[i,:] = sum_j dS[i,j] d[j,:] (rows q_begin..q_end) ; d_d[j,:] = sum_i dS[i,j] q[i,:] (rows d_begin..d_end).
+ * Either output may be NULL.  accumulate != 0 adds into the outputs. Outputs are full-size [Nq,V] / [Nd,V]. */
+int sb200_scores_bwd(const float* dS, const float* q, const float* d, int Nq, int Nd, int V, int in_batch,
+                     int q_begin, int q_end, int d_begin, int d_end, int accumulate, float* d_q, float* d_d,
+                     sb200_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (6) Ranking losses on a score matrix.   Replaces loss.py:33-42 (KLDiv), 64-76 (MarginMSE),
+ *     94-106 (InfoNCE incl. the boolean-mask negative gather and the one-hot CE).
+ *   S        f32 [Nq, C]   C = Nd (in_batch) or G
+ *   teacher  f32 [Nq, C]   (kldiv / marginmse; NULL for infonce)
+ *   G        docs per query (positive first); in_batch infonce drops other queries' positives
+ *   loss     f32 [1] out ;  dS f32 [Nq, C] out (nullable): d loss / d S
+ * ------------------------------------------------------------------------------------------- */
+int sb200_rank_loss(int mode, const float* S, const float* teacher, int Nq, int C, int G, int in_batch,
+                    float temperature, float* loss, float* dS, sb200_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (7) "next" rows: encode output path (sparse_encoders.py:137-150, 178-179) and the teacher
+ *     ensemble normalisation (bi_encoder_wrapper.py:133-138).
+ * ------------------------------------------------------------------------------------------- */
+/* CSR compaction of rep>0 entries; also df_count[v] += [rep[b,v] > 0] (i64, nullable).
+ * row_ptr i32 [B+1]; cols i32 / vals f32 sized capacity; *row_ptr[B] = total nnz (entries past capacity dropped). */
+size_t sb200_compact_workspace_bytes(int B, int V);
+int sb200_compact_rows(const float* rep, int B, int V, int32_t* row_ptr, int32_t* cols, float* vals, int capacity,
+                       int64_t* df_count, void* workspace, size_t workspace_bytes, sb200_stream_t stream);
+/* acc[i,:] (+)= scale * (S[i,:] - min_i) / (max_i - min_i + 1e-6) */
+int sb200_minmax_accumulate(const float* S, int Nq, int C, float scale, int accumulate, float* acc,
+                            sb200_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPARSE_B200_H_ */

@@ -1,0 +1,424 @@
+// Fused sparse head forward for sm_100a.
+//
+// Reference semantics (scripts/model/sparse_encoders.py:108-114 + the MLM decoder Linear inside
+// self.backbone): logits[b,l,v] = hidden[b,l,:].W[v,:] + bias[v]; values = max_l(logits * mask);
+// rep = log1p(relu(values)) (log1p twice with use_l0).
+//
+// Mapping to the hardware
+//   * one tcgen05.mma tile is D[128 vocab rows, N token columns] = W_tile[128, K] * hidden_tile[N, K]^T
+//     (both operands K-major in shared memory, 128-byte swizzle, fed by TMA), fp32 accumulators in TMEM;
+//   * vocab is the MMA M dimension, so TMEM lane i <-> vocab row i and TMEM column j <-> token j: the
+//     max over the sequence is a per-thread running max over the columns a thread reads with
+//     tcgen05.ld -- no shuffles, no shared memory, and the B x L x V logits never leave the SM;
+//   * a token tile never straddles sequences: the hidden tensor map is 3-D [B, L, H] with box
+//     {64, LC, S}; LC (chunk length, multiple of 16) and S (sequences per tile) are chosen on the host so
+//     that N = S*LC <= 256. Out-of-range rows are zero-filled by TMA and masked out by the tile bitmap;
+//   * bias is constant along l, so it is added after the max; log1p(relu(.)) is monotone and is applied
+//     once per (b, v). Masked tokens contribute an exact 0 (the reference multiplies by the mask), which is
+//     folded in as "max(x, 0) if the sequence has any masked slot";
+//   * warp roles: warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4..11 = two
+//     epilogue warpgroups that alternate work units, double-buffered accumulators (2 x 256 TMEM columns);
+//   * persistent CTAs (one per SM), static contiguous partition of the (sequence-group, vocab-tile) units.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace sb200 {
+
+namespace {
+
+constexpr int kBlockM = 128;     // vocab rows per tile (UMMA M)
+constexpr int kBlockK = 64;      // bf16 per smem row = 128 B = swizzle span
+constexpr int kUmmaK = 16;
+constexpr int kMaxN = 256;       // token columns per tile (UMMA N upper bound)
+constexpr int kStages = 4;
+constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KB
+constexpr int kBBytes = kMaxN * kBlockK * 2;    // 32 KB
+constexpr int kAccCols = 256;
+constexpr int kTmemCols = 512;
+constexpr int kFirstEpiWarp = 4;
+constexpr int kNumEpiWarps = 8;
+constexpr int kThreads = (kFirstEpiWarp + kNumEpiWarps) * 32;  // 384
+constexpr int kMaskWords = kMaxN / 32;                          // 8
+constexpr size_t kSmemBytes = 1024 /*align slack*/ + size_t(kStages) * (kABytes + kBBytes) + 256;
+
+struct HeadFwdParams {
+    const float* bias;
+    const uint32_t* tilemask;  // [n_groups][NC][8] validity bits per tile column
+    const int2* seqinfo;       // [B] (number of masked slots, first masked slot)
+    float* rep;
+    float* xmax;
+    int32_t* argmax;
+    int B, L, H, V;
+    int LC, S, NC, N;          // chunk length, sequences per tile, chunks per sequence, S*LC
+    int n_vtiles, n_groups, kblocks;
+    int l0;
+};
+
+// Packs the attention mask into per-tile column bitmaps and per-sequence padding info.
+__global__ void head_prep_kernel(const void* __restrict__ mask, int elem_bytes, int B, int L, int LC, int S, int NC,
+                                 int n_groups, uint32_t* __restrict__ tilemask, int2* __restrict__ seqinfo) {
+    const int lane = threadIdx.x & 31;
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int n_words = n_groups * NC * kMaskWords;
+    auto mask_at = [&](size_t i) -> bool {
+        if (elem_bytes == 8) return reinterpret_cast<const int64_t*>(mask)[i] != 0;
+        if (elem_bytes == 4) return reinterpret_cast<const int32_t*>(mask)[i] != 0;
+        return reinterpret_cast<const uint8_t*>(mask)[i] != 0;
+    };
+    if (w < n_words) {
+        const int word = w % kMaskWords;
+        const int c = (w / kMaskWords) % NC;
+        const int g = w / (kMaskWords * NC);
+        const int n = word * 32 + lane;
+        const int s = n / LC, j = n - s * LC;
+        const int b = g * S + s, l = c * LC + j;
+        bool valid = (s < S) && (b < B) && (l < L);
+        if (valid) valid = mask_at(size_t(b) * L + l);
+        const uint32_t bits = __ballot_sync(0xffffffffu, valid);
+        if (lane == 0) tilemask[w] = bits;
+    } else if (w - n_words < B) {
+        const int b = w - n_words;
+        int count = 0, first = L;
+        for (int l = lane; l < L; l += 32) {
+            const bool v = mask_at(size_t(b) * L + l);
+            count += v ? 1 : 0;
+            if (!v && l < first) first = l;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            count += __shfl_xor_sync(0xffffffffu, count, o);
+            first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+        }
+        if (lane == 0) seqinfo[b] = make_int2(L - count, first);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+head_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_h,
+                const HeadFwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + size_t(kStages) * kABytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + size_t(kStages) * (kABytes + kBBytes));
+    uint64_t* full_bar = bars;                   // [kStages]  TMA -> MMA
+    uint64_t* empty_bar = bars + kStages;        // [kStages]  MMA -> TMA
+    uint64_t* tfull_bar = bars + 2 * kStages;    // [2]        MMA -> epilogue
+    uint64_t* tempty_bar = bars + 2 * kStages + 2;  // [2]     epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_w);
+        tma_prefetch_desc(&tmap_h);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < kStages; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tfull_bar[i], 1);
+            mbar_init(&tempty_bar[i], 4);  // one arrive per warp of the consuming epilogue warpgroup
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_slot, kTmemCols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const long long total_units = (long long)p.n_vtiles * p.n_groups;
+    const int u_begin = int((long long)blockIdx.x * total_units / gridDim.x);
+    const int u_end = int((long long)(blockIdx.x + 1) * total_units / gridDim.x);
+    const uint32_t tx_bytes = uint32_t(kABytes + p.N * kBlockK * 2);
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ------------------------------------------------ TMA producer
+            uint32_t it = 0;
+            for (int u0 = u_begin; u0 < u_end; u0 += 2) {
+                for (int c = 0; c < p.NC; ++c) {
+                    for (int which = 0; which < 2; ++which) {
+                        const int u = u0 + which;
+                        if (u >= u_end) break;
+                        const int g = u / p.n_vtiles, vt = u - g * p.n_vtiles;
+                        for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
+                            const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+                            mbar_wait(&empty_bar[s], ph ^ 1);
+                            mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
+                            tma_load_2d(smem_a + s * kABytes, &tmap_w, &full_bar[s], kb * kBlockK, vt * kBlockM);
+                            tma_load_3d(smem_b + s * kBBytes, &tmap_h, &full_bar[s], kb * kBlockK, c * p.LC, g * p.S);
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ------------------------------------------------ MMA issuer (single thread)
+            const uint32_t idesc = umma_idesc_bf16(kBlockM, p.N);
+            uint32_t it = 0;
+            for (int u0 = u_begin, pi = 0; u0 < u_end; u0 += 2, ++pi) {
+                for (int c = 0; c < p.NC; ++c) {
+                    for (int which = 0; which < 2; ++which) {
+                        if (u0 + which >= u_end) break;
+                        const uint32_t as = which, aph = uint32_t(pi * p.NC + c) & 1;
+                        mbar_wait(&tempty_bar[as], aph ^ 1);
+                        tc_fence_after();
+                        const uint32_t tmem_d = tmem_base + as * kAccCols;
+                        for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
+                            const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+                            mbar_wait(&full_bar[s], ph);
+                            tc_fence_after();
+                            const uint64_t da = umma_desc_sw128(smem_u32(smem_a + s * kABytes));
+                            const uint64_t db = umma_desc_sw128(smem_u32(smem_b + s * kBBytes));
+#pragma unroll
+                            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                                // advance 32 bytes (= 16 bf16) inside the 128-byte swizzle row
+                                umma_bf16(tmem_d, da + uint64_t(k * 2), db + uint64_t(k * 2), idesc,
+                                          (kb | k) != 0 ? 1u : 0u);
+                            }
+                            umma_commit(&empty_bar[s]);  // frees the smem stage when these MMAs retire
+                        }
+                        umma_commit(&tfull_bar[as]);     // accumulator ready for the epilogue
+                    }
+                }
+            }
+        }
+    } else if (warp >= kFirstEpiWarp) {
+        // ---------------------------------------------------- epilogue warpgroups
+        const int ew = warp - kFirstEpiWarp;
+        const int wg = ew >> 2;
+        const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+        const uint32_t lane_base = uint32_t(quarter * 32) << 16;
+        // Units are processed in pairs; warpgroup `wg` owns the unit (and the TMEM accumulator stage) with that
+        // parity, so each warpgroup observes every phase of its own tfull/tempty barriers, and the running
+        // (max, argmax) of a sequence split over NC chunks stays in this thread's registers.
+        const uint32_t as = uint32_t(wg);
+        for (int u = u_begin + wg, pi = 0; u < u_end; u += 2, ++pi) {
+            const int g = u / p.n_vtiles, vt = u - g * p.n_vtiles;
+            const int v = vt * kBlockM + quarter * 32 + lane;
+            const bool v_ok = v < p.V;
+            const float bias_v = (v_ok && p.bias != nullptr) ? __ldg(p.bias + v) : 0.f;
+            float m = -CUDART_INF_F;
+            int idx = 0;
+            for (int c = 0; c < p.NC; ++c) {
+                const uint32_t aph = uint32_t(pi * p.NC + c) & 1;
+                const uint32_t* tm = p.tilemask + (size_t(g) * p.NC + c) * kMaskWords;
+                uint32_t cur = __ldg(tm);
+                mbar_wait(&tfull_bar[as], aph);
+                tc_fence_after();
+                const uint32_t tmem_acc = tmem_base + lane_base + as * kAccCols;
+                int s = 0, jrem = p.LC;
+                for (int n0 = 0; n0 < p.N; n0 += 16) {
+                    uint32_t bits;
+                    if ((n0 & 16) == 0) {
+                        bits = cur & 0xffffu;
+                    } else {
+                        bits = cur >> 16;
+                        if (n0 + 16 < p.N) cur = __ldg(tm + ((n0 + 16) >> 5));
+                    }
+                    if (bits != 0) {
+                        uint32_t r[16];
+                        tmem_ld16(tmem_acc + n0, r);
+                        tmem_ld_wait();
+                        const int lbase = c * p.LC + (p.LC - jrem);
+                        if (bits == 0xffffu) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                const float x = __uint_as_float(r[i]);
+                                if (x > m) {
+                                    m = x;
+                                    idx = lbase + i;
+                                }
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                const float x = __uint_as_float(r[i]);
+                                if (((bits >> i) & 1u) && x > m) {
+                                    m = x;
+                                    idx = lbase + i;
+                                }
+                            }
+                        }
+                    }
+                    jrem -= 16;
+                    if (jrem == 0) {
+                        // end of sequence s inside this tile
+                        const int b = g * p.S + s;
+                        if (c == p.NC - 1 && b < p.B && v_ok) {
+                            const int2 si = __ldg(p.seqinfo + b);
+                            float x = m + bias_v;
+                            if (si.x > 0) {
+                                if (x < 0.f || (x == 0.f && si.y < idx)) idx = si.y;
+                                x = fmaxf(x, 0.f);
+                            }
+                            const size_t o = size_t(b) * p.V + v;
+                            if (p.xmax != nullptr) p.xmax[o] = x;
+                            if (p.argmax != nullptr) p.argmax[o] = idx;
+                            float r1 = log1pf(fmaxf(x, 0.f));
+                            if (p.l0) r1 = log1pf(r1);
+                            p.rep[o] = r1;
+                        }
+                        ++s;
+                        jrem = p.LC;
+                        if (p.NC == 1) {
+                            m = -CUDART_INF_F;
+                            idx = 0;
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[as]);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess) return nullptr;
+        if (qres != cudaDriverEntryPointSuccess) return nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+struct HeadTiling {
+    int LC, S, NC, N, n_groups;
+};
+
+HeadTiling head_tiling(int B, int L) {
+    HeadTiling t;
+    if (L <= kMaxN) {
+        t.NC = 1;
+        t.LC = int(align_up(size_t(L), 16));
+        t.S = kMaxN / t.LC;
+        if (t.S > B) t.S = B;
+        if (t.S < 1) t.S = 1;
+    } else {
+        t.NC = (L + kMaxN - 1) / kMaxN;
+        t.LC = int(align_up(size_t((L + t.NC - 1) / t.NC), 16));
+        t.S = 1;
+    }
+    t.N = t.S * t.LC;
+    t.n_groups = (B + t.S - 1) / t.S;
+    return t;
+}
+
+}  // namespace
+
+}  // namespace sb200
+
+using namespace sb200;
+
+extern "C" size_t sb200_head_fwd_workspace_bytes(int B, int L) {
+    if (B <= 0 || L <= 0) return 0;
+    const HeadTiling t = head_tiling(B, L);
+    return align_up(size_t(t.n_groups) * t.NC * kMaskWords * sizeof(uint32_t), 256) + align_up(size_t(B) * sizeof(int2), 256);
+}
+
+extern "C" int sb200_head_fwd(const void* hidden, const void* W, const float* bias, const void* mask,
+                              int mask_elem_bytes, int B, int L, int H, int V, int flags, float* rep, float* xmax,
+                              int32_t* argmax, void* workspace, size_t workspace_bytes, sb200_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    SB200_REQUIRE(hidden && W && mask && rep, "head_fwd: null pointer");
+    SB200_REQUIRE(B >= 1 && V >= 1 && L >= 1 && L <= 4096, "head_fwd: bad shape B=%d L=%d V=%d", B, L, V);
+    SB200_REQUIRE(H >= 8 && H % 8 == 0, "head_fwd: H=%d must be a positive multiple of 8", H);
+    SB200_REQUIRE(mask_elem_bytes == 1 || mask_elem_bytes == 4 || mask_elem_bytes == 8, "head_fwd: mask_elem_bytes=%d",
+                  mask_elem_bytes);
+    SB200_REQUIRE((reinterpret_cast<uintptr_t>(hidden) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0,
+                  "head_fwd: hidden/W must be 16-byte aligned");
+    const size_t need = sb200_head_fwd_workspace_bytes(B, L);
+    if (workspace == nullptr || workspace_bytes < need)
+        return fail(SB200_ERR_WORKSPACE, "head_fwd: workspace %zu < %zu", workspace_bytes, need);
+
+    const HeadTiling t = head_tiling(B, L);
+    uint32_t* tilemask = static_cast<uint32_t*>(workspace);
+    int2* seqinfo = reinterpret_cast<int2*>(static_cast<uint8_t*>(workspace) +
+                                            align_up(size_t(t.n_groups) * t.NC * kMaskWords * sizeof(uint32_t), 256));
+
+    EncodeTiledFn encode = get_encode_fn();
+    if (encode == nullptr) return fail(SB200_ERR_CUDA, "head_fwd: cuTensorMapEncodeTiled unavailable");
+
+    CUtensorMap tmap_w, tmap_h;
+    {
+        cuuint64_t dims[2] = {cuuint64_t(H), cuuint64_t(V)};
+        cuuint64_t strides[1] = {cuuint64_t(H) * 2};
+        cuuint32_t box[2] = {kBlockK, kBlockM};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = encode(&tmap_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(W), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(SB200_ERR_CUDA, "head_fwd: tensor map (W) encode failed: %d", int(r));
+    }
+    {
+        cuuint64_t dims[3] = {cuuint64_t(H), cuuint64_t(L), cuuint64_t(B)};
+        cuuint64_t strides[2] = {cuuint64_t(H) * 2, cuuint64_t(L) * cuuint64_t(H) * 2};
+        cuuint32_t box[3] = {kBlockK, cuuint32_t(t.LC), cuuint32_t(t.S)};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = encode(&tmap_h, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(hidden), dims, strides, box,
+                            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(SB200_ERR_CUDA, "head_fwd: tensor map (hidden) encode failed: %d", int(r));
+    }
+
+    {
+        const int n_warps = t.n_groups * t.NC * kMaskWords + B;
+        const int threads = 256;
+        const int blocks = (n_warps * 32 + threads - 1) / threads;
+        head_prep_kernel<<<blocks, threads, 0, stream>>>(mask, mask_elem_bytes, B, L, t.LC, t.S, t.NC, t.n_groups,
+                                                         tilemask, seqinfo);
+        SB200_CHECK_LAUNCH("head_prep_kernel");
+    }
+
+    HeadFwdParams p;
+    p.bias = bias;
+    p.tilemask = tilemask;
+    p.seqinfo = seqinfo;
+    p.rep = rep;
+    p.xmax = xmax;
+    p.argmax = argmax;
+    p.B = B; p.L = L; p.H = H; p.V = V;
+    p.LC = t.LC; p.S = t.S; p.NC = t.NC; p.N = t.N;
+    p.n_vtiles = (V + kBlockM - 1) / kBlockM;
+    p.n_groups = t.n_groups;
+    p.kblocks = (H + kBlockK - 1) / kBlockK;
+    p.l0 = (flags & SB200_HEAD_L0) ? 1 : 0;
+
+    // per-device attribute; setting it on every call keeps multi-device processes correct and costs ~1 us
+    SB200_CUDA(cudaFuncSetAttribute(head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBytes)));
+    const long long total_units = (long long)p.n_vtiles * p.n_groups;
+    int grid = num_sms();
+    if (grid > total_units) grid = int(total_units);
+    head_fwd_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tmap_w, tmap_h, p);
+    SB200_CHECK_LAUNCH("head_fwd_kernel");
+    return SB200_OK;
+}
