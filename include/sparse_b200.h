@@ -148,11 +148,12 @@ int sb200_rank_loss(int mode, const float* S, const float* teacher, int Nq, int 
  * (7) "next" rows: encode output path (sparse_encoders.py:137-150, 178-179) and the teacher
  *     ensemble normalisation (bi_encoder_wrapper.py:133-138).
  * ------------------------------------------------------------------------------------------- */
-/* CSR compaction of rep>0 entries; also df_count[v] += [rep[b,v] > 0] (i64, nullable).
- * row_ptr i32 [B+1]; cols i32 / vals f32 sized capacity; *row_ptr[B] = total nnz (entries past capacity dropped). */
+/* CSR compaction of the non-zero entries of columns >= first_col (first_col = 1 reproduces the post-processor's
+ * column-0 sentinel being dropped), columns ascending inside a row; also df_count[v] += [rep[b,v] > 0] (i64, nullable).
+ * row_ptr i32 [B+1]; cols i32 / vals f32 sized capacity; row_ptr[B] = total nnz (entries past capacity are dropped). */
 size_t sb200_compact_workspace_bytes(int B, int V);
-int sb200_compact_rows(const float* rep, int B, int V, int32_t* row_ptr, int32_t* cols, float* vals, int capacity,
-                       int64_t* df_count, void* workspace, size_t workspace_bytes, sb200_stream_t stream);
+int sb200_compact_rows(const float* rep, int B, int V, int first_col, int32_t* row_ptr, int32_t* cols, float* vals,
+                       int capacity, int64_t* df_count, void* workspace, size_t workspace_bytes, sb200_stream_t stream);
 /* acc[i,:] (+)= scale * (S[i,:] - min_i) / (max_i - min_i + 1e-6) */
 int sb200_minmax_accumulate(const float* S, int Nq, int C, float scale, int accumulate, float* acc,
                             sb200_stream_t stream);

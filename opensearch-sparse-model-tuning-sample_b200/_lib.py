@@ -40,7 +40,7 @@ _PROTOTYPES = {
                                   _c_int, _vp, _vp, _vp]),
     "sb200_rank_loss": (_c_int, [_c_int, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_f, _vp, _vp, _vp]),
     "sb200_compact_workspace_bytes": (_sz, [_c_int, _c_int]),
-    "sb200_compact_rows": (_c_int, [_vp, _c_int, _c_int, _vp, _vp, _vp, _c_int, _vp, _vp, _sz, _vp]),
+    "sb200_compact_rows": (_c_int, [_vp, _c_int, _c_int, _c_int, _vp, _vp, _vp, _c_int, _vp, _vp, _sz, _vp]),
     "sb200_minmax_accumulate": (_c_int, [_vp, _c_int, _c_int, _c_f, _c_int, _vp, _vp]),
 }
 

@@ -1,0 +1,359 @@
+// Sparse head backward for sm_100a.
+//
+// Reference: autograd backward of scripts/model/sparse_encoders.py:108-114. There it materialises a dense
+// dlogits[B,L,V] (non-zero only at the B*V arg-max positions) and runs two dense GEMMs. Here the B*V coefficients
+//     c[b,v] = d_rep[b,v] * f'(xmax[b,v]),   f = log1p o relu  (o log1p with use_l0)
+// are applied directly at the winning positions l* = argmax[b,v]:
+//     dW[v,:]        = sum_b c[b,v] * hidden[b, l*(b,v), :]       (gather, one owner per v -> no atomics)
+//     dbias[v]       = sum_b c[b,v]
+//     d_hidden[b,l,:] = sum_{v: l*(b,v)=l} c[b,v] * W[v,:]        (entries bucketed by l, then gathered)
+// B*V*H multiply-adds instead of 2*B*L*V*H, and entries with c == 0 (inactive vocabulary) cost nothing.
+// All three kernels are gather-bound on L2 (hidden and W are L2-resident: tens of MB).
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "common.h"
+
+namespace sb200 {
+namespace {
+
+constexpr int kMaxChunks = 4;          // H <= 1024: 16-byte chunks per lane
+constexpr int kDwRows = 32;            // vocab rows per dW block
+constexpr int kDwThreads = 256;
+constexpr int kDhEntriesPerBlock = 256;
+constexpr int kBucketThreads = 1024;
+constexpr int kMaxL = 4096;
+
+__device__ __forceinline__ float head_coef(float g, float x, int l0) {
+    // matches torch autograd order: grad/(1+r1) [l0], then /(1+relu(x)), then relu mask (0 at x <= 0)
+    if (!(x > 0.f) || g == 0.f) return 0.f;
+    float c = g;
+    if (l0) c = c / (1.f + log1pf(x));
+    return c / (1.f + x);
+}
+
+__device__ __forceinline__ void fma_bf16x8(float (&acc)[8], const uint4& raw, float c) {
+    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 f = __bfloat1622float2(h2[i]);
+        acc[2 * i] = fmaf(c, f.x, acc[2 * i]);
+        acc[2 * i + 1] = fmaf(c, f.y, acc[2 * i + 1]);
+    }
+}
+
+// ---------------------------------------------------------------- dW / dbias
+// Block = 32 consecutive vocab rows; (c, l*) for [Bc sequences x 32 rows] staged in smem (coalesced),
+// then each warp owns 4 rows and walks the sequences, gathering hidden rows with 16-byte loads.
+template <int NCHUNK>
+__global__ void __launch_bounds__(kDwThreads)
+bwd_dw_kernel(const float* __restrict__ d_rep, const float* __restrict__ xmax, const int32_t* __restrict__ argmax,
+              const __nv_bfloat16* __restrict__ hidden, int B, int L, int H, int V, int l0, int Bc,
+              float* __restrict__ dW, float* __restrict__ dbias) {
+    extern __shared__ float2 stage[];  // [Bc][32] (c, l as int bits)
+    const int v0 = blockIdx.x * kDwRows;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_chunks = H >> 3;
+
+    for (int b0 = 0; b0 < B; b0 += Bc) {
+        const int nb = min(Bc, B - b0);
+        __syncthreads();
+        for (int t = threadIdx.x; t < nb * kDwRows; t += kDwThreads) {
+            const int bo = t >> 5, vo = t & 31;
+            const int v = v0 + vo;
+            float c = 0.f;
+            int l = 0;
+            if (v < V) {
+                const size_t o = size_t(b0 + bo) * V + v;
+                c = head_coef(__ldg(d_rep + o), __ldg(xmax + o), l0);
+                l = __ldg(argmax + o);
+                l = min(max(l, 0), L - 1);
+            }
+            stage[t] = make_float2(c, __int_as_float(l));
+        }
+        __syncthreads();
+        for (int r = 0; r < 4; ++r) {
+            const int vo = warp * 4 + r;
+            const int v = v0 + vo;
+            if (v >= V) break;  // warp-uniform
+            float acc[NCHUNK][8];
+            float bsum = 0.f;
+#pragma unroll
+            for (int k = 0; k < NCHUNK; ++k)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[k][i] = 0.f;
+#pragma unroll 4
+            for (int bo = 0; bo < nb; ++bo) {
+                const float2 e = stage[bo * kDwRows + vo];  // broadcast
+                if (e.x == 0.f) continue;                   // warp-uniform
+                bsum += e.x;
+                const __nv_bfloat16* row = hidden + (size_t(b0 + bo) * L + __float_as_int(e.y)) * H;
+#pragma unroll
+                for (int k = 0; k < NCHUNK; ++k) {
+                    const int ch = lane + 32 * k;
+                    if (ch < n_chunks) {
+                        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(row) + ch);
+                        fma_bf16x8(acc[k], raw, e.x);
+                    }
+                }
+            }
+            // this block is the only writer of rows v0..v0+31: first pass stores, later passes accumulate
+#pragma unroll
+            for (int k = 0; k < NCHUNK; ++k) {
+                const int ch = lane + 32 * k;
+                if (ch < n_chunks) {
+                    float4* dst = reinterpret_cast<float4*>(dW + size_t(v) * H + ch * 8);
+                    float4 lo = make_float4(acc[k][0], acc[k][1], acc[k][2], acc[k][3]);
+                    float4 hi = make_float4(acc[k][4], acc[k][5], acc[k][6], acc[k][7]);
+                    if (b0 > 0) {
+                        const float4 plo = dst[0], phi = dst[1];
+                        lo.x += plo.x; lo.y += plo.y; lo.z += plo.z; lo.w += plo.w;
+                        hi.x += phi.x; hi.y += phi.y; hi.z += phi.z; hi.w += phi.w;
+                    }
+                    dst[0] = lo;
+                    dst[1] = hi;
+                }
+            }
+            if (dbias != nullptr && lane == 0) dbias[v] = (b0 > 0 ? dbias[v] : 0.f) + bsum;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- bucket active entries of one sequence by l*
+// entries[b][pos] = (key = l << 20 | v, c), sorted by l (order inside a bucket is arbitrary); nact[b] = count.
+__global__ void __launch_bounds__(kBucketThreads)
+bwd_bucket_kernel(const float* __restrict__ d_rep, const float* __restrict__ xmax, const int32_t* __restrict__ argmax,
+                  int L, int V, int l0, uint2* __restrict__ entries, int* __restrict__ nact) {
+    __shared__ int cnt[kMaxL];
+    __shared__ int warp_tot[32];
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int l = tid; l < L; l += kBucketThreads) cnt[l] = 0;
+    __syncthreads();
+    const size_t base = size_t(b) * V;
+    for (int v = tid; v < V; v += kBucketThreads) {
+        const float c = head_coef(__ldg(d_rep + base + v), __ldg(xmax + base + v), l0);
+        if (c != 0.f) {
+            int l = __ldg(argmax + base + v);
+            l = min(max(l, 0), L - 1);
+            atomicAdd(&cnt[l], 1);
+        }
+    }
+    __syncthreads();
+    // exclusive scan of cnt[0..L) in place; each thread owns a contiguous run of 4 counters
+    {
+        constexpr int per = kMaxL / kBucketThreads;  // 4
+        int vals[per];
+        int sum = 0;
+#pragma unroll
+        for (int i = 0; i < per; ++i) {
+            const int l = tid * per + i;
+            vals[i] = (l < L) ? cnt[l] : 0;
+            sum += vals[i];
+        }
+        int incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int w = warp_tot[lane];
+            int wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += t;
+            }
+            warp_tot[lane] = wi - w;  // exclusive
+            if (lane == 31) nact[b] = wi;
+        }
+        __syncthreads();
+        int run = warp_tot[warp] + incl - sum;
+#pragma unroll
+        for (int i = 0; i < per; ++i) {
+            const int l = tid * per + i;
+            if (l < L) cnt[l] = run;
+            run += vals[i];
+        }
+    }
+    __syncthreads();
+    uint2* out = entries + base;
+    for (int v = tid; v < V; v += kBucketThreads) {
+        const float c = head_coef(__ldg(d_rep + base + v), __ldg(xmax + base + v), l0);
+        if (c != 0.f) {
+            int l = __ldg(argmax + base + v);
+            l = min(max(l, 0), L - 1);
+            const int pos = atomicAdd(&cnt[l], 1);
+            out[pos] = make_uint2((uint32_t(l) << 20) | uint32_t(v), __float_as_uint(c));
+        }
+    }
+}
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// ---------------------------------------------------------------- d_hidden
+// grid (ceil(V / 256), B). Each warp takes 32 consecutive bucketed entries, accumulates runs of equal l in
+// registers and flushes a run with vector reductions into the (pre-zeroed) fp32 d_hidden row.
+template <int NCHUNK>
+__global__ void __launch_bounds__(256)
+bwd_dh_kernel(const uint2* __restrict__ entries, const int* __restrict__ nact, const __nv_bfloat16* __restrict__ W,
+              int L, int H, int V, float* __restrict__ d_hidden) {
+    const int b = blockIdx.y;
+    const int n = __ldg(nact + b);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int first = blockIdx.x * kDhEntriesPerBlock + warp * 32;
+    if (first >= n) return;
+    const int cnt = min(32, n - first);
+    const int n_chunks = H >> 3;
+    uint2 mine = make_uint2(0u, 0u);
+    if (lane < cnt) mine = __ldg(entries + size_t(b) * V + first + lane);
+
+    float acc[NCHUNK][8];
+#pragma unroll
+    for (int k = 0; k < NCHUNK; ++k)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[k][i] = 0.f;
+
+    auto flush = [&](int l) {
+        float* row = d_hidden + (size_t(b) * L + l) * H;
+#pragma unroll
+        for (int k = 0; k < NCHUNK; ++k) {
+            const int ch = lane + 32 * k;
+            if (ch < n_chunks) {
+                red_add_v4(row + ch * 8, acc[k][0], acc[k][1], acc[k][2], acc[k][3]);
+                red_add_v4(row + ch * 8 + 4, acc[k][4], acc[k][5], acc[k][6], acc[k][7]);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[k][i] = 0.f;
+        }
+    };
+
+    int cur_l = int(__shfl_sync(0xffffffffu, mine.x, 0) >> 20);
+    for (int e0 = 0; e0 < cnt; e0 += 4) {
+        uint4 raw[4][NCHUNK];
+        uint32_t key[4];
+        float cf[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int e = min(e0 + j, cnt - 1);
+            key[j] = __shfl_sync(0xffffffffu, mine.x, e);
+            cf[j] = (e0 + j < cnt) ? __uint_as_float(__shfl_sync(0xffffffffu, mine.y, e)) : 0.f;
+            const __nv_bfloat16* row = W + size_t(key[j] & 0xFFFFFu) * H;
+#pragma unroll
+            for (int k = 0; k < NCHUNK; ++k) {
+                const int ch = lane + 32 * k;
+                raw[j][k] = (ch < n_chunks) ? __ldg(reinterpret_cast<const uint4*>(row) + ch) : make_uint4(0, 0, 0, 0);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (e0 + j < cnt) {
+                const int l = int(key[j] >> 20);
+                if (l != cur_l) {
+                    flush(cur_l);
+                    cur_l = l;
+                }
+#pragma unroll
+                for (int k = 0; k < NCHUNK; ++k) fma_bf16x8(acc[k], raw[j][k], cf[j]);
+            }
+        }
+    }
+    flush(cur_l);
+}
+
+// rep[b,v] *= (rep[b,v] > ratio * rowmax)   (sparse_encoders.py:118-119)
+__global__ void __launch_bounds__(256) prune_rows_kernel(float* __restrict__ rep, int V, float ratio) {
+    __shared__ float red[8];
+    float* row = rep + size_t(blockIdx.x) * V;
+    float m = -INFINITY;
+    for (int v = threadIdx.x; v < V; v += 256) m = fmaxf(m, row[v]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    m = red[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+    const float thr = m * ratio;
+    for (int v = threadIdx.x; v < V; v += 256) {
+        const float x = row[v];
+        row[v] = (x > thr) ? x : x * 0.f;
+    }
+}
+
+template <int NCHUNK>
+int launch_bwd(const float* d_rep, const float* xmax, const int32_t* argmax, const __nv_bfloat16* hidden,
+               const __nv_bfloat16* W, int B, int L, int H, int V, int l0, float* d_hidden, float* dW, float* dbias,
+               uint2* entries, int* nact, cudaStream_t stream) {
+    // dW / dbias
+    {
+        int Bc = B;
+        const int max_smem = 96 * 1024;
+        if (size_t(Bc) * kDwRows * sizeof(float2) > size_t(max_smem)) Bc = max_smem / int(kDwRows * sizeof(float2));
+        const size_t smem = size_t(Bc) * kDwRows * sizeof(float2);
+        SB200_CUDA(cudaFuncSetAttribute(bwd_dw_kernel<NCHUNK>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        bwd_dw_kernel<NCHUNK><<<(V + kDwRows - 1) / kDwRows, kDwThreads, smem, stream>>>(
+            d_rep, xmax, argmax, hidden, B, L, H, V, l0, Bc, dW, dbias);
+        SB200_CHECK_LAUNCH("bwd_dw_kernel");
+    }
+    // d_hidden
+    SB200_CUDA(cudaMemsetAsync(d_hidden, 0, size_t(B) * L * H * sizeof(float), stream));
+    bwd_bucket_kernel<<<B, kBucketThreads, 0, stream>>>(d_rep, xmax, argmax, L, V, l0, entries, nact);
+    SB200_CHECK_LAUNCH("bwd_bucket_kernel");
+    dim3 grid((V + kDhEntriesPerBlock - 1) / kDhEntriesPerBlock, B);
+    bwd_dh_kernel<NCHUNK><<<grid, 256, 0, stream>>>(entries, nact, W, L, H, V, d_hidden);
+    SB200_CHECK_LAUNCH("bwd_dh_kernel");
+    return SB200_OK;
+}
+
+}  // namespace
+}  // namespace sb200
+
+using namespace sb200;
+
+extern "C" size_t sb200_head_bwd_workspace_bytes(int B, int L, int H, int V) {
+    (void)L;
+    (void)H;
+    if (B <= 0 || V <= 0) return 0;
+    return align_up(size_t(B) * V * sizeof(uint2), 256) + align_up(size_t(B) * sizeof(int), 256);
+}
+
+extern "C" int sb200_head_bwd(const float* d_rep, const float* xmax, const int32_t* argmax, const void* hidden,
+                              const void* W, int B, int L, int H, int V, int flags, float* d_hidden, float* dW,
+                              float* dbias, void* workspace, size_t workspace_bytes, sb200_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    SB200_REQUIRE(d_rep && xmax && argmax && hidden && W && d_hidden && dW, "head_bwd: null pointer");
+    SB200_REQUIRE(B >= 1 && L >= 1 && L <= kMaxL && V >= 1 && V <= (1 << 20), "head_bwd: bad shape B=%d L=%d V=%d", B,
+                  L, V);
+    SB200_REQUIRE(H >= 8 && H % 8 == 0 && H <= 256 * kMaxChunks, "head_bwd: H=%d must be a multiple of 8, <= %d", H,
+                  256 * kMaxChunks);
+    SB200_REQUIRE(B <= 65535, "head_bwd: B=%d exceeds grid.y", B);
+    const size_t need = sb200_head_bwd_workspace_bytes(B, L, H, V);
+    if (workspace == nullptr || workspace_bytes < need)
+        return fail(SB200_ERR_WORKSPACE, "head_bwd: workspace %zu < %zu", workspace_bytes, need);
+    uint2* entries = static_cast<uint2*>(workspace);
+    int* nact = reinterpret_cast<int*>(static_cast<uint8_t*>(workspace) + align_up(size_t(B) * V * sizeof(uint2), 256));
+    const int l0 = (flags & SB200_HEAD_L0) ? 1 : 0;
+    const __nv_bfloat16* h = static_cast<const __nv_bfloat16*>(hidden);
+    const __nv_bfloat16* w = static_cast<const __nv_bfloat16*>(W);
+    const int nchunk = (H / 8 + 31) / 32;
+    switch (nchunk) {
+        case 1: return launch_bwd<1>(d_rep, xmax, argmax, h, w, B, L, H, V, l0, d_hidden, dW, dbias, entries, nact, stream);
+        case 2: return launch_bwd<2>(d_rep, xmax, argmax, h, w, B, L, H, V, l0, d_hidden, dW, dbias, entries, nact, stream);
+        case 3: return launch_bwd<3>(d_rep, xmax, argmax, h, w, B, L, H, V, l0, d_hidden, dW, dbias, entries, nact, stream);
+        default: return launch_bwd<4>(d_rep, xmax, argmax, h, w, B, L, H, V, l0, d_hidden, dW, dbias, entries, nact, stream);
+    }
+}
+
+extern "C" int sb200_prune_rows(float* rep, int B, int V, float ratio, sb200_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    SB200_REQUIRE(rep && B >= 1 && V >= 1, "prune_rows: bad arguments");
+    prune_rows_kernel<<<B, 256, 0, stream>>>(rep, V, ratio);
+    SB200_CHECK_LAUNCH("prune_rows_kernel");
+    return SB200_OK;
+}

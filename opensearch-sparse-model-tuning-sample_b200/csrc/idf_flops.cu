@@ -1,0 +1,280 @@
+// HBM-bound vector kernels of the training step: inf-free IDF query lookup (sparse_encoders.py:121-127)
+// and the FLOPS / L0-thresholded FLOPS regulariser (trainer.py:61-73), forward and backward.
+// All are streaming passes with 128-bit accesses where alignment allows, warp-shuffle reductions, no tensor cores.
+#include <cuda_runtime.h>
+
+#include "common.h"
+
+namespace sb200 {
+namespace {
+
+__device__ __forceinline__ float warp_sum(float x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+}
+__device__ __forceinline__ float warp_max(float x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, o));
+    return x;
+}
+
+// ------------------------------------------------------------------------------------------ IDF query
+// grid (slabs, Nq): a block zero-fills its slab of the row, barriers, then stores relu(idf[id]) for the ids of the
+// row that fall into the slab. Duplicate ids store the same value (idempotent), specials and bad ids are skipped.
+constexpr int kIdfThreads = 256;
+
+__global__ void __launch_bounds__(kIdfThreads)
+idf_query_kernel(const int64_t* __restrict__ ids, const float* __restrict__ idf, const int32_t* __restrict__ special,
+                 int n_special, int Lq, int V, int slab, float* __restrict__ q, int32_t* __restrict__ bad_ids) {
+    const int b = blockIdx.y;
+    const int s0 = blockIdx.x * slab;
+    const int s1 = min(V, s0 + slab);
+    float* row = q + size_t(b) * V;
+    // zero fill [s0, s1): scalar head up to 16-byte alignment, float4 body, scalar tail
+    {
+        const uintptr_t addr = reinterpret_cast<uintptr_t>(row + s0);
+        int head = int(((16 - (addr & 15)) & 15) >> 2);
+        head = min(head, s1 - s0);
+        const int body4 = (s1 - s0 - head) >> 2;
+        const int tail0 = s0 + head + body4 * 4;
+        if (int(threadIdx.x) < head) row[s0 + threadIdx.x] = 0.f;
+        float4* p4 = reinterpret_cast<float4*>(row + s0 + head);
+        for (int i = threadIdx.x; i < body4; i += kIdfThreads) p4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (tail0 + int(threadIdx.x) < s1) row[tail0 + threadIdx.x] = 0.f;
+    }
+    __syncthreads();
+    int bad = 0;
+    for (int l = threadIdx.x; l < Lq; l += kIdfThreads) {
+        const int64_t id = __ldg(ids + size_t(b) * Lq + l);
+        if (id < 0 || id >= V) {
+            ++bad;
+            continue;
+        }
+        if (id < s0 || id >= s1) continue;
+        bool is_special = false;
+        for (int k = 0; k < n_special; ++k) is_special |= (__ldg(special + k) == int32_t(id));
+        if (!is_special) row[id] = fmaxf(__ldg(idf + id), 0.f);
+    }
+    if (bad_ids != nullptr && blockIdx.x == 0 && bad > 0) atomicAdd(bad_ids, bad);
+}
+
+// d_idf[v] = sum_b d_q[b,v] * [q[b,v] > 0]
+__global__ void __launch_bounds__(256)
+idf_query_bwd_kernel(const float* __restrict__ d_q, const float* __restrict__ q, int Nq, int V, float* __restrict__ d_idf) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    float acc = 0.f;
+    for (int b = 0; b < Nq; ++b) {
+        const size_t o = size_t(b) * V + v;
+        if (__ldg(q + o) > 0.f) acc += __ldg(d_q + o);
+    }
+    d_idf[v] = acc;
+}
+
+// ------------------------------------------------------------------------------------------ FLOPS regulariser
+// Pass 1 (threshold >= 0 or stats wanted): one block per row -> nnz, rowmask, stats.
+__global__ void __launch_bounds__(256)
+flops_rowstat_kernel(const float* __restrict__ rep, int V, float threshold, float* __restrict__ rowmask,
+                     float* __restrict__ stats) {
+    __shared__ float red[3][8];
+    const float* row = rep + size_t(blockIdx.x) * V;
+    float nnz = 0.f, psum = 0.f, pmax = 0.f;
+    for (int v = threadIdx.x; v < V; v += 256) {
+        const float x = __ldg(row + v);
+        nnz += (x != 0.f) ? 1.f : 0.f;
+        if (x > 0.f) {
+            psum += x;
+            pmax = fmaxf(pmax, x);
+        }
+    }
+    nnz = warp_sum(nnz);
+    psum = warp_sum(psum);
+    pmax = warp_max(pmax);
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) {
+        red[0][w] = nnz;
+        red[1][w] = psum;
+        red[2][w] = pmax;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float a = 0.f, s = 0.f, m = 0.f;
+        for (int i = 0; i < 8; ++i) {
+            a += red[0][i];
+            s += red[1][i];
+            m = fmaxf(m, red[2][i]);
+        }
+        // torch.norm(p=0) counts non-zeros; mask = (doc_length > threshold)
+        rowmask[blockIdx.x] = (threshold < 0.f || a > threshold) ? 1.f : 0.f;
+        if (stats != nullptr) {
+            atomicAdd(stats + 0, a);
+            atomicAdd(stats + 1, s);
+            // entries are >= 0 here, so the int ordering of the bit patterns matches the float ordering
+            atomicMax(reinterpret_cast<int*>(stats + 2), __float_as_int(m));
+        }
+    }
+}
+
+// Pass 2: colsum[g,v] = sum_n rowmask[n*G+g] * |rep[n,g,v]| ; value += sum (colsum/N)^2 over this block's columns.
+// grid.x covers G*V columns, grid.y splits n (partial sums merged with atomics when gridDim.y > 1).
+template <int VEC>
+__global__ void __launch_bounds__(256)
+flops_colsum_kernel(const float* __restrict__ rep, const float* __restrict__ rowmask, int N, int GV,
+                    int G, int V, float* __restrict__ colsum) {
+    const int col = (blockIdx.x * 256 + threadIdx.x) * VEC;
+    if (col >= GV) return;
+    const int g = col / V;
+    const int n_per = (N + gridDim.y - 1) / gridDim.y;
+    const int n0 = blockIdx.y * n_per, n1 = min(N, n0 + n_per);
+    float acc[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+#pragma unroll 4
+    for (int n = n0; n < n1; ++n) {
+        const float mk = __ldg(rowmask + size_t(n) * G + g);
+        const float* p = rep + size_t(n) * GV + col;
+        if (VEC == 4) {
+            const float4 x = __ldg(reinterpret_cast<const float4*>(p));
+            acc[0] += mk * fabsf(x.x);
+            acc[1 % VEC] += mk * fabsf(x.y);
+            acc[2 % VEC] += mk * fabsf(x.z);
+            acc[3 % VEC] += mk * fabsf(x.w);
+        } else if (VEC == 2) {
+            const float2 x = __ldg(reinterpret_cast<const float2*>(p));
+            acc[0] += mk * fabsf(x.x);
+            acc[1 % VEC] += mk * fabsf(x.y);
+        } else {
+            acc[0] += mk * fabsf(__ldg(p));
+        }
+    }
+    if (gridDim.y == 1) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) colsum[col + i] = acc[i];
+    } else {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) atomicAdd(colsum + col + i, acc[i]);
+    }
+}
+
+// value = sum_c (colsum[c] / N)^2
+__global__ void __launch_bounds__(256)
+flops_value_kernel(const float* __restrict__ colsum, int GV, float invN, float* __restrict__ value) {
+    __shared__ float red[8];
+    float acc = 0.f;
+    for (int c = blockIdx.x * 256 + threadIdx.x; c < GV; c += gridDim.x * 256) {
+        const float m = __ldg(colsum + c) * invN;
+        acc = fmaf(m, m, acc);
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int i = 0; i < 8; ++i) s += red[i];
+        atomicAdd(value, s);
+    }
+}
+
+// d_rep[row, v] (+)= gscale * 2*colsum[g,v]/N^2 * sign(rep) * rowmask[row], rows [row_begin, row_end)
+__global__ void __launch_bounds__(256)
+flops_bwd_kernel(const float* __restrict__ rep, const float* __restrict__ colsum, const float* __restrict__ rowmask,
+                 const float* __restrict__ gscale, int G, int V, int row_begin, float k, int accumulate,
+                 float* __restrict__ d_rep) {
+    const int row = row_begin + blockIdx.y;
+    const int g = row % G;
+    const float s = __ldg(gscale) * k * __ldg(rowmask + row);
+    const float* r = rep + size_t(row) * V;
+    const float* cs = colsum + size_t(g) * V;
+    float* o = d_rep + size_t(row) * V;
+    for (int v = blockIdx.x * 256 + threadIdx.x; v < V; v += gridDim.x * 256) {
+        const float x = __ldg(r + v);
+        const float sg = (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f);
+        const float gval = s * __ldg(cs + v) * sg;
+        o[v] = accumulate ? (o[v] + gval) : gval;
+    }
+}
+
+}  // namespace
+}  // namespace sb200
+
+using namespace sb200;
+
+extern "C" int sb200_idf_query(const int64_t* ids, const float* idf, const int32_t* special, int n_special, int Nq,
+                               int Lq, int V, float* q, int32_t* bad_ids, sb200_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    SB200_REQUIRE(ids && idf && q && (special || n_special == 0), "idf_query: null pointer");
+    SB200_REQUIRE(Nq >= 1 && Lq >= 1 && V >= 1 && n_special >= 0 && Nq <= 65535, "idf_query: bad shape");
+    // enough blocks to fill the machine: Nq rows x slabs
+    int slabs = (2 * num_sms() + Nq - 1) / Nq;
+    if (slabs < 1) slabs = 1;
+    int slab = (V + slabs - 1) / slabs;
+    slab = int(align_up(size_t(slab), 1024));
+    slabs = (V + slab - 1) / slab;
+    if (bad_ids != nullptr) SB200_CUDA(cudaMemsetAsync(bad_ids, 0, sizeof(int32_t), stream));
+    idf_query_kernel<<<dim3(slabs, Nq), kIdfThreads, 0, stream>>>(ids, idf, special, n_special, Lq, V, slab, q, bad_ids);
+    SB200_CHECK_LAUNCH("idf_query_kernel");
+    return SB200_OK;
+}
+
+extern "C" int sb200_idf_query_bwd(const float* d_q, const float* q, int Nq, int V, float* d_idf, sb200_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    SB200_REQUIRE(d_q && q && d_idf && Nq >= 1 && V >= 1, "idf_query_bwd: bad arguments");
+    idf_query_bwd_kernel<<<(V + 255) / 256, 256, 0, stream>>>(d_q, q, Nq, V, d_idf);
+    SB200_CHECK_LAUNCH("idf_query_bwd_kernel");
+    return SB200_OK;
+}
+
+extern "C" int sb200_flops_fwd(const float* rep, int N, int G, int V, float threshold, float* colsum, float* rowmask,
+                               float* value, float* stats, sb200_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    SB200_REQUIRE(rep && colsum && rowmask && value, "flops_fwd: null pointer");
+    SB200_REQUIRE(N >= 1 && G >= 1 && V >= 1, "flops_fwd: bad shape");
+    const long long rows = (long long)N * G;
+    const long long GV = (long long)G * V;
+    SB200_REQUIRE(rows <= 0x7fffffffLL && GV <= 0x7fffffffLL, "flops_fwd: shape too large");
+    SB200_CUDA(cudaMemsetAsync(value, 0, sizeof(float), stream));
+    if (stats != nullptr) SB200_CUDA(cudaMemsetAsync(stats, 0, 4 * sizeof(float), stream));
+    flops_rowstat_kernel<<<int(rows), 256, 0, stream>>>(rep, V, threshold, rowmask, stats);
+    SB200_CHECK_LAUNCH("flops_rowstat_kernel");
+
+    const bool a16 = (reinterpret_cast<uintptr_t>(rep) & 15) == 0;
+    const int vec = (a16 && V % 4 == 0) ? 4 : ((a16 && V % 2 == 0) ? 2 : 1);
+    const int threads_x = int((GV / vec + 255) / 256);
+    int ysplit = 1;
+    const int target = 4 * num_sms();
+    if (threads_x < target) ysplit = (target + threads_x - 1) / threads_x;
+    if (ysplit > N) ysplit = N;
+    if (ysplit > 1) SB200_CUDA(cudaMemsetAsync(colsum, 0, size_t(GV) * sizeof(float), stream));
+    dim3 grid(threads_x, ysplit);
+    if (vec == 4)
+        flops_colsum_kernel<4><<<grid, 256, 0, stream>>>(rep, rowmask, N, int(GV), G, V, colsum);
+    else if (vec == 2)
+        flops_colsum_kernel<2><<<grid, 256, 0, stream>>>(rep, rowmask, N, int(GV), G, V, colsum);
+    else
+        flops_colsum_kernel<1><<<grid, 256, 0, stream>>>(rep, rowmask, N, int(GV), G, V, colsum);
+    SB200_CHECK_LAUNCH("flops_colsum_kernel");
+    int vblocks = int((GV + 255) / 256);
+    if (vblocks > 2 * num_sms()) vblocks = 2 * num_sms();
+    flops_value_kernel<<<vblocks, 256, 0, stream>>>(colsum, int(GV), 1.f / float(N), value);
+    SB200_CHECK_LAUNCH("flops_value_kernel");
+    return SB200_OK;
+}
+
+extern "C" int sb200_flops_bwd(const float* rep, const float* colsum, const float* rowmask, const float* gscale, int N,
+                               int G, int V, int row_begin, int row_end, int accumulate, float* d_rep,
+                               sb200_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    SB200_REQUIRE(rep && colsum && rowmask && gscale && d_rep, "flops_bwd: null pointer");
+    SB200_REQUIRE(N >= 1 && G >= 1 && V >= 1 && row_begin >= 0 && row_end <= N * G && row_begin <= row_end,
+                  "flops_bwd: bad shape");
+    if (row_end == row_begin) return SB200_OK;
+    SB200_REQUIRE(row_end - row_begin <= 65535, "flops_bwd: too many rows");
+    int xb = (V + 255) / 256;
+    if (xb > 32) xb = 32;
+    const float k = 2.f / (float(N) * float(N));
+    flops_bwd_kernel<<<dim3(xb, row_end - row_begin), 256, 0, stream>>>(rep, colsum, rowmask, gscale, G, V, row_begin, k,
+                                                                        accumulate, d_rep);
+    SB200_CHECK_LAUNCH("flops_bwd_kernel");
+    return SB200_OK;
+}

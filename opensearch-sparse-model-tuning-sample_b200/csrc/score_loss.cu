@@ -1,0 +1,551 @@
+// In-batch query x doc scoring and the ranking losses of scripts/train/loss.py, plus the encode-output
+// compaction (sparse_encoders.py:137-150, 178-179) and the teacher min-max normalisation
+// (bi_encoder_wrapper.py:133-138). fp32 CUDA-core arithmetic throughout (the reference runs these GEMMs in
+// fp32 with TF32 off); the score kernels are HBM/L2-bound: (Nq+Nd)*V*4 bytes against Nq*Nd*V*2 flop.
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include "common.h"
+
+namespace sb200 {
+namespace {
+
+// ------------------------------------------------------------------------------------------ block reductions
+template <int THREADS>
+__device__ __forceinline__ float block_sum(float x, float* red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = x;
+    __syncthreads();
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < THREADS / 32; ++i) s += red[i];
+    return s;
+}
+template <int THREADS>
+__device__ __forceinline__ float block_max(float x, float* red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, o));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = x;
+    __syncthreads();
+    float s = -CUDART_INF_F;
+#pragma unroll
+    for (int i = 0; i < THREADS / 32; ++i) s = fmaxf(s, red[i]);
+    return s;
+}
+template <int THREADS>
+__device__ __forceinline__ float block_min(float x, float* red) {
+    return -block_max<THREADS>(-x, red);
+}
+
+// ------------------------------------------------------------------------------------------ scores, in-batch
+// S[i,j] += sum_{k in split} q[i,k] d[j,k].  64x64 output tile per block, 4x4 per thread, K staged 32 at a time
+// through shared memory (transposed, stride 65 -> conflict-free), split-K over blockIdx.z merged with atomics.
+constexpr int kST = 64, kSK = 32, kSStride = kST + 1;
+
+__global__ void __launch_bounds__(256)
+scores_tile_kernel(const float* __restrict__ q, const float* __restrict__ d, int Nq, int Nd, int V, int kchunk,
+                   float* __restrict__ S) {
+    __shared__ float qs[kSK * kSStride];
+    __shared__ float ds[kSK * kSStride];
+    const int i0 = blockIdx.y * kST, j0 = blockIdx.x * kST;
+    const int k_begin = blockIdx.z * kchunk;
+    const int k_end = min(V, k_begin + kchunk);
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+    const int lk = threadIdx.x & 31, lr = threadIdx.x >> 5;  // loader: k offset, row offset
+    float acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+
+    for (int k0 = k_begin; k0 < k_end; k0 += kSK) {
+        const int k = k0 + lk;
+        const bool k_ok = k < k_end;
+        float qv[8], dv[8];
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+            const int r = lr + 8 * p;
+            qv[p] = (k_ok && i0 + r < Nq) ? __ldg(q + size_t(i0 + r) * V + k) : 0.f;
+            dv[p] = (k_ok && j0 + r < Nd) ? __ldg(d + size_t(j0 + r) * V + k) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+            const int r = lr + 8 * p;
+            qs[lk * kSStride + r] = qv[p];
+            ds[lk * kSStride + r] = dv[p];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < kSK; ++kk) {
+            float a[4], b[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                a[e] = qs[kk * kSStride + ty * 4 + e];
+                b[e] = ds[kk * kSStride + tx + 16 * e];
+            }
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y) acc[x][y] = fmaf(a[x], b[y], acc[x][y]);
+        }
+    }
+#pragma unroll
+    for (int x = 0; x < 4; ++x) {
+        const int i = i0 + ty * 4 + x;
+        if (i >= Nq) continue;
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+            const int j = j0 + tx + 16 * y;
+            if (j < Nd) {
+                if (gridDim.z == 1) S[size_t(i) * Nd + j] = acc[x][y];
+                else atomicAdd(S + size_t(i) * Nd + j, acc[x][y]);
+            }
+        }
+    }
+}
+
+// scores, own docs only: S[i,g] = q[i,:] . d[i*G+g,:]   grid (ksplit, Nq)
+__global__ void __launch_bounds__(256)
+scores_group_kernel(const float* __restrict__ q, const float* __restrict__ d, int G, int V, int kchunk,
+                    float* __restrict__ S) {
+    __shared__ float red[8];
+    const int i = blockIdx.y;
+    const int k_begin = blockIdx.x * kchunk, k_end = min(V, k_begin + kchunk);
+    const float* qi = q + size_t(i) * V;
+    for (int g0 = 0; g0 < G; g0 += 8) {
+        float acc[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+        for (int k = k_begin + threadIdx.x; k < k_end; k += 256) {
+            const float qv = __ldg(qi + k);
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+                if (g0 + e < G) acc[e] = fmaf(qv, __ldg(d + (size_t(i) * G + g0 + e) * V + k), acc[e]);
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            if (g0 + e < G) {  // block-uniform
+                const float s = block_sum<256>(acc[e], red);
+                if (threadIdx.x == 0) {
+                    if (gridDim.x == 1) S[size_t(i) * G + g0 + e] = s;
+                    else atomicAdd(S + size_t(i) * G + g0 + e, s);
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ scores backward
+// out[r, v] (+)= sum_k coef(r,k) * in[k, v],  coef(r,k) = dS[r*sr + k*sk];  r in [r_begin, r_end), k in [0, K).
+// 16 output rows per block, 2 columns per thread; coefficients staged in shared memory.
+constexpr int kBR = 16, kBKc = 256;
+
+template <int VECW>
+__global__ void __launch_bounds__(256)
+scores_bwd_kernel(const float* __restrict__ dS, int sr, int sk, const float* __restrict__ in, int K, int V, int r_begin,
+                  int r_end, int accumulate, float* __restrict__ out) {
+    __shared__ float coef[kBR][kBKc];
+    const int r0 = r_begin + blockIdx.y * kBR;
+    const int v = (blockIdx.x * 256 + threadIdx.x) * VECW;
+    float acc[kBR][VECW];
+#pragma unroll
+    for (int r = 0; r < kBR; ++r)
+#pragma unroll
+        for (int e = 0; e < VECW; ++e) acc[r][e] = 0.f;
+    for (int kc = 0; kc < K; kc += kBKc) {
+        const int nk = min(kBKc, K - kc);
+        __syncthreads();
+        for (int t = threadIdx.x; t < kBR * nk; t += 256) {
+            const int r = t / nk, k = t - r * nk;
+            coef[r][k] = (r0 + r < r_end) ? __ldg(dS + size_t(r0 + r) * sr + size_t(kc + k) * sk) : 0.f;
+        }
+        __syncthreads();
+        if (v < V) {
+#pragma unroll 4
+            for (int k = 0; k < nk; ++k) {
+                float x[VECW];
+                const float* p = in + size_t(kc + k) * V + v;
+                if (VECW == 2) {
+                    const float2 t2 = __ldg(reinterpret_cast<const float2*>(p));
+                    x[0] = t2.x;
+                    x[VECW - 1] = t2.y;
+                } else {
+                    x[0] = __ldg(p);
+                }
+#pragma unroll
+                for (int r = 0; r < kBR; ++r)
+#pragma unroll
+                    for (int e = 0; e < VECW; ++e) acc[r][e] = fmaf(coef[r][k], x[e], acc[r][e]);
+            }
+        }
+    }
+    if (v >= V) return;
+#pragma unroll
+    for (int r = 0; r < kBR; ++r) {
+        if (r0 + r >= r_end) break;
+        float* o = out + size_t(r0 + r) * V + v;
+#pragma unroll
+        for (int e = 0; e < VECW; ++e) o[e] = accumulate ? (o[e] + acc[r][e]) : acc[r][e];
+    }
+}
+
+// own-docs backward: d_d[i*G+g, v] (+)= dS[i,g] q[i,v]    grid (xb, rows)
+__global__ void __launch_bounds__(256)
+scores_group_bwd_d_kernel(const float* __restrict__ dS, const float* __restrict__ q, int G, int V, int d_begin,
+                          int accumulate, float* __restrict__ d_d) {
+    const int row = d_begin + blockIdx.y;
+    const int i = row / G;
+    const float c = __ldg(dS + row);  // dS is [Nq, G] row-major == index row
+    const float* qi = q + size_t(i) * V;
+    float* o = d_d + size_t(row) * V;
+    for (int v = blockIdx.x * 256 + threadIdx.x; v < V; v += gridDim.x * 256) {
+        const float gval = c * __ldg(qi + v);
+        o[v] = accumulate ? (o[v] + gval) : gval;
+    }
+}
+// own-docs backward: d_q[i, v] (+)= sum_g dS[i,g] d[i*G+g, v]
+__global__ void __launch_bounds__(256)
+scores_group_bwd_q_kernel(const float* __restrict__ dS, const float* __restrict__ d, int G, int V, int q_begin,
+                          int accumulate, float* __restrict__ d_q) {
+    const int i = q_begin + blockIdx.y;
+    float* o = d_q + size_t(i) * V;
+    for (int v = blockIdx.x * 256 + threadIdx.x; v < V; v += gridDim.x * 256) {
+        float acc = 0.f;
+        for (int g = 0; g < G; ++g) acc = fmaf(__ldg(dS + size_t(i) * G + g), __ldg(d + (size_t(i) * G + g) * V + v), acc);
+        o[v] = accumulate ? (o[v] + acc) : acc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ ranking losses
+// One block per query row. loss is accumulated with one atomicAdd per row (already scaled by the batch mean).
+__global__ void __launch_bounds__(256)
+rank_loss_kernel(int mode, const float* __restrict__ S, const float* __restrict__ teacher, int Nq, int C, int G,
+                 int in_batch, float invT, float* __restrict__ loss, float* __restrict__ dS) {
+    __shared__ float red[8];
+    const int i = blockIdx.x;
+    const float* s = S + size_t(i) * C;
+    float* g = dS != nullptr ? dS + size_t(i) * C : nullptr;
+    const float invNq = 1.f / float(Nq);
+
+    if (mode == SB200_LOSS_INFONCE) {
+        // selected columns: own positive + every hard negative (loss.py:90-101); own docs only when !in_batch
+        const int pos = in_batch ? i * G : 0;
+        auto selected = [&](int j) { return !in_batch || j == pos || (j % G) != 0; };
+        float m = -CUDART_INF_F;
+        for (int j = threadIdx.x; j < C; j += 256)
+            if (selected(j)) m = fmaxf(m, s[j]);
+        m = block_max<256>(m, red);
+        float z = 0.f;
+        for (int j = threadIdx.x; j < C; j += 256)
+            if (selected(j)) z += expf(s[j] - m);
+        z = block_sum<256>(z, red);
+        const float lse = m + logf(z);
+        if (threadIdx.x == 0) atomicAdd(loss, (lse - s[pos]) * invNq);
+        if (g != nullptr) {
+            for (int j = threadIdx.x; j < C; j += 256) {
+                float v = 0.f;
+                if (selected(j)) v = (expf(s[j] - lse) - (j == pos ? 1.f : 0.f)) * invNq;
+                g[j] = v;
+            }
+        }
+    } else if (mode == SB200_LOSS_KLDIV) {
+        const float* t = teacher + size_t(i) * C;
+        float ms = -CUDART_INF_F, mt = -CUDART_INF_F;
+        for (int j = threadIdx.x; j < C; j += 256) {
+            ms = fmaxf(ms, s[j] * invT);
+            mt = fmaxf(mt, t[j] * invT);
+        }
+        ms = block_max<256>(ms, red);
+        mt = block_max<256>(mt, red);
+        float zs = 0.f, zt = 0.f;
+        for (int j = threadIdx.x; j < C; j += 256) {
+            zs += expf(s[j] * invT - ms);
+            zt += expf(t[j] * invT - mt);
+        }
+        zs = block_sum<256>(zs, red);
+        zt = block_sum<256>(zt, red);
+        const float lzs = logf(zs), lzt = logf(zt);
+        float acc = 0.f;
+        for (int j = threadIdx.x; j < C; j += 256) {
+            const float lps = s[j] * invT - ms - lzs;
+            const float lpt = t[j] * invT - mt - lzt;
+            const float pt = expf(lpt);
+            if (pt > 0.f) acc += pt * (lpt - lps);  // xlogy(t,t) - t*input
+            if (g != nullptr) g[j] = (expf(lps) - pt) * invT * invNq;
+        }
+        acc = block_sum<256>(acc, red);
+        if (threadIdx.x == 0) atomicAdd(loss, acc * invNq);
+    } else {  // margin MSE: margins against column 0 (loss.py:52-55)
+        const float* t = teacher + size_t(i) * C;
+        const float s0 = s[0] * invT, t0 = t[0] * invT;
+        const float norm = 1.f / (float(Nq) * float(C - 1));
+        float acc = 0.f, g0 = 0.f;
+        for (int j = 1 + threadIdx.x; j < C; j += 256) {
+            const float diff = (s0 - s[j] * invT) - (t0 - t[j] * invT);
+            acc = fmaf(diff, diff, acc);
+            const float gj = 2.f * diff * norm * invT;
+            g0 += gj;
+            if (g != nullptr) g[j] = -gj;
+        }
+        acc = block_sum<256>(acc, red);
+        g0 = block_sum<256>(g0, red);
+        if (threadIdx.x == 0) {
+            atomicAdd(loss, acc * norm);
+            if (g != nullptr) g[0] = g0;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ CSR compaction
+__global__ void __launch_bounds__(256)
+compact_count_kernel(const float* __restrict__ rep, int V, int first_col, int* __restrict__ counts) {
+    __shared__ float red[8];
+    const float* row = rep + size_t(blockIdx.x) * V;
+    float c = 0.f;
+    for (int v = first_col + threadIdx.x; v < V; v += 256) c += (__ldg(row + v) != 0.f) ? 1.f : 0.f;
+    c = block_sum<256>(c, red);
+    if (threadIdx.x == 0) counts[blockIdx.x] = int(c);
+}
+
+__global__ void __launch_bounds__(1024) compact_scan_kernel(const int* __restrict__ counts, int B, int32_t* __restrict__ row_ptr) {
+    __shared__ int warp_tot[32];
+    __shared__ int carry_s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base < B; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int c = (i < B) ? counts[i] : 0;
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const int w = warp_tot[lane];
+            int wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += t;
+            }
+            warp_tot[lane] = wi - w;
+        }
+        __syncthreads();
+        const int carry = carry_s;
+        const int excl = carry + warp_tot[warp] + incl - c;
+        if (i < B) row_ptr[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = excl + c;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) row_ptr[B] = carry_s;
+}
+
+// ordered fill: columns ascending inside a row (matches torch.nonzero order)
+__global__ void __launch_bounds__(256)
+compact_fill_kernel(const float* __restrict__ rep, int V, int first_col, const int32_t* __restrict__ row_ptr,
+                    int32_t* __restrict__ cols, float* __restrict__ vals, int capacity,
+                    unsigned long long* __restrict__ df_count) {
+    __shared__ int warp_cnt[8];
+    __shared__ int base_s;
+    const float* row = rep + size_t(blockIdx.x) * V;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) base_s = row_ptr[blockIdx.x];
+    __syncthreads();
+    for (int v0 = first_col; v0 < V; v0 += 256) {
+        const int v = v0 + threadIdx.x;
+        const float x = (v < V) ? __ldg(row + v) : 0.f;
+        const bool nz = x != 0.f;
+        const uint32_t bal = __ballot_sync(0xffffffffu, nz);
+        if (lane == 0) warp_cnt[warp] = __popc(bal);
+        __syncthreads();
+        int off = base_s;
+        for (int w = 0; w < warp; ++w) off += warp_cnt[w];
+        off += __popc(bal & ((1u << lane) - 1u));
+        if (nz) {
+            if (off < capacity) {
+                cols[off] = v;
+                vals[off] = x;
+            }
+            if (df_count != nullptr && x > 0.f) atomicAdd(df_count + v, 1ull);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int tot = 0;
+            for (int w = 0; w < 8; ++w) tot += warp_cnt[w];
+            base_s += tot;
+        }
+        __syncthreads();
+    }
+}
+
+// acc[i,:] (+)= scale * (S[i,:] - min) / (max - min + 1e-6)
+__global__ void __launch_bounds__(256)
+minmax_kernel(const float* __restrict__ S, int C, float scale, int accumulate, float* __restrict__ acc) {
+    __shared__ float red[8];
+    const float* s = S + size_t(blockIdx.x) * C;
+    float* a = acc + size_t(blockIdx.x) * C;
+    float mx = -CUDART_INF_F, mn = CUDART_INF_F;
+    for (int j = threadIdx.x; j < C; j += 256) {
+        mx = fmaxf(mx, s[j]);
+        mn = fminf(mn, s[j]);
+    }
+    mx = block_max<256>(mx, red);
+    mn = block_min<256>(mn, red);
+    const float den = (mx - mn) + 1e-6f;
+    for (int j = threadIdx.x; j < C; j += 256) {
+        const float v = (s[j] - mn) / den * scale;
+        a[j] = accumulate ? (a[j] + v) : v;
+    }
+}
+
+int pick_ksplit(int base_blocks, int V, int quantum, int* kchunk) {
+    int ks = (2 * num_sms() + base_blocks - 1) / base_blocks;
+    if (ks < 1) ks = 1;
+    int kc = (V + ks - 1) / ks;
+    kc = int(align_up(size_t(kc), size_t(quantum)));
+    ks = (V + kc - 1) / kc;
+    *kchunk = kc;
+    return ks;
+}
+
+}  // namespace
+}  // namespace sb200
+
+using namespace sb200;
+
+extern "C" size_t sb200_scores_workspace_bytes(int Nq, int Nd, int V, int in_batch) {
+    (void)Nq; (void)Nd; (void)V; (void)in_batch;
+    return 0;  // split-K partials are merged with atomics; kept in the ABI for a deterministic two-pass variant
+}
+
+extern "C" int sb200_scores_fwd(const float* q, const float* d, int Nq, int Nd, int V, int in_batch, float* S,
+                                void* workspace, size_t workspace_bytes, sb200_stream_t stream_) {
+    (void)workspace; (void)workspace_bytes;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    SB200_REQUIRE(q && d && S, "scores_fwd: null pointer");
+    SB200_REQUIRE(Nq >= 1 && Nd >= 1 && V >= 1, "scores_fwd: bad shape");
+    if (in_batch) {
+        const int tj = (Nd + kST - 1) / kST, ti = (Nq + kST - 1) / kST;
+        SB200_REQUIRE(ti <= 65535, "scores_fwd: Nq too large");
+        int kchunk;
+        const int ks = pick_ksplit(tj * ti, V, kSK, &kchunk);
+        if (ks > 1) SB200_CUDA(cudaMemsetAsync(S, 0, size_t(Nq) * Nd * sizeof(float), stream));
+        scores_tile_kernel<<<dim3(tj, ti, ks), 256, 0, stream>>>(q, d, Nq, Nd, V, kchunk, S);
+        SB200_CHECK_LAUNCH("scores_tile_kernel");
+    } else {
+        SB200_REQUIRE(Nd % Nq == 0, "scores_fwd: Nd=%d is not a multiple of Nq=%d", Nd, Nq);
+        SB200_REQUIRE(Nq <= 65535, "scores_fwd: Nq too large");
+        const int G = Nd / Nq;
+        int kchunk;
+        const int ks = pick_ksplit(Nq, V, 256, &kchunk);
+        if (ks > 1) SB200_CUDA(cudaMemsetAsync(S, 0, size_t(Nq) * G * sizeof(float), stream));
+        scores_group_kernel<<<dim3(ks, Nq), 256, 0, stream>>>(q, d, G, V, kchunk, S);
+        SB200_CHECK_LAUNCH("scores_group_kernel");
+    }
+    return SB200_OK;
+}
+
+extern "C" int sb200_scores_bwd(const float* dS, const float* q, const float* d, int Nq, int Nd, int V, int in_batch,
+                                int q_begin, int q_end, int d_begin, int d_end, int accumulate, float* d_q, float* d_d,
+                                sb200_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    SB200_REQUIRE(dS && q && d, "scores_bwd: null pointer");
+    SB200_REQUIRE(Nq >= 1 && Nd >= 1 && V >= 1, "scores_bwd: bad shape");
+    SB200_REQUIRE(0 <= q_begin && q_begin <= q_end && q_end <= Nq && 0 <= d_begin && d_begin <= d_end && d_end <= Nd,
+                  "scores_bwd: bad row ranges");
+    const bool vec2 = (V % 2 == 0) && ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(d) |
+                                        reinterpret_cast<uintptr_t>(d_q) | reinterpret_cast<uintptr_t>(d_d)) & 7) == 0;
+    if (in_batch) {
+        const int xb = vec2 ? (V / 2 + 255) / 256 : (V + 255) / 256;
+        if (d_d != nullptr && d_end > d_begin) {
+            dim3 grid(xb, (d_end - d_begin + kBR - 1) / kBR);
+            // out row r = doc j, k = query i: coef = dS[i*Nd + j]
+            if (vec2) scores_bwd_kernel<2><<<grid, 256, 0, stream>>>(dS, 1, Nd, q, Nq, V, d_begin, d_end, accumulate, d_d);
+            else scores_bwd_kernel<1><<<grid, 256, 0, stream>>>(dS, 1, Nd, q, Nq, V, d_begin, d_end, accumulate, d_d);
+            SB200_CHECK_LAUNCH("scores_bwd_kernel(d_d)");
+        }
+        if (d_q != nullptr && q_end > q_begin) {
+            dim3 grid(xb, (q_end - q_begin + kBR - 1) / kBR);
+            if (vec2) scores_bwd_kernel<2><<<grid, 256, 0, stream>>>(dS, Nd, 1, d, Nd, V, q_begin, q_end, accumulate, d_q);
+            else scores_bwd_kernel<1><<<grid, 256, 0, stream>>>(dS, Nd, 1, d, Nd, V, q_begin, q_end, accumulate, d_q);
+            SB200_CHECK_LAUNCH("scores_bwd_kernel(d_q)");
+        }
+    } else {
+        SB200_REQUIRE(Nd % Nq == 0, "scores_bwd: Nd=%d is not a multiple of Nq=%d", Nd, Nq);
+        const int G = Nd / Nq;
+        int xb = (V + 255) / 256;
+        if (xb > 32) xb = 32;
+        if (d_d != nullptr && d_end > d_begin) {
+            SB200_REQUIRE(d_end - d_begin <= 65535, "scores_bwd: too many rows");
+            scores_group_bwd_d_kernel<<<dim3(xb, d_end - d_begin), 256, 0, stream>>>(dS, q, G, V, d_begin, accumulate, d_d);
+            SB200_CHECK_LAUNCH("scores_group_bwd_d_kernel");
+        }
+        if (d_q != nullptr && q_end > q_begin) {
+            SB200_REQUIRE(q_end - q_begin <= 65535, "scores_bwd: too many rows");
+            scores_group_bwd_q_kernel<<<dim3(xb, q_end - q_begin), 256, 0, stream>>>(dS, d, G, V, q_begin, accumulate, d_q);
+            SB200_CHECK_LAUNCH("scores_group_bwd_q_kernel");
+        }
+    }
+    return SB200_OK;
+}
+
+extern "C" int sb200_rank_loss(int mode, const float* S, const float* teacher, int Nq, int C, int G, int in_batch,
+                               float temperature, float* loss, float* dS, sb200_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    SB200_REQUIRE(S && loss, "rank_loss: null pointer");
+    SB200_REQUIRE(mode >= SB200_LOSS_INFONCE && mode <= SB200_LOSS_MARGINMSE, "rank_loss: bad mode %d", mode);
+    SB200_REQUIRE(Nq >= 1 && C >= 1 && G >= 1, "rank_loss: bad shape");
+    SB200_REQUIRE(mode == SB200_LOSS_INFONCE || teacher != nullptr, "rank_loss: teacher scores required");
+    SB200_REQUIRE(mode != SB200_LOSS_MARGINMSE || C >= 2, "rank_loss: marginmse needs >= 2 columns");
+    SB200_REQUIRE(temperature > 0.f, "rank_loss: temperature must be positive");
+    if (mode == SB200_LOSS_INFONCE) {
+        if (in_batch) SB200_REQUIRE(C == Nq * G, "rank_loss: in-batch infonce expects C == Nq*G");
+        else SB200_REQUIRE(C == G, "rank_loss: infonce expects C == G");
+    }
+    SB200_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), stream));
+    rank_loss_kernel<<<Nq, 256, 0, stream>>>(mode, S, teacher, Nq, C, G, in_batch, 1.f / temperature, loss, dS);
+    SB200_CHECK_LAUNCH("rank_loss_kernel");
+    return SB200_OK;
+}
+
+extern "C" size_t sb200_compact_workspace_bytes(int B, int V) {
+    (void)V;
+    return B > 0 ? align_up(size_t(B) * sizeof(int), 256) : 0;
+}
+
+extern "C" int sb200_compact_rows(const float* rep, int B, int V, int first_col, int32_t* row_ptr, int32_t* cols,
+                                  float* vals, int capacity, int64_t* df_count, void* workspace, size_t workspace_bytes,
+                                  sb200_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    SB200_REQUIRE(rep && row_ptr && cols && vals, "compact_rows: null pointer");
+    SB200_REQUIRE(B >= 1 && V >= 1 && first_col >= 0 && capacity >= 0, "compact_rows: bad shape");
+    if (workspace == nullptr || workspace_bytes < sb200_compact_workspace_bytes(B, V))
+        return fail(SB200_ERR_WORKSPACE, "compact_rows: workspace too small");
+    int* counts = static_cast<int*>(workspace);
+    compact_count_kernel<<<B, 256, 0, stream>>>(rep, V, first_col, counts);
+    SB200_CHECK_LAUNCH("compact_count_kernel");
+    compact_scan_kernel<<<1, 1024, 0, stream>>>(counts, B, row_ptr);
+    SB200_CHECK_LAUNCH("compact_scan_kernel");
+    compact_fill_kernel<<<B, 256, 0, stream>>>(rep, V, first_col, row_ptr, cols, vals, capacity,
+                                               reinterpret_cast<unsigned long long*>(df_count));
+    SB200_CHECK_LAUNCH("compact_fill_kernel");
+    return SB200_OK;
+}
+
+extern "C" int sb200_minmax_accumulate(const float* S, int Nq, int C, float scale, int accumulate, float* acc,
+                                       sb200_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    SB200_REQUIRE(S && acc && Nq >= 1 && C >= 1, "minmax_accumulate: bad arguments");
+    minmax_kernel<<<Nq, 256, 0, stream>>>(S, C, scale, accumulate, acc);
+    SB200_CHECK_LAUNCH("minmax_kernel");
+    return SB200_OK;
+}
