@@ -67,3 +67,272 @@ def head_forward(hidden, weight, bias, attention_mask, use_l0=False, want_aux=Tr
                                   ws.numel(), _stream())
     _lib.check(code, "sb200_head_fwd")
     return rep, xmax, argmax
+
+
+def head_backward(d_rep, xmax, argmax, hidden, weight, use_l0=False, want_bias_grad=True):
+    """Sparse head backward -> (d_hidden [B,L,H] fp32, dW [V,H] fp32, dbias [V] fp32 | None)."""
+    _need_cuda(d_rep, xmax, argmax, hidden, weight)
+    B, L, H = hidden.shape
+    V = weight.shape[0]
+    lib = _lib.load()
+    dev = hidden.device
+    d_rep = d_rep.float().contiguous()
+    d_hidden = torch.empty(B, L, H, dtype=torch.float32, device=dev)
+    dW = torch.empty(V, H, dtype=torch.float32, device=dev)
+    dbias = torch.empty(V, dtype=torch.float32, device=dev) if want_bias_grad else None
+    ws = _workspace(lib.sb200_head_bwd_workspace_bytes(B, L, H, V), dev)
+    with torch.cuda.device(dev):
+        code = lib.sb200_head_bwd(_ptr(d_rep), _ptr(xmax), _ptr(argmax), _ptr(hidden), _ptr(weight), B, L, H, V,
+                                  _lib.HEAD_L0 if use_l0 else 0, _ptr(d_hidden), _ptr(dW), _ptr(dbias), _ptr(ws),
+                                  ws.numel(), _stream())
+    _lib.check(code, "sb200_head_bwd")
+    return d_hidden, dW, dbias
+
+
+def prune_rows_(rep, ratio):
+    """In-place row pruning (sparse_encoders.py:115-119)."""
+    _need_cuda(rep)
+    if rep.dtype != torch.float32 or not rep.is_contiguous():
+        raise TypeError("prune_rows_ expects a contiguous fp32 matrix")
+    with torch.cuda.device(rep.device):
+        code = _lib.load().sb200_prune_rows(_ptr(rep), rep.shape[0], rep.shape[1], float(ratio), _stream())
+    _lib.check(code, "sb200_prune_rows")
+    return rep
+
+
+class SparseHeadFunction(torch.autograd.Function):
+    """rep = head(hidden, weight, bias, mask); gradients flow to hidden, weight and bias."""
+
+    @staticmethod
+    def forward(ctx, hidden, weight, bias, attention_mask, use_l0):
+        h16 = hidden.detach().to(torch.bfloat16).contiguous()
+        w16 = weight.detach().to(torch.bfloat16).contiguous()
+        needs_grad = any(t is not None and t.requires_grad for t in (hidden, weight, bias))
+        rep, xmax, argmax = head_forward(h16, w16, bias, attention_mask, use_l0, want_aux=needs_grad)
+        if needs_grad:
+            ctx.save_for_backward(h16, w16, xmax, argmax)
+        ctx.use_l0 = bool(use_l0)
+        ctx.has_bias = bias is not None
+        ctx.in_dtypes = (hidden.dtype, weight.dtype, None if bias is None else bias.dtype)
+        return rep
+
+    @staticmethod
+    def backward(ctx, d_rep):
+        h16, w16, xmax, argmax = ctx.saved_tensors
+        need_h, need_w, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        d_hidden, dW, dbias = head_backward(d_rep, xmax, argmax, h16, w16, ctx.use_l0, want_bias_grad=ctx.has_bias)
+        hd, wd, bd = ctx.in_dtypes
+        return (d_hidden.to(hd) if need_h else None, dW.to(wd) if need_w else None,
+                dbias.to(bd) if (need_b and ctx.has_bias) else None, None, None)
+
+
+def sparse_head(hidden, weight, bias, attention_mask, use_l0=False):
+    return SparseHeadFunction.apply(hidden, weight, bias, attention_mask, use_l0)
+
+
+# --------------------------------------------------------------------------------------------- inf-free query
+def idf_query_forward(input_ids, idf_vector, special_ids):
+    _need_cuda(input_ids, idf_vector, special_ids)
+    ids = input_ids.to(torch.int64).contiguous()
+    Nq, Lq = ids.shape
+    idf = idf_vector.detach().float().contiguous()
+    V = idf.numel()
+    q = torch.empty(Nq, V, dtype=torch.float32, device=ids.device)
+    with torch.cuda.device(ids.device):
+        code = _lib.load().sb200_idf_query(_ptr(ids), _ptr(idf), _ptr(special_ids), int(special_ids.numel()), Nq, Lq, V,
+                                           _ptr(q), 0, _stream())
+    _lib.check(code, "sb200_idf_query")
+    return q
+
+
+class IdfQueryFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, input_ids, idf_vector, special_ids):
+        q = idf_query_forward(input_ids, idf_vector, special_ids)
+        if idf_vector.requires_grad:
+            ctx.save_for_backward(q)
+        ctx.idf_dtype = idf_vector.dtype
+        return q
+
+    @staticmethod
+    def backward(ctx, d_q):
+        (q,) = ctx.saved_tensors
+        d_q = d_q.float().contiguous()
+        d_idf = torch.empty(q.shape[1], dtype=torch.float32, device=q.device)
+        with torch.cuda.device(q.device):
+            code = _lib.load().sb200_idf_query_bwd(_ptr(d_q), _ptr(q), q.shape[0], q.shape[1], _ptr(d_idf), _stream())
+        _lib.check(code, "sb200_idf_query_bwd")
+        return None, d_idf.to(ctx.idf_dtype), None
+
+
+def idf_query(input_ids, idf_vector, special_ids):
+    return IdfQueryFunction.apply(input_ids, idf_vector, special_ids)
+
+
+# --------------------------------------------------------------------------------------------- FLOPS regulariser
+def flops_forward(rep, group_num=1, threshold=None, want_stats=False):
+    """-> (value [] fp32, colsum [G,V], rowmask [N*G], stats [4] | None)"""
+    _need_cuda(rep)
+    rep = rep.float().contiguous()
+    rows, V = rep.shape
+    if rows % group_num != 0:
+        raise ValueError(f"{rows} rows are not divisible by group_num={group_num}")
+    N = rows // group_num
+    dev = rep.device
+    colsum = torch.empty(group_num, V, dtype=torch.float32, device=dev)
+    rowmask = torch.empty(rows, dtype=torch.float32, device=dev)
+    value = torch.empty((), dtype=torch.float32, device=dev)
+    stats = torch.empty(4, dtype=torch.float32, device=dev) if want_stats else None
+    with torch.cuda.device(dev):
+        code = _lib.load().sb200_flops_fwd(_ptr(rep), N, group_num, V, -1.0 if threshold is None else float(threshold),
+                                           _ptr(colsum), _ptr(rowmask), _ptr(value), _ptr(stats), _stream())
+    _lib.check(code, "sb200_flops_fwd")
+    return value, colsum, rowmask, stats
+
+
+class FlopsFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rep, group_num, threshold):
+        rep32 = rep.detach().float().contiguous()
+        value, colsum, rowmask, _ = flops_forward(rep32, group_num, threshold)
+        ctx.save_for_backward(rep32, colsum, rowmask)
+        ctx.group_num = group_num
+        ctx.rep_dtype = rep.dtype
+        return value
+
+    @staticmethod
+    def backward(ctx, g):
+        rep, colsum, rowmask = ctx.saved_tensors
+        rows, V = rep.shape
+        G = ctx.group_num
+        g = g.detach().float().reshape(1).contiguous()
+        d_rep = torch.empty_like(rep)
+        with torch.cuda.device(rep.device):
+            code = _lib.load().sb200_flops_bwd(_ptr(rep), _ptr(colsum), _ptr(rowmask), _ptr(g), rows // G, G, V, 0, rows,
+                                               0, _ptr(d_rep), _stream())
+        _lib.check(code, "sb200_flops_bwd")
+        return d_rep.to(ctx.rep_dtype), None, None
+
+
+def flops_value(rep, group_num=1, threshold=None):
+    """trainer.py:61-73"""
+    shape_v = rep.shape[-1]
+    return FlopsFunction.apply(rep.reshape(-1, shape_v), int(group_num), threshold)
+
+
+# --------------------------------------------------------------------------------------------- scores + losses
+def scores_forward(q, d, in_batch):
+    _need_cuda(q, d)
+    q = q.float().contiguous()
+    d = d.float().contiguous()
+    Nq, V = q.shape
+    Nd = d.shape[0]
+    if d.shape[1] != V:
+        raise ValueError("q and d must share the vocabulary dimension")
+    if not in_batch and Nd % Nq != 0:
+        raise ValueError("number of docs must be a multiple of the number of queries")
+    C = Nd if in_batch else Nd // Nq
+    S = torch.empty(Nq, C, dtype=torch.float32, device=q.device)
+    with torch.cuda.device(q.device):
+        code = _lib.load().sb200_scores_fwd(_ptr(q), _ptr(d), Nq, Nd, V, 1 if in_batch else 0, _ptr(S), 0, 0, _stream())
+    _lib.check(code, "sb200_scores_fwd")
+    return S
+
+
+class ScoresFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, d, in_batch):
+        q32 = q.detach().float().contiguous()
+        d32 = d.detach().float().contiguous()
+        ctx.save_for_backward(q32, d32)
+        ctx.in_batch = bool(in_batch)
+        ctx.dtypes = (q.dtype, d.dtype)
+        return scores_forward(q32, d32, in_batch)
+
+    @staticmethod
+    def backward(ctx, dS):
+        q, d = ctx.saved_tensors
+        need_q, need_d = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        dS = dS.float().contiguous()
+        Nq, V = q.shape
+        Nd = d.shape[0]
+        d_q = torch.empty_like(q) if need_q else None
+        d_d = torch.empty_like(d) if need_d else None
+        with torch.cuda.device(q.device):
+            code = _lib.load().sb200_scores_bwd(_ptr(dS), _ptr(q), _ptr(d), Nq, Nd, V, 1 if ctx.in_batch else 0, 0, Nq, 0,
+                                                Nd, 0, _ptr(d_q), _ptr(d_d), _stream())
+        _lib.check(code, "sb200_scores_bwd")
+        return (d_q.to(ctx.dtypes[0]) if need_q else None, d_d.to(ctx.dtypes[1]) if need_d else None, None)
+
+
+def scores(q, d, in_batch):
+    """q . d^T (all pairs) or each query against its own docs (loss.py:30-37)."""
+    return ScoresFunction.apply(q, d, in_batch)
+
+
+_LOSS_MODES = {"infonce": _lib.LOSS_INFONCE, "kldiv": _lib.LOSS_KLDIV, "marginmse": _lib.LOSS_MARGINMSE}
+
+
+class RankLossFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, S, teacher, mode, G, in_batch, temperature):
+        _need_cuda(S, teacher)
+        S32 = S.detach().float().contiguous()
+        Nq, C = S32.shape
+        t32 = None
+        if teacher is not None:
+            t32 = teacher.detach().float().contiguous()
+            if tuple(t32.shape) != (Nq, C):
+                raise ValueError(f"teacher scores {tuple(t32.shape)} do not match student scores {(Nq, C)}")
+        loss = torch.empty((), dtype=torch.float32, device=S.device)
+        dS = torch.empty_like(S32) if S.requires_grad else None
+        with torch.cuda.device(S.device):
+            code = _lib.load().sb200_rank_loss(_LOSS_MODES[mode], _ptr(S32), _ptr(t32), Nq, C, int(G), 1 if in_batch else 0,
+                                               float(temperature), _ptr(loss), _ptr(dS), _stream())
+        _lib.check(code, "sb200_rank_loss")
+        if dS is not None:
+            ctx.save_for_backward(dS)
+        ctx.s_dtype = S.dtype
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (dS,) = ctx.saved_tensors
+        return (dS * g).to(ctx.s_dtype), None, None, None, None, None
+
+
+def rank_loss(S, teacher, mode, G, in_batch, temperature=1.0):
+    return RankLossFunction.apply(S, teacher, mode, G, in_batch, temperature)
+
+
+# --------------------------------------------------------------------------------------------- encode output path
+def compact_rows(rep, first_col=1, df_count=None, capacity=None):
+    """Dense [B,V] -> CSR (row_ptr [B+1] i32, cols i32, vals f32) of the non-zero entries of columns >= first_col.
+    df_count (int64 [V], optional) is incremented where rep > 0 (sparse_encoders.py:178-179)."""
+    _need_cuda(rep, df_count)
+    rep = rep.float().contiguous()
+    B, V = rep.shape
+    dev = rep.device
+    cap = B * V if capacity is None else int(capacity)
+    row_ptr = torch.empty(B + 1, dtype=torch.int32, device=dev)
+    cols = torch.empty(cap, dtype=torch.int32, device=dev)
+    vals = torch.empty(cap, dtype=torch.float32, device=dev)
+    lib = _lib.load()
+    ws = _workspace(lib.sb200_compact_workspace_bytes(B, V), dev)
+    with torch.cuda.device(dev):
+        code = lib.sb200_compact_rows(_ptr(rep), B, V, int(first_col), _ptr(row_ptr), _ptr(cols), _ptr(vals), cap,
+                                      _ptr(df_count), _ptr(ws), ws.numel(), _stream())
+    _lib.check(code, "sb200_compact_rows")
+    return row_ptr, cols, vals
+
+
+def minmax_accumulate(S, acc=None, scale=1.0):
+    """acc (+)= scale * (S - rowmin) / (rowmax - rowmin + 1e-6)   (bi_encoder_wrapper.py:133-138)"""
+    _need_cuda(S, acc)
+    S = S.float().contiguous()
+    out = torch.empty_like(S) if acc is None else acc
+    with torch.cuda.device(S.device):
+        code = _lib.load().sb200_minmax_accumulate(_ptr(S), S.shape[0], S.shape[1], float(scale), 0 if acc is None else 1,
+                                                   _ptr(out), _stream())
+    _lib.check(code, "sb200_minmax_accumulate")
+    return out

@@ -1,0 +1,240 @@
+"""Drop-in for the hot-path half of the reference's ``scripts/train/trainer.py``.
+
+``ModelWrapper`` and ``SparseModelTrainer.{flops_value, get_lambda, compute_loss, _save, set_bi_encoder_teacher}``
+keep the reference's names, arguments and arithmetic; the arithmetic runs in the sm_100a kernels (``ops``).
+``transformers.Trainer`` cannot be used in this stack (accelerate is absent), so ``SparseModelTrainer`` carries its
+own minimal data-parallel loop: one process per GPU, torch DDP (NCCL) for the gradient all-reduce, ``gather_rep``
+for the representation all-gather, bf16/fp16 autocast around the model forward, AdamW + linear warm-up as built by
+train_ir.py.
+"""
+import json
+import logging
+import os
+import types
+
+import torch
+
+from ... import ops
+from ..utils import DistEnv, gather_rep
+
+logger = logging.getLogger(__name__)
+
+
+class ModelWrapper(torch.nn.Module):
+    """One forward for docs (always through the network) and queries (IDF lookup when inf_free) -- reference :18-49."""
+
+    def __init__(self, sparse_model, inf_free=True):
+        super().__init__()
+        self.sparse_model = sparse_model
+        self.inf_free = inf_free
+
+    def forward(self, inputs):
+        d_rep = self.sparse_model(inf_free=False, input_ids=inputs["input_ids"],
+                                  attention_mask=inputs["attention_mask"])
+        q_rep = self.sparse_model(inf_free=self.inf_free, input_ids=inputs["q_input_ids"],
+                                  attention_mask=inputs["q_attention_mask"])
+        return d_rep, q_rep
+
+    def save(self, output_dir, **kwargs):
+        sm = self.sparse_model
+        sm.backbone.save_pretrained(output_dir, **kwargs)
+        if sm.tokenizer is not None and hasattr(sm.tokenizer, "save_pretrained"):
+            sm.tokenizer.save_pretrained(output_dir)
+        if sm.idf_requires_grad:
+            weights = sm.idf_vector.detach().cpu()
+            table = {sm.tokenizer._convert_id_to_token(int(i)): float(weights[i]) for i in weights.nonzero().flatten()}
+            with open(os.path.join(output_dir, "idf.json"), "w") as f:
+                json.dump(table, f)
+
+
+class SparseModelTrainer:
+    def __init__(self, model_args, data_args, loss_functions, model=None, args=None, train_dataset=None,
+                 data_collator=None, optimizers=(None, None), accelerator=None, **unused):
+        self.model_args = model_args
+        self.data_args = data_args
+        self.loss_functions = loss_functions
+        self.args = args
+        self.train_dataset = train_dataset
+        self.data_collator = data_collator
+        self.optimizer, self.lr_scheduler = optimizers
+        self.accelerator = accelerator if accelerator is not None else DistEnv()
+        self.state = types.SimpleNamespace(global_step=0)
+        self._ema = None
+        self._ema_host = 0
+        self.last_stats = None
+        wrapper = ModelWrapper(model, model_args.inf_free)
+        self.model_wrapper = wrapper
+        self.model = wrapper
+        if self.accelerator.num_processes > 1 and next(wrapper.parameters()).is_cuda:
+            dev = next(wrapper.parameters()).device
+            self.model = torch.nn.parallel.DistributedDataParallel(wrapper, device_ids=[dev.index],
+                                                                   gradient_as_bucket_view=True)
+        self.scaler = None
+        if args is not None and getattr(args, "fp16", False):
+            self.scaler = torch.amp.GradScaler("cuda")
+
+    # ------------------------------------------------------------------ reference attribute, without a per-step sync
+    @property
+    def ranking_loss_moving_avg(self):
+        """0.99/0.01 EMA of the ranking loss (reference :120-122). Kept on the device; reading it synchronises."""
+        return self._ema_host if self._ema is None else float(self._ema)
+
+    @ranking_loss_moving_avg.setter
+    def ranking_loss_moving_avg(self, value):
+        self._ema, self._ema_host = None, value
+
+    # ------------------------------------------------------------------ regularisers
+    def flops_value(self, representation, group_num=1):
+        """reference :61-73"""
+        return ops.flops_value(representation, group_num, self.data_args.flops_threshold)
+
+    def get_lambda(self, lambda_value, lambda_T):
+        """reference :75-79"""
+        if self.state.global_step >= lambda_T:
+            return lambda_value
+        return lambda_value * ((self.state.global_step + 1) / lambda_T) ** 2
+
+    # ------------------------------------------------------------------ the hot loop body
+    def compute_loss(self, model, inputs, return_outputs=False, num_items_in_batch=None):
+        """reference :81-143"""
+        if hasattr(self, "bi_encoder_teacher"):
+            inputs["scores"] = self.bi_encoder_teacher.get_scores_batch(q_features_list=inputs["query"][1:],
+                                                                        d_features_list=inputs["docs"][1:])
+        student = {"q_input_ids": inputs["query"][0]["input_ids"],
+                   "q_attention_mask": inputs["query"][0]["attention_mask"],
+                   "input_ids": inputs["docs"][0]["input_ids"],
+                   "attention_mask": inputs["docs"][0]["attention_mask"]}
+        d_rep, q_rep = model(student)
+        d_rep = gather_rep(d_rep, self.accelerator)
+        q_rep = gather_rep(q_rep, self.accelerator)
+        if "scores" in inputs:
+            inputs["scores"] = gather_rep(inputs["scores"], self.accelerator)
+
+        d_flops = self.flops_value(d_rep, d_rep.shape[0] // q_rep.shape[0])
+        flops_loss = d_flops * self.get_lambda(self.data_args.flops_d_lambda, self.data_args.flops_d_T)
+        if not self.model_args.inf_free:
+            flops_loss = flops_loss + self.flops_value(q_rep) * self.get_lambda(self.data_args.flops_q_lambda,
+                                                                                 self.data_args.flops_q_T)
+        ranking_loss = 0
+        for loss_function in self.loss_functions:
+            ranking_loss = ranking_loss + loss_function.get_loss(q_rep=q_rep, d_rep=d_rep, inputs=inputs)
+
+        # moving average without the reference's per-step .item() host sync
+        r = ranking_loss.detach().float()
+        if self._ema is None:
+            self._ema = torch.full_like(r, float(self._ema_host))
+        self._ema.mul_(0.99).add_(r, alpha=0.01)
+
+        loss = ranking_loss + flops_loss
+        if self.args is not None and self.state.global_step % max(1, self.args.logging_steps) == 0:
+            self._log_step(d_rep, d_flops, flops_loss)
+        # DDP averages gradients over ranks while every rank holds the full global loss (reference :139-141)
+        loss = loss * self.accelerator.num_processes
+        return (loss, {"q_rep": q_rep, "d_rep": d_rep}) if return_outputs else loss
+
+    def _log_step(self, d_rep, d_flops, flops_loss):
+        with torch.no_grad():
+            _, _, _, stats = ops.flops_forward(d_rep.detach(), 1, None, want_stats=True)
+            nnz, psum, pmax, _ = stats.tolist()
+        self.last_stats = {"avg_doc_length": nnz / d_rep.shape[0], "nonzero_mean": psum / max(nnz, 1.0), "nonzero_max": pmax}
+        logger.info("Step %d. ranking loss moving avg:%s, d_flops: %s, flops_loss: %s avg doc length: %s",
+                    self.state.global_step, self.ranking_loss_moving_avg, float(d_flops), float(flops_loss),
+                    self.last_stats["avg_doc_length"])
+        logger.info("nonzero entries: %s %s %s", self.last_stats["nonzero_mean"], self.last_stats["nonzero_mean"],
+                    self.last_stats["nonzero_max"])
+
+    # ------------------------------------------------------------------ step / loop
+    def _autocast(self):
+        if self.args is not None and getattr(self.args, "fp16", False):
+            return torch.autocast("cuda", dtype=torch.float16)
+        return torch.autocast("cuda", dtype=torch.bfloat16)
+
+    def training_step(self, inputs):
+        """forward (autocast) + loss + backward + optimizer step; returns the detached loss tensor (no sync)."""
+        self.model.train()
+
+        def run(student):
+            with self._autocast():
+                return self.model(student)
+
+        loss = self.compute_loss(run, inputs)
+        if self.scaler is not None:
+            self.scaler.scale(loss).backward()
+            self.scaler.unscale_(self.optimizer)
+        else:
+            loss.backward()
+        max_norm = getattr(self.args, "max_grad_norm", None) if self.args is not None else None
+        if max_norm:
+            torch.nn.utils.clip_grad_norm_(self.model.parameters(), max_norm)
+        if self.scaler is not None:
+            self.scaler.step(self.optimizer)
+            self.scaler.update()
+        else:
+            self.optimizer.step()
+        if self.lr_scheduler is not None:
+            self.lr_scheduler.step()
+        self.optimizer.zero_grad(set_to_none=True)
+        self.state.global_step += 1
+        return loss.detach()
+
+    def get_train_dataloader(self):
+        if self.train_dataset is None:
+            raise ValueError("Trainer: training requires a train_dataset.")
+        from torch.utils.data import DataLoader
+        from torch.utils.data.distributed import DistributedSampler
+        sampler = None
+        if self.accelerator.num_processes > 1 and not getattr(self.train_dataset, "no_prepare", False):
+            sampler = DistributedSampler(self.train_dataset, num_replicas=self.accelerator.num_processes,
+                                         rank=self.accelerator.process_index, shuffle=True, seed=self.args.seed)
+        return DataLoader(self.train_dataset, batch_size=self.args.per_device_train_batch_size, sampler=sampler,
+                          shuffle=sampler is None, collate_fn=self.data_collator,
+                          num_workers=self.args.dataloader_num_workers, drop_last=self.args.dataloader_drop_last,
+                          pin_memory=True)
+
+    @staticmethod
+    def _to_device(obj, device):
+        if torch.is_tensor(obj):
+            return obj.to(device, non_blocking=True)
+        if isinstance(obj, dict):
+            return {k: SparseModelTrainer._to_device(v, device) for k, v in obj.items()}
+        if isinstance(obj, (list, tuple)):
+            return type(obj)(SparseModelTrainer._to_device(v, device) for v in obj)
+        return obj
+
+    def train(self):
+        device = next(self.model_wrapper.parameters()).device
+        loader = self.get_train_dataloader()
+        epoch = 0
+        while self.state.global_step < self.args.max_steps:
+            if hasattr(loader.sampler, "set_epoch"):
+                loader.sampler.set_epoch(epoch)
+            for batch in loader:
+                self.training_step(self._to_device(batch, device))
+                if self.args.save_strategy == "steps" and self.state.global_step % self.args.save_steps == 0:
+                    self._save(os.path.join(self.args.output_dir, f"checkpoint-{self.state.global_step}"))
+                if self.state.global_step >= self.args.max_steps:
+                    break
+            epoch += 1
+        return self.state.global_step
+
+    def _save(self, output_dir=None, state_dict=None):
+        """reference :145-156 -- main process only, ModelWrapper.save layout."""
+        output_dir = output_dir if output_dir is not None else self.args.output_dir
+        os.makedirs(output_dir, exist_ok=True)
+        logger.info("Saving model checkpoint to %s", output_dir)
+        if self.accelerator.is_main_process:
+            self.accelerator.unwrap_model(self.model).save(output_dir, state_dict=state_dict,
+                                                           safe_serialization=getattr(self.args, "save_safetensors", True))
+
+    def set_bi_encoder_teacher(self, embedding_service=None, models=None):
+        """reference :158-178"""
+        from .bi_encoder_wrapper import BiEncoderWrapper
+        kw = self.data_args.kd_ensemble_teacher_kwargs
+        self.bi_encoder_teacher = BiEncoderWrapper(types=kw["types"], model_ids=kw["model_ids"],
+                                                   use_in_batch_negatives=self.data_args.use_in_batch_negatives,
+                                                   score_scale=kw.get("score_scale", 30),
+                                                   embedding_service=embedding_service, models=models)
+        self.bi_encoder_teacher.accelerator = self.accelerator
+        device = next(self.model_wrapper.parameters()).device
+        for m in self.bi_encoder_teacher.models:
+            m.to(device)

@@ -1,0 +1,95 @@
+"""Hot-path helpers of the reference's ``scripts/utils.py``: ``gather_rep`` (NCCL all-gather whose local slice keeps
+its gradient), ``is_ddp_enabled``, ``get_model``, ``set_logging``; plus ``DistEnv``, the small stand-in for the
+``accelerate.Accelerator`` attributes the hot path uses (accelerate is not part of this stack).
+
+The OpenSearch client / bulk / search helpers of the reference file are out of scope.
+"""
+import json
+import logging
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+
+class _GatherKeepLocalGrad(torch.autograd.Function):
+    """Rank-major all-gather; backward hands each rank the gradient slice of its own rows.
+
+    Equivalent to the reference's ``all_rep = accelerator.gather(rep); all_rep[i*n:(i+1)*n] = rep``
+    (scripts/utils.py:16-23): remote rows are constants, local rows carry grad.
+    """
+
+    @staticmethod
+    def forward(ctx, rep, env):
+        ctx.env = env
+        ctx.rows = rep.shape[0]
+        return env.gather(rep.detach())
+
+    @staticmethod
+    def backward(ctx, grad_all):
+        lo = ctx.env.local_process_index * ctx.rows
+        return grad_all[lo:lo + ctx.rows].contiguous(), None
+
+
+def gather_rep(rep, accelerator):
+    """``accelerator`` needs ``num_processes``, ``local_process_index`` and ``gather`` (DistEnv or accelerate)."""
+    if accelerator.num_processes == 1:
+        return rep
+    return _GatherKeepLocalGrad.apply(rep, accelerator)
+
+
+class DistEnv:
+    """One process per GPU over torch.distributed (NCCL on CUDA tensors, gloo on CPU tensors in tests)."""
+
+    def __init__(self, group=None):
+        self.group = group
+        on = dist.is_available() and dist.is_initialized()
+        self.num_processes = dist.get_world_size(group) if on else 1
+        self.process_index = dist.get_rank(group) if on else 0
+        # single node: the reference indexes the gathered tensor with local_process_index (utils.py:21)
+        self.local_process_index = self.process_index
+        self.is_main_process = self.process_index == 0
+
+    def gather(self, tensor):
+        if self.num_processes == 1:
+            return tensor
+        tensor = tensor.contiguous()
+        out = tensor.new_empty((self.num_processes * tensor.shape[0],) + tuple(tensor.shape[1:]))
+        dist.all_gather_into_tensor(out, tensor, group=self.group)
+        return out
+
+    def wait_for_everyone(self):
+        if self.num_processes > 1:
+            dist.barrier(group=self.group)
+
+    def unwrap_model(self, model):
+        return model.module if hasattr(model, "module") else model
+
+
+def is_ddp_enabled():
+    return bool(dist.is_available() and dist.is_initialized())
+
+
+def set_logging(training_args, log_file_name):
+    level = getattr(logging, str(getattr(training_args, "log_level", "info")).upper(), logging.INFO)
+    handlers = [logging.StreamHandler(sys.stdout)]
+    if getattr(training_args, "output_dir", None):
+        os.makedirs(training_args.output_dir, exist_ok=True)
+        handlers.append(logging.FileHandler(os.path.join(training_args.output_dir, log_file_name)))
+    logging.basicConfig(level=level, format="%(asctime)s - %(levelname)s - %(name)s - %(message)s",
+                        datefmt="%m/%d/%Y %H:%M:%S", handlers=handlers, force=True)
+
+
+def get_model(model_args, backbone=None, tokenizer=None):
+    """Builds the SparseModel from ModelArguments; idf.json is read only for inf-free models (reference :50-68)."""
+    from .model.sparse_encoders import SparseModel
+
+    idf = None
+    if model_args.inf_free and model_args.idf_path:
+        with open(model_args.idf_path) as f:
+            idf = json.load(f)
+    return SparseModel(model_args.model_name_or_path, idf=idf, tokenizer_id=model_args.tokenizer_name,
+                       idf_requires_grad=model_args.idf_requires_grad, prune_ratio=model_args.prune_ratio,
+                       preprocess_func=model_args.preprocess_func, use_l0=model_args.use_l0, backbone=backbone,
+                       tokenizer=tokenizer)

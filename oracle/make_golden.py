@@ -108,19 +108,36 @@ def main():
     golden["head"] = head_cases
 
     # ------------------------------------------------------------------ head from hidden states (decoder GEMM in fp32)
-    B, L, H, V = 3, 12, 16, 70
-    hidden = torch.randn(B, L, H, generator=gen).bfloat16().float()
-    W = (torch.randn(V, H, generator=gen) * 0.3).bfloat16().float()
-    bias = torch.randn(V, generator=gen) * 0.2
-    mask = ragged_mask(gen, B, L)
-    lin = torch.nn.Linear(H, V)
-    with torch.no_grad():
-        lin.weight.copy_(W)
-        lin.bias.copy_(bias)
-    logits = lin(hidden)
-    m = make_sparse_model(enc, logits, V, [0], torch.ones(V), None, True)
-    golden["head_hidden"] = {"hidden": hidden, "W": W, "bias": bias, "mask": mask,
-                             "rep_l0": m(inf_free=False, input_ids=None, attention_mask=mask).detach().clone()}
+    # bf16-representable inputs, so the CUDA kernels (bf16 operands, fp32 accumulate) see exactly these numbers
+    hh = []
+    for (B, L, H, V, shift) in [(3, 12, 16, 70, 0.0), (2, 40, 64, 300, -1.0), (5, 7, 8, 33, 0.5), (2, 130, 32, 150, -0.5)]:
+        hidden = torch.randn(B, L, H, generator=gen).bfloat16().float()
+        W = (torch.randn(V, H, generator=gen) * 0.3).bfloat16().float()
+        bias = torch.randn(V, generator=gen) * 0.2 + shift
+        mask = ragged_mask(gen, B, L)
+        case = {"hidden": hidden, "W": W, "bias": bias, "mask": mask, "rep": {}, "grads": {}}
+        for use_l0 in (False, True):
+            lin = torch.nn.Linear(H, V)
+            with torch.no_grad():
+                lin.weight.copy_(W)
+                lin.bias.copy_(bias)
+            hid = hidden.clone().requires_grad_(True)
+            m = make_sparse_model(enc, lin(hid), V, [0], torch.ones(V), None, use_l0)
+            rep = m(inf_free=False, input_ids=None, attention_mask=mask)
+            wgt = torch.randn(B, V, generator=gen)
+            (rep * wgt).sum().backward()
+            case["rep"][use_l0] = rep.detach().clone()
+            case["grads"][use_l0] = {"d_rep": wgt, "hidden": hid.grad.clone(), "W": lin.weight.grad.clone(),
+                                     "bias": lin.bias.grad.clone()}
+        t = bew.BiSparseModel.__new__(bew.BiSparseModel)
+        torch.nn.Module.__init__(t)
+        with torch.no_grad():
+            t.backbone = FakeBackbone(lin(hidden))
+            t.special_token_ids = [0, 2]
+            case["teacher_special"] = [0, 2]
+            case["teacher_out"] = t(input_ids=None, attention_mask=mask).clone()
+        hh.append(case)
+    golden["head_hidden"] = hh
 
     # ------------------------------------------------------------------ inf-free query
     idf_cases = []

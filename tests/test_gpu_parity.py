@@ -1,0 +1,332 @@
+"""Parity of the sm_100a kernels (called through the C ABI via ops.py) against the CPU oracle and the committed
+reference outputs. Tolerances are stated per test; integer/index work is bit-exact."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import reference_path as R  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import sparse_b200  # noqa: F401
+    from sparse_b200 import ops as _ops
+    return _ops
+
+
+def cuda(t):
+    return t.cuda() if t is not None else None
+
+
+def assert_close(got, want, rtol, atol, what=""):
+    torch.testing.assert_close(got.detach().float().cpu(), want.detach().float().cpu(), rtol=rtol, atol=atol, msg=lambda m: f"{what}: {m}")
+
+
+def make_head_inputs(B, L, H, V, seed, ragged=True, shift=0.0, scale=0.05, mask_mode="prefix"):
+    g = torch.Generator().manual_seed(seed)
+    hidden = torch.randn(B, L, H, generator=g).bfloat16()
+    W = (torch.randn(V, H, generator=g) * scale).bfloat16()
+    bias = torch.randn(V, generator=g) * 0.1 + shift
+    if mask_mode == "prefix":
+        lens = torch.randint(max(1, L // 2), L + 1, (B,), generator=g) if ragged else torch.full((B,), L)
+        mask = (torch.arange(L)[None, :] < lens[:, None]).long()
+    elif mask_mode == "random":
+        mask = (torch.rand(B, L, generator=g) > 0.3).long()
+        mask[:, 0] = 1
+    else:  # one fully masked row, one single-token row
+        mask = torch.ones(B, L, dtype=torch.long)
+        mask[0] = 0
+        if B > 1:
+            mask[1, 1:] = 0
+    return hidden, W, bias, mask
+
+
+def check_argmax(hidden, W, bias, mask, values, amax_gpu, tol=2e-5):
+    """The position the kernel reports must hold the maximum (ties and rounding allowed within tol)."""
+    logits = R.decoder_logits(hidden, W, bias) * mask.unsqueeze(-1).float()
+    picked = torch.gather(logits, 1, amax_gpu.long().cpu().unsqueeze(1)).squeeze(1)
+    scale = values.abs().clamp_min(1.0)
+    assert bool(((values - picked).abs() <= tol * scale).all())
+
+
+# ------------------------------------------------------------------------------------------------------ head forward
+@pytest.mark.parametrize("B,L,H,V,mode", [
+    (2, 128, 64, 128, "prefix"), (8, 128, 384, 30522, "prefix"), (5, 100, 384, 3000, "prefix"),
+    (3, 37, 128, 1000, "random"), (4, 256, 768, 2000, "prefix"), (3, 512, 384, 1500, "prefix"),
+    (2, 300, 64, 999, "random"), (3, 16, 32, 130, "edge"), (1, 1, 8, 9, "prefix"), (17, 48, 96, 700, "prefix"),
+    (2, 1000, 64, 500, "prefix"),
+])
+@pytest.mark.parametrize("use_l0", [False, True])
+def test_head_forward_vs_oracle(ops, B, L, H, V, mode, use_l0):
+    hidden, W, bias, mask = make_head_inputs(B, L, H, V, seed=B * 1000 + L, shift=-0.3, mask_mode=mode)
+    rep, xmax, amax = ops.head_forward(cuda(hidden), cuda(W), cuda(bias), cuda(mask), use_l0=use_l0)
+    want, values, where = R.sparse_head(hidden.float(), W.float(), bias, mask, use_l0=use_l0)
+    # fp32 accumulation in a different order than the CPU GEMM: rel 1e-4 / abs 2e-5 (north_star allows 1e-3)
+    assert_close(rep, want, 1e-4, 2e-5, "rep")
+    assert_close(xmax, values, 1e-4, 2e-5, "xmax")
+    check_argmax(hidden, W, bias, mask, values, amax)
+    active = want > 1e-4
+    agree = (amax.long().cpu() == where)[active].float().mean() if active.any() else torch.tensor(1.0)
+    assert float(agree) > 0.999
+
+
+def test_head_forward_mask_dtypes_and_no_bias(ops):
+    hidden, W, bias, mask = make_head_inputs(4, 64, 64, 300, seed=5)
+    base, _, _ = ops.head_forward(cuda(hidden), cuda(W), cuda(bias), cuda(mask))
+    for m in (mask.int(), mask.to(torch.uint8), mask.bool()):
+        rep, _, _ = ops.head_forward(cuda(hidden), cuda(W), cuda(bias), cuda(m))
+        assert torch.equal(rep, base)
+    rep, _, _ = ops.head_forward(cuda(hidden), cuda(W), None, cuda(mask))
+    want, _, _ = R.sparse_head(hidden.float(), W.float(), None, mask)
+    assert_close(rep, want, 1e-4, 2e-5)
+
+
+def test_head_golden_reference_outputs(ops, golden):
+    for c in golden["head_hidden"]:
+        for use_l0 in (False, True):
+            rep = ops.sparse_head(cuda(c["hidden"]).bfloat16(), cuda(c["W"]).bfloat16(), cuda(c["bias"]), cuda(c["mask"]),
+                                  use_l0=use_l0)
+            assert_close(rep, c["rep"][use_l0], 1e-4, 2e-5, "golden rep")
+
+
+def test_head_is_deterministic_and_idempotent(ops):
+    hidden, W, bias, mask = make_head_inputs(6, 200, 128, 4000, seed=11)
+    a = ops.head_forward(cuda(hidden), cuda(W), cuda(bias), cuda(mask))
+    b = ops.head_forward(cuda(hidden), cuda(W), cuda(bias), cuda(mask))
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
+
+
+def test_head_full_size_properties(ops):
+    """BASELINE sizes (160 x 256 x 384 x 30522): properties that need no CPU GEMM."""
+    B, L, H, V = 160, 256, 384, 30522
+    g = torch.Generator(device="cuda").manual_seed(3)
+    hidden = torch.randn(B, L, H, device="cuda", generator=g).bfloat16()
+    W = (torch.randn(V, H, device="cuda", generator=g) * 0.05).bfloat16()
+    bias = torch.randn(V, device="cuda", generator=g) * 0.1
+    lens = torch.randint(L // 2, L + 1, (B,), device="cuda", generator=g)
+    mask = (torch.arange(L, device="cuda")[None, :] < lens[:, None]).long()
+    rep, xmax, amax = ops.head_forward(hidden, W, bias, mask, use_l0=True)
+    # (1) the reported position reproduces the reported value (checked on the GPU with an fp32 gather-dot)
+    bsel = torch.arange(0, B, 7, device="cuda")
+    vsel = torch.arange(0, V, 97, device="cuda")
+    h = hidden[bsel][:, :, :].float()
+    pos = amax[bsel][:, vsel].long()
+    rows = torch.gather(h, 1, pos.unsqueeze(-1).expand(-1, -1, H))            # [b, v, H]
+    dots = (rows * W[vsel].float().unsqueeze(0)).sum(-1) + bias[vsel]
+    valid = torch.gather(mask[bsel], 1, pos).bool()
+    dots = torch.where(valid, dots, torch.zeros_like(dots))
+    torch.testing.assert_close(dots, xmax[bsel][:, vsel], rtol=1e-4, atol=2e-5)
+    # (2) rep = log1p(log1p(relu(xmax))) exactly as torch computes it on the same values
+    torch.testing.assert_close(rep, torch.log1p(torch.log1p(torch.relu(xmax))), rtol=2e-6, atol=1e-7)
+    # (3) batch-permutation equivariance: encoding a permuted batch permutes the rows bit-exactly
+    perm = torch.randperm(B, device="cuda", generator=g)
+    rep2, _, _ = ops.head_forward(hidden[perm].contiguous(), W, bias, mask[perm].contiguous(), use_l0=True)
+    assert torch.equal(rep2, rep[perm])
+    # (4) extending the padding never changes a result (max is over real tokens, masked slots contribute 0)
+    pad = 32
+    hidden_p = torch.cat([hidden, torch.randn(B, pad, H, device="cuda", generator=g).bfloat16()], dim=1)
+    mask_p = torch.cat([mask, torch.zeros(B, pad, dtype=torch.long, device="cuda")], dim=1)
+    rep3, xmax3, _ = ops.head_forward(hidden_p, W, bias, mask_p, use_l0=True)
+    full = lens == L  # rows without padding gain a masked slot -> value clamps at 0
+    assert torch.equal(xmax3[~full], xmax[~full])
+    assert torch.equal(xmax3[full], torch.relu(xmax[full]))
+
+
+# ------------------------------------------------------------------------------------------------------ head backward
+@pytest.mark.parametrize("B,L,H,V,mode,shift", [
+    (3, 40, 64, 500, "prefix", 0.0), (4, 128, 384, 3000, "prefix", -0.5), (2, 300, 128, 1000, "random", 0.0),
+    (5, 33, 768, 700, "prefix", -1.0), (3, 16, 32, 130, "edge", 0.0), (2, 64, 1024, 300, "prefix", 0.0),
+])
+@pytest.mark.parametrize("use_l0", [False, True])
+def test_head_backward_vs_oracle_autograd(ops, B, L, H, V, mode, shift, use_l0):
+    hidden, W, bias, mask = make_head_inputs(B, L, H, V, seed=B + L + H, shift=shift, scale=0.1, mask_mode=mode)
+    g = torch.Generator().manual_seed(99)
+    d_rep = torch.randn(B, V, generator=g)
+    hc = cuda(hidden).requires_grad_(True)
+    wc = cuda(W).float().requires_grad_(True)
+    bc = cuda(bias).requires_grad_(True)
+    rep = ops.sparse_head(hc, wc, bc, cuda(mask), use_l0=use_l0)
+    (rep * cuda(d_rep)).sum().backward()
+    gh, gw, gb = R.sparse_head_grads(hidden.float(), W.float(), bias, mask, d_rep, use_l0=use_l0)
+    # d_hidden is returned in the dtype of hidden (bf16): compare with bf16 resolution; dW/dbias are fp32
+    assert_close(hc.grad, gh, 1e-2, 1e-3 * float(gh.abs().max()), "d_hidden")
+    assert_close(wc.grad, gw, 1e-4, 1e-5 * float(gw.abs().max() + 1), "dW")
+    assert_close(bc.grad, gb, 1e-4, 1e-5 * float(gb.abs().max() + 1), "dbias")
+
+
+def test_head_backward_fp32_outputs(ops):
+    hidden, W, bias, mask = make_head_inputs(4, 96, 384, 2000, seed=21, shift=-0.5, scale=0.1)
+    g = torch.Generator().manual_seed(7)
+    d_rep = torch.randn(4, 2000, generator=g)
+    rep, xmax, amax = ops.head_forward(cuda(hidden), cuda(W), cuda(bias), cuda(mask), use_l0=True)
+    dh, dw, db = ops.head_backward(cuda(d_rep), xmax, amax, cuda(hidden), cuda(W), use_l0=True)
+    gh, gw, gb = R.sparse_head_grads(hidden.float(), W.float(), bias, mask, d_rep, use_l0=True)
+    assert_close(dh, gh, 1e-4, 1e-5 * float(gh.abs().max()), "d_hidden fp32")
+    assert_close(dw, gw, 1e-4, 1e-5 * float(gw.abs().max()), "dW")
+    assert_close(db, gb, 1e-4, 1e-5 * float(gb.abs().max()), "dbias")
+    # linearity in d_rep
+    dh2, dw2, db2 = ops.head_backward(cuda(d_rep) * 3.0, xmax, amax, cuda(hidden), cuda(W), use_l0=True)
+    assert_close(dw2, dw * 3.0, 1e-5, 1e-6)
+    assert_close(db2, db * 3.0, 1e-5, 1e-6)
+
+
+def test_head_backward_golden_reference_grads(ops, golden):
+    for c in golden["head_hidden"]:
+        for use_l0 in (False, True):
+            g = c["grads"][use_l0]
+            rep, xmax, amax = ops.head_forward(cuda(c["hidden"]).bfloat16(), cuda(c["W"]).bfloat16(), cuda(c["bias"]),
+                                               cuda(c["mask"]), use_l0=use_l0)
+            dh, dw, db = ops.head_backward(cuda(g["d_rep"]), xmax, amax, cuda(c["hidden"]).bfloat16(),
+                                           cuda(c["W"]).bfloat16(), use_l0=use_l0)
+            assert_close(dh, g["hidden"], 1e-4, 1e-5, "golden d_hidden")
+            assert_close(dw, g["W"], 1e-4, 1e-5, "golden dW")
+            assert_close(db, g["bias"], 1e-4, 1e-5, "golden dbias")
+
+
+def test_prune_rows(ops):
+    g = torch.Generator().manual_seed(1)
+    rep = torch.relu(torch.randn(7, 3001, generator=g))
+    got = ops.prune_rows_(cuda(rep).clone(), 0.3)
+    assert torch.equal(got.cpu(), R.prune(rep, 0.3))
+
+
+# ------------------------------------------------------------------------------------------------------ inf-free query
+def test_idf_query_bit_exact_golden(ops, golden):
+    for c in golden["idf_query"]:
+        sp = torch.tensor(c["special"], dtype=torch.int32, device="cuda")
+        got = ops.idf_query(cuda(c["ids"]), cuda(c["idf"]), sp)
+        assert torch.equal(got.cpu(), c["out"])
+
+
+@pytest.mark.parametrize("Nq,Lq", [(32, 32), (1, 1), (7, 513), (256, 64)])
+def test_idf_query_real_table(ops, idf_vector, Nq, Lq):
+    g = torch.Generator().manual_seed(Nq * 31 + Lq)
+    ids = torch.randint(0, 30522, (Nq, Lq), generator=g)
+    ids[:, 0] = 101
+    ids[:, -1] = 102
+    if Lq > 4:
+        ids[:, Lq // 2:] = torch.where(torch.rand(Nq, Lq - Lq // 2, generator=g) > 0.5, ids[:, Lq // 2:], torch.zeros((), dtype=torch.long))
+    special = [100, 102, 0, 101, 103]
+    got = ops.idf_query(cuda(ids), cuda(idf_vector), torch.tensor(special, dtype=torch.int32, device="cuda"))
+    assert torch.equal(got.cpu(), R.idf_query(ids, idf_vector, special))
+
+
+def test_idf_query_grad(ops):
+    g = torch.Generator().manual_seed(4)
+    V, Nq, Lq = 777, 9, 20
+    ids = torch.randint(0, V, (Nq, Lq), generator=g)
+    idf = (torch.rand(V, generator=g) * 4 - 0.3)
+    w = torch.randn(Nq, V, generator=g)
+    special = [0, 5]
+    p = cuda(idf).requires_grad_(True)
+    out = ops.idf_query(cuda(ids), p, torch.tensor(special, dtype=torch.int32, device="cuda"))
+    (out * cuda(w)).sum().backward()
+    pr = idf.clone().requires_grad_(True)
+    present = torch.zeros(Nq, V)
+    present.scatter_(1, ids, 1.0)
+    present[:, special] = 0
+    ((present * torch.relu(pr)) * w).sum().backward()
+    assert_close(p.grad, pr.grad, 1e-6, 1e-6)
+
+
+# ------------------------------------------------------------------------------------------------------ regulariser
+def test_flops_golden(ops, golden):
+    for c in golden["flops"]:
+        got = ops.flops_value(cuda(c["rep"]), c["G"], c["thr"])
+        assert_close(got, c["value"], 1e-5, 1e-6, f"flops G={c['G']} thr={c['thr']}")
+
+
+@pytest.mark.parametrize("rows,G,V,thr", [(160, 5, 30522, None), (160, 5, 30522, 150), (64, 2, 30522, 9000), (30, 1, 1001, None),
+                                           (512, 2, 30522, None)])
+def test_flops_value_and_grad(ops, rows, G, V, thr):
+    g = torch.Generator().manual_seed(rows + V)
+    rep = torch.relu(torch.randn(rows, V, generator=g) - (1.0 if thr else 0.0) + torch.randn(rows, 1, generator=g) * 0.5)
+    x = cuda(rep).requires_grad_(True)
+    val = ops.flops_value(x, G, thr)
+    (val * 0.37).backward()
+    xr = rep.clone().requires_grad_(True)
+    want = R.flops_value(xr, G, thr)
+    (want * 0.37).backward()
+    assert_close(val, want, 2e-5, 1e-6, "flops value")
+    assert_close(x.grad, xr.grad, 1e-4, 1e-7, "flops grad")
+
+
+# ------------------------------------------------------------------------------------------------------ scores + losses
+def test_losses_golden_values_and_grads(ops, golden):
+    from sparse_b200.scripts.train.loss import LOSS_CLS_MAP
+    for c in golden["loss"]:
+        for (name, in_batch, T), (val, gq, gd) in c["out"].items():
+            fn = LOSS_CLS_MAP[name](use_in_batch_negatives=in_batch, weight=0.7, temperature=T)
+            q = cuda(c["q"]).requires_grad_(True)
+            d = cuda(c["d"]).requires_grad_(True)
+            got = fn.get_loss(q, d, {"scores": cuda(c[("teacher", in_batch)])})
+            got.backward()
+            assert_close(got, val, 2e-5, 2e-6, f"{name} in_batch={in_batch} T={T}")
+            assert_close(q.grad, gq, 1e-4, 1e-6, f"{name} dq")
+            assert_close(d.grad, gd, 1e-4, 1e-6, f"{name} dd")
+
+
+@pytest.mark.parametrize("Nq,G,V,in_batch", [(32, 5, 30522, True), (32, 5, 30522, False), (64, 2, 30522, False),
+                                              (256, 2, 30522, True), (3, 1, 17, True), (70, 3, 1000, True)])
+def test_scores_vs_oracle(ops, Nq, G, V, in_batch):
+    g = torch.Generator().manual_seed(Nq + G)
+    q = torch.relu(torch.randn(Nq, V, generator=g)) * (torch.rand(Nq, V, generator=g) > 0.9)
+    d = torch.relu(torch.randn(Nq * G, V, generator=g)) * (torch.rand(Nq * G, V, generator=g) > 0.7)
+    S = ops.scores(cuda(q), cuda(d), in_batch)
+    want = R.student_scores(q, d, in_batch)
+    assert_close(S, want, 1e-5, 1e-4, "scores")
+
+
+@pytest.mark.parametrize("name", ["infonce", "kldiv", "marginmse"])
+@pytest.mark.parametrize("in_batch", [False, True])
+def test_loss_full_size_vs_oracle(ops, name, in_batch):
+    from sparse_b200.scripts.train.loss import LOSS_CLS_MAP
+    Nq, G, V = 32, 5, 30522
+    g = torch.Generator().manual_seed(17)
+    q = torch.relu(torch.randn(Nq, V, generator=g)) * (torch.rand(Nq, V, generator=g) > 0.999) * 3
+    d = torch.relu(torch.randn(Nq * G, V, generator=g)) * (torch.rand(Nq * G, V, generator=g) > 0.99)
+    teacher = torch.randn(Nq, Nq * G if in_batch else G, generator=g) * 3
+    fn = LOSS_CLS_MAP[name](use_in_batch_negatives=in_batch, weight=1.0, temperature=2.0)
+    qc, dc = cuda(q).requires_grad_(True), cuda(d).requires_grad_(True)
+    got = fn.get_loss(qc, dc, {"scores": cuda(teacher)})
+    got.backward()
+    qr, dr = q.clone().requires_grad_(True), d.clone().requires_grad_(True)
+    want = R.ranking_loss(name, qr, dr, teacher, in_batch, 2.0)
+    want.backward()
+    assert_close(got, want, 1e-4, 1e-5, name)
+    assert_close(qc.grad, qr.grad, 1e-3, 1e-6, "dq")
+    assert_close(dc.grad, dr.grad, 1e-3, 1e-6, "dd")
+
+
+# ------------------------------------------------------------------------------------------------------ next rows
+def test_compact_rows_and_df(ops, golden):
+    p = golden["post"]
+    rep = p["rep"]
+    df = torch.zeros(rep.shape[1], dtype=torch.int64, device="cuda")
+    row_ptr, cols, vals = ops.compact_rows(cuda(rep), first_col=1, df_count=df)
+    row_ptr, cols, vals = row_ptr.cpu(), cols.cpu(), vals.cpu()
+    want = R.post_process(rep)
+    for i, w in enumerate(want):
+        lo, hi = int(row_ptr[i]), int(row_ptr[i + 1])
+        assert cols[lo:hi].tolist() == list(w.keys())
+        assert vals[lo:hi].tolist() == list(w.values())
+    assert torch.equal(df.cpu(), R.document_frequency(rep))
+    g = torch.Generator().manual_seed(2)
+    big = torch.relu(torch.randn(50, 30522, generator=g) - 2.0)
+    row_ptr, cols, vals = ops.compact_rows(cuda(big), first_col=1)
+    nz = torch.nonzero(big[:, 1:], as_tuple=True)
+    assert int(row_ptr[-1]) == nz[0].numel()
+    assert torch.equal(cols[: nz[0].numel()].cpu().long(), nz[1] + 1)
+    assert torch.equal(vals[: nz[0].numel()].cpu(), big[:, 1:][nz])
+
+
+def test_minmax_ensemble(ops, golden):
+    for c in golden["ensemble"]:
+        acc = None
+        for q, d in zip(c["q"], c["d"]):
+            S = ops.scores(cuda(q), cuda(d), c["in_batch"])
+            acc = ops.minmax_accumulate(S, acc, scale=30.0 / len(c["q"]))
+        assert_close(acc, c["out"], 1e-4, 1e-4, "ensemble scores")

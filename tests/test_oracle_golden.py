@@ -53,11 +53,17 @@ def test_teacher_head(golden):
 
 
 def test_head_from_hidden(golden):
-    c = golden["head_hidden"]
-    rep, _, _ = R.sparse_head(c["hidden"], c["W"], c["bias"], c["mask"], use_l0=True)
-    close(rep, c["rep_l0"], rtol=1e-5, atol=1e-6)
-    gh, gw, gb = R.sparse_head_grads(c["hidden"], c["W"], c["bias"], c["mask"], torch.ones_like(rep), use_l0=True)
-    assert gh.shape == c["hidden"].shape and gw.shape == c["W"].shape and gb.shape == c["bias"].shape
+    for c in golden["head_hidden"]:
+        for use_l0 in (False, True):
+            rep, _, _ = R.sparse_head(c["hidden"], c["W"], c["bias"], c["mask"], use_l0=use_l0)
+            close(rep, c["rep"][use_l0], rtol=1e-5, atol=1e-6)
+            g = c["grads"][use_l0]
+            gh, gw, gb = R.sparse_head_grads(c["hidden"], c["W"], c["bias"], c["mask"], g["d_rep"], use_l0=use_l0)
+            close(gh, g["hidden"], rtol=1e-5, atol=1e-6)
+            close(gw, g["W"], rtol=1e-5, atol=1e-6)
+            close(gb, g["bias"], rtol=1e-5, atol=1e-6)
+        close(R.teacher_sparse_head(c["hidden"], c["W"], c["bias"], c["mask"], c["teacher_special"]), c["teacher_out"],
+              rtol=1e-5, atol=1e-6)
 
 
 def test_idf_query_bit_exact(golden):
