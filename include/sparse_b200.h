@@ -149,7 +149,8 @@ int sb200_rank_loss(int mode, const float* S, const float* teacher, int Nq, int 
  *     ensemble normalisation (bi_encoder_wrapper.py:133-138).
  * ------------------------------------------------------------------------------------------- */
 /* CSR compaction of the non-zero entries of columns >= first_col (first_col = 1 reproduces the post-processor's
- * column-0 sentinel being dropped), columns ascending inside a row; also df_count[v] += [rep[b,v] > 0] (i64, nullable).
+ * column-0 sentinel being dropped), columns ascending inside a row; also df_count[v] += [rep[b,v] > 0] for EVERY
+ * column v (i64, nullable; sparse_encoders.py:178-179).
  * row_ptr i32 [B+1]; cols i32 / vals f32 sized capacity; row_ptr[B] = total nnz (entries past capacity are dropped). */
 size_t sb200_compact_workspace_bytes(int B, int V);
 int sb200_compact_rows(const float* rep, int B, int V, int first_col, int32_t* row_ptr, int32_t* cols, float* vals,

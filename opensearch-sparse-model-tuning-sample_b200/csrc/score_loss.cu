@@ -360,10 +360,12 @@ compact_fill_kernel(const float* __restrict__ rep, int V, int first_col, const i
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) base_s = row_ptr[blockIdx.x];
     __syncthreads();
-    for (int v0 = first_col; v0 < V; v0 += 256) {
+    for (int v0 = 0; v0 < V; v0 += 256) {
         const int v = v0 + threadIdx.x;
         const float x = (v < V) ? __ldg(row + v) : 0.f;
-        const bool nz = x != 0.f;
+        // document frequency counts every column; only columns >= first_col are compacted
+        if (df_count != nullptr && x > 0.f) atomicAdd(df_count + v, 1ull);
+        const bool nz = (v >= first_col) && x != 0.f;
         const uint32_t bal = __ballot_sync(0xffffffffu, nz);
         if (lane == 0) warp_cnt[warp] = __popc(bal);
         __syncthreads();
@@ -375,7 +377,6 @@ compact_fill_kernel(const float* __restrict__ rep, int V, int first_col, const i
                 cols[off] = v;
                 vals[off] = x;
             }
-            if (df_count != nullptr && x > 0.f) atomicAdd(df_count + v, 1ull);
         }
         __syncthreads();
         if (threadIdx.x == 0) {

@@ -28,6 +28,41 @@ def _workspace(nbytes, device):
     return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
 
 
+# Optional per-call CUDA-event timing of named C-ABI calls (used by bench.py for the live roofline numbers).
+_PROFILE = None
+
+
+def start_event_profile(names):
+    global _PROFILE
+    _PROFILE = {n: [] for n in names}
+
+
+def stop_event_profile():
+    """-> {name: [milliseconds per call]}; synchronises the device."""
+    global _PROFILE
+    prof, _PROFILE = _PROFILE, None
+    if not prof:
+        return {}
+    torch.cuda.synchronize()
+    return {n: [a.elapsed_time(b) for a, b in pairs] for n, pairs in prof.items()}
+
+
+class _timed:
+    def __init__(self, name):
+        self.pair = None
+        if _PROFILE is not None and name in _PROFILE:
+            self.pair = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            _PROFILE[name].append(self.pair)
+
+    def __enter__(self):
+        if self.pair is not None:
+            self.pair[0].record()
+
+    def __exit__(self, *exc):
+        if self.pair is not None:
+            self.pair[1].record()
+
+
 # --------------------------------------------------------------------------------------------- sparse head
 def head_forward(hidden, weight, bias, attention_mask, use_l0=False, want_aux=True):
     """Fused MLM-decoder GEMM + mask + max-pool + log1p(relu) (sparse_encoders.py:108-114).
@@ -61,7 +96,7 @@ def head_forward(hidden, weight, bias, attention_mask, use_l0=False, want_aux=Tr
     argmax = torch.empty(B, V, dtype=torch.int32, device=dev) if want_aux else None
     ws_bytes = lib.sb200_head_fwd_workspace_bytes(B, L)
     ws = _workspace(ws_bytes, dev)
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), _timed("head_fwd"):
         code = lib.sb200_head_fwd(_ptr(hidden), _ptr(weight), _ptr(bias), _ptr(mask), mask.element_size(), B, L, H, V,
                                   _lib.HEAD_L0 if use_l0 else 0, _ptr(rep), _ptr(xmax), _ptr(argmax), _ptr(ws),
                                   ws.numel(), _stream())
@@ -81,7 +116,7 @@ def head_backward(d_rep, xmax, argmax, hidden, weight, use_l0=False, want_bias_g
     dW = torch.empty(V, H, dtype=torch.float32, device=dev)
     dbias = torch.empty(V, dtype=torch.float32, device=dev) if want_bias_grad else None
     ws = _workspace(lib.sb200_head_bwd_workspace_bytes(B, L, H, V), dev)
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), _timed("head_bwd"):
         code = lib.sb200_head_bwd(_ptr(d_rep), _ptr(xmax), _ptr(argmax), _ptr(hidden), _ptr(weight), B, L, H, V,
                                   _lib.HEAD_L0 if use_l0 else 0, _ptr(d_hidden), _ptr(dW), _ptr(dbias), _ptr(ws),
                                   ws.numel(), _stream())

@@ -222,9 +222,6 @@ class SparseEncoder:
     def encode_output(self, output):
         """Post-processing half of encode(): fused CSR compaction + DF count (reference :178-180)."""
         row_ptr, cols, vals = ops.compact_rows(output, first_col=1, df_count=self._df if self.do_count else None)
-        if self.do_count:
-            # column 0 is skipped by the compaction but counted by the reference's (output > 0).sum(0)
-            self._df[0] += (output[:, 0] > 0).sum()
         bounds = row_ptr.tolist()
         total = bounds[-1]
         id_to_token = self.post_processor.id_to_token
