@@ -24,6 +24,14 @@ int num_sms() {
     return cached[dev];
 }
 
+bool device_flag_test_and_set(int slot) {
+    static std::atomic<unsigned> flags[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return false;
+    const unsigned bit = 1u << (slot & 7);
+    return (flags[dev].fetch_or(bit) & bit) != 0;
+}
+
 }  // namespace sb200
 
 extern "C" int sb200_abi_version(void) { return SB200_ABI_VERSION; }

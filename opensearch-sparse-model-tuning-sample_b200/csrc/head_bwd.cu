@@ -296,7 +296,8 @@ int launch_bwd(const float* d_rep, const float* xmax, const int32_t* argmax, con
         const int max_smem = 96 * 1024;
         if (size_t(Bc) * kDwRows * sizeof(float2) > size_t(max_smem)) Bc = max_smem / int(kDwRows * sizeof(float2));
         const size_t smem = size_t(Bc) * kDwRows * sizeof(float2);
-        SB200_CUDA(cudaFuncSetAttribute(bwd_dw_kernel<NCHUNK>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        if (!device_flag_test_and_set(NCHUNK))
+            SB200_CUDA(cudaFuncSetAttribute(bwd_dw_kernel<NCHUNK>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         bwd_dw_kernel<NCHUNK><<<(V + kDwRows - 1) / kDwRows, kDwThreads, smem, stream>>>(
             d_rep, xmax, argmax, hidden, B, L, H, V, l0, Bc, dW, dbias);
         SB200_CHECK_LAUNCH("bwd_dw_kernel");

@@ -413,8 +413,9 @@ extern "C" int sb200_head_fwd(const void* hidden, const void* W, const float* bi
     p.kblocks = (H + kBlockK - 1) / kBlockK;
     p.l0 = (flags & SB200_HEAD_L0) ? 1 : 0;
 
-    // per-device attribute; setting it on every call keeps multi-device processes correct and costs ~1 us
-    SB200_CUDA(cudaFuncSetAttribute(head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBytes)));
+    // per-device attribute, set once per device (and never while a stream capture may be in progress later on)
+    if (!device_flag_test_and_set(0))
+        SB200_CUDA(cudaFuncSetAttribute(head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBytes)));
     const long long total_units = (long long)p.n_vtiles * p.n_groups;
     int grid = num_sms();
     if (grid > total_units) grid = int(total_units);

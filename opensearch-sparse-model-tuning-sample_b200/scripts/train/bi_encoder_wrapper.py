@@ -30,6 +30,7 @@ class BiSparseModel(torch.nn.Module):
         self.tokenizer = tokenizer if tokenizer is not None else transformers.AutoTokenizer.from_pretrained(model_id)
         self.special_token_ids = [self.tokenizer.vocab[t] for t in self.tokenizer.special_tokens_map.values()]
         self._split = None
+        self._special_cols = {}
 
     def forward(self, **kwargs):
         if self._split is None:
@@ -37,8 +38,10 @@ class BiSparseModel(torch.nn.Module):
         hidden = self._split.transform(self._split.body(**kwargs)[0])
         dec = self._split.decoder
         values = ops.sparse_head(hidden, dec.weight, dec.bias, kwargs.get("attention_mask"), use_l0=False)
-        cols = torch.tensor(list(self.special_token_ids), dtype=torch.long, device=values.device)
-        return values.index_fill(1, cols, 0.0)
+        key = (values.device.type, values.device.index)
+        if key not in self._special_cols:
+            self._special_cols[key] = torch.tensor(list(self.special_token_ids), dtype=torch.long, device=values.device)
+        return values.index_fill(1, self._special_cols[key], 0.0)
 
 
 class DenseModel(torch.nn.Module):

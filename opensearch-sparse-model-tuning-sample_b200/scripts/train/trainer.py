@@ -67,11 +67,21 @@ class SparseModelTrainer:
         self.model = wrapper
         if self.accelerator.num_processes > 1 and next(wrapper.parameters()).is_cuda:
             dev = next(wrapper.parameters()).device
-            self.model = torch.nn.parallel.DistributedDataParallel(wrapper, device_ids=[dev.index],
-                                                                   gradient_as_bucket_view=True)
+            # built on a side stream so that the step can later be captured into a CUDA graph (PyTorch requirement)
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                self.model = torch.nn.parallel.DistributedDataParallel(wrapper, device_ids=[dev.index],
+                                                                       gradient_as_bucket_view=True)
+            torch.cuda.current_stream(dev).wait_stream(side)
         self.scaler = None
         if args is not None and getattr(args, "fp16", False):
             self.scaler = torch.amp.GradScaler("cuda")
+        # CUDA-graph mode (enable_cuda_graph): the whole step replays as one graph launch
+        self._graph = None
+        self._static_inputs = None
+        self._static_loss = None
+        self._step_t = None
 
     # ------------------------------------------------------------------ reference attribute, without a per-step sync
     @property
@@ -89,7 +99,11 @@ class SparseModelTrainer:
         return ops.flops_value(representation, group_num, self.data_args.flops_threshold)
 
     def get_lambda(self, lambda_value, lambda_T):
-        """reference :75-79"""
+        """reference :75-79. In CUDA-graph mode the same schedule is evaluated on the device from a step counter
+        that lives inside the graph, so a replay never bakes in a stale host value."""
+        if self._step_t is not None:
+            ramp = torch.clamp((self._step_t + 1.0) / float(lambda_T), max=1.0)
+            return float(lambda_value) * ramp * ramp
         if self.state.global_step >= lambda_T:
             return lambda_value
         return lambda_value * ((self.state.global_step + 1) / lambda_T) ** 2
@@ -126,7 +140,9 @@ class SparseModelTrainer:
         self._ema.mul_(0.99).add_(r, alpha=0.01)
 
         loss = ranking_loss + flops_loss
-        if self.args is not None and self.state.global_step % max(1, self.args.logging_steps) == 0:
+        capturing = torch.cuda.is_current_stream_capturing() if d_rep.is_cuda else False
+        if (self.args is not None and not capturing and self._graph is None
+                and self.state.global_step % max(1, self.args.logging_steps) == 0):
             self._log_step(d_rep, d_flops, flops_loss)
         # DDP averages gradients over ranks while every rank holds the full global loss (reference :139-141)
         loss = loss * self.accelerator.num_processes
@@ -149,8 +165,81 @@ class SparseModelTrainer:
             return torch.autocast("cuda", dtype=torch.float16)
         return torch.autocast("cuda", dtype=torch.bfloat16)
 
+    def _eager_step_body(self, inputs):
+        """forward (autocast) + loss + backward + optimizer.step, no scheduler / bookkeeping."""
+        def run(student):
+            with self._autocast():
+                return self.model(student)
+
+        loss = self.compute_loss(run, inputs)
+        loss.backward()
+        self.optimizer.step()
+        return loss
+
+    @staticmethod
+    def _copy_into(dst, src):
+        if torch.is_tensor(dst):
+            dst.copy_(src, non_blocking=True)
+        elif isinstance(dst, dict):
+            for k in dst:
+                SparseModelTrainer._copy_into(dst[k], src[k])
+        else:
+            for a, b in zip(dst, src):
+                SparseModelTrainer._copy_into(a, b)
+
+    def enable_cuda_graph(self, example_inputs, warmup_steps=3):
+        """Captures forward + loss + backward + optimizer step as ONE CUDA graph (fixed batch shapes).
+
+        The PyTorch backbone issues ~1000 small launches per step and is host-bound in eager mode; replaying a graph
+        removes that. Requirements: bf16 (no GradScaler), no gradient clipping, an optimizer built with
+        capturable=True whose lr is a tensor, batches padded to the shapes of `example_inputs`. The regulariser
+        warm-up (get_lambda) is computed on the device from an in-graph step counter. Single process or DDP.
+        """
+        if self.scaler is not None:
+            raise RuntimeError("CUDA-graph mode supports bf16 only (fp16 needs GradScaler's host-side decisions)")
+        if self.args is not None and getattr(self.args, "max_grad_norm", None):
+            raise RuntimeError("CUDA-graph mode does not support gradient clipping")
+        device = next(self.model_wrapper.parameters()).device
+        self.model.train()
+        self._static_inputs = self._to_device(example_inputs, device)
+        self._static_inputs = {k: (list(v) if isinstance(v, list) else v) for k, v in self._static_inputs.items()}
+        self._step_t = torch.full((), float(self.state.global_step), device=device, dtype=torch.float32)
+        if self._ema is None:
+            self._ema = torch.full((), float(self._ema_host), device=device, dtype=torch.float32)
+
+        def one_step():
+            loss = self._eager_step_body(dict(self._static_inputs))
+            self._step_t += 1.0
+            return loss
+
+        side = torch.cuda.Stream(device=device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):
+            for _ in range(warmup_steps):
+                self.optimizer.zero_grad(set_to_none=True)
+                one_step()
+                if self.lr_scheduler is not None:
+                    self.lr_scheduler.step()
+                self.state.global_step += 1
+        torch.cuda.current_stream(device).wait_stream(side)
+        torch.cuda.synchronize(device)
+        graph = torch.cuda.CUDAGraph()
+        self.optimizer.zero_grad(set_to_none=True)
+        with torch.cuda.graph(graph):
+            self._static_loss = one_step().detach()
+        self._graph = graph
+        # the capture itself does not execute; host-side counters stay where the warm-up left them
+        return self
+
     def training_step(self, inputs):
         """forward (autocast) + loss + backward + optimizer step; returns the detached loss tensor (no sync)."""
+        if self._graph is not None:
+            self._copy_into(self._static_inputs, inputs)
+            self._graph.replay()
+            if self.lr_scheduler is not None:
+                self.lr_scheduler.step()
+            self.state.global_step += 1
+            return self._static_loss
         self.model.train()
 
         def run(student):

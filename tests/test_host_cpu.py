@@ -1,0 +1,90 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every symbol of include/sparse_b200.h, the
+product path refuses to run without CUDA (no fallback), configs parse with the reference's keys."""
+import os
+import re
+
+import pytest
+import torch
+import yaml
+
+import sparse_b200
+from sparse_b200 import _lib, ops
+from conftest import ROOT
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "sparse_b200.h")).read()
+    declared = set(re.findall(r"\b(sb200_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations found"
+    assert declared == set(_lib.EXPORTED_SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.sb200_abi_version() == 1
+    assert lib.sb200_head_fwd_workspace_bytes(160, 256) > 0
+    assert lib.sb200_head_bwd_workspace_bytes(160, 256, 384, 30522) >= 160 * 30522 * 8
+
+
+def test_argument_errors_are_reported_not_crashes():
+    lib = _lib.load()
+    code = lib.sb200_head_fwd(0, 0, 0, 0, 8, 1, 1, 8, 1, 0, 0, 0, 0, 0, 0, 0)
+    assert code == 1 and b"null" in lib.sb200_last_error()
+    code = lib.sb200_rank_loss(7, 1, 0, 1, 1, 1, 0, 1.0, 1, 0, 0)
+    assert code == 1 and b"mode" in lib.sb200_last_error()
+
+
+def test_no_cpu_fallback():
+    h = torch.zeros(1, 4, 8, dtype=torch.bfloat16)
+    w = torch.zeros(16, 8, dtype=torch.bfloat16)
+    with pytest.raises(_lib.SparseB200Error):
+        ops.head_forward(h, w, None, torch.ones(1, 4, dtype=torch.long))
+    with pytest.raises(_lib.SparseB200Error):
+        ops.flops_value(torch.zeros(4, 8), 1)
+    with pytest.raises(_lib.SparseB200Error):
+        ops.scores(torch.zeros(2, 8), torch.zeros(4, 8), True)
+
+
+def test_product_package_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "opensearch-sparse-model-tuning-sample_b200")
+    for base, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(base, f)).read()
+                assert "oracle" not in src.replace("oracle/", ""), os.path.join(base, f)
+
+
+def test_reference_configs_parse():
+    from sparse_b200.scripts.args import parse_dict
+    cfg_dir = os.path.join(ROOT, "opensearch-sparse-model-tuning-sample_b200", "configs")
+    for name in ("config_infonce.yaml", "config_kd.yaml", "config_l0.yaml"):
+        m, d, t = parse_dict(yaml.safe_load(open(os.path.join(cfg_dir, name))))
+        assert m.inf_free is True and t.max_steps > 0 and d.loss_types
+    m, d, t = parse_dict(yaml.safe_load(open(os.path.join(cfg_dir, "config_l0.yaml"))))
+    assert d.flops_threshold == 150 and m.use_l0 is True and d.loss_types == ["kldiv"]
+
+
+def test_trainer_lambda_schedule_matches_reference_values(golden):
+    from sparse_b200.scripts.args import DataTrainingArguments, ModelArguments
+    from sparse_b200.scripts.train.trainer import SparseModelTrainer
+
+    class Dummy(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.p = torch.nn.Parameter(torch.zeros(1))
+    tr = SparseModelTrainer(ModelArguments(), DataTrainingArguments(), [], model=Dummy())
+    for step, expect in golden["lambda"]:
+        tr.state.global_step = step
+        assert tr.get_lambda(0.05, 200) == pytest.approx(expect, rel=1e-12)
+
+
+def test_synthetic_batches_layout():
+    from sparse_b200.scripts import synthetic
+    b = synthetic.train_batch(4, 3, 64, query_len=16)
+    docs = b["docs"][0]
+    assert docs["input_ids"].shape == (12, 64) and docs["attention_mask"].shape == (12, 64)
+    assert (docs["input_ids"][:, 0] == 101).all()
+    lens = docs["attention_mask"].sum(1)
+    assert (docs["input_ids"][torch.arange(12), lens - 1] == 102).all()
+    assert ((docs["input_ids"] == 0) == (docs["attention_mask"] == 0)).all()
+    tok = synthetic.SyntheticTokenizer()
+    assert sorted(tok.vocab[t] for t in tok.special_tokens_map.values()) == [0, 100, 101, 102, 103]
