@@ -216,42 +216,42 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
             for (int c = 0; c < p.NC; ++c) {
                 const uint32_t aph = uint32_t(pi * p.NC + c) & 1;
                 const uint32_t* tm = p.tilemask + (size_t(g) * p.NC + c) * kMaskWords;
-                uint32_t cur = __ldg(tm);
+                uint32_t word = __ldg(tm);
                 mbar_wait(&tfull_bar[as], aph);
                 tc_fence_after();
                 const uint32_t tmem_acc = tmem_base + lane_base + as * kAccCols;
                 int s = 0, jrem = p.LC;
-                for (int n0 = 0; n0 < p.N; n0 += 16) {
-                    uint32_t bits;
-                    if ((n0 & 16) == 0) {
-                        bits = cur & 0xffffu;
-                    } else {
-                        bits = cur >> 16;
-                        if (n0 + 16 < p.N) cur = __ldg(tm + ((n0 + 16) >> 5));
-                    }
+
+                // One 16-column block: tree arg-max (depth 4, all nodes of a level independent), then one merge
+                // into the running (m, idx). Strict '>' everywhere keeps the lowest position on ties.
+                auto consume = [&](uint32_t (&r)[16], uint32_t bits) {
                     if (bits != 0) {
-                        uint32_t r[16];
-                        tmem_ld16(tmem_acc + n0, r);
-                        tmem_ld_wait();
+                        float v[16];
+                        int ix[8];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            v[i] = __uint_as_float(r[i]);
+                            if (bits != 0xffffu && !((bits >> i) & 1u)) v[i] = -CUDART_INF_F;  // warp-uniform
+                        }
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const bool pr = v[2 * i + 1] > v[2 * i];
+                            ix[i] = pr ? 2 * i + 1 : 2 * i;
+                            v[i] = fmaxf(v[2 * i], v[2 * i + 1]);
+                        }
+#pragma unroll
+                        for (int w = 4; w >= 1; w >>= 1) {
+#pragma unroll
+                            for (int i = 0; i < w; ++i) {
+                                const bool pr = v[2 * i + 1] > v[2 * i];
+                                ix[i] = pr ? ix[2 * i + 1] : ix[2 * i];
+                                v[i] = fmaxf(v[2 * i], v[2 * i + 1]);
+                            }
+                        }
                         const int lbase = c * p.LC + (p.LC - jrem);
-                        if (bits == 0xffffu) {
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) {
-                                const float x = __uint_as_float(r[i]);
-                                if (x > m) {
-                                    m = x;
-                                    idx = lbase + i;
-                                }
-                            }
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) {
-                                const float x = __uint_as_float(r[i]);
-                                if (((bits >> i) & 1u) && x > m) {
-                                    m = x;
-                                    idx = lbase + i;
-                                }
-                            }
+                        if (v[0] > m) {
+                            m = v[0];
+                            idx = lbase + ix[0];
                         }
                     }
                     jrem -= 16;
@@ -279,6 +279,19 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
                             idx = 0;
                         }
                     }
+                };
+
+                for (int n0 = 0; n0 < p.N; n0 += 32) {
+                    const uint32_t lo = word & 0xffffu;
+                    const bool has_hi = n0 + 16 < p.N;
+                    const uint32_t hi = has_hi ? (word >> 16) : 0u;
+                    if (n0 + 32 < p.N) word = __ldg(tm + ((n0 + 32) >> 5));  // prefetch the next mask word
+                    uint32_t ra[16], rb[16];
+                    if (lo != 0) tmem_ld16(tmem_acc + n0, ra);
+                    if (hi != 0) tmem_ld16(tmem_acc + n0 + 16, rb);
+                    if ((lo | hi) != 0) tmem_ld_wait();
+                    consume(ra, lo);
+                    if (has_hi) consume(rb, hi);
                 }
                 tc_fence_before();
                 __syncwarp();

@@ -43,19 +43,20 @@ class SyntheticTokenizer:
             json.dump({"size": len(self.vocab)}, f)
 
 
-def build_backbone(shape="mini", vocab_size=VOCAB_SIZE, seed=0, max_position_embeddings=512):
+def build_backbone(shape="mini", vocab_size=VOCAB_SIZE, seed=0, max_position_embeddings=512, dropout=0.1):
     import transformers
     cfg = transformers.BertConfig(vocab_size=vocab_size, max_position_embeddings=max_position_embeddings,
+                                  hidden_dropout_prob=dropout, attention_probs_dropout_prob=dropout,
                                   **MODEL_SHAPES[shape])
     torch.manual_seed(seed)
     return transformers.BertForMaskedLM(cfg)
 
 
 def build_sparse_model(shape="mini", idf_vector=None, use_l0=False, vocab_size=VOCAB_SIZE, seed=0, bias_shift=0.0,
-                       prune_ratio=None, idf_requires_grad=False):
+                       prune_ratio=None, idf_requires_grad=False, dropout=0.1):
     """SparseModel over a random-init backbone. bias_shift < 0 gives the "trained-like" activation regime."""
     from .model.sparse_encoders import SparseModel
-    backbone = build_backbone(shape, vocab_size, seed)
+    backbone = build_backbone(shape, vocab_size, seed, dropout=dropout)
     model = SparseModel(None, backbone=backbone, tokenizer=SyntheticTokenizer(vocab_size), use_l0=use_l0,
                         prune_ratio=prune_ratio, idf_requires_grad=idf_requires_grad)
     if idf_vector is not None:

@@ -18,7 +18,8 @@ def _trainer(shape="tiny", loss="infonce", in_batch=True, use_l0=False, threshol
     from sparse_b200.scripts.train.loss import LOSS_CLS_MAP
     from sparse_b200.scripts.train.trainer import SparseModelTrainer
     idf = torch.rand(V, generator=torch.Generator().manual_seed(3)) * 5
-    model = synthetic.build_sparse_model(shape, idf_vector=idf, use_l0=use_l0, vocab_size=V, seed=seed, bias_shift=-0.1).cuda()
+    model = synthetic.build_sparse_model(shape, idf_vector=idf, use_l0=use_l0, vocab_size=V, seed=seed, bias_shift=-0.1,
+                                         dropout=0.0).cuda()
     margs = ModelArguments(inf_free=inf_free, use_l0=use_l0)
     dargs = DataTrainingArguments(loss_types=[loss], use_in_batch_negatives=in_batch, flops_d_lambda=0.05, flops_d_T=50,
                                   flops_q_lambda=0.02, flops_q_T=30, flops_threshold=threshold)
