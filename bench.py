@@ -203,8 +203,8 @@ def run_ours(args):
 
     # ---------------- CUDA-graph capture of the whole step (forward, loss, backward, optimizer)
     graphed = False
-    if not args.no_graph:
-        trainer.enable_cuda_graph(hosts[0], warmup_steps=11 if world > 1 else 3)
+    if args.graph and world == 1:
+        trainer.enable_cuda_graph(hosts[0], warmup_steps=3)
         graphed = True
         for i in range(3):
             trainer.training_step(resident[i % n_pool])
@@ -438,7 +438,9 @@ def main():
     ap.add_argument("--regime", default="dense", choices=["dense", "trained"],
                     help="dense = random-init decoder (about all 30522 columns active per doc); trained = decoder bias "
                          "shifted so that a few hundred columns are active, like a trained checkpoint")
-    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--graph", action="store_true",
+                    help="replay the whole step as one CUDA graph (single GPU only; default is eager launches so that "
+                         "every GPU count runs the same code path)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)

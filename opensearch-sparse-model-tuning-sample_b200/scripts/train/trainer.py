@@ -67,13 +67,8 @@ class SparseModelTrainer:
         self.model = wrapper
         if self.accelerator.num_processes > 1 and next(wrapper.parameters()).is_cuda:
             dev = next(wrapper.parameters()).device
-            # built on a side stream so that the step can later be captured into a CUDA graph (PyTorch requirement)
-            side = torch.cuda.Stream(device=dev)
-            side.wait_stream(torch.cuda.current_stream(dev))
-            with torch.cuda.stream(side):
-                self.model = torch.nn.parallel.DistributedDataParallel(wrapper, device_ids=[dev.index],
-                                                                       gradient_as_bucket_view=True)
-            torch.cuda.current_stream(dev).wait_stream(side)
+            self.model = torch.nn.parallel.DistributedDataParallel(wrapper, device_ids=[dev.index],
+                                                                   gradient_as_bucket_view=True)
         self.scaler = None
         if args is not None and getattr(args, "fp16", False):
             self.scaler = torch.amp.GradScaler("cuda")
@@ -193,8 +188,11 @@ class SparseModelTrainer:
         The PyTorch backbone issues ~1000 small launches per step and is host-bound in eager mode; replaying a graph
         removes that. Requirements: bf16 (no GradScaler), no gradient clipping, an optimizer built with
         capturable=True whose lr is a tensor, batches padded to the shapes of `example_inputs`. The regulariser
-        warm-up (get_lambda) is computed on the device from an in-graph step counter. Single process or DDP.
+        warm-up (get_lambda) is computed on the device from an in-graph step counter. Single process only.
         """
+        if self.accelerator.num_processes > 1:
+            raise RuntimeError("CUDA-graph mode is single-process for now: capturing the DDP all-reduce needs the DDP "
+                               "wrapper and its warm-up on the capture side stream; multi-GPU runs launch eagerly")
         if self.scaler is not None:
             raise RuntimeError("CUDA-graph mode supports bf16 only (fp16 needs GradScaler's host-side decisions)")
         if self.args is not None and getattr(self.args, "max_grad_norm", None):
