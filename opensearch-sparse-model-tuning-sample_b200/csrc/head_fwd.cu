@@ -19,6 +19,8 @@
 //   * warp roles: warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4..11 = two
 //     epilogue warpgroups that alternate work units, double-buffered accumulators (2 x 256 TMEM columns);
 //   * persistent CTAs (one per SM), static contiguous partition of the (sequence-group, vocab-tile) units.
+#include <cstdlib>
+#include <type_traits>
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <math_constants.h>
@@ -34,16 +36,19 @@ constexpr int kBlockM = 128;     // vocab rows per tile (UMMA M)
 constexpr int kBlockK = 64;      // bf16 per smem row = 128 B = swizzle span
 constexpr int kUmmaK = 16;
 constexpr int kMaxN = 256;       // token columns per tile (UMMA N upper bound)
-constexpr int kStages = 4;
-constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KB
-constexpr int kBBytes = kMaxN * kBlockK * 2;    // 32 KB
+constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KB per stage (this CTA's 128 vocab rows)
+// B bytes per stage held by ONE CTA: the whole token tile (1-CTA) or half of it (CTA pair)
+template <int kCG> struct StageCfg {
+    static constexpr int kBBytes = kMaxN * kBlockK * 2 / kCG;   // 32 KB / 16 KB
+    static constexpr int kStages = (kCG == 1) ? 4 : 6;          // 4 x 48 KB or 6 x 32 KB = 192 KB
+    static constexpr size_t kSmemBytes = 1024 /*align slack*/ + size_t(kStages) * (kABytes + kBBytes) + 256 + 2 * kBlockM * 8;
+};
 constexpr int kAccCols = 256;
 constexpr int kTmemCols = 512;
 constexpr int kFirstEpiWarp = 4;
 constexpr int kNumEpiWarps = 8;
 constexpr int kThreads = (kFirstEpiWarp + kNumEpiWarps) * 32;  // 384
 constexpr int kMaskWords = kMaxN / 32;                          // 8
-constexpr size_t kSmemBytes = 1024 /*align slack*/ + size_t(kStages) * (kABytes + kBBytes) + 256;
 
 struct HeadFwdParams {
     const float* bias;
@@ -54,8 +59,9 @@ struct HeadFwdParams {
     int32_t* argmax;
     int B, L, H, V;
     int LC, S, NC, N;          // chunk length, sequences per tile, chunks per sequence, S*LC
-    int n_vtiles, n_groups, kblocks;
+    int n_vtiles, n_groups, kblocks;   // n_vtiles counts tiles of 128 * kCG vocab rows
     int l0;
+    int b_l_off, b_s_off;      // CTA pair: token / sequence offset of the second CTA's half of the B tile
 };
 
 // Packs the attention mask into per-tile column bitmaps and per-sequence padding info.
@@ -97,9 +103,12 @@ __global__ void head_prep_kernel(const void* __restrict__ mask, int elem_bytes, 
     }
 }
 
+template <int kCG>
 __global__ void __launch_bounds__(kThreads, 1)
 head_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_h,
                 const HeadFwdParams p) {
+    constexpr int kStages = StageCfg<kCG>::kStages;
+    constexpr int kBBytes = StageCfg<kCG>::kBBytes;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
@@ -110,9 +119,14 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
     uint64_t* tfull_bar = bars + 2 * kStages;    // [2]        MMA -> epilogue
     uint64_t* tempty_bar = bars + 2 * kStages + 2;  // [2]     epilogue -> MMA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+    float2* comb = reinterpret_cast<float2*>(bars + 2 * kStages + 6);  // [2][128] half-sequence (max, argmax) exchange
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    // CTA pair (kCG == 2): rank 0 is the leader (issues the MMAs, owns the full/tempty barriers that are waited on)
+    const uint32_t rank = (kCG == 2) ? cluster_ctarank() : 0u;
+    const int cluster_id = blockIdx.x / kCG;
+    const int n_clusters = gridDim.x / kCG;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_w);
@@ -125,186 +139,225 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull_bar[i], 1);
-            mbar_init(&tempty_bar[i], 4);  // one arrive per warp of the consuming epilogue warpgroup
+            mbar_init(&tempty_bar[i], kNumEpiWarps * kCG);  // one arrive per epilogue warp (of both CTAs)
         }
         fence_mbar_init();
     }
     if (warp == 2) {
-        tmem_alloc(tmem_slot, kTmemCols);
-        tmem_relinquish();
+        if (kCG == 2) {
+            tmem_alloc_pair(tmem_slot, kTmemCols);
+            tmem_relinquish_pair();
+        } else {
+            tmem_alloc(tmem_slot, kTmemCols);
+            tmem_relinquish();
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if (kCG == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     const long long total_units = (long long)p.n_vtiles * p.n_groups;
-    const int u_begin = int((long long)blockIdx.x * total_units / gridDim.x);
-    const int u_end = int((long long)(blockIdx.x + 1) * total_units / gridDim.x);
-    const uint32_t tx_bytes = uint32_t(kABytes + p.N * kBlockK * 2);
+    const int u_begin = int((long long)cluster_id * total_units / n_clusters);
+    const int u_end = int((long long)(cluster_id + 1) * total_units / n_clusters);
+    // bytes landing per stage over the whole CTA group (credited to the leader's barrier)
+    const uint32_t tx_bytes = uint32_t(kCG * kABytes + p.N * kBlockK * 2);
 
     if (warp == 0) {
         if (lane == 0) {
             // ------------------------------------------------ TMA producer
             uint32_t it = 0;
-            for (int u0 = u_begin; u0 < u_end; u0 += 2) {
+            for (int u = u_begin; u < u_end; ++u) {
+                const int g = u / p.n_vtiles, vt = u - g * p.n_vtiles;
                 for (int c = 0; c < p.NC; ++c) {
-                    for (int which = 0; which < 2; ++which) {
-                        const int u = u0 + which;
-                        if (u >= u_end) break;
-                        const int g = u / p.n_vtiles, vt = u - g * p.n_vtiles;
-                        for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
-                            const uint32_t s = it % kStages, ph = (it / kStages) & 1;
-                            mbar_wait(&empty_bar[s], ph ^ 1);
+                    for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
+                        const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+                        mbar_wait(&empty_bar[s], ph ^ 1);
+                        if (kCG == 1) {
                             mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
                             tma_load_2d(smem_a + s * kABytes, &tmap_w, &full_bar[s], kb * kBlockK, vt * kBlockM);
                             tma_load_3d(smem_b + s * kBBytes, &tmap_h, &full_bar[s], kb * kBlockK, c * p.LC, g * p.S);
+                        } else {
+                            // each CTA loads its 128 vocab rows and its half of the token tile
+                            if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
+                            tma_load_2d_pair(smem_a + s * kABytes, &tmap_w, &full_bar[s], kb * kBlockK,
+                                             (vt * 2 + int(rank)) * kBlockM);
+                            tma_load_3d_pair(smem_b + s * kBBytes, &tmap_h, &full_bar[s], kb * kBlockK,
+                                             c * p.LC + int(rank) * p.b_l_off, g * p.S + int(rank) * p.b_s_off);
                         }
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ------------------------------------------------ MMA issuer (single thread)
-            const uint32_t idesc = umma_idesc_bf16(kBlockM, p.N);
-            uint32_t it = 0;
-            for (int u0 = u_begin, pi = 0; u0 < u_end; u0 += 2, ++pi) {
-                for (int c = 0; c < p.NC; ++c) {
-                    for (int which = 0; which < 2; ++which) {
-                        if (u0 + which >= u_end) break;
-                        const uint32_t as = which, aph = uint32_t(pi * p.NC + c) & 1;
-                        mbar_wait(&tempty_bar[as], aph ^ 1);
+        if (lane == 0 && rank == 0) {
+            // ------------------------------------------------ MMA issuer (single thread of the leader CTA)
+            const uint32_t idesc = umma_idesc_bf16(kBlockM * kCG, p.N);
+            uint32_t it = 0, ci = 0;
+            for (int u = u_begin; u < u_end; ++u) {
+                for (int c = 0; c < p.NC; ++c, ++ci) {
+                    const uint32_t as = ci & 1, aph = (ci >> 1) & 1;
+                    mbar_wait(&tempty_bar[as], aph ^ 1);
+                    tc_fence_after();
+                    const uint32_t tmem_d = tmem_base + as * kAccCols;
+                    for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
+                        const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+                        mbar_wait(&full_bar[s], ph);
                         tc_fence_after();
-                        const uint32_t tmem_d = tmem_base + as * kAccCols;
-                        for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
-                            const uint32_t s = it % kStages, ph = (it / kStages) & 1;
-                            mbar_wait(&full_bar[s], ph);
-                            tc_fence_after();
-                            const uint64_t da = umma_desc_sw128(smem_u32(smem_a + s * kABytes));
-                            const uint64_t db = umma_desc_sw128(smem_u32(smem_b + s * kBBytes));
+                        const uint64_t da = umma_desc_sw128(smem_u32(smem_a + s * kABytes));
+                        const uint64_t db = umma_desc_sw128(smem_u32(smem_b + s * kBBytes));
 #pragma unroll
-                            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-                                // advance 32 bytes (= 16 bf16) inside the 128-byte swizzle row
-                                umma_bf16(tmem_d, da + uint64_t(k * 2), db + uint64_t(k * 2), idesc,
-                                          (kb | k) != 0 ? 1u : 0u);
-                            }
-                            umma_commit(&empty_bar[s]);  // frees the smem stage when these MMAs retire
+                        for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                            // advance 32 bytes (= 16 bf16) inside the 128-byte swizzle row
+                            if (kCG == 1)
+                                umma_bf16(tmem_d, da + uint64_t(k * 2), db + uint64_t(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+                            else
+                                umma_bf16_pair(tmem_d, da + uint64_t(k * 2), db + uint64_t(k * 2), idesc,
+                                               (kb | k) != 0 ? 1u : 0u);
                         }
-                        umma_commit(&tfull_bar[as]);     // accumulator ready for the epilogue
+                        // frees the smem stage (in both CTAs of a pair) when these MMAs retire
+                        if (kCG == 1) umma_commit(&empty_bar[s]); else umma_commit_pair(&empty_bar[s], 3);
                     }
+                    // accumulator ready for the epilogue (of both CTAs)
+                    if (kCG == 1) umma_commit(&tfull_bar[as]); else umma_commit_pair(&tfull_bar[as], 3);
                 }
             }
         }
     } else if (warp >= kFirstEpiWarp) {
-        // ---------------------------------------------------- epilogue warpgroups
+        // ---------------------------------------------------- epilogue: 2 warpgroups share EVERY accumulator tile.
+        // The epilogue of a tile must fit inside the MMA time of the next one (two accumulator stages), so both
+        // warpgroups work on each tile: whole sequences alternate between them (S >= 2), or a single sequence is
+        // split in two column halves whose (max, argmax) are merged through shared memory (S == 1).
         const int ew = warp - kFirstEpiWarp;
         const int wg = ew >> 2;
         const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+        const int row = quarter * 32 + lane;
         const uint32_t lane_base = uint32_t(quarter * 32) << 16;
-        // Units are processed in pairs; warpgroup `wg` owns the unit (and the TMEM accumulator stage) with that
-        // parity, so each warpgroup observes every phase of its own tfull/tempty barriers, and the running
-        // (max, argmax) of a sequence split over NC chunks stays in this thread's registers.
-        const uint32_t as = uint32_t(wg);
-        for (int u = u_begin + wg, pi = 0; u < u_end; u += 2, ++pi) {
+        const int half_cols = int((unsigned(p.LC / 2) + 15u) & ~15u);  // S == 1: warpgroup 0 takes [0, half_cols)
+        uint32_t ci = 0;
+        float m = -CUDART_INF_F;
+        int idx = 0;
+
+        // 16-column block: tree arg-max (depth 4) merged into the running (m, idx); strict '>' keeps the lowest
+        // position on ties. kMasked: columns whose bit is clear are excluded.
+        auto block16 = [&](const uint32_t (&r)[16], uint32_t bits, int lbase, auto masked) {
+            constexpr bool kMasked = decltype(masked)::value;
+            float v[16];
+            int ix[8];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                v[i] = __uint_as_float(r[i]);
+                if (kMasked && !((bits >> i) & 1u)) v[i] = -CUDART_INF_F;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const bool pr = v[2 * i + 1] > v[2 * i];
+                ix[i] = pr ? 2 * i + 1 : 2 * i;
+                v[i] = fmaxf(v[2 * i], v[2 * i + 1]);
+            }
+#pragma unroll
+            for (int w = 4; w >= 1; w >>= 1) {
+#pragma unroll
+                for (int i = 0; i < w; ++i) {
+                    const bool pr = v[2 * i + 1] > v[2 * i];
+                    ix[i] = pr ? ix[2 * i + 1] : ix[2 * i];
+                    v[i] = fmaxf(v[2 * i], v[2 * i + 1]);
+                }
+            }
+            if (v[0] > m) {
+                m = v[0];
+                idx = lbase + ix[0];
+            }
+        };
+        // columns [n_begin, n_end) of the accumulator (multiples of 16) hold tokens l_begin.. of one sequence
+        auto scan_columns = [&](uint32_t tmem_acc, const uint32_t* tm, int n_begin, int n_end, int l_begin) {
+            for (int n0 = n_begin; n0 < n_end; n0 += 32) {
+                const int n1 = n0 + 16;
+                const uint32_t lo = (__ldg(tm + (n0 >> 5)) >> (n0 & 31)) & 0xffffu;
+                const uint32_t hi = (n1 < n_end) ? ((__ldg(tm + (n1 >> 5)) >> (n1 & 31)) & 0xffffu) : 0u;
+                uint32_t ra[16], rb[16];
+                if (lo != 0) tmem_ld16(tmem_acc + n0, ra);
+                if (hi != 0) tmem_ld16(tmem_acc + n1, rb);
+                if ((lo | hi) != 0) tmem_ld_wait();
+                const int l0 = l_begin + (n0 - n_begin);
+                if (lo == 0xffffu) block16(ra, lo, l0, std::false_type{});
+                else if (lo != 0) block16(ra, lo, l0, std::true_type{});
+                if (hi == 0xffffu) block16(rb, hi, l0 + 16, std::false_type{});
+                else if (hi != 0) block16(rb, hi, l0 + 16, std::true_type{});
+            }
+        };
+        auto finalize = [&](int b, int v, float bias_v) {
+            const int2 si = __ldg(p.seqinfo + b);
+            float x = m + bias_v;
+            if (si.x > 0) {
+                if (x < 0.f || (x == 0.f && si.y < idx)) idx = si.y;
+                x = fmaxf(x, 0.f);
+            }
+            const size_t o = size_t(b) * p.V + v;
+            if (p.xmax != nullptr) p.xmax[o] = x;
+            if (p.argmax != nullptr) p.argmax[o] = idx;
+            float r1 = log1pf(fmaxf(x, 0.f));
+            if (p.l0) r1 = log1pf(r1);
+            p.rep[o] = r1;
+        };
+
+        for (int u = u_begin; u < u_end; ++u) {
             const int g = u / p.n_vtiles, vt = u - g * p.n_vtiles;
-            const int v = vt * kBlockM + quarter * 32 + lane;
+            const int v = (vt * kCG + int(rank)) * kBlockM + row;
             const bool v_ok = v < p.V;
             const float bias_v = (v_ok && p.bias != nullptr) ? __ldg(p.bias + v) : 0.f;
-            float m = -CUDART_INF_F;
-            int idx = 0;
-            for (int c = 0; c < p.NC; ++c) {
-                const uint32_t aph = uint32_t(pi * p.NC + c) & 1;
+            if (p.S == 1) {
+                m = -CUDART_INF_F;
+                idx = 0;
+            }
+            for (int c = 0; c < p.NC; ++c, ++ci) {
+                const uint32_t as = ci & 1, aph = (ci >> 1) & 1;
                 const uint32_t* tm = p.tilemask + (size_t(g) * p.NC + c) * kMaskWords;
-                uint32_t word = __ldg(tm);
                 mbar_wait(&tfull_bar[as], aph);
                 tc_fence_after();
                 const uint32_t tmem_acc = tmem_base + lane_base + as * kAccCols;
-                int s = 0, jrem = p.LC;
-
-                // One 16-column block: tree arg-max (depth 4, all nodes of a level independent), then one merge
-                // into the running (m, idx). Strict '>' everywhere keeps the lowest position on ties.
-                auto consume = [&](uint32_t (&r)[16], uint32_t bits) {
-                    if (bits != 0) {
-                        float v[16];
-                        int ix[8];
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            v[i] = __uint_as_float(r[i]);
-                            if (bits != 0xffffu && !((bits >> i) & 1u)) v[i] = -CUDART_INF_F;  // warp-uniform
-                        }
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const bool pr = v[2 * i + 1] > v[2 * i];
-                            ix[i] = pr ? 2 * i + 1 : 2 * i;
-                            v[i] = fmaxf(v[2 * i], v[2 * i + 1]);
-                        }
-#pragma unroll
-                        for (int w = 4; w >= 1; w >>= 1) {
-#pragma unroll
-                            for (int i = 0; i < w; ++i) {
-                                const bool pr = v[2 * i + 1] > v[2 * i];
-                                ix[i] = pr ? ix[2 * i + 1] : ix[2 * i];
-                                v[i] = fmaxf(v[2 * i], v[2 * i + 1]);
-                            }
-                        }
-                        const int lbase = c * p.LC + (p.LC - jrem);
-                        if (v[0] > m) {
-                            m = v[0];
-                            idx = lbase + ix[0];
-                        }
-                    }
-                    jrem -= 16;
-                    if (jrem == 0) {
-                        // end of sequence s inside this tile
+                if (p.S >= 2) {
+                    for (int s = wg; s < p.S; s += 2) {
+                        m = -CUDART_INF_F;
+                        idx = 0;
+                        scan_columns(tmem_acc, tm, s * p.LC, (s + 1) * p.LC, 0);
                         const int b = g * p.S + s;
-                        if (c == p.NC - 1 && b < p.B && v_ok) {
-                            const int2 si = __ldg(p.seqinfo + b);
-                            float x = m + bias_v;
-                            if (si.x > 0) {
-                                if (x < 0.f || (x == 0.f && si.y < idx)) idx = si.y;
-                                x = fmaxf(x, 0.f);
-                            }
-                            const size_t o = size_t(b) * p.V + v;
-                            if (p.xmax != nullptr) p.xmax[o] = x;
-                            if (p.argmax != nullptr) p.argmax[o] = idx;
-                            float r1 = log1pf(fmaxf(x, 0.f));
-                            if (p.l0) r1 = log1pf(r1);
-                            p.rep[o] = r1;
-                        }
-                        ++s;
-                        jrem = p.LC;
-                        if (p.NC == 1) {
-                            m = -CUDART_INF_F;
-                            idx = 0;
-                        }
+                        if (b < p.B && v_ok) finalize(b, v, bias_v);
                     }
-                };
-
-                for (int n0 = 0; n0 < p.N; n0 += 32) {
-                    const uint32_t lo = word & 0xffffu;
-                    const bool has_hi = n0 + 16 < p.N;
-                    const uint32_t hi = has_hi ? (word >> 16) : 0u;
-                    if (n0 + 32 < p.N) word = __ldg(tm + ((n0 + 32) >> 5));  // prefetch the next mask word
-                    uint32_t ra[16], rb[16];
-                    if (lo != 0) tmem_ld16(tmem_acc + n0, ra);
-                    if (hi != 0) tmem_ld16(tmem_acc + n0 + 16, rb);
-                    if ((lo | hi) != 0) tmem_ld_wait();
-                    consume(ra, lo);
-                    if (has_hi) consume(rb, hi);
+                } else {
+                    const int n_begin = wg == 0 ? 0 : half_cols;
+                    const int n_end = wg == 0 ? half_cols : p.LC;
+                    scan_columns(tmem_acc, tm, n_begin, n_end, c * p.LC + n_begin);
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty_bar[as]);
+                if (lane == 0) {
+                    if (kCG == 1) mbar_arrive(&tempty_bar[as]); else mbar_arrive_cluster(&tempty_bar[as], 0);
+                }
+            }
+            if (p.S == 1) {
+                // merge the two column halves: larger value wins, equal values keep the lower position
+                float2* slot = comb + ((u - u_begin) & 1) * kBlockM + row;
+                if (wg == 1) *slot = make_float2(m, __int_as_float(idx));
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (wg == 0) {
+                    const float2 o = *slot;
+                    const int oi = __float_as_int(o.y);
+                    if (o.x > m || (o.x == m && oi < idx)) {
+                        m = o.x;
+                        idx = oi;
+                    }
+                    if (g < p.B && v_ok) finalize(g, v, bias_v);
+                }
             }
         }
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (kCG == 2) cluster_sync_all(); else __syncthreads();  // the peer may still signal barriers in this CTA's smem
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, kTmemCols);
+        if (kCG == 2) tmem_dealloc_pair(tmem_base, kTmemCols); else tmem_dealloc(tmem_base, kTmemCols);
     }
 }
 
@@ -328,7 +381,8 @@ struct HeadTiling {
     int LC, S, NC, N, n_groups;
 };
 
-HeadTiling head_tiling(int B, int L) {
+// pair != 0: the token tile must split into two equal halves along whole sequences (S even) or inside one (S == 1)
+HeadTiling head_tiling(int B, int L, int pair = 0) {
     HeadTiling t;
     if (L <= kMaxN) {
         t.NC = 1;
@@ -336,6 +390,7 @@ HeadTiling head_tiling(int B, int L) {
         t.S = kMaxN / t.LC;
         if (t.S > B) t.S = B;
         if (t.S < 1) t.S = 1;
+        if (pair && t.S > 1 && (t.S & 1)) t.S -= 1;
     } else {
         t.NC = (L + kMaxN - 1) / kMaxN;
         t.LC = int(align_up(size_t((L + t.NC - 1) / t.NC), 16));
@@ -352,10 +407,24 @@ HeadTiling head_tiling(int B, int L) {
 
 using namespace sb200;
 
+static size_t head_ws_bytes(const HeadTiling& t, int B) {
+    return align_up(size_t(t.n_groups) * t.NC * kMaskWords * sizeof(uint32_t), 256) + align_up(size_t(B) * sizeof(int2), 256);
+}
+
+// 1 = single-CTA tiles (128 x N), 2 = CTA pairs (256 x N, cta_group::2). SB200_HEAD_CTA_GROUP overrides (A/B testing).
+static int head_cta_group() {
+    static int cached = [] {
+        const char* e = getenv("SB200_HEAD_CTA_GROUP");
+        if (e != nullptr && (e[0] == '1' || e[0] == '2')) return e[0] - '0';
+        return 2;
+    }();
+    return cached;
+}
+
 extern "C" size_t sb200_head_fwd_workspace_bytes(int B, int L) {
     if (B <= 0 || L <= 0) return 0;
-    const HeadTiling t = head_tiling(B, L);
-    return align_up(size_t(t.n_groups) * t.NC * kMaskWords * sizeof(uint32_t), 256) + align_up(size_t(B) * sizeof(int2), 256);
+    const size_t a = head_ws_bytes(head_tiling(B, L, 0), B), b = head_ws_bytes(head_tiling(B, L, 1), B);
+    return a > b ? a : b;
 }
 
 extern "C" int sb200_head_fwd(const void* hidden, const void* W, const float* bias, const void* mask,
@@ -373,7 +442,9 @@ extern "C" int sb200_head_fwd(const void* hidden, const void* W, const float* bi
     if (workspace == nullptr || workspace_bytes < need)
         return fail(SB200_ERR_WORKSPACE, "head_fwd: workspace %zu < %zu", workspace_bytes, need);
 
-    const HeadTiling t = head_tiling(B, L);
+    const int sms = num_sms();
+    const int cg = (head_cta_group() == 2 && sms >= 2) ? 2 : 1;
+    const HeadTiling t = head_tiling(B, L, cg == 2);
     uint32_t* tilemask = static_cast<uint32_t*>(workspace);
     int2* seqinfo = reinterpret_cast<int2*>(static_cast<uint8_t*>(workspace) +
                                             align_up(size_t(t.n_groups) * t.NC * kMaskWords * sizeof(uint32_t), 256));
@@ -381,6 +452,12 @@ extern "C" int sb200_head_fwd(const void* hidden, const void* W, const float* bi
     EncodeTiledFn encode = get_encode_fn();
     if (encode == nullptr) return fail(SB200_ERR_CUDA, "head_fwd: cuTensorMapEncodeTiled unavailable");
 
+    // the B box is what ONE CTA loads per stage: the whole token tile, or (CTA pair) half of it
+    int box_l = t.LC, box_s = t.S, b_l_off = 0, b_s_off = 0;
+    if (cg == 2) {
+        if (t.S >= 2) { box_s = t.S / 2; b_s_off = t.S / 2; }
+        else          { box_l = t.LC / 2; b_l_off = t.LC / 2; }
+    }
     CUtensorMap tmap_w, tmap_h;
     {
         cuuint64_t dims[2] = {cuuint64_t(H), cuuint64_t(V)};
@@ -395,7 +472,7 @@ extern "C" int sb200_head_fwd(const void* hidden, const void* W, const float* bi
     {
         cuuint64_t dims[3] = {cuuint64_t(H), cuuint64_t(L), cuuint64_t(B)};
         cuuint64_t strides[2] = {cuuint64_t(H) * 2, cuuint64_t(L) * cuuint64_t(H) * 2};
-        cuuint32_t box[3] = {kBlockK, cuuint32_t(t.LC), cuuint32_t(t.S)};
+        cuuint32_t box[3] = {kBlockK, cuuint32_t(box_l), cuuint32_t(box_s)};
         cuuint32_t estr[3] = {1, 1, 1};
         CUresult r = encode(&tmap_h, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(hidden), dims, strides, box,
                             estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -421,18 +498,42 @@ extern "C" int sb200_head_fwd(const void* hidden, const void* W, const float* bi
     p.argmax = argmax;
     p.B = B; p.L = L; p.H = H; p.V = V;
     p.LC = t.LC; p.S = t.S; p.NC = t.NC; p.N = t.N;
-    p.n_vtiles = (V + kBlockM - 1) / kBlockM;
+    p.n_vtiles = (V + kBlockM * cg - 1) / (kBlockM * cg);
     p.n_groups = t.n_groups;
     p.kblocks = (H + kBlockK - 1) / kBlockK;
     p.l0 = (flags & SB200_HEAD_L0) ? 1 : 0;
+    p.b_l_off = b_l_off;
+    p.b_s_off = b_s_off;
 
-    // per-device attribute, set once per device (and never while a stream capture may be in progress later on)
-    if (!device_flag_test_and_set(0))
-        SB200_CUDA(cudaFuncSetAttribute(head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBytes)));
     const long long total_units = (long long)p.n_vtiles * p.n_groups;
-    int grid = num_sms();
-    if (grid > total_units) grid = int(total_units);
-    head_fwd_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tmap_w, tmap_h, p);
+    if (cg == 1) {
+        // per-device attribute, set once per device (never while a stream capture may be in progress later on)
+        if (!device_flag_test_and_set(0))
+            SB200_CUDA(cudaFuncSetAttribute(head_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            int(StageCfg<1>::kSmemBytes)));
+        int grid = sms;
+        if (grid > total_units) grid = int(total_units);
+        head_fwd_kernel<1><<<grid, kThreads, StageCfg<1>::kSmemBytes, stream>>>(tmap_w, tmap_h, p);
+    } else {
+        if (!device_flag_test_and_set(5))
+            SB200_CUDA(cudaFuncSetAttribute(head_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            int(StageCfg<2>::kSmemBytes)));
+        int clusters = sms / 2;
+        if (clusters > total_units) clusters = int(total_units);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(unsigned(clusters * 2));
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = StageCfg<2>::kSmemBytes;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        SB200_CUDA(cudaLaunchKernelEx(&cfg, head_fwd_kernel<2>, tmap_w, tmap_h, p));
+    }
     SB200_CHECK_LAUNCH("head_fwd_kernel");
     return SB200_OK;
 }
