@@ -36,24 +36,25 @@ constexpr int kBlockM = 128;     // vocab rows per tile (UMMA M)
 constexpr int kBlockK = 64;      // bf16 per smem row = 128 B = swizzle span
 constexpr int kUmmaK = 16;
 constexpr int kMaxN = 256;       // token columns per tile (UMMA N upper bound)
+constexpr int kNumEpiWG = 2;                 // epilogue warpgroups; every one of them works on every tile
+constexpr int kNumEpiWarps = 4 * kNumEpiWG;  // 8 (16 were measured slower: register cap 96 + TMEM port contention)
 constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KB per stage (this CTA's 128 vocab rows)
 // B bytes per stage held by ONE CTA: the whole token tile (1-CTA) or half of it (CTA pair)
 template <int kCG> struct StageCfg {
     static constexpr int kBBytes = kMaxN * kBlockK * 2 / kCG;   // 32 KB / 16 KB
     static constexpr int kStages = (kCG == 1) ? 4 : 6;          // 4 x 48 KB or 6 x 32 KB = 192 KB
-    static constexpr size_t kSmemBytes = 1024 /*align slack*/ + size_t(kStages) * (kABytes + kBBytes) + 256 + 2 * kBlockM * 8;
+    static constexpr size_t kSmemBytes = 1024 /*align slack*/ + size_t(kStages) * (kABytes + kBBytes) + 256 + 2 * kNumEpiWG * kBlockM * 8;
 };
 constexpr int kAccCols = 256;
 constexpr int kTmemCols = 512;
 constexpr int kFirstEpiWarp = 4;
-constexpr int kNumEpiWarps = 8;
 constexpr int kThreads = (kFirstEpiWarp + kNumEpiWarps) * 32;  // 384
 constexpr int kMaskWords = kMaxN / 32;                          // 8
 
 struct HeadFwdParams {
     const float* bias;
     const uint32_t* tilemask;  // [n_groups][NC][8] validity bits per tile column
-    const int2* seqinfo;       // [B] (number of masked slots, first masked slot)
+    const int4* seqinfo;       // [B] (number of masked slots, first masked slot, last real position + 1, 0)
     float* rep;
     float* xmax;
     int32_t* argmax;
@@ -61,12 +62,13 @@ struct HeadFwdParams {
     int LC, S, NC, N;          // chunk length, sequences per tile, chunks per sequence, S*LC
     int n_vtiles, n_groups, kblocks;   // n_vtiles counts tiles of 128 * kCG vocab rows
     int l0;
+    int dbg;                   // bring-up experiments only (0 in production)
     int b_l_off, b_s_off;      // CTA pair: token / sequence offset of the second CTA's half of the B tile
 };
 
 // Packs the attention mask into per-tile column bitmaps and per-sequence padding info.
 __global__ void head_prep_kernel(const void* __restrict__ mask, int elem_bytes, int B, int L, int LC, int S, int NC,
-                                 int n_groups, uint32_t* __restrict__ tilemask, int2* __restrict__ seqinfo) {
+                                 int n_groups, uint32_t* __restrict__ tilemask, int4* __restrict__ seqinfo) {
     const int lane = threadIdx.x & 31;
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int n_words = n_groups * NC * kMaskWords;
@@ -88,19 +90,30 @@ __global__ void head_prep_kernel(const void* __restrict__ mask, int elem_bytes, 
         if (lane == 0) tilemask[w] = bits;
     } else if (w - n_words < B) {
         const int b = w - n_words;
-        int count = 0, first = L;
+        int count = 0, first = L, extent = 0;
         for (int l = lane; l < L; l += 32) {
             const bool v = mask_at(size_t(b) * L + l);
             count += v ? 1 : 0;
             if (!v && l < first) first = l;
+            if (v) extent = l + 1;
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             count += __shfl_xor_sync(0xffffffffu, count, o);
             first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+            extent = max(extent, __shfl_xor_sync(0xffffffffu, extent, o));
         }
-        if (lane == 0) seqinfo[b] = make_int2(L - count, first);
+        if (lane == 0) seqinfo[b] = make_int4(L - count, first, extent, 0);
     }
+}
+
+// Token columns a tile really needs (S == 1: one sequence per tile): padding beyond the last real token of the
+// chunk is neither multiplied nor read back. Multiple of 16, at least 16.
+__device__ __forceinline__ int tile_columns(const HeadFwdParams& p, int g, int c) {
+    if (p.S != 1 || (p.dbg & 2)) return p.N;
+    const int extent = __ldg(p.seqinfo + g).z - c * p.LC;
+    const int n = (min(max(extent, 1), p.LC) + 15) & ~15;
+    return n;
 }
 
 template <int kCG>
@@ -119,7 +132,7 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
     uint64_t* tfull_bar = bars + 2 * kStages;    // [2]        MMA -> epilogue
     uint64_t* tempty_bar = bars + 2 * kStages + 2;  // [2]     epilogue -> MMA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
-    float2* comb = reinterpret_cast<float2*>(bars + 2 * kStages + 6);  // [2][128] half-sequence (max, argmax) exchange
+    float2* comb = reinterpret_cast<float2*>(bars + 2 * kStages + 6);  // [2][kNumEpiWG][128] partial (max, argmax)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -139,7 +152,7 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull_bar[i], 1);
-            mbar_init(&tempty_bar[i], kNumEpiWarps * kCG);  // one arrive per epilogue warp (of both CTAs)
+            mbar_init(&tempty_bar[i], (blockDim.x / 32 - kFirstEpiWarp) * kCG);  // one arrive per epilogue warp (of both CTAs)
         }
         fence_mbar_init();
     }
@@ -170,6 +183,8 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
             for (int u = u_begin; u < u_end; ++u) {
                 const int g = u / p.n_vtiles, vt = u - g * p.n_vtiles;
                 for (int c = 0; c < p.NC; ++c) {
+                    // CTA pair, one sequence per tile: the second CTA's half starts where the first one's ends
+                    const int l_off = (p.S == 1) ? tile_columns(p, g, c) / 2 : 0;
                     for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
                         const uint32_t s = it % kStages, ph = (it / kStages) & 1;
                         mbar_wait(&empty_bar[s], ph ^ 1);
@@ -183,7 +198,7 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
                             tma_load_2d_pair(smem_a + s * kABytes, &tmap_w, &full_bar[s], kb * kBlockK,
                                              (vt * 2 + int(rank)) * kBlockM);
                             tma_load_3d_pair(smem_b + s * kBBytes, &tmap_h, &full_bar[s], kb * kBlockK,
-                                             c * p.LC + int(rank) * p.b_l_off, g * p.S + int(rank) * p.b_s_off);
+                                             c * p.LC + int(rank) * l_off, g * p.S + int(rank) * p.b_s_off);
                         }
                     }
                 }
@@ -192,10 +207,17 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
     } else if (warp == 1) {
         if (lane == 0 && rank == 0) {
             // ------------------------------------------------ MMA issuer (single thread of the leader CTA)
-            const uint32_t idesc = umma_idesc_bf16(kBlockM * kCG, p.N);
             uint32_t it = 0, ci = 0;
+            // the column count of the next tile is fetched one tile ahead (global load off the issue path)
+            int n_next = (u_begin < u_end) ? tile_columns(p, u_begin / p.n_vtiles, 0) : 16;
             for (int u = u_begin; u < u_end; ++u) {
                 for (int c = 0; c < p.NC; ++c, ++ci) {
+                    const uint32_t idesc = umma_idesc_bf16(kBlockM * kCG, n_next);
+                    {
+                        int un = u, cn = c + 1;
+                        if (cn == p.NC) { cn = 0; ++un; }
+                        if (un < u_end) n_next = tile_columns(p, un / p.n_vtiles, cn);
+                    }
                     const uint32_t as = ci & 1, aph = (ci >> 1) & 1;
                     mbar_wait(&tempty_bar[as], aph ^ 1);
                     tc_fence_after();
@@ -224,20 +246,31 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
             }
         }
     } else if (warp >= kFirstEpiWarp) {
-        // ---------------------------------------------------- epilogue: 2 warpgroups share EVERY accumulator tile.
-        // The epilogue of a tile must fit inside the MMA time of the next one (two accumulator stages), so both
-        // warpgroups work on each tile: whole sequences alternate between them (S >= 2), or a single sequence is
-        // split in two column halves whose (max, argmax) are merged through shared memory (S == 1).
+        // ---------------------------------------------------- epilogue: all warpgroups share EVERY accumulator tile
+        // (the epilogue of a tile has to fit inside the MMA time of the next one: two accumulator stages).
         const int ew = warp - kFirstEpiWarp;
         const int wg = ew >> 2;
         const int quarter = warp & 3;  // TMEM lane quarter this warp may access
         const int row = quarter * 32 + lane;
         const uint32_t lane_base = uint32_t(quarter * 32) << 16;
-        const int half_cols = int((unsigned(p.LC / 2) + 15u) & ~15u);  // S == 1: warpgroup 0 takes [0, half_cols)
         uint32_t ci = 0;
         float m = -CUDART_INF_F;
         int idx = 0;
 
+        const bool want_arg = p.argmax != nullptr;
+        // value-only variant (inference: no arg-max wanted): 8 three-input max instructions per 16 columns
+        auto block16_value = [&](const uint32_t (&r)[16], uint32_t bits, auto masked) {
+            constexpr bool kMasked = decltype(masked)::value;
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                v[i] = __uint_as_float(r[i]);
+                if (kMasked && !((bits >> i) & 1u)) v[i] = -CUDART_INF_F;
+            }
+            const float a0 = max3f(v[0], v[1], v[2]), a1 = max3f(v[3], v[4], v[5]), a2 = max3f(v[6], v[7], v[8]);
+            const float a3 = max3f(v[9], v[10], v[11]), a4 = max3f(v[12], v[13], v[14]);
+            m = max3f(max3f(a0, a1, a2), max3f(a3, a4, v[15]), m);
+        };
         // 16-column block: tree arg-max (depth 4) merged into the running (m, idx); strict '>' keeps the lowest
         // position on ties. kMasked: columns whose bit is clear are excluded.
         auto block16 = [&](const uint32_t (&r)[16], uint32_t bits, int lbase, auto masked) {
@@ -280,6 +313,20 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
                 if (hi != 0) tmem_ld16(tmem_acc + n1, rb);
                 if ((lo | hi) != 0) tmem_ld_wait();
                 const int l0 = l_begin + (n0 - n_begin);
+                if (p.dbg & 1) {  // experiment: TMEM loads only
+                    uint32_t acc = 0;
+                    if (lo != 0) for (int i = 0; i < 16; ++i) acc |= ra[i];
+                    if (hi != 0) for (int i = 0; i < 16; ++i) acc |= rb[i];
+                    if (acc == 0x12345678u) idx = 1;
+                    continue;
+                }
+                if (!want_arg) {
+                    if (lo == 0xffffu) block16_value(ra, lo, std::false_type{});
+                    else if (lo != 0) block16_value(ra, lo, std::true_type{});
+                    if (hi == 0xffffu) block16_value(rb, hi, std::false_type{});
+                    else if (hi != 0) block16_value(rb, hi, std::true_type{});
+                    continue;
+                }
                 if (lo == 0xffffu) block16(ra, lo, l0, std::false_type{});
                 else if (lo != 0) block16(ra, lo, l0, std::true_type{});
                 if (hi == 0xffffu) block16(rb, hi, l0 + 16, std::false_type{});
@@ -287,7 +334,7 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
             }
         };
         auto finalize = [&](int b, int v, float bias_v) {
-            const int2 si = __ldg(p.seqinfo + b);
+            const int4 si = __ldg(p.seqinfo + b);
             float x = m + bias_v;
             if (si.x > 0) {
                 if (x < 0.f || (x == 0.f && si.y < idx)) idx = si.y;
@@ -301,23 +348,32 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
             p.rep[o] = r1;
         };
 
+        // Work split of one tile over the n_wg warpgroups:
+        //   S >= n_wg sequences per tile: whole sequences round-robin, nothing to merge;
+        //   fewer: each sequence is cut into n_wg/S column ranges, one per warpgroup; the partial (max, argmax) pairs
+        //          go through shared memory and one warpgroup of the group (rotating per unit) merges and writes.
+        const int n_wg = int(blockDim.x / 32 - kFirstEpiWarp) / 4;   // = kNumEpiWG
+        const bool split = p.S < n_wg && n_wg % p.S == 0;         // a sequence is shared by several warpgroups
+        const int gsz = split ? n_wg / p.S : 1;
+        const int my_s = wg / gsz, part = wg - my_s * gsz;
         for (int u = u_begin; u < u_end; ++u) {
             const int g = u / p.n_vtiles, vt = u - g * p.n_vtiles;
             const int v = (vt * kCG + int(rank)) * kBlockM + row;
             const bool v_ok = v < p.V;
             const float bias_v = (v_ok && p.bias != nullptr) ? __ldg(p.bias + v) : 0.f;
-            if (p.S == 1) {
+            if (split) {
                 m = -CUDART_INF_F;
                 idx = 0;
             }
             for (int c = 0; c < p.NC; ++c, ++ci) {
                 const uint32_t as = ci & 1, aph = (ci >> 1) & 1;
                 const uint32_t* tm = p.tilemask + (size_t(g) * p.NC + c) * kMaskWords;
+                const int n_seq = (p.S == 1) ? tile_columns(p, g, c) : p.LC;  // columns worth scanning per sequence
                 mbar_wait(&tfull_bar[as], aph);
                 tc_fence_after();
                 const uint32_t tmem_acc = tmem_base + lane_base + as * kAccCols;
-                if (p.S >= 2) {
-                    for (int s = wg; s < p.S; s += 2) {
+                if (!split) {
+                    for (int s = wg; s < p.S; s += n_wg) {
                         m = -CUDART_INF_F;
                         idx = 0;
                         scan_columns(tmem_acc, tm, s * p.LC, (s + 1) * p.LC, 0);
@@ -325,9 +381,10 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
                         if (b < p.B && v_ok) finalize(b, v, bias_v);
                     }
                 } else {
-                    const int n_begin = wg == 0 ? 0 : half_cols;
-                    const int n_end = wg == 0 ? half_cols : p.LC;
-                    scan_columns(tmem_acc, tm, n_begin, n_end, c * p.LC + n_begin);
+                    const int nb = n_seq >> 4;  // 16-column blocks of this sequence in this chunk
+                    const int b0 = part * nb / gsz, b1 = (part + 1) * nb / gsz;
+                    const int base = my_s * p.LC;
+                    scan_columns(tmem_acc, tm, base + 16 * b0, base + 16 * b1, c * p.LC + 16 * b0);
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -335,19 +392,25 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
                     if (kCG == 1) mbar_arrive(&tempty_bar[as]); else mbar_arrive_cluster(&tempty_bar[as], 0);
                 }
             }
-            if (p.S == 1) {
-                // merge the two column halves: larger value wins, equal values keep the lower position
-                float2* slot = comb + ((u - u_begin) & 1) * kBlockM + row;
-                if (wg == 1) *slot = make_float2(m, __int_as_float(idx));
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                if (wg == 0) {
-                    const float2 o = *slot;
-                    const int oi = __float_as_int(o.y);
-                    if (o.x > m || (o.x == m && oi < idx)) {
-                        m = o.x;
-                        idx = oi;
+            if (split) {
+                // merge the partial results of the group: larger value wins, equal values keep the lower position
+                const int ui = u - u_begin;
+                float2* buf = comb + (ui & 1) * (kNumEpiWG * kBlockM);
+                const int merger = my_s * gsz + ui % gsz;
+                if (wg != merger) buf[wg * kBlockM + row] = make_float2(m, __int_as_float(idx));
+                asm volatile("bar.sync 1, %0;" ::"r"(n_wg * 128) : "memory");
+                if (wg == merger) {
+                    for (int k = my_s * gsz; k < (my_s + 1) * gsz; ++k) {
+                        if (k == wg) continue;
+                        const float2 o = buf[k * kBlockM + row];
+                        const int oi = __float_as_int(o.y);
+                        if (o.x > m || (o.x == m && oi < idx)) {
+                            m = o.x;
+                            idx = oi;
+                        }
                     }
-                    if (g < p.B && v_ok) finalize(g, v, bias_v);
+                    const int b = g * p.S + my_s;
+                    if (b < p.B && v_ok) finalize(b, v, bias_v);
                 }
             }
         }
@@ -408,7 +471,7 @@ HeadTiling head_tiling(int B, int L, int pair = 0) {
 using namespace sb200;
 
 static size_t head_ws_bytes(const HeadTiling& t, int B) {
-    return align_up(size_t(t.n_groups) * t.NC * kMaskWords * sizeof(uint32_t), 256) + align_up(size_t(B) * sizeof(int2), 256);
+    return align_up(size_t(t.n_groups) * t.NC * kMaskWords * sizeof(uint32_t), 256) + align_up(size_t(B) * sizeof(int4), 256);
 }
 
 // 1 = single-CTA tiles (128 x N), 2 = CTA pairs (256 x N, cta_group::2). SB200_HEAD_CTA_GROUP overrides (A/B testing).
@@ -446,7 +509,7 @@ extern "C" int sb200_head_fwd(const void* hidden, const void* W, const float* bi
     const int cg = (head_cta_group() == 2 && sms >= 2) ? 2 : 1;
     const HeadTiling t = head_tiling(B, L, cg == 2);
     uint32_t* tilemask = static_cast<uint32_t*>(workspace);
-    int2* seqinfo = reinterpret_cast<int2*>(static_cast<uint8_t*>(workspace) +
+    int4* seqinfo = reinterpret_cast<int4*>(static_cast<uint8_t*>(workspace) +
                                             align_up(size_t(t.n_groups) * t.NC * kMaskWords * sizeof(uint32_t), 256));
 
     EncodeTiledFn encode = get_encode_fn();
@@ -502,6 +565,7 @@ extern "C" int sb200_head_fwd(const void* hidden, const void* W, const float* bi
     p.n_groups = t.n_groups;
     p.kblocks = (H + kBlockK - 1) / kBlockK;
     p.l0 = (flags & SB200_HEAD_L0) ? 1 : 0;
+    p.dbg = (flags >> 8) & 0xff;
     p.b_l_off = b_l_off;
     p.b_s_off = b_s_off;
 

@@ -28,6 +28,9 @@ def _workspace(nbytes, device):
     return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
 
 
+import os as _os
+_DEBUG_FLAGS = int(_os.environ.get("SB200_HEAD_DEBUG", "0")) << 8  # kernel bring-up experiments only
+
 # Optional per-call CUDA-event timing of named C-ABI calls (used by bench.py for the live roofline numbers).
 _PROFILE = None
 
@@ -98,8 +101,8 @@ def head_forward(hidden, weight, bias, attention_mask, use_l0=False, want_aux=Tr
     ws = _workspace(ws_bytes, dev)
     with torch.cuda.device(dev), _timed("head_fwd"):
         code = lib.sb200_head_fwd(_ptr(hidden), _ptr(weight), _ptr(bias), _ptr(mask), mask.element_size(), B, L, H, V,
-                                  _lib.HEAD_L0 if use_l0 else 0, _ptr(rep), _ptr(xmax), _ptr(argmax), _ptr(ws),
-                                  ws.numel(), _stream())
+                                  (_lib.HEAD_L0 if use_l0 else 0) | _DEBUG_FLAGS, _ptr(rep), _ptr(xmax), _ptr(argmax),
+                                  _ptr(ws), ws.numel(), _stream())
     _lib.check(code, "sb200_head_fwd")
     return rep, xmax, argmax
 

@@ -37,37 +37,42 @@ def case(B, L, H, V, ragged=True, l0=False, bias_shift=0.0, seed=0):
           f"argmax agree(active)={agree:.6f} (all)={agree_all:.6f} active={act.float().mean().item():.3f}", flush=True)
     return err
 
-def bench(B, L, H, V, iters=20):
-    hidden = torch.randn(B, L, H, device="cuda").bfloat16()
-    W = (torch.randn(V, H, device="cuda") * 0.05).bfloat16()
+def bench(B, L, H, V, iters=20, ragged=False, reps=5):
+    g = torch.Generator(device="cuda").manual_seed(1)
+    hidden = torch.randn(B, L, H, device="cuda", generator=g).bfloat16()
+    W = (torch.randn(V, H, device="cuda", generator=g) * 0.05).bfloat16()
     bias = torch.zeros(V, device="cuda")
-    mask = torch.ones(B, L, dtype=torch.long, device="cuda")
-    for _ in range(3):
+    if ragged:
+        lens = torch.randint(L // 2, L + 1, (B,), device="cuda", generator=g)
+    else:
+        lens = torch.full((B,), L, device="cuda")
+    mask = (torch.arange(L, device="cuda")[None, :] < lens[:, None]).long()
+    for _ in range(5):
         ops.head_forward(hidden, W, bias, mask)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(iters):
-        ops.head_forward(hidden, W, bias, mask)
-    e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / iters
+    times = []
+    for _ in range(reps):
+        e0.record()
+        for _ in range(iters):
+            ops.head_forward(hidden, W, bias, mask)
+        e1.record(); torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1) / iters)
+    ms = min(times)
     fl = 2.0 * B * L * H * V
-    print(f"bench B={B} L={L} H={H}: {ms:.3f} ms  {fl/ms/1e9:.1f} TFLOP/s", flush=True)
-    # unfused torch bf16
-    def unf():
-        logits = hidden @ W.t()
-        vals, _ = torch.max(logits * mask.unsqueeze(-1), dim=1)
-        return torch.log1p(torch.relu(vals.float()))
-    if B * L * V > 2e9:
-        return
-    for _ in range(2): unf()
-    torch.cuda.synchronize(); e0.record()
-    for _ in range(5): unf()
-    e1.record(); torch.cuda.synchronize()
-    print(f"   unfused torch bf16: {e0.elapsed_time(e1)/5:.3f} ms", flush=True)
+    print(f"bench B={B} L={L} H={H} ragged={ragged}: min {ms:.3f} ms median {sorted(times)[len(times)//2]:.3f} ms  "
+          f"{fl/ms/1e9:.1f} TFLOP/s (all positions counted)", flush=True)
+
 
 if __name__ == "__main__":
     print(torch.cuda.get_device_name(0))
+    if len(sys.argv) > 1 and sys.argv[1] == "bench":
+        bench(160, 256, 384, 30522)
+        bench(160, 256, 384, 30522, ragged=True)
+        bench(64, 512, 768, 30522)
+        bench(64, 512, 768, 30522, ragged=True)
+        bench(256, 128, 384, 30522)
+        sys.exit(0)
     case(2, 128, 64, 128, ragged=False)
     case(2, 128, 384, 1000, ragged=False)
     case(8, 128, 384, 30522)
@@ -78,6 +83,10 @@ if __name__ == "__main__":
     case(6, 512, 384, 30522, l0=True)
     case(3, 1000, 128, 30522)
     case(4, 37, 128, 3000, bias_shift=-1.0)
+    if len(sys.argv) > 1 and sys.argv[1] == "bench":
+        pass
     bench(160, 256, 384, 30522)
+    bench(160, 256, 384, 30522, ragged=True)
     bench(64, 512, 768, 30522)
+    bench(64, 512, 768, 30522, ragged=True)
     bench(256, 128, 384, 30522)
