@@ -341,24 +341,34 @@ def extras(trainer, wl, device, peaks):
         ms = _time_cuda(enc, 10, flush)
         out[name + "_docs_per_sec"] = round(B / (ms / 1e3), 1)
     model.train()
-    # HBM-bound kernels on the step's shapes, L2 flushed before each launch
-    nq, nd = wl["n_queries"], wl["n_queries"] * wl["docs_per_query"]
-    g = torch.Generator(device=device).manual_seed(5)
-    d_rep = torch.relu(torch.randn(nd, V, device=device, generator=g))
-    q_rep = torch.relu(torch.randn(nq, V, device=device, generator=g))
+    # HBM-bound kernels: at the step's shapes (launch-latency regime: a few MB per call) and at a large shape
+    # (8-GPU global batch of BERT-base C3 scale) where the HBM roofline is the meaningful yardstick. L2 is flushed
+    # before every launch; bytes are the algorithmic single-pass figures of DESIGN.md section 4.3.
     hbm = peaks["hbm_gbs"]
-
-    def add(name, fn, nbytes):
-        for _ in range(3):
-            fn()
-        ms = _time_cuda(fn, 10, flush)
-        gbs = nbytes / (ms / 1e3) / 1e9
-        out[name] = {"ms": round(ms, 4), "GB/s": round(gbs, 1), "frac_of_hbm_peak": round(gbs / hbm, 4), "bytes": nbytes}
-    add("flops_fwd", lambda: ops.flops_forward(d_rep, wl["docs_per_query"], wl["flops_threshold"]), nd * V * 4)
-    add("scores_fwd_in_batch", lambda: ops.scores_forward(q_rep, d_rep, True), (nq + nd) * V * 4)
-    ids = synthetic.token_batch(nq, wl["query_len"], seed=9, device=device)["input_ids"]
     sp = model._special_ids_on(device)
-    add("idf_query", lambda: ops.idf_query_forward(ids, model.idf_vector, sp), nq * wl["query_len"] * 12 + nq * V * 4)
+
+    def suite(tag, nq, nd, G, lq, thr):
+        g = torch.Generator(device=device).manual_seed(5)
+        d_rep = torch.relu(torch.randn(nd, V, device=device, generator=g))
+        q_rep = torch.relu(torch.randn(nq, V, device=device, generator=g))
+        ids = synthetic.token_batch(nq, lq, seed=9, device=device)["input_ids"]
+        res = {}
+
+        def add(name, fn, nbytes):
+            for _ in range(3):
+                fn()
+            ms = _time_cuda(fn, 10, flush)
+            gbs = nbytes / (ms / 1e3) / 1e9
+            res[name] = {"ms": round(ms, 4), "GB/s": round(gbs, 1), "frac_of_hbm_peak": round(gbs / hbm, 4), "bytes": nbytes}
+        add("flops_fwd", lambda: ops.flops_forward(d_rep, G, None), nd * V * 4)
+        add("flops_fwd_l0_threshold", lambda: ops.flops_forward(d_rep, G, 150), 2 * nd * V * 4)
+        add("scores_fwd_in_batch", lambda: ops.scores_forward(q_rep, d_rep, True), (nq + nd) * V * 4)
+        add("idf_query", lambda: ops.idf_query_forward(ids, model.idf_vector, sp), nq * lq * 12 + nq * V * 4)
+        add("compact_rows", lambda: ops.compact_rows(d_rep), 2 * nd * V * 4)
+        out[tag] = res
+    nq, nd = wl["n_queries"], wl["n_queries"] * wl["docs_per_query"]
+    suite("hbm_kernels_step_shape", nq, nd, wl["docs_per_query"], wl["query_len"], wl["flops_threshold"])
+    suite("hbm_kernels_large_shape_nq256_nd2048", 256, 2048, 8, 64, 150)
     return out
 
 

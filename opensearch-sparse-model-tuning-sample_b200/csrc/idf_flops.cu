@@ -116,64 +116,55 @@ flops_rowstat_kernel(const float* __restrict__ rep, int V, float threshold, floa
     }
 }
 
-// Pass 2: colsum[g,v] = sum_n rowmask[n*G+g] * |rep[n,g,v]| ; value += sum (colsum/N)^2 over this block's columns.
-// grid.x covers G*V columns, grid.y splits n (partial sums merged with atomics when gridDim.y > 1).
+// Pass 2: colsum[g,v] = sum_n rowmask[n*G+g] * |rep[n,g,v]| and value += sum_c (colsum[c]/N)^2, one pass over rep.
+// Each thread owns VEC adjacent columns and walks all N rows (8 independent 16-byte loads in flight per thread,
+// enough to cover the HBM latency-bandwidth product with G*V/VEC threads).
 template <int VEC>
-__global__ void __launch_bounds__(256)
-flops_colsum_kernel(const float* __restrict__ rep, const float* __restrict__ rowmask, int N, int GV,
-                    int G, int V, float* __restrict__ colsum) {
-    const int col = (blockIdx.x * 256 + threadIdx.x) * VEC;
-    if (col >= GV) return;
-    const int g = col / V;
-    const int n_per = (N + gridDim.y - 1) / gridDim.y;
-    const int n0 = blockIdx.y * n_per, n1 = min(N, n0 + n_per);
-    float acc[VEC];
+__global__ void __launch_bounds__(128)
+flops_colsum_kernel(const float* __restrict__ rep, const float* __restrict__ rowmask, int N, int GV, int G, int V,
+                    float invN, float* __restrict__ colsum, float* __restrict__ value) {
+    __shared__ float red[4];
+    const int col = (blockIdx.x * 128 + threadIdx.x) * VEC;
+    float sq = 0.f;
+    if (col < GV) {
+        const int g = col / V;
+        float acc[VEC];
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
-#pragma unroll 4
-    for (int n = n0; n < n1; ++n) {
-        const float mk = __ldg(rowmask + size_t(n) * G + g);
-        const float* p = rep + size_t(n) * GV + col;
-        if (VEC == 4) {
-            const float4 x = __ldg(reinterpret_cast<const float4*>(p));
-            acc[0] += mk * fabsf(x.x);
-            acc[1 % VEC] += mk * fabsf(x.y);
-            acc[2 % VEC] += mk * fabsf(x.z);
-            acc[3 % VEC] += mk * fabsf(x.w);
-        } else if (VEC == 2) {
-            const float2 x = __ldg(reinterpret_cast<const float2*>(p));
-            acc[0] += mk * fabsf(x.x);
-            acc[1 % VEC] += mk * fabsf(x.y);
-        } else {
-            acc[0] += mk * fabsf(__ldg(p));
+        for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+#pragma unroll 8
+        for (int n = 0; n < N; ++n) {
+            const float mk = (rowmask != nullptr) ? __ldg(rowmask + size_t(n) * G + g) : 1.f;
+            const float* p = rep + size_t(n) * GV + col;
+            if (VEC == 4) {
+                const float4 x = __ldg(reinterpret_cast<const float4*>(p));
+                acc[0] += mk * fabsf(x.x);
+                acc[1 % VEC] += mk * fabsf(x.y);
+                acc[2 % VEC] += mk * fabsf(x.z);
+                acc[3 % VEC] += mk * fabsf(x.w);
+            } else if (VEC == 2) {
+                const float2 x = __ldg(reinterpret_cast<const float2*>(p));
+                acc[0] += mk * fabsf(x.x);
+                acc[1 % VEC] += mk * fabsf(x.y);
+            } else {
+                acc[0] += mk * fabsf(__ldg(p));
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            colsum[col + i] = acc[i];
+            const float mean = acc[i] * invN;
+            sq = fmaf(mean, mean, sq);
         }
     }
-    if (gridDim.y == 1) {
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) colsum[col + i] = acc[i];
-    } else {
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) atomicAdd(colsum + col + i, acc[i]);
-    }
+    sq = warp_sum(sq);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sq;
+    __syncthreads();
+    if (threadIdx.x == 0) atomicAdd(value, red[0] + red[1] + red[2] + red[3]);
 }
 
-// value = sum_c (colsum[c] / N)^2
-__global__ void __launch_bounds__(256)
-flops_value_kernel(const float* __restrict__ colsum, int GV, float invN, float* __restrict__ value) {
-    __shared__ float red[8];
-    float acc = 0.f;
-    for (int c = blockIdx.x * 256 + threadIdx.x; c < GV; c += gridDim.x * 256) {
-        const float m = __ldg(colsum + c) * invN;
-        acc = fmaf(m, m, acc);
-    }
-    acc = warp_sum(acc);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float s = 0.f;
-        for (int i = 0; i < 8; ++i) s += red[i];
-        atomicAdd(value, s);
-    }
+__global__ void fill_ones_kernel(float* __restrict__ p, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = 1.f;
 }
 
 // d_rep[row, v] (+)= gscale * 2*colsum[g,v]/N^2 * sign(rep) * rowmask[row], rows [row_begin, row_end)
@@ -234,30 +225,27 @@ extern "C" int sb200_flops_fwd(const float* rep, int N, int G, int V, float thre
     const long long GV = (long long)G * V;
     SB200_REQUIRE(rows <= 0x7fffffffLL && GV <= 0x7fffffffLL, "flops_fwd: shape too large");
     SB200_CUDA(cudaMemsetAsync(value, 0, sizeof(float), stream));
-    if (stats != nullptr) SB200_CUDA(cudaMemsetAsync(stats, 0, 4 * sizeof(float), stream));
-    flops_rowstat_kernel<<<int(rows), 256, 0, stream>>>(rep, V, threshold, rowmask, stats);
-    SB200_CHECK_LAUNCH("flops_rowstat_kernel");
-
+    if (threshold >= 0.f || stats != nullptr) {
+        // row pass: nnz per row -> L0 row mask (+ logging stats). Only the thresholded variant needs it.
+        if (stats != nullptr) SB200_CUDA(cudaMemsetAsync(stats, 0, 4 * sizeof(float), stream));
+        flops_rowstat_kernel<<<int(rows), 256, 0, stream>>>(rep, V, threshold, rowmask, stats);
+        SB200_CHECK_LAUNCH("flops_rowstat_kernel");
+    } else {
+        fill_ones_kernel<<<int((rows + 255) / 256), 256, 0, stream>>>(rowmask, int(rows));
+        SB200_CHECK_LAUNCH("fill_ones_kernel");
+    }
+    const float* mask_in = (threshold >= 0.f) ? rowmask : nullptr;
     const bool a16 = (reinterpret_cast<uintptr_t>(rep) & 15) == 0;
     const int vec = (a16 && V % 4 == 0) ? 4 : ((a16 && V % 2 == 0) ? 2 : 1);
-    const int threads_x = int((GV / vec + 255) / 256);
-    int ysplit = 1;
-    const int target = 4 * num_sms();
-    if (threads_x < target) ysplit = (target + threads_x - 1) / threads_x;
-    if (ysplit > N) ysplit = N;
-    if (ysplit > 1) SB200_CUDA(cudaMemsetAsync(colsum, 0, size_t(GV) * sizeof(float), stream));
-    dim3 grid(threads_x, ysplit);
+    const int blocks = int((GV / vec + 127) / 128);
+    const float invN = 1.f / float(N);
     if (vec == 4)
-        flops_colsum_kernel<4><<<grid, 256, 0, stream>>>(rep, rowmask, N, int(GV), G, V, colsum);
+        flops_colsum_kernel<4><<<blocks, 128, 0, stream>>>(rep, mask_in, N, int(GV), G, V, invN, colsum, value);
     else if (vec == 2)
-        flops_colsum_kernel<2><<<grid, 256, 0, stream>>>(rep, rowmask, N, int(GV), G, V, colsum);
+        flops_colsum_kernel<2><<<blocks, 128, 0, stream>>>(rep, mask_in, N, int(GV), G, V, invN, colsum, value);
     else
-        flops_colsum_kernel<1><<<grid, 256, 0, stream>>>(rep, rowmask, N, int(GV), G, V, colsum);
+        flops_colsum_kernel<1><<<blocks, 128, 0, stream>>>(rep, mask_in, N, int(GV), G, V, invN, colsum, value);
     SB200_CHECK_LAUNCH("flops_colsum_kernel");
-    int vblocks = int((GV + 255) / 256);
-    if (vblocks > 2 * num_sms()) vblocks = 2 * num_sms();
-    flops_value_kernel<<<vblocks, 256, 0, stream>>>(colsum, int(GV), 1.f / float(N), value);
-    SB200_CHECK_LAUNCH("flops_value_kernel");
     return SB200_OK;
 }
 

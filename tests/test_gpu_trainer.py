@@ -11,7 +11,7 @@ from oracle import reference_path as R  # noqa: E402
 
 
 def _trainer(shape="tiny", loss="infonce", in_batch=True, use_l0=False, threshold=None, inf_free=True, V=2000, seed=0,
-             capturable=False):
+             capturable=False, base_lr=1e-3):
     import sparse_b200  # noqa: F401
     from sparse_b200.scripts import synthetic
     from sparse_b200.scripts.args import DataTrainingArguments, ModelArguments, TrainingArguments
@@ -23,8 +23,8 @@ def _trainer(shape="tiny", loss="infonce", in_batch=True, use_l0=False, threshol
     margs = ModelArguments(inf_free=inf_free, use_l0=use_l0)
     dargs = DataTrainingArguments(loss_types=[loss], use_in_batch_negatives=in_batch, flops_d_lambda=0.05, flops_d_T=50,
                                   flops_q_lambda=0.02, flops_q_T=30, flops_threshold=threshold)
-    targs = TrainingArguments(bf16=True, learning_rate=1e-3, logging_steps=10 ** 9, max_grad_norm=None, max_steps=100)
-    lr = torch.tensor(1e-3, device="cuda") if capturable else 1e-3
+    targs = TrainingArguments(bf16=True, learning_rate=base_lr, logging_steps=10 ** 9, max_grad_norm=None, max_steps=100)
+    lr = torch.tensor(base_lr, device="cuda") if capturable else base_lr
     opt = torch.optim.AdamW(model.parameters(), lr=lr, weight_decay=0.01, fused=True, capturable=capturable)
     sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda s: min(1.0, (s + 1) / 5))
     fns = [LOSS_CLS_MAP[loss](use_in_batch_negatives=in_batch, weight=1.0, temperature=2.0)]
@@ -106,12 +106,14 @@ def test_cuda_graph_replay_matches_eager():
     from sparse_b200.scripts import synthetic
     V = 2000
     batches = [synthetic.train_batch(4, 3, 40, query_len=10, vocab_size=V, seed=50 + i, device="cuda") for i in range(8)]
-    eager = _trainer(V=V, capturable=True)
-    graph = _trainer(V=V, capturable=True)
+    # AdamW moves every weight by ~lr per step whatever the gradient size, so the fp32-atomic ordering noise of the
+    # backward kernels is amplified at a large lr; a small lr keeps the two trajectories comparable
+    eager = _trainer(V=V, capturable=True, base_lr=1e-5)
+    graph = _trainer(V=V, capturable=True, base_lr=1e-5)
     graph.model_wrapper.load_state_dict(copy.deepcopy(eager.model_wrapper.state_dict()))
     losses_e = [float(eager.training_step(dict(b))) for b in batches]
     # graph mode: its 3 warm-up steps run on batches[0]; mirror that on a third trainer for a like-for-like sequence
-    ref = _trainer(V=V, capturable=True)
+    ref = _trainer(V=V, capturable=True, base_lr=1e-5)
     ref.model_wrapper.load_state_dict(copy.deepcopy(graph.model_wrapper.state_dict()))
     for _ in range(3):
         ref.training_step(dict(batches[0]))
@@ -120,7 +122,7 @@ def test_cuda_graph_replay_matches_eager():
     for b in batches[1:]:
         lg = float(graph.training_step(b))
         lr = float(ref.training_step(dict(b)))
-        assert lg == pytest.approx(lr, rel=1e-2, abs=1e-3)  # atomics order + bf16: trajectories drift slightly
+        assert lg == pytest.approx(lr, rel=2e-3, abs=1e-4)
     assert graph.state.global_step == ref.state.global_step
-    assert graph.ranking_loss_moving_avg == pytest.approx(ref.ranking_loss_moving_avg, rel=1e-2)
+    assert graph.ranking_loss_moving_avg == pytest.approx(ref.ranking_loss_moving_avg, rel=2e-3)
     assert losses_e[0] > 0
