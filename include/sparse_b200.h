@@ -125,13 +125,18 @@ int sb200_flops_bwd(const float* rep, const float* colsum, const float* rowmask,
  *   against its own docs i*G .. i*G+G-1.
  * ------------------------------------------------------------------------------------------- */
 size_t sb200_scores_workspace_bytes(int Nq, int Nd, int V, int in_batch);
+/* With a workspace (in_batch only) the query rows are thresholded (!= 0) into (column, value) lists and every document
+ * row is staged in shared memory once and gathered by all query lists: one HBM pass over d, no atomics. If a query row
+ * has more than 512 non-zeros a device-side flag routes the work to the dense fp32 tile kernel instead (no host sync).
+ * Without a workspace only the dense kernel runs. */
 int sb200_scores_fwd(const float* q, const float* d, int Nq, int Nd, int V, int in_batch, float* S, void* workspace,
                      size_t workspace_bytes, sb200_stream_t stream);
 /* d_q[i,:] = sum_j dS[i,j] d[j,:] (rows q_begin..q_end) ; d_d[j,:] = sum_i dS[i,j] q[i,:] (rows d_begin..d_end).
- * Either output may be NULL.  accumulate != 0 adds into the outputs. Outputs are full-size [Nq,V] / [Nd,V]. */
+ * Either output may be NULL.  accumulate != 0 adds into the outputs. Outputs are full-size [Nq,V] / [Nd,V].
+ * fwd_workspace (nullable): the workspace sb200_scores_fwd filled for the same q; enables the sparse-query path. */
 int sb200_scores_bwd(const float* dS, const float* q, const float* d, int Nq, int Nd, int V, int in_batch,
                      int q_begin, int q_end, int d_begin, int d_end, int accumulate, float* d_q, float* d_d,
-                     sb200_stream_t stream);
+                     const void* fwd_workspace, size_t workspace_bytes, sb200_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * (6) Ranking losses on a score matrix.   Replaces loss.py:33-42 (KLDiv), 64-76 (MarginMSE),

@@ -10,6 +10,8 @@
 namespace sb200 {
 namespace {
 
+__host__ __device__ inline size_t align_up_sz(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
 // ------------------------------------------------------------------------------------------ block reductions
 template <int THREADS>
 __device__ __forceinline__ float block_sum(float x, float* red) {
@@ -47,9 +49,10 @@ constexpr int kST = 64, kSK = 32, kSStride = kST + 1;
 
 __global__ void __launch_bounds__(256)
 scores_tile_kernel(const float* __restrict__ q, const float* __restrict__ d, int Nq, int Nd, int V, int kchunk,
-                   float* __restrict__ S) {
+                   const int* __restrict__ dense_flag, float* __restrict__ S) {
     __shared__ float qs[kSK * kSStride];
     __shared__ float ds[kSK * kSStride];
+    if (dense_flag != nullptr && *dense_flag == 0) return;  // the sparse-query kernel produced S
     const int i0 = blockIdx.y * kST, j0 = blockIdx.x * kST;
     const int k_begin = blockIdx.z * kchunk;
     const int k_end = min(V, k_begin + kchunk);
@@ -139,6 +142,128 @@ scores_group_kernel(const float* __restrict__ q, const float* __restrict__ d, in
     }
 }
 
+// ------------------------------------------------------------------------------------------ sparse-query path
+// Queries are very sparse (inf-free: at most Lq token ids; learned: tens to hundreds of entries once trained), so
+// q.d^T = sum over the query's non-zeros of val * d[j, col]. The query rows are thresholded (!= 0) into (col, val)
+// lists once; then each DOCUMENT row is staged in shared memory (V*4 B = 122 KB) exactly once and every query's list
+// is gathered from it: HBM traffic = one pass over d, S[i,j] written once, no atomics (deterministic).
+// Dispatch is on the device: if any query row has more than kQCap non-zeros the flag is set, the sparse kernels exit
+// and the dense tile kernel (which exits when the flag is clear) does the work instead -- no host synchronisation.
+constexpr int kQCap = 512;
+constexpr int kRowThreads = 512;
+
+struct QLists {
+    int* flag;      // [1]  1 = some row overflowed -> dense path
+    int* nnz;       // [Nq]
+    int* cols;      // [Nq][kQCap]
+    float* vals;    // [Nq][kQCap]
+};
+
+__host__ __device__ inline size_t qlists_bytes(int Nq) {
+    return 256 + align_up_sz(size_t(Nq) * 4, 256) + 2 * align_up_sz(size_t(Nq) * kQCap * 4, 256);
+}
+inline QLists qlists_carve(void* ws, int Nq) {
+    uint8_t* p = static_cast<uint8_t*>(ws);
+    QLists q;
+    q.flag = reinterpret_cast<int*>(p);
+    q.nnz = reinterpret_cast<int*>(p + 256);
+    q.cols = reinterpret_cast<int*>(p + 256 + align_up_sz(size_t(Nq) * 4, 256));
+    q.vals = reinterpret_cast<float*>(p + 256 + align_up_sz(size_t(Nq) * 4, 256) + align_up_sz(size_t(Nq) * kQCap * 4, 256));
+    return q;
+}
+
+__global__ void __launch_bounds__(256)
+q_compact_kernel(const float* __restrict__ q, int V, QLists L) {
+    __shared__ int cnt;
+    const int i = blockIdx.x;
+    if (threadIdx.x == 0) cnt = 0;
+    __syncthreads();
+    const float* row = q + size_t(i) * V;
+    for (int v = threadIdx.x; v < V; v += 256) {
+        const float x = __ldg(row + v);
+        if (x != 0.f) {
+            const int slot = atomicAdd(&cnt, 1);
+            if (slot < kQCap) {
+                L.cols[size_t(i) * kQCap + slot] = v;
+                L.vals[size_t(i) * kQCap + slot] = x;
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        L.nnz[i] = min(cnt, kQCap);
+        if (cnt > kQCap) atomicOr(L.flag, 1);
+    }
+}
+
+__device__ __forceinline__ void stage_row(float* __restrict__ dst, const float* __restrict__ src, int V) {
+    // 8-byte vector loads when the row start allows it (V even keeps every row 8-byte aligned), scalar otherwise
+    if ((reinterpret_cast<uintptr_t>(src) & 7) == 0) {
+        const float2* s2 = reinterpret_cast<const float2*>(src);
+        float2* d2 = reinterpret_cast<float2*>(dst);
+        const int n2 = V >> 1;
+        for (int t = threadIdx.x; t < n2; t += kRowThreads) d2[t] = __ldg(s2 + t);
+        if ((V & 1) && threadIdx.x == 0) dst[V - 1] = __ldg(src + V - 1);
+    } else {
+        for (int t = threadIdx.x; t < V; t += kRowThreads) dst[t] = __ldg(src + t);
+    }
+}
+
+// persistent blocks, one document row at a time in shared memory
+__global__ void __launch_bounds__(kRowThreads)
+scores_docrow_kernel(const float* __restrict__ d, int Nq, int Nd, int V, QLists L, float* __restrict__ S) {
+    extern __shared__ float row_s[];
+    if (*L.flag != 0) return;  // dense path handles it
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = kRowThreads / 32;
+    for (int j = blockIdx.x; j < Nd; j += gridDim.x) {
+        __syncthreads();
+        stage_row(row_s, d + size_t(j) * V, V);
+        __syncthreads();
+        for (int i = warp; i < Nq; i += nw) {
+            const int n = __ldg(L.nnz + i);
+            const int* c = L.cols + size_t(i) * kQCap;
+            const float* w = L.vals + size_t(i) * kQCap;
+            float acc = 0.f;
+            for (int k = lane; k < n; k += 32) acc = fmaf(__ldg(w + k), row_s[__ldg(c + k)], acc);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) S[size_t(i) * Nd + j] = acc;
+        }
+    }
+}
+
+// zero-fills S only when the dense fallback is going to accumulate split-K partials into it
+__global__ void zero_if_dense_kernel(float* __restrict__ S, size_t n, const int* __restrict__ dense_flag) {
+    if (*dense_flag == 0) return;
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) S[i] = 0.f;
+}
+
+// d_d[j, :] (+)= sum_i dS[i,j] * q[i,:] for rows [d_begin, d_end): the row is accumulated in shared memory
+// (zero-fill, shared-memory atomics over the query lists) and written to HBM once.
+__global__ void __launch_bounds__(kRowThreads)
+scores_docrow_bwd_kernel(const float* __restrict__ dS, int Nq, int Nd, int V, QLists L, int d_begin, int d_end,
+                         int accumulate, float* __restrict__ d_d) {
+    extern __shared__ float row_s[];
+    if (*L.flag != 0) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = kRowThreads / 32;
+    for (int j = d_begin + blockIdx.x; j < d_end; j += gridDim.x) {
+        __syncthreads();
+        for (int t = threadIdx.x; t < V; t += kRowThreads) row_s[t] = 0.f;
+        __syncthreads();
+        for (int i = warp; i < Nq; i += nw) {
+            const float g = __ldg(dS + size_t(i) * Nd + j);
+            if (g == 0.f) continue;
+            const int n = __ldg(L.nnz + i);
+            const int* c = L.cols + size_t(i) * kQCap;
+            const float* w = L.vals + size_t(i) * kQCap;
+            for (int k = lane; k < n; k += 32) atomicAdd(&row_s[__ldg(c + k)], g * __ldg(w + k));
+        }
+        __syncthreads();
+        float* out = d_d + size_t(j) * V;
+        for (int t = threadIdx.x; t < V; t += kRowThreads) out[t] = accumulate ? (out[t] + row_s[t]) : row_s[t];
+    }
+}
+
 // ------------------------------------------------------------------------------------------ scores backward
 // out[r, v] (+)= sum_k coef(r,k) * in[k, v],  coef(r,k) = dS[r*sr + k*sk];  r in [r_begin, r_end), k in [0, K).
 // 16 output rows per block, 2 columns per thread; coefficients staged in shared memory.
@@ -147,8 +272,9 @@ constexpr int kBR = 16, kBKc = 256;
 template <int VECW>
 __global__ void __launch_bounds__(256)
 scores_bwd_kernel(const float* __restrict__ dS, int sr, int sk, const float* __restrict__ in, int K, int V, int r_begin,
-                  int r_end, int accumulate, float* __restrict__ out) {
+                  int r_end, int accumulate, const int* __restrict__ dense_flag, float* __restrict__ out) {
     __shared__ float coef[kBR][kBKc];
+    if (dense_flag != nullptr && *dense_flag == 0) return;  // the sparse-query kernel produced the rows
     const int r0 = r_begin + blockIdx.y * kBR;
     const int v = (blockIdx.x * 256 + threadIdx.x) * VECW;
     float acc[kBR][VECW];
@@ -424,23 +550,51 @@ int pick_ksplit(int base_blocks, int V, int quantum, int* kchunk) {
 using namespace sb200;
 
 extern "C" size_t sb200_scores_workspace_bytes(int Nq, int Nd, int V, int in_batch) {
-    (void)Nq; (void)Nd; (void)V; (void)in_batch;
-    return 0;  // split-K partials are merged with atomics; kept in the ABI for a deterministic two-pass variant
+    (void)Nd; (void)V;
+    if (!in_batch || Nq <= 0) return 0;
+    return qlists_bytes(Nq);  // thresholded query lists (+ dispatch flag); reused by sb200_scores_bwd
+}
+
+static int row_kernel_grid(int rows) {
+    int g = num_sms();  // one 122 KB row per SM at a time
+    return g < rows ? g : rows;
 }
 
 extern "C" int sb200_scores_fwd(const float* q, const float* d, int Nq, int Nd, int V, int in_batch, float* S,
                                 void* workspace, size_t workspace_bytes, sb200_stream_t stream_) {
-    (void)workspace; (void)workspace_bytes;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     SB200_REQUIRE(q && d && S, "scores_fwd: null pointer");
     SB200_REQUIRE(Nq >= 1 && Nd >= 1 && V >= 1, "scores_fwd: bad shape");
     if (in_batch) {
         const int tj = (Nd + kST - 1) / kST, ti = (Nq + kST - 1) / kST;
         SB200_REQUIRE(ti <= 65535, "scores_fwd: Nq too large");
+        const size_t row_smem = size_t(V) * sizeof(float);
+        const bool sparse_ok = workspace != nullptr && workspace_bytes >= qlists_bytes(Nq) && row_smem <= 200 * 1024;
+        const int* dense_flag = nullptr;
+        if (sparse_ok) {
+            QLists L = qlists_carve(workspace, Nq);
+            SB200_CUDA(cudaMemsetAsync(L.flag, 0, sizeof(int), stream));
+            q_compact_kernel<<<Nq, 256, 0, stream>>>(q, V, L);
+            SB200_CHECK_LAUNCH("q_compact_kernel");
+            if (!device_flag_test_and_set(6))
+                SB200_CUDA(cudaFuncSetAttribute(scores_docrow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            scores_docrow_kernel<<<row_kernel_grid(Nd), kRowThreads, row_smem, stream>>>(d, Nq, Nd, V, L, S);
+            SB200_CHECK_LAUNCH("scores_docrow_kernel");
+            dense_flag = L.flag;
+        }
+        // dense fp32 tiles: the only path without a workspace, the fallback (device-side flag) with one
         int kchunk;
         const int ks = pick_ksplit(tj * ti, V, kSK, &kchunk);
-        if (ks > 1) SB200_CUDA(cudaMemsetAsync(S, 0, size_t(Nq) * Nd * sizeof(float), stream));
-        scores_tile_kernel<<<dim3(tj, ti, ks), 256, 0, stream>>>(q, d, Nq, Nd, V, kchunk, S);
+        if (ks > 1) {
+            if (sparse_ok) {
+                // split-K partials need a zeroed S, but only if the dense kernel is really going to run
+                zero_if_dense_kernel<<<2 * num_sms(), 256, 0, stream>>>(S, size_t(Nq) * Nd, dense_flag);
+                SB200_CHECK_LAUNCH("zero_if_dense_kernel");
+            } else {
+                SB200_CUDA(cudaMemsetAsync(S, 0, size_t(Nq) * Nd * sizeof(float), stream));
+            }
+        }
+        scores_tile_kernel<<<dim3(tj, ti, ks), 256, 0, stream>>>(q, d, Nq, Nd, V, kchunk, dense_flag, S);
         SB200_CHECK_LAUNCH("scores_tile_kernel");
     } else {
         SB200_REQUIRE(Nd % Nq == 0, "scores_fwd: Nd=%d is not a multiple of Nq=%d", Nd, Nq);
@@ -457,7 +611,7 @@ extern "C" int sb200_scores_fwd(const float* q, const float* d, int Nq, int Nd, 
 
 extern "C" int sb200_scores_bwd(const float* dS, const float* q, const float* d, int Nq, int Nd, int V, int in_batch,
                                 int q_begin, int q_end, int d_begin, int d_end, int accumulate, float* d_q, float* d_d,
-                                sb200_stream_t stream_) {
+                                const void* fwd_workspace, size_t workspace_bytes, sb200_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     SB200_REQUIRE(dS && q && d, "scores_bwd: null pointer");
     SB200_REQUIRE(Nq >= 1 && Nd >= 1 && V >= 1, "scores_bwd: bad shape");
@@ -468,16 +622,29 @@ extern "C" int sb200_scores_bwd(const float* dS, const float* q, const float* d,
     if (in_batch) {
         const int xb = vec2 ? (V / 2 + 255) / 256 : (V + 255) / 256;
         if (d_d != nullptr && d_end > d_begin) {
+            const size_t row_smem = size_t(V) * sizeof(float);
+            const int* dense_flag = nullptr;
+            if (fwd_workspace != nullptr && workspace_bytes >= qlists_bytes(Nq) && row_smem <= 200 * 1024) {
+                // query lists built by sb200_scores_fwd: one shared-memory row per document, written to HBM once
+                QLists L = qlists_carve(const_cast<void*>(fwd_workspace), Nq);
+                if (!device_flag_test_and_set(7))
+                    SB200_CUDA(cudaFuncSetAttribute(scores_docrow_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                    200 * 1024));
+                scores_docrow_bwd_kernel<<<row_kernel_grid(d_end - d_begin), kRowThreads, row_smem, stream>>>(
+                    dS, Nq, Nd, V, L, d_begin, d_end, accumulate, d_d);
+                SB200_CHECK_LAUNCH("scores_docrow_bwd_kernel");
+                dense_flag = L.flag;
+            }
             dim3 grid(xb, (d_end - d_begin + kBR - 1) / kBR);
             // out row r = doc j, k = query i: coef = dS[i*Nd + j]
-            if (vec2) scores_bwd_kernel<2><<<grid, 256, 0, stream>>>(dS, 1, Nd, q, Nq, V, d_begin, d_end, accumulate, d_d);
-            else scores_bwd_kernel<1><<<grid, 256, 0, stream>>>(dS, 1, Nd, q, Nq, V, d_begin, d_end, accumulate, d_d);
+            if (vec2) scores_bwd_kernel<2><<<grid, 256, 0, stream>>>(dS, 1, Nd, q, Nq, V, d_begin, d_end, accumulate, dense_flag, d_d);
+            else scores_bwd_kernel<1><<<grid, 256, 0, stream>>>(dS, 1, Nd, q, Nq, V, d_begin, d_end, accumulate, dense_flag, d_d);
             SB200_CHECK_LAUNCH("scores_bwd_kernel(d_d)");
         }
         if (d_q != nullptr && q_end > q_begin) {
             dim3 grid(xb, (q_end - q_begin + kBR - 1) / kBR);
-            if (vec2) scores_bwd_kernel<2><<<grid, 256, 0, stream>>>(dS, Nd, 1, d, Nd, V, q_begin, q_end, accumulate, d_q);
-            else scores_bwd_kernel<1><<<grid, 256, 0, stream>>>(dS, Nd, 1, d, Nd, V, q_begin, q_end, accumulate, d_q);
+            if (vec2) scores_bwd_kernel<2><<<grid, 256, 0, stream>>>(dS, Nd, 1, d, Nd, V, q_begin, q_end, accumulate, nullptr, d_q);
+            else scores_bwd_kernel<1><<<grid, 256, 0, stream>>>(dS, Nd, 1, d, Nd, V, q_begin, q_end, accumulate, nullptr, d_q);
             SB200_CHECK_LAUNCH("scores_bwd_kernel(d_q)");
         }
     } else {

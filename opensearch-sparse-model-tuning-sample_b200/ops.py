@@ -259,7 +259,7 @@ def flops_value(rep, group_num=1, threshold=None):
 
 
 # --------------------------------------------------------------------------------------------- scores + losses
-def scores_forward(q, d, in_batch):
+def scores_forward(q, d, in_batch, return_workspace=False):
     _need_cuda(q, d)
     q = q.float().contiguous()
     d = d.float().contiguous()
@@ -271,10 +271,14 @@ def scores_forward(q, d, in_batch):
         raise ValueError("number of docs must be a multiple of the number of queries")
     C = Nd if in_batch else Nd // Nq
     S = torch.empty(Nq, C, dtype=torch.float32, device=q.device)
+    lib = _lib.load()
+    nbytes = lib.sb200_scores_workspace_bytes(Nq, Nd, V, 1 if in_batch else 0)
+    ws = _workspace(nbytes, q.device) if nbytes > 0 else None
     with torch.cuda.device(q.device):
-        code = _lib.load().sb200_scores_fwd(_ptr(q), _ptr(d), Nq, Nd, V, 1 if in_batch else 0, _ptr(S), 0, 0, _stream())
+        code = lib.sb200_scores_fwd(_ptr(q), _ptr(d), Nq, Nd, V, 1 if in_batch else 0, _ptr(S), _ptr(ws),
+                                    0 if ws is None else ws.numel(), _stream())
     _lib.check(code, "sb200_scores_fwd")
-    return S
+    return (S, ws) if return_workspace else S
 
 
 class ScoresFunction(torch.autograd.Function):
@@ -282,10 +286,12 @@ class ScoresFunction(torch.autograd.Function):
     def forward(ctx, q, d, in_batch):
         q32 = q.detach().float().contiguous()
         d32 = d.detach().float().contiguous()
+        S, ws = scores_forward(q32, d32, in_batch, return_workspace=True)
         ctx.save_for_backward(q32, d32)
+        ctx.ws = ws  # thresholded query lists, reused by the backward kernels
         ctx.in_batch = bool(in_batch)
         ctx.dtypes = (q.dtype, d.dtype)
-        return scores_forward(q32, d32, in_batch)
+        return S
 
     @staticmethod
     def backward(ctx, dS):
@@ -296,9 +302,11 @@ class ScoresFunction(torch.autograd.Function):
         Nd = d.shape[0]
         d_q = torch.empty_like(q) if need_q else None
         d_d = torch.empty_like(d) if need_d else None
+        ws = ctx.ws
         with torch.cuda.device(q.device):
             code = _lib.load().sb200_scores_bwd(_ptr(dS), _ptr(q), _ptr(d), Nq, Nd, V, 1 if ctx.in_batch else 0, 0, Nq, 0,
-                                                Nd, 0, _ptr(d_q), _ptr(d_d), _stream())
+                                                Nd, 0, _ptr(d_q), _ptr(d_d), _ptr(ws), 0 if ws is None else ws.numel(),
+                                                _stream())
         _lib.check(code, "sb200_scores_bwd")
         return (d_q.to(ctx.dtypes[0]) if need_q else None, d_d.to(ctx.dtypes[1]) if need_d else None, None)
 

@@ -330,3 +330,26 @@ def test_minmax_ensemble(ops, golden):
             S = ops.scores(cuda(q), cuda(d), c["in_batch"])
             acc = ops.minmax_accumulate(S, acc, scale=30.0 / len(c["q"]))
         assert_close(acc, c["out"], 1e-4, 1e-4, "ensemble scores")
+
+
+@pytest.mark.parametrize("nnz_q", [3, 64, 511, 513, 5000])
+def test_scores_sparse_and_dense_dispatch_agree(ops, nnz_q):
+    """The sparse-query path (<= 512 non-zeros per query row) and the dense fallback give the same scores and
+    gradients; the switch happens on the device."""
+    Nq, G, V = 9, 4, 30522
+    g = torch.Generator().manual_seed(nnz_q)
+    q = torch.zeros(Nq, V)
+    for i in range(Nq):
+        cols = torch.randperm(V, generator=g)[:nnz_q if i != 2 else max(1, nnz_q // 2)]
+        q[i, cols] = torch.rand(cols.numel(), generator=g) + 0.1
+    d = torch.relu(torch.randn(Nq * G, V, generator=g)) * (torch.rand(Nq * G, V, generator=g) > 0.8)
+    w = torch.randn(Nq, Nq * G, generator=g)
+    qc, dc = cuda(q).requires_grad_(True), cuda(d).requires_grad_(True)
+    S = ops.scores(qc, dc, True)
+    (S * cuda(w)).sum().backward()
+    qr, dr = q.clone().requires_grad_(True), d.clone().requires_grad_(True)
+    Sr = qr @ dr.t()
+    (Sr * w).sum().backward()
+    assert_close(S, Sr, 1e-5, 1e-4, "scores")
+    assert_close(dc.grad, dr.grad, 1e-5, 1e-5, "d_d")
+    assert_close(qc.grad, qr.grad, 1e-5, 1e-5, "d_q")
