@@ -350,8 +350,9 @@ def extras(trainer, wl, device, peaks):
     def suite(tag, nq, nd, G, lq, thr):
         g = torch.Generator(device=device).manual_seed(5)
         d_rep = torch.relu(torch.randn(nd, V, device=device, generator=g))
-        q_rep = torch.relu(torch.randn(nq, V, device=device, generator=g))
         ids = synthetic.token_batch(nq, lq, seed=9, device=device)["input_ids"]
+        q_rep = ops.idf_query_forward(ids, model.idf_vector, sp)       # inf-free queries: <= lq non-zeros per row
+        q_dense = torch.relu(torch.randn(nq, V, device=device, generator=g))  # learned-query worst case (dense init)
         res = {}
 
         def add(name, fn, nbytes):
@@ -363,6 +364,7 @@ def extras(trainer, wl, device, peaks):
         add("flops_fwd", lambda: ops.flops_forward(d_rep, G, None), nd * V * 4)
         add("flops_fwd_l0_threshold", lambda: ops.flops_forward(d_rep, G, 150), 2 * nd * V * 4)
         add("scores_fwd_in_batch", lambda: ops.scores_forward(q_rep, d_rep, True), (nq + nd) * V * 4)
+        add("scores_fwd_in_batch_dense_queries", lambda: ops.scores_forward(q_dense, d_rep, True), (nq + nd) * V * 4)
         add("idf_query", lambda: ops.idf_query_forward(ids, model.idf_vector, sp), nq * lq * 12 + nq * V * 4)
         add("compact_rows", lambda: ops.compact_rows(d_rep), 2 * nd * V * 4)
         out[tag] = res

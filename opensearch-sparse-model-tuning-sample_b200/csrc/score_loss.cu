@@ -6,6 +6,7 @@
 #include <math_constants.h>
 
 #include "common.h"
+#include "ptx.cuh"
 
 namespace sb200 {
 namespace {
@@ -172,63 +173,98 @@ inline QLists qlists_carve(void* ws, int Nq) {
     return q;
 }
 
+// grid (column slabs, Nq): slots are claimed with one atomic per non-zero on the row's counter (zeroed by the caller);
+// the order of a list is irrelevant. nnz[i] ends up as the true count (may exceed the capacity: then the flag is set).
 __global__ void __launch_bounds__(256)
-q_compact_kernel(const float* __restrict__ q, int V, QLists L) {
-    __shared__ int cnt;
-    const int i = blockIdx.x;
-    if (threadIdx.x == 0) cnt = 0;
-    __syncthreads();
+q_compact_kernel(const float* __restrict__ q, int V, int cap, QLists L) {
+    const int i = blockIdx.y;
     const float* row = q + size_t(i) * V;
-    for (int v = threadIdx.x; v < V; v += 256) {
+    for (int v = blockIdx.x * 256 + threadIdx.x; v < V; v += gridDim.x * 256) {
         const float x = __ldg(row + v);
         if (x != 0.f) {
-            const int slot = atomicAdd(&cnt, 1);
+            const int slot = atomicAdd(L.nnz + i, 1);
             if (slot < kQCap) {
                 L.cols[size_t(i) * kQCap + slot] = v;
                 L.vals[size_t(i) * kQCap + slot] = x;
             }
+            if (slot == cap) atomicOr(L.flag, 1);  // the row does not fit the register budget of the row kernels
         }
+    }
+}
+
+// Asynchronous global->shared copy of src[0, n) (cp.async, no registers held): every thread issues all its
+// requests before anyone waits, so a whole slab is in flight per CTA.
+__device__ __forceinline__ void stage_async(float* __restrict__ dst, const float* __restrict__ src, int n) {
+    const uint32_t d0 = static_cast<uint32_t>(__cvta_generic_to_shared(dst));
+    if ((reinterpret_cast<uintptr_t>(src) & 7) == 0) {
+        const int n2 = n >> 1;
+        for (int t = threadIdx.x; t < n2; t += kRowThreads)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d0 + t * 8), "l"(src + 2 * t) : "memory");
+        if ((n & 1) && threadIdx.x == 0)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d0 + (n - 1) * 4), "l"(src + n - 1) : "memory");
+    } else {
+        for (int t = threadIdx.x; t < n; t += kRowThreads)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d0 + t * 4), "l"(src + t) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void stage_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// grid (row slots, query chunks of kRowThreads/tpq queries). Each thread keeps up to kEPT (column, value) entries of ONE
+// query in registers for the whole kernel (tpq threads share a query); a block walks document rows: the row is
+// staged in shared memory with cp.async (whole row in flight), every thread gathers its entries from it, the tpq
+// partial sums are shuffled together and S[i,j] is written once -- no atomics, deterministic, d is read from HBM once
+// per query chunk. Rows longer than the register budget (nnz > kEPT*tpq) raise the device-side flag instead.
+constexpr int kEPT = 32;
+
+__global__ void __launch_bounds__(kRowThreads, 1)
+scores_docrow_kernel(const float* __restrict__ d, int Nq, int Nd, int V, int tpq, QLists L, float* __restrict__ S) {
+    extern __shared__ __align__(128) float row_s[];
+    if (*L.flag != 0) return;  // dense path handles it
+    const int qi = blockIdx.y * (kRowThreads / tpq) + threadIdx.x / tpq;
+    const int sub = threadIdx.x % tpq;
+    int col[kEPT];
+    float val[kEPT];
+    const int n = (qi < Nq) ? min(__ldg(L.nnz + qi), kQCap) : 0;
+#pragma unroll
+    for (int e = 0; e < kEPT; ++e) {
+        const int k = sub + e * tpq;
+        const bool ok = k < n;
+        col[e] = ok ? __ldg(L.cols + size_t(qi) * kQCap + k) : 0;
+        val[e] = ok ? __ldg(L.vals + size_t(qi) * kQCap + k) : 0.f;
+    }
+    // rows are pulled with ONE bulk async copy each (TMA engine, completion on an mbarrier); the few floats before
+    // the first / after the last 16-byte boundary are moved by ordinary loads. `shift` keeps source and destination
+    // in the same 16-byte phase.
+    __shared__ __align__(8) uint64_t bar;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        L.nnz[i] = min(cnt, kQCap);
-        if (cnt > kQCap) atomicOr(L.flag, 1);
-    }
-}
-
-__device__ __forceinline__ void stage_row(float* __restrict__ dst, const float* __restrict__ src, int V) {
-    // 8-byte vector loads when the row start allows it (V even keeps every row 8-byte aligned), scalar otherwise
-    if ((reinterpret_cast<uintptr_t>(src) & 7) == 0) {
-        const float2* s2 = reinterpret_cast<const float2*>(src);
-        float2* d2 = reinterpret_cast<float2*>(dst);
-        const int n2 = V >> 1;
-        for (int t = threadIdx.x; t < n2; t += kRowThreads) d2[t] = __ldg(s2 + t);
-        if ((V & 1) && threadIdx.x == 0) dst[V - 1] = __ldg(src + V - 1);
-    } else {
-        for (int t = threadIdx.x; t < V; t += kRowThreads) dst[t] = __ldg(src + t);
-    }
-}
-
-// persistent blocks, one document row at a time in shared memory
-__global__ void __launch_bounds__(kRowThreads)
-scores_docrow_kernel(const float* __restrict__ d, int Nq, int Nd, int V, QLists L, float* __restrict__ S) {
-    extern __shared__ float row_s[];
-    if (*L.flag != 0) return;  // dense path handles it
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = kRowThreads / 32;
+    uint32_t phase = 0;
     for (int j = blockIdx.x; j < Nd; j += gridDim.x) {
-        __syncthreads();
-        stage_row(row_s, d + size_t(j) * V, V);
-        __syncthreads();
-        for (int i = warp; i < Nq; i += nw) {
-            const int n = __ldg(L.nnz + i);
-            const int* c = L.cols + size_t(i) * kQCap;
-            const float* w = L.vals + size_t(i) * kQCap;
-            float acc = 0.f;
-            for (int k = lane; k < n; k += 32) acc = fmaf(__ldg(w + k), row_s[__ldg(c + k)], acc);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (lane == 0) S[size_t(i) * Nd + j] = acc;
+        const float* src = d + size_t(j) * V;
+        const int head = min(V, int(((16 - (reinterpret_cast<uintptr_t>(src) & 15)) & 15) >> 2));
+        const int shift = (4 - head) & 3;
+        const int nbulk = ((V - head) >> 2) << 2;
+        __syncthreads();  // everyone is done gathering from the previous row
+        if (threadIdx.x == 0 && nbulk > 0) {
+            mbar_arrive_expect_tx(&bar, uint32_t(nbulk) * 4u);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_u32(row_s + head + shift)), "l"(src + head), "r"(uint32_t(nbulk) * 4u), "r"(smem_u32(&bar))
+                         : "memory");
         }
+        if (int(threadIdx.x) < head) row_s[threadIdx.x + shift] = __ldg(src + threadIdx.x);
+        for (int t = head + nbulk + threadIdx.x; t < V; t += kRowThreads) row_s[t + shift] = __ldg(src + t);
+        if (nbulk > 0) mbar_wait(&bar, phase);
+        phase ^= 1;
+        __syncthreads();
+        float acc = 0.f;
+#pragma unroll
+        for (int e = 0; e < kEPT; ++e) acc = fmaf(val[e], row_s[col[e] + shift], acc);
+        for (int o = tpq >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (sub == 0 && qi < Nq) S[size_t(qi) * Nd + j] = acc;
     }
 }
 
@@ -238,25 +274,28 @@ __global__ void zero_if_dense_kernel(float* __restrict__ S, size_t n, const int*
     for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) S[i] = 0.f;
 }
 
-// d_d[j, :] (+)= sum_i dS[i,j] * q[i,:] for rows [d_begin, d_end): the row is accumulated in shared memory
-// (zero-fill, shared-memory atomics over the query lists) and written to HBM once.
-__global__ void __launch_bounds__(kRowThreads)
-scores_docrow_bwd_kernel(const float* __restrict__ dS, int Nq, int Nd, int V, QLists L, int d_begin, int d_end,
+// d_d[j, :] (+)= sum_i dS[i,j] * q[i,:] for rows [d_begin, d_end): same register-resident lists; the row is built in
+// shared memory (zero-fill + shared-memory atomics) and written to HBM once. Query chunks beyond the first accumulate.
+__global__ void __launch_bounds__(kRowThreads, 1)
+scores_docrow_bwd_kernel(const float* __restrict__ dS, int Nq, int Nd, int V, int tpq, QLists L, int d_begin, int d_end,
                          int accumulate, float* __restrict__ d_d) {
     extern __shared__ float row_s[];
     if (*L.flag != 0) return;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = kRowThreads / 32;
+    const int per = kRowThreads / tpq;
+    const int sub = threadIdx.x % tpq;
     for (int j = d_begin + blockIdx.x; j < d_end; j += gridDim.x) {
         __syncthreads();
         for (int t = threadIdx.x; t < V; t += kRowThreads) row_s[t] = 0.f;
         __syncthreads();
-        for (int i = warp; i < Nq; i += nw) {
-            const float g = __ldg(dS + size_t(i) * Nd + j);
-            if (g == 0.f) continue;
-            const int n = __ldg(L.nnz + i);
-            const int* c = L.cols + size_t(i) * kQCap;
-            const float* w = L.vals + size_t(i) * kQCap;
-            for (int k = lane; k < n; k += 32) atomicAdd(&row_s[__ldg(c + k)], g * __ldg(w + k));
+        for (int q0 = 0; q0 < Nq; q0 += per) {   // all query chunks by the same block: one owner per output row
+            const int qi = q0 + threadIdx.x / tpq;
+            if (qi < Nq) {
+                const float g = __ldg(dS + size_t(qi) * Nd + j);
+                const int n = min(__ldg(L.nnz + qi), kQCap);
+                if (g != 0.f)
+                    for (int k = sub; k < n; k += tpq)
+                        atomicAdd(&row_s[__ldg(L.cols + size_t(qi) * kQCap + k)], g * __ldg(L.vals + size_t(qi) * kQCap + k));
+            }
         }
         __syncthreads();
         float* out = d_d + size_t(j) * V;
@@ -555,9 +594,17 @@ extern "C" size_t sb200_scores_workspace_bytes(int Nq, int Nd, int V, int in_bat
     return qlists_bytes(Nq);  // thresholded query lists (+ dispatch flag); reused by sb200_scores_bwd
 }
 
-static int row_kernel_grid(int rows) {
-    int g = num_sms();  // one 122 KB row per SM at a time
+static int row_kernel_grid(int rows, int chunks) {
+    int g = num_sms() / chunks;  // one row (V*4 B of shared memory) per SM at a time
+    if (g < 1) g = 1;
     return g < rows ? g : rows;
+}
+static size_t row_slab_bytes(int V) { return size_t(V + 4) * sizeof(float); }
+// threads that share one query (power of two <= 32): as many as the block allows, so short lists stay in registers
+static int threads_per_query(int Nq) {
+    int tpq = 32;
+    while (tpq > 2 && kRowThreads / tpq < Nq) tpq >>= 1;  // >= 2: lists of up to 64 entries always fit
+    return tpq;
 }
 
 extern "C" int sb200_scores_fwd(const float* q, const float* d, int Nq, int Nd, int V, int in_batch, float* S,
@@ -568,17 +615,21 @@ extern "C" int sb200_scores_fwd(const float* q, const float* d, int Nq, int Nd, 
     if (in_batch) {
         const int tj = (Nd + kST - 1) / kST, ti = (Nq + kST - 1) / kST;
         SB200_REQUIRE(ti <= 65535, "scores_fwd: Nq too large");
-        const size_t row_smem = size_t(V) * sizeof(float);
+        const size_t row_smem = row_slab_bytes(V);
         const bool sparse_ok = workspace != nullptr && workspace_bytes >= qlists_bytes(Nq) && row_smem <= 200 * 1024;
         const int* dense_flag = nullptr;
         if (sparse_ok) {
             QLists L = qlists_carve(workspace, Nq);
-            SB200_CUDA(cudaMemsetAsync(L.flag, 0, sizeof(int), stream));
-            q_compact_kernel<<<Nq, 256, 0, stream>>>(q, V, L);
+            // flag and the per-row counters are adjacent: one memset
+            SB200_CUDA(cudaMemsetAsync(L.flag, 0, 256 + align_up_sz(size_t(Nq) * 4, 256), stream));
+            const int tpq = threads_per_query(Nq);
+            const int per = kRowThreads / tpq, chunks = (Nq + per - 1) / per;
+            const int cap = kEPT * tpq < kQCap ? kEPT * tpq : kQCap;
+            q_compact_kernel<<<dim3(8, Nq), 256, 0, stream>>>(q, V, cap, L);
             SB200_CHECK_LAUNCH("q_compact_kernel");
             if (!device_flag_test_and_set(6))
                 SB200_CUDA(cudaFuncSetAttribute(scores_docrow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            scores_docrow_kernel<<<row_kernel_grid(Nd), kRowThreads, row_smem, stream>>>(d, Nq, Nd, V, L, S);
+            scores_docrow_kernel<<<dim3(row_kernel_grid(Nd, chunks), chunks), kRowThreads, row_smem, stream>>>(d, Nq, Nd, V, tpq, L, S);
             SB200_CHECK_LAUNCH("scores_docrow_kernel");
             dense_flag = L.flag;
         }
@@ -587,7 +638,6 @@ extern "C" int sb200_scores_fwd(const float* q, const float* d, int Nq, int Nd, 
         const int ks = pick_ksplit(tj * ti, V, kSK, &kchunk);
         if (ks > 1) {
             if (sparse_ok) {
-                // split-K partials need a zeroed S, but only if the dense kernel is really going to run
                 zero_if_dense_kernel<<<2 * num_sms(), 256, 0, stream>>>(S, size_t(Nq) * Nd, dense_flag);
                 SB200_CHECK_LAUNCH("zero_if_dense_kernel");
             } else {
@@ -622,7 +672,7 @@ extern "C" int sb200_scores_bwd(const float* dS, const float* q, const float* d,
     if (in_batch) {
         const int xb = vec2 ? (V / 2 + 255) / 256 : (V + 255) / 256;
         if (d_d != nullptr && d_end > d_begin) {
-            const size_t row_smem = size_t(V) * sizeof(float);
+            const size_t row_smem = row_slab_bytes(V);
             const int* dense_flag = nullptr;
             if (fwd_workspace != nullptr && workspace_bytes >= qlists_bytes(Nq) && row_smem <= 200 * 1024) {
                 // query lists built by sb200_scores_fwd: one shared-memory row per document, written to HBM once
@@ -630,8 +680,8 @@ extern "C" int sb200_scores_bwd(const float* dS, const float* q, const float* d,
                 if (!device_flag_test_and_set(7))
                     SB200_CUDA(cudaFuncSetAttribute(scores_docrow_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                     200 * 1024));
-                scores_docrow_bwd_kernel<<<row_kernel_grid(d_end - d_begin), kRowThreads, row_smem, stream>>>(
-                    dS, Nq, Nd, V, L, d_begin, d_end, accumulate, d_d);
+                scores_docrow_bwd_kernel<<<row_kernel_grid(d_end - d_begin, 1), kRowThreads, row_smem, stream>>>(
+                    dS, Nq, Nd, V, threads_per_query(Nq), L, d_begin, d_end, accumulate, d_d);
                 SB200_CHECK_LAUNCH("scores_docrow_bwd_kernel");
                 dense_flag = L.flag;
             }
