@@ -616,7 +616,8 @@ extern "C" int sb200_scores_fwd(const float* q, const float* d, int Nq, int Nd, 
         const int tj = (Nd + kST - 1) / kST, ti = (Nq + kST - 1) / kST;
         SB200_REQUIRE(ti <= 65535, "scores_fwd: Nq too large");
         const size_t row_smem = row_slab_bytes(V);
-        const bool sparse_ok = workspace != nullptr && workspace_bytes >= qlists_bytes(Nq) && row_smem <= 200 * 1024;
+        const bool sparse_ok = workspace != nullptr && workspace_bytes >= qlists_bytes(Nq) && row_smem <= 200 * 1024 &&
+                               Nq <= 65535;
         const int* dense_flag = nullptr;
         if (sparse_ok) {
             QLists L = qlists_carve(workspace, Nq);

@@ -126,3 +126,80 @@ def test_cuda_graph_replay_matches_eager():
     assert graph.state.global_step == ref.state.global_step
     assert graph.ranking_loss_moving_avg == pytest.approx(ref.ranking_loss_moving_avg, rel=2e-3)
     assert losses_e[0] > 0
+
+
+def test_train_ir_cli_synthetic_runs_and_checkpoints(tmp_path):
+    """The reference command line (flags form) end to end on a tiny random-init model: 4 steps, checkpoint layout."""
+    import sparse_b200  # noqa: F401
+    from sparse_b200 import train_ir
+    from sparse_b200.scripts import synthetic
+    V = 2000
+    out = tmp_path / "run"
+    argv = ["--output_dir", str(out), "--data_type", "synthetic_posnegs", "--loss_types", "[infonce]", "--use_in_batch_negatives",
+            "true", "--sample_num_one_query", "2", "--max_seq_length", "48", "--per_device_train_batch_size", "4",
+            "--max_steps", "4", "--save_steps", "2", "--bf16", "true", "--learning_rate", "0.0001", "--flops_d_lambda", "0.05",
+            "--flops_d_T", "10", "--max_grad_norm", "null", "--inf_free", "true", "--logging_steps", "2"]
+    trainer = train_ir.main(argv, backbone=synthetic.build_backbone("tiny", V, dropout=0.0),
+                            tokenizer=synthetic.SyntheticTokenizer(V))
+    assert trainer.state.global_step == 4
+    assert (out / "checkpoint-2" / "config.json").exists() and (out / "checkpoint-4" / "config.json").exists()
+    assert (out / "config.yaml").exists() and (out / "train.log").exists()
+    assert trainer.ranking_loss_moving_avg > 0
+    assert trainer.last_stats is not None and trainer.last_stats["avg_doc_length"] > 0
+
+
+def test_kd_ensemble_teachers_match_oracle():
+    """BiEncoderWrapper with a sparse and a dense teacher (random-init) against the oracle's ensemble arithmetic."""
+    import sparse_b200  # noqa: F401
+    from sparse_b200.scripts import synthetic
+    from sparse_b200.scripts.train.bi_encoder_wrapper import BiEncoderWrapper, BiSparseModel, DenseModel
+    import transformers
+    V, nq, G = 1500, 4, 3
+    tok = synthetic.SyntheticTokenizer(V)
+    sparse_t = BiSparseModel(None, backbone=synthetic.build_backbone("tiny", V, seed=3, dropout=0.0), tokenizer=tok).cuda().eval()
+    torch.manual_seed(5)
+    dense_t = DenseModel(None, backbone=transformers.BertModel(transformers.BertConfig(
+        vocab_size=V, hidden_size=64, num_hidden_layers=2, num_attention_heads=4, intermediate_size=128))).cuda().eval()
+    batch = synthetic.train_batch(nq, G, 40, query_len=12, vocab_size=V, device="cuda")
+    qf, df = batch["query"][0], batch["docs"][0]
+    for in_batch in (False, True):
+        wrap = BiEncoderWrapper(["dense", "sparse"], ["d", "s"], score_scale=30, use_in_batch_negatives=in_batch,
+                                models=[dense_t, sparse_t])
+        from sparse_b200.scripts.utils import DistEnv
+        wrap.accelerator = DistEnv()
+        got = wrap.get_scores_batch([qf, qf], [df, df])
+        with torch.no_grad():
+            reps_q = [dense_t(**qf).float().cpu(), sparse_t(**qf).float().cpu()]
+            reps_d = [dense_t(**df).float().cpu(), sparse_t(**df).float().cpu()]
+        want = R.ensemble_teacher_scores(reps_q, reps_d, in_batch, 30.0)
+        torch.testing.assert_close(got.cpu(), want, rtol=1e-4, atol=1e-3)
+    # the sparse teacher head itself against the oracle (single log, specials zeroed)
+    with torch.no_grad():
+        hidden = sparse_t._split.transform(sparse_t._split.body(**df)[0])
+        dec = sparse_t._split.decoder
+        want = R.teacher_sparse_head(hidden.bfloat16().float().cpu(), dec.weight.bfloat16().float().cpu(), dec.bias.float().cpu(),
+                                     df["attention_mask"].cpu(), sparse_t.special_token_ids)
+        torch.testing.assert_close(sparse_t(**df).cpu(), want, rtol=1e-4, atol=2e-5)
+
+
+def test_sparse_encoder_encode_output_and_flops_metric():
+    import sparse_b200  # noqa: F401
+    from sparse_b200.scripts import synthetic
+    from sparse_b200.scripts.model.sparse_encoders import SparseEncoder, sparse_embedding_to_query
+    from sparse_b200.scripts.search import flops_metric
+    V = 1500
+    model = synthetic.build_sparse_model("tiny", vocab_size=V, bias_shift=-0.5, dropout=0.0).cuda().eval()
+    enc = SparseEncoder(model, max_length=32)
+    feats = synthetic.token_batch(6, 32, seed=3, vocab_size=V, device="cuda")
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        rep = model(inf_free=False, **feats)
+    out = enc.encode_output(rep)
+    id_to_token = enc.post_processor.id_to_token
+    want = R.post_process(rep.cpu(), id_to_token)
+    assert out == want
+    assert torch.equal(enc.count_tensor.cpu().long(), R.document_frequency(rep.cpu()))
+    q = sparse_embedding_to_query(out[0], query_prune=0.2)["neural_sparse"]["text_sparse"]["query_tokens"]
+    assert q == R.query_prune(out[0], 0.2)
+    fl, ql, dl = flops_metric(enc.count_tensor, 6, enc.count_tensor, 6)
+    assert fl == pytest.approx(R.search_flops(enc.count_tensor.cpu(), 6, enc.count_tensor.cpu(), 6), rel=1e-6)
+    assert dl == pytest.approx(float((rep > 0).sum()) / 6, rel=1e-6) and ql == dl
