@@ -149,7 +149,7 @@ class SparseModelTrainer:
             nnz, psum, pmax, _ = stats.tolist()
         self.last_stats = {"avg_doc_length": nnz / d_rep.shape[0], "nonzero_mean": psum / max(nnz, 1.0), "nonzero_max": pmax}
         logger.info("Step %d. ranking loss moving avg:%s, d_flops: %s, flops_loss: %s avg doc length: %s",
-                    self.state.global_step, self.ranking_loss_moving_avg, float(d_flops), float(flops_loss),
+                    self.state.global_step, self.ranking_loss_moving_avg, float(d_flops.detach()), float(flops_loss.detach()),
                     self.last_stats["avg_doc_length"])
         logger.info("nonzero entries: %s %s %s", self.last_stats["nonzero_mean"], self.last_stats["nonzero_mean"],
                     self.last_stats["nonzero_max"])

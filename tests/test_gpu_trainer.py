@@ -153,13 +153,24 @@ def test_kd_ensemble_teachers_match_oracle():
     import sparse_b200  # noqa: F401
     from sparse_b200.scripts import synthetic
     from sparse_b200.scripts.train.bi_encoder_wrapper import BiEncoderWrapper, BiSparseModel, DenseModel
-    import transformers
     V, nq, G = 1500, 4, 3
     tok = synthetic.SyntheticTokenizer(V)
     sparse_t = BiSparseModel(None, backbone=synthetic.build_backbone("tiny", V, seed=3, dropout=0.0), tokenizer=tok).cuda().eval()
-    torch.manual_seed(5)
-    dense_t = DenseModel(None, backbone=transformers.BertModel(transformers.BertConfig(
-        vocab_size=V, hidden_size=64, num_hidden_layers=2, num_attention_heads=4, intermediate_size=128))).cuda().eval()
+    class BagBackbone(torch.nn.Module):
+        """Stand-in dense backbone with well-spread outputs (a random-init BERT gives nearly identical CLS vectors,
+        which makes the min-max normalisation ill-conditioned): position 0 = mean token embedding."""
+
+        def __init__(self):
+            super().__init__()
+            torch.manual_seed(5)
+            self.emb = torch.nn.Embedding(V, 48)
+
+        def forward(self, input_ids=None, attention_mask=None, **kw):
+            e = self.emb(input_ids) * attention_mask.unsqueeze(-1)
+            pooled = e.sum(1, keepdim=True) / attention_mask.sum(1).clamp_min(1).view(-1, 1, 1)
+            return (pooled.expand(-1, input_ids.shape[1], -1),)
+
+    dense_t = DenseModel(None, backbone=BagBackbone()).cuda().eval()
     batch = synthetic.train_batch(nq, G, 40, query_len=12, vocab_size=V, device="cuda")
     qf, df = batch["query"][0], batch["docs"][0]
     for in_batch in (False, True):
