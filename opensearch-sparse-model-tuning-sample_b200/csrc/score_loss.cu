@@ -466,25 +466,34 @@ rank_loss_kernel(int mode, const float* __restrict__ S, const float* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------ CSR compaction
+// Three passes, all parallel over (row, 1024-column segment): count non-zeros per segment, scan the counts (one block),
+// ordered fill inside each segment (ballot/popc), so columns stay ascending inside a row (= torch.nonzero order).
+constexpr int kSeg = 1024;
+
 __global__ void __launch_bounds__(256)
-compact_count_kernel(const float* __restrict__ rep, int V, int first_col, int* __restrict__ counts) {
+compact_count_kernel(const float* __restrict__ rep, int V, int first_col, int nseg, int* __restrict__ segcnt) {
     __shared__ float red[8];
-    const float* row = rep + size_t(blockIdx.x) * V;
+    const int b = blockIdx.y, sgm = blockIdx.x;
+    const float* row = rep + size_t(b) * V;
+    const int c0 = max(first_col, sgm * kSeg), c1 = min(V, (sgm + 1) * kSeg);
     float c = 0.f;
-    for (int v = first_col + threadIdx.x; v < V; v += 256) c += (__ldg(row + v) != 0.f) ? 1.f : 0.f;
+    for (int v = c0 + threadIdx.x; v < c1; v += 256) c += (__ldg(row + v) != 0.f) ? 1.f : 0.f;
     c = block_sum<256>(c, red);
-    if (threadIdx.x == 0) counts[blockIdx.x] = int(c);
+    if (threadIdx.x == 0) segcnt[b * nseg + sgm] = int(c);
 }
 
-__global__ void __launch_bounds__(1024) compact_scan_kernel(const int* __restrict__ counts, int B, int32_t* __restrict__ row_ptr) {
+// exclusive scan of n counts -> offsets; row_ptr[b] = offset of the row's first segment; row_ptr[B] = total
+__global__ void __launch_bounds__(1024)
+compact_scan_kernel(const int* __restrict__ counts, int n, int nseg, int B, int* __restrict__ offsets,
+                    int32_t* __restrict__ row_ptr) {
     __shared__ int warp_tot[32];
     __shared__ int carry_s;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) carry_s = 0;
     __syncthreads();
-    for (int base = 0; base < B; base += 1024) {
+    for (int base = 0; base < n; base += 1024) {
         const int i = base + threadIdx.x;
-        const int c = (i < B) ? counts[i] : 0;
+        const int c = (i < n) ? counts[i] : 0;
         int incl = c;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -504,9 +513,11 @@ __global__ void __launch_bounds__(1024) compact_scan_kernel(const int* __restric
             warp_tot[lane] = wi - w;
         }
         __syncthreads();
-        const int carry = carry_s;
-        const int excl = carry + warp_tot[warp] + incl - c;
-        if (i < B) row_ptr[i] = excl;
+        const int excl = carry_s + warp_tot[warp] + incl - c;
+        if (i < n) {
+            offsets[i] = excl;
+            if (i % nseg == 0) row_ptr[i / nseg] = excl;
+        }
         __syncthreads();
         if (threadIdx.x == 1023) carry_s = excl + c;
         __syncthreads();
@@ -514,42 +525,38 @@ __global__ void __launch_bounds__(1024) compact_scan_kernel(const int* __restric
     if (threadIdx.x == 0) row_ptr[B] = carry_s;
 }
 
-// ordered fill: columns ascending inside a row (matches torch.nonzero order)
 __global__ void __launch_bounds__(256)
-compact_fill_kernel(const float* __restrict__ rep, int V, int first_col, const int32_t* __restrict__ row_ptr,
+compact_fill_kernel(const float* __restrict__ rep, int V, int first_col, int nseg, const int* __restrict__ offsets,
                     int32_t* __restrict__ cols, float* __restrict__ vals, int capacity,
                     unsigned long long* __restrict__ df_count) {
     __shared__ int warp_cnt[8];
-    __shared__ int base_s;
-    const float* row = rep + size_t(blockIdx.x) * V;
+    const int b = blockIdx.y, sgm = blockIdx.x;
+    const float* row = rep + size_t(b) * V;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) base_s = row_ptr[blockIdx.x];
-    __syncthreads();
-    for (int v0 = 0; v0 < V; v0 += 256) {
+    int base = offsets[b * nseg + sgm];
+    const int c1 = min(V, (sgm + 1) * kSeg);
+    for (int v0 = sgm * kSeg; v0 < c1; v0 += 256) {
         const int v = v0 + threadIdx.x;
-        const float x = (v < V) ? __ldg(row + v) : 0.f;
+        const float x = (v < c1) ? __ldg(row + v) : 0.f;
         // document frequency counts every column; only columns >= first_col are compacted
         if (df_count != nullptr && x > 0.f) atomicAdd(df_count + v, 1ull);
         const bool nz = (v >= first_col) && x != 0.f;
         const uint32_t bal = __ballot_sync(0xffffffffu, nz);
+        __syncthreads();
         if (lane == 0) warp_cnt[warp] = __popc(bal);
         __syncthreads();
-        int off = base_s;
-        for (int w = 0; w < warp; ++w) off += warp_cnt[w];
+        int off = base, tot = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            if (w < warp) off += warp_cnt[w];
+            tot += warp_cnt[w];
+        }
         off += __popc(bal & ((1u << lane) - 1u));
-        if (nz) {
-            if (off < capacity) {
-                cols[off] = v;
-                vals[off] = x;
-            }
+        if (nz && off < capacity) {
+            cols[off] = v;
+            vals[off] = x;
         }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            int tot = 0;
-            for (int w = 0; w < 8; ++w) tot += warp_cnt[w];
-            base_s += tot;
-        }
-        __syncthreads();
+        base += tot;
     }
 }
 
@@ -737,8 +744,9 @@ extern "C" int sb200_rank_loss(int mode, const float* S, const float* teacher, i
 }
 
 extern "C" size_t sb200_compact_workspace_bytes(int B, int V) {
-    (void)V;
-    return B > 0 ? align_up(size_t(B) * sizeof(int), 256) : 0;
+    if (B <= 0 || V <= 0) return 0;
+    const size_t nseg = size_t((V + kSeg - 1) / kSeg);
+    return 2 * align_up(size_t(B) * nseg * sizeof(int), 256);
 }
 
 extern "C" int sb200_compact_rows(const float* rep, int B, int V, int first_col, int32_t* row_ptr, int32_t* cols,
@@ -746,16 +754,18 @@ extern "C" int sb200_compact_rows(const float* rep, int B, int V, int first_col,
                                   sb200_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     SB200_REQUIRE(rep && row_ptr && cols && vals, "compact_rows: null pointer");
-    SB200_REQUIRE(B >= 1 && V >= 1 && first_col >= 0 && capacity >= 0, "compact_rows: bad shape");
+    SB200_REQUIRE(B >= 1 && B <= 65535 && V >= 1 && first_col >= 0 && capacity >= 0, "compact_rows: bad shape");
     if (workspace == nullptr || workspace_bytes < sb200_compact_workspace_bytes(B, V))
         return fail(SB200_ERR_WORKSPACE, "compact_rows: workspace too small");
-    int* counts = static_cast<int*>(workspace);
-    compact_count_kernel<<<B, 256, 0, stream>>>(rep, V, first_col, counts);
+    const int nseg = (V + kSeg - 1) / kSeg;
+    int* segcnt = static_cast<int*>(workspace);
+    int* segoff = reinterpret_cast<int*>(static_cast<uint8_t*>(workspace) + align_up(size_t(B) * nseg * sizeof(int), 256));
+    compact_count_kernel<<<dim3(nseg, B), 256, 0, stream>>>(rep, V, first_col, nseg, segcnt);
     SB200_CHECK_LAUNCH("compact_count_kernel");
-    compact_scan_kernel<<<1, 1024, 0, stream>>>(counts, B, row_ptr);
+    compact_scan_kernel<<<1, 1024, 0, stream>>>(segcnt, B * nseg, nseg, B, segoff, row_ptr);
     SB200_CHECK_LAUNCH("compact_scan_kernel");
-    compact_fill_kernel<<<B, 256, 0, stream>>>(rep, V, first_col, row_ptr, cols, vals, capacity,
-                                               reinterpret_cast<unsigned long long*>(df_count));
+    compact_fill_kernel<<<dim3(nseg, B), 256, 0, stream>>>(rep, V, first_col, nseg, segoff, cols, vals, capacity,
+                                                           reinterpret_cast<unsigned long long*>(df_count));
     SB200_CHECK_LAUNCH("compact_fill_kernel");
     return SB200_OK;
 }
