@@ -104,7 +104,8 @@ def build_trainer(wl, regime, device):
     from sparse_b200.scripts.train.trainer import SparseModelTrainer
 
     shift = TRAINED_BIAS_SHIFT[wl["shape"]] if regime == "trained" else 0.0
-    model = synthetic.build_sparse_model(wl["shape"], idf_vector=idf_vector(), use_l0=wl["use_l0"], bias_shift=shift)
+    model = synthetic.build_sparse_model(wl["shape"], idf_vector=idf_vector(), use_l0=wl["use_l0"], bias_shift=shift,
+                                         fuse_body=not getattr(build_trainer, "no_fused_body", False))
     model.to(device)
     model_args = ModelArguments(inf_free=True, use_l0=wl["use_l0"])
     data_args = DataTrainingArguments(loss_types=[wl["loss"]], use_in_batch_negatives=wl["in_batch"],
@@ -163,6 +164,7 @@ def run_ours(args):
 
     wl = WORKLOADS[args.workload]
     peaks = load_peaks()
+    build_trainer.no_fused_body = args.no_fused_body
     trainer = build_trainer(wl, args.regime, device)
     n_pool = 4
     hosts = [host_batch(wl, rank, i) for i in range(n_pool)]
@@ -270,7 +272,8 @@ def run_ours(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": wl["name"], "regime": args.regime, "per_gpu_queries": nq, "per_gpu_docs": nd,
                        "global_queries": world * nq, "parallelism": f"dp{world}",
-                       "backbone": f"random-init BertForMaskedLM {wl['shape']} (PyTorch body, bf16 autocast)",
+                       "backbone": f"random-init BertForMaskedLM {wl['shape']} (PyTorch body, bf16 autocast, "
+                                   f"{trainer.model_wrapper.sparse_model.fused_layers} LayerNorms on fused sm_100a kernels)",
                        "l2": "no explicit flush: one step touches > 126 MB (activations, fp32 params, AdamW state)",
                        "launch": "whole step replayed as one CUDA graph" if graphed else "eager launches"},
             "e2e": {"value": round(e2e, 2), "unit": "samples/s", "h2d_bytes_per_step": batch_bytes(hosts[0]),
@@ -465,6 +468,8 @@ def main():
     ap.add_argument("--graph", action="store_true",
                     help="replay the whole step as one CUDA graph (single GPU only; default is eager launches so that "
                          "every GPU count runs the same code path)")
+    ap.add_argument("--no-fused-body", action="store_true",
+                    help="keep torch.nn.LayerNorm in the backbone (A/B of the fused LayerNorm kernels)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)

@@ -164,6 +164,22 @@ int sb200_compact_rows(const float* rep, int B, int V, int first_col, int32_t* r
 int sb200_minmax_accumulate(const float* S, int Nq, int C, float scale, int accumulate, float* acc,
                             sb200_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * (8) "next" row, rank 4 (encoder body): fused LayerNorm forward / backward replacing
+ *     torch.nn.functional.layer_norm inside the third-party backbone (transformers BertLayer /
+ *     BertEmbeddings / BertPredictionHeadTransform), whose backward was the largest single item of the
+ *     training step once the head is fused.
+ *   x, y, dy, dx  [R, H] bf16 (elem_bytes 2) or fp32 (elem_bytes 4);  gamma, beta, dgamma, dbeta f32 [H]
+ *   mean, rstd    f32 [R] saved by the forward for the backward.  H % 128 == 0, H/128 in {1,2,3,4,6,8}.
+ * ------------------------------------------------------------------------------------------- */
+int sb200_layer_norm_supported(int H);
+int sb200_layer_norm_fwd(const void* x, int elem_bytes, const float* gamma, const float* beta, int R, int H, float eps,
+                         void* y, float* mean, float* rstd, sb200_stream_t stream);
+size_t sb200_layer_norm_bwd_workspace_bytes(int R, int H);
+int sb200_layer_norm_bwd(const void* x, const void* dy, int elem_bytes, const float* gamma, const float* mean,
+                         const float* rstd, int R, int H, void* dx, float* dgamma, float* dbeta, void* workspace,
+                         size_t workspace_bytes, sb200_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -42,6 +42,10 @@ _PROTOTYPES = {
     "sb200_compact_workspace_bytes": (_sz, [_c_int, _c_int]),
     "sb200_compact_rows": (_c_int, [_vp, _c_int, _c_int, _c_int, _vp, _vp, _vp, _c_int, _vp, _vp, _sz, _vp]),
     "sb200_minmax_accumulate": (_c_int, [_vp, _c_int, _c_int, _c_f, _c_int, _vp, _vp]),
+    "sb200_layer_norm_supported": (_c_int, [_c_int]),
+    "sb200_layer_norm_fwd": (_c_int, [_vp, _c_int, _vp, _vp, _c_int, _c_int, _c_f, _vp, _vp, _vp, _vp]),
+    "sb200_layer_norm_bwd_workspace_bytes": (_sz, [_c_int, _c_int]),
+    "sb200_layer_norm_bwd": (_c_int, [_vp, _vp, _c_int, _vp, _vp, _vp, _c_int, _c_int, _vp, _vp, _vp, _vp, _sz, _vp]),
 }
 
 EXPORTED_SYMBOLS = tuple(_PROTOTYPES)

@@ -1,0 +1,262 @@
+// Fused LayerNorm forward / backward for the encoder body (once the sparse head is
+// fused, the third-party BERT body dominates the step, and its LayerNorm backward -- PyTorch's gamma/beta reduction
+// kernel -- was the largest single item of the r01 launch list: 19.5 % of the C2 step).
+//
+// Rows = tokens (R = B*L, tens of thousands), H = hidden size (384 / 768 / 1024, H % 128 == 0). HBM-bound:
+//   forward : read x, write y                       (2 * R*H*sizeof(T))
+//   backward: read x, g, write dx                   (3 * R*H*sizeof(T)) + partial gamma/beta sums (tiny)
+// One warp per row, each lane owns H/32 elements as 4-wide vectors (coalesced 8/16-byte accesses), statistics in fp32
+// by warp shuffles. The backward kernel accumulates the gamma/beta partial sums of all rows a block walks in registers,
+// reduces them across the block's warps in shared memory and writes one partial row per block; a second tiny kernel
+// sums the partials in a fixed order (deterministic, no atomics).
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "common.h"
+
+namespace sb200 {
+namespace {
+
+constexpr int kLnWarps = 8;           // rows in flight per block
+constexpr int kLnThreads = kLnWarps * 32;
+
+template <typename T> struct Vec4;
+template <> struct Vec4<float> {
+    static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+    static __device__ __forceinline__ void store(float* p, const float (&v)[4]) {
+        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+};
+template <> struct Vec4<__nv_bfloat16> {
+    static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[4]) {
+        const uint2 raw = __ldg(reinterpret_cast<const uint2*>(p));
+        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+        const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+    }
+    static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[4]) {
+        uint2 raw;
+        *reinterpret_cast<__nv_bfloat162*>(&raw.x) = __floats2bfloat162_rn(v[0], v[1]);
+        *reinterpret_cast<__nv_bfloat162*>(&raw.y) = __floats2bfloat162_rn(v[2], v[3]);
+        *reinterpret_cast<uint2*>(p) = raw;
+    }
+};
+
+__device__ __forceinline__ float warp_sum(float x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+}
+
+// NV = H / 128 four-wide vectors per lane; lane's vector k covers columns (lane + 32*k)*4 .. +3
+template <typename T, int NV>
+__global__ void __launch_bounds__(kLnThreads)
+ln_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, int R, float eps,
+              T* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+    constexpr int H = NV * 128;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float gm[NV][4], bt[NV][4];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        Vec4<float>::load(gamma + (lane + 32 * k) * 4, gm[k]);
+        Vec4<float>::load(beta + (lane + 32 * k) * 4, bt[k]);
+    }
+    for (int r = blockIdx.x * kLnWarps + warp; r < R; r += gridDim.x * kLnWarps) {
+        const T* xr = x + size_t(r) * H;
+        float v[NV][4];
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            Vec4<T>::load(xr + (lane + 32 * k) * 4, v[k]);
+            s += (v[k][0] + v[k][1]) + (v[k][2] + v[k][3]);
+        }
+        const float mean = warp_sum(s) * (1.f / H);
+        float q = 0.f;
+#pragma unroll
+        for (int k = 0; k < NV; ++k)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float dlt = v[k][i] - mean;
+                q = fmaf(dlt, dlt, q);
+            }
+        const float rstd = rsqrtf(warp_sum(q) * (1.f / H) + eps);
+        T* yr = y + size_t(r) * H;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            float o[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o[i] = fmaf((v[k][i] - mean) * rstd, gm[k][i], bt[k][i]);
+            Vec4<T>::store(yr + (lane + 32 * k) * 4, o);
+        }
+        if (lane == 0) {
+            mean_out[r] = mean;
+            rstd_out[r] = rstd;
+        }
+    }
+}
+
+template <typename T, int NV>
+__global__ void __launch_bounds__(kLnThreads)
+ln_bwd_kernel(const T* __restrict__ x, const T* __restrict__ g, const float* __restrict__ gamma,
+              const float* __restrict__ mean_in, const float* __restrict__ rstd_in, int R, T* __restrict__ dx,
+              float* __restrict__ partial /* [gridDim.x][2][H] */) {
+    constexpr int H = NV * 128;
+    __shared__ float red[kLnWarps][H];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float gm[NV][4], dg[NV][4], db[NV][4];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        Vec4<float>::load(gamma + (lane + 32 * k) * 4, gm[k]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dg[k][i] = db[k][i] = 0.f;
+    }
+    for (int r = blockIdx.x * kLnWarps + warp; r < R; r += gridDim.x * kLnWarps) {
+        const float mean = __ldg(mean_in + r), rstd = __ldg(rstd_in + r);
+        float xh[NV][4], gy[NV][4];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            Vec4<T>::load(x + size_t(r) * H + (lane + 32 * k) * 4, xh[k]);
+            Vec4<T>::load(g + size_t(r) * H + (lane + 32 * k) * 4, gy[k]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                xh[k][i] = (xh[k][i] - mean) * rstd;
+                dg[k][i] = fmaf(gy[k][i], xh[k][i], dg[k][i]);
+                db[k][i] += gy[k][i];
+                gy[k][i] *= gm[k][i];          // gradient w.r.t. the normalised value
+                s1 += gy[k][i];
+                s2 = fmaf(gy[k][i], xh[k][i], s2);
+            }
+        }
+        s1 = warp_sum(s1) * (1.f / H);
+        s2 = warp_sum(s2) * (1.f / H);
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            float o[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o[i] = rstd * (gy[k][i] - s1 - xh[k][i] * s2);
+            Vec4<T>::store(dx + size_t(r) * H + (lane + 32 * k) * 4, o);
+        }
+    }
+    // block-level reduction of the gamma / beta partial sums (two rounds through the same shared buffer)
+    float* out = partial + size_t(blockIdx.x) * 2 * H;
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < NV; ++k)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) red[warp][(lane + 32 * k) * 4 + i] = pass == 0 ? dg[k][i] : db[k][i];
+        __syncthreads();
+        for (int c = threadIdx.x; c < H; c += kLnThreads) {
+            float s = 0.f;
+#pragma unroll
+            for (int w = 0; w < kLnWarps; ++w) s += red[w][c];
+            out[pass * H + c] = s;
+        }
+    }
+}
+
+// dgamma[c] = sum_b partial[b][0][c], dbeta[c] = sum_b partial[b][1][c]   (fixed order)
+__global__ void __launch_bounds__(256)
+ln_bwd_finish_kernel(const float* __restrict__ partial, int nblocks, int H, float* __restrict__ dgamma,
+                     float* __restrict__ dbeta) {
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c >= 2 * H) return;
+    float s = 0.f;
+    for (int b = 0; b < nblocks; ++b) s += __ldg(partial + size_t(b) * 2 * H + c);
+    if (c < H) dgamma[c] = s; else dbeta[c - H] = s;
+}
+
+int ln_grid(int R) {
+    int g = 4 * num_sms();
+    const int need = (R + kLnWarps - 1) / kLnWarps;
+    return g < need ? g : need;
+}
+
+template <typename T>
+int launch_fwd(const void* x, const float* gamma, const float* beta, int R, int H, float eps, void* y, float* mean,
+               float* rstd, cudaStream_t stream) {
+    const T* xi = static_cast<const T*>(x);
+    T* yo = static_cast<T*>(y);
+    const int grid = ln_grid(R);
+    switch (H / 128) {
+        case 1: ln_fwd_kernel<T, 1><<<grid, kLnThreads, 0, stream>>>(xi, gamma, beta, R, eps, yo, mean, rstd); break;
+        case 2: ln_fwd_kernel<T, 2><<<grid, kLnThreads, 0, stream>>>(xi, gamma, beta, R, eps, yo, mean, rstd); break;
+        case 3: ln_fwd_kernel<T, 3><<<grid, kLnThreads, 0, stream>>>(xi, gamma, beta, R, eps, yo, mean, rstd); break;
+        case 4: ln_fwd_kernel<T, 4><<<grid, kLnThreads, 0, stream>>>(xi, gamma, beta, R, eps, yo, mean, rstd); break;
+        case 6: ln_fwd_kernel<T, 6><<<grid, kLnThreads, 0, stream>>>(xi, gamma, beta, R, eps, yo, mean, rstd); break;
+        case 8: ln_fwd_kernel<T, 8><<<grid, kLnThreads, 0, stream>>>(xi, gamma, beta, R, eps, yo, mean, rstd); break;
+        default: return fail(SB200_ERR_ARG, "layer_norm: unsupported H=%d", H);
+    }
+    SB200_CHECK_LAUNCH("ln_fwd_kernel");
+    return SB200_OK;
+}
+
+template <typename T>
+int launch_bwd(const void* x, const void* g, const float* gamma, const float* mean, const float* rstd, int R, int H,
+               void* dx, float* partial, int grid, cudaStream_t stream) {
+    const T* xi = static_cast<const T*>(x);
+    const T* gi = static_cast<const T*>(g);
+    T* dxo = static_cast<T*>(dx);
+    switch (H / 128) {
+        case 1: ln_bwd_kernel<T, 1><<<grid, kLnThreads, 0, stream>>>(xi, gi, gamma, mean, rstd, R, dxo, partial); break;
+        case 2: ln_bwd_kernel<T, 2><<<grid, kLnThreads, 0, stream>>>(xi, gi, gamma, mean, rstd, R, dxo, partial); break;
+        case 3: ln_bwd_kernel<T, 3><<<grid, kLnThreads, 0, stream>>>(xi, gi, gamma, mean, rstd, R, dxo, partial); break;
+        case 4: ln_bwd_kernel<T, 4><<<grid, kLnThreads, 0, stream>>>(xi, gi, gamma, mean, rstd, R, dxo, partial); break;
+        case 6: ln_bwd_kernel<T, 6><<<grid, kLnThreads, 0, stream>>>(xi, gi, gamma, mean, rstd, R, dxo, partial); break;
+        case 8: ln_bwd_kernel<T, 8><<<grid, kLnThreads, 0, stream>>>(xi, gi, gamma, mean, rstd, R, dxo, partial); break;
+        default: return fail(SB200_ERR_ARG, "layer_norm: unsupported H=%d", H);
+    }
+    SB200_CHECK_LAUNCH("ln_bwd_kernel");
+    return SB200_OK;
+}
+
+bool ln_supported(int H) {
+    const int nv = H / 128;
+    return H % 128 == 0 && (nv == 1 || nv == 2 || nv == 3 || nv == 4 || nv == 6 || nv == 8);
+}
+
+}  // namespace
+}  // namespace sb200
+
+using namespace sb200;
+
+extern "C" int sb200_layer_norm_supported(int H) { return ln_supported(H) ? 1 : 0; }
+
+extern "C" int sb200_layer_norm_fwd(const void* x, int elem_bytes, const float* gamma, const float* beta, int R, int H,
+                                    float eps, void* y, float* mean, float* rstd, sb200_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    SB200_REQUIRE(x && gamma && beta && y && mean && rstd, "layer_norm_fwd: null pointer");
+    SB200_REQUIRE(R >= 1 && ln_supported(H), "layer_norm_fwd: unsupported shape R=%d H=%d", R, H);
+    SB200_REQUIRE(elem_bytes == 2 || elem_bytes == 4, "layer_norm_fwd: elem_bytes=%d (2 = bf16, 4 = fp32)", elem_bytes);
+    if (elem_bytes == 2) return launch_fwd<__nv_bfloat16>(x, gamma, beta, R, H, eps, y, mean, rstd, stream);
+    return launch_fwd<float>(x, gamma, beta, R, H, eps, y, mean, rstd, stream);
+}
+
+extern "C" size_t sb200_layer_norm_bwd_workspace_bytes(int R, int H) {
+    if (R <= 0 || H <= 0) return 0;
+    return size_t(ln_grid(R)) * 2 * H * sizeof(float);
+}
+
+extern "C" int sb200_layer_norm_bwd(const void* x, const void* dy, int elem_bytes, const float* gamma, const float* mean,
+                                    const float* rstd, int R, int H, void* dx, float* dgamma, float* dbeta,
+                                    void* workspace, size_t workspace_bytes, sb200_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    SB200_REQUIRE(x && dy && gamma && mean && rstd && dx && dgamma && dbeta, "layer_norm_bwd: null pointer");
+    SB200_REQUIRE(R >= 1 && ln_supported(H), "layer_norm_bwd: unsupported shape R=%d H=%d", R, H);
+    SB200_REQUIRE(elem_bytes == 2 || elem_bytes == 4, "layer_norm_bwd: elem_bytes=%d", elem_bytes);
+    if (workspace == nullptr || workspace_bytes < sb200_layer_norm_bwd_workspace_bytes(R, H))
+        return fail(SB200_ERR_WORKSPACE, "layer_norm_bwd: workspace too small");
+    const int grid = ln_grid(R);
+    float* partial = static_cast<float*>(workspace);
+    int rc = elem_bytes == 2 ? launch_bwd<__nv_bfloat16>(x, dy, gamma, mean, rstd, R, H, dx, partial, grid, stream)
+                             : launch_bwd<float>(x, dy, gamma, mean, rstd, R, H, dx, partial, grid, stream);
+    if (rc != SB200_OK) return rc;
+    ln_bwd_finish_kernel<<<(2 * H + 255) / 256, 256, 0, stream>>>(partial, grid, H, dgamma, dbeta);
+    SB200_CHECK_LAUNCH("ln_bwd_finish_kernel");
+    return SB200_OK;
+}

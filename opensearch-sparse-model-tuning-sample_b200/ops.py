@@ -382,3 +382,56 @@ def minmax_accumulate(S, acc=None, scale=1.0):
                                                    _ptr(out), _stream())
     _lib.check(code, "sb200_minmax_accumulate")
     return out
+
+
+# --------------------------------------------------------------------------------------------- encoder body: LayerNorm
+def layer_norm_supported(hidden_size):
+    return bool(_lib.load().sb200_layer_norm_supported(int(hidden_size)))
+
+
+class LayerNormFunction(torch.autograd.Function):
+    """y = LayerNorm(x) over the last dimension; x bf16 or fp32 (kept), gamma/beta fp32, statistics in fp32."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        _need_cuda(x, gamma, beta)
+        H = x.shape[-1]
+        xc = x.detach()
+        if xc.dtype not in (torch.bfloat16, torch.float32):
+            xc = xc.float()
+        xc = xc.contiguous()
+        R = xc.numel() // H
+        g32 = gamma.detach().float().contiguous()
+        b32 = beta.detach().float().contiguous()
+        y = torch.empty_like(xc)
+        mean = torch.empty(R, dtype=torch.float32, device=xc.device)
+        rstd = torch.empty(R, dtype=torch.float32, device=xc.device)
+        with torch.cuda.device(xc.device):
+            code = _lib.load().sb200_layer_norm_fwd(_ptr(xc), xc.element_size(), _ptr(g32), _ptr(b32), R, H, float(eps),
+                                                    _ptr(y), _ptr(mean), _ptr(rstd), _stream())
+        _lib.check(code, "sb200_layer_norm_fwd")
+        ctx.save_for_backward(xc, g32, mean, rstd)
+        ctx.in_dtypes = (x.dtype, gamma.dtype, beta.dtype)
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        xc, g32, mean, rstd = ctx.saved_tensors
+        H = xc.shape[-1]
+        R = xc.numel() // H
+        dyc = dy.to(xc.dtype).contiguous()
+        dx = torch.empty_like(xc)
+        dgamma = torch.empty(H, dtype=torch.float32, device=xc.device)
+        dbeta = torch.empty(H, dtype=torch.float32, device=xc.device)
+        lib = _lib.load()
+        ws = _workspace(lib.sb200_layer_norm_bwd_workspace_bytes(R, H), xc.device)
+        with torch.cuda.device(xc.device):
+            code = lib.sb200_layer_norm_bwd(_ptr(xc), _ptr(dyc), xc.element_size(), _ptr(g32), _ptr(mean), _ptr(rstd), R, H,
+                                            _ptr(dx), _ptr(dgamma), _ptr(dbeta), _ptr(ws), ws.numel(), _stream())
+        _lib.check(code, "sb200_layer_norm_bwd")
+        xd, gd, bd = ctx.in_dtypes
+        return dx.view(xc.shape).to(xd), dgamma.to(gd), dbeta.to(bd), None
+
+
+def layer_norm(x, gamma, beta, eps=1e-12):
+    return LayerNormFunction.apply(x, gamma, beta, eps)

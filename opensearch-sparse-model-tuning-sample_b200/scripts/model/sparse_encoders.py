@@ -102,9 +102,10 @@ class _PruneFunction(torch.autograd.Function):
 
 class SparseModel(torch.nn.Module):
     def __init__(self, model_id, idf=None, tokenizer_id=None, idf_requires_grad=False, prune_ratio=None,
-                 preprocess_func=None, use_l0=True, backbone=None, tokenizer=None):
+                 preprocess_func=None, use_l0=True, backbone=None, tokenizer=None, fuse_body=True):
         """Arguments as in the reference (:43-52). ``backbone``/``tokenizer`` may be passed pre-built (offline use:
-        random-init architectures, tests, benchmarks); otherwise they are loaded with transformers as upstream."""
+        random-init architectures, tests, benchmarks); otherwise they are loaded with transformers as upstream.
+        ``fuse_body`` swaps the backbone's LayerNorm modules for the fused sm_100a kernels (same parameters)."""
         super().__init__()
         import transformers
         if backbone is None:
@@ -112,6 +113,10 @@ class SparseModel(torch.nn.Module):
         if tokenizer is None and (tokenizer_id or model_id) is not None:
             tokenizer = transformers.AutoTokenizer.from_pretrained(tokenizer_id or model_id)
         self.backbone = backbone
+        self.fused_layers = 0
+        if fuse_body:
+            from .fused_layers import fuse_backbone
+            self.fused_layers = fuse_backbone(self.backbone)
         self.tokenizer = tokenizer
         if preprocess_func is not None:
             func = getattr(TextPreProcessors, preprocess_func)

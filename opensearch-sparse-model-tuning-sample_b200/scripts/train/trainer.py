@@ -115,7 +115,7 @@ class SparseModelTrainer:
                    "attention_mask": inputs["docs"][0]["attention_mask"]}
         d_rep, q_rep = model(student)
         d_rep = gather_rep(d_rep, self.accelerator)
-        q_rep = gather_rep(q_rep, self.accelerator)
+        q_rep = self._gather_queries(q_rep, student["q_input_ids"])
         if "scores" in inputs:
             inputs["scores"] = gather_rep(inputs["scores"], self.accelerator)
 
@@ -142,6 +142,19 @@ class SparseModelTrainer:
         # DDP averages gradients over ranks while every rank holds the full global loss (reference :139-141)
         loss = loss * self.accelerator.num_processes
         return (loss, {"q_rep": q_rep, "d_rep": d_rep}) if return_outputs else loss
+
+    def _gather_queries(self, q_rep, q_input_ids):
+        """Cross-rank query vectors. Inf-free queries with a frozen IDF table are a pure function of the token ids, so
+        the compact form is exchanged -- int64 ids [n_q, Lq] instead of dense fp32 [n_q, V] (~500x fewer bytes) -- and the
+        vectors of all ranks are rebuilt locally by the IDF kernel (bit-exact, no gradient involved). Everything else
+        goes through the reference's dense gather (scripts/utils.py:16-23)."""
+        env = self.accelerator
+        sm = self.model_wrapper.sparse_model
+        if (env.num_processes > 1 and self.model_args.inf_free and not sm.idf_requires_grad and q_rep.is_cuda
+                and hasattr(env, "gather")):
+            all_ids = env.gather(q_input_ids.contiguous())
+            return ops.idf_query(all_ids, sm.idf_vector, sm._special_ids_on(all_ids.device))
+        return gather_rep(q_rep, env)
 
     def _log_step(self, d_rep, d_flops, flops_loss):
         with torch.no_grad():

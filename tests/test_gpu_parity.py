@@ -353,3 +353,50 @@ def test_scores_sparse_and_dense_dispatch_agree(ops, nnz_q):
     assert_close(S, Sr, 1e-5, 1e-4, "scores")
     assert_close(dc.grad, dr.grad, 1e-5, 1e-5, "d_d")
     assert_close(qc.grad, qr.grad, 1e-5, 1e-5, "d_q")
+
+
+# ------------------------------------------------------------------------------------------------------ encoder body
+@pytest.mark.parametrize("R,H", [(37, 128), (4096, 384), (1000, 768), (513, 1024), (8, 256), (300, 512)])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_fused_layer_norm_vs_torch(ops, R, H, dtype):
+    g = torch.Generator().manual_seed(R + H)
+    x = (torch.randn(R, H, generator=g) * 2 + 0.5).to(dtype)
+    gamma = torch.randn(H, generator=g) * 0.5 + 1
+    beta = torch.randn(H, generator=g) * 0.3
+    dy = torch.randn(R, H, generator=g).to(dtype)
+    xc, gc, bc = cuda(x).requires_grad_(True), cuda(gamma).requires_grad_(True), cuda(beta).requires_grad_(True)
+    y = ops.layer_norm(xc, gc, bc, 1e-12)
+    assert y.dtype == dtype
+    y.backward(cuda(dy))
+    xr, gr, br = x.float().requires_grad_(True), gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    yr = torch.nn.functional.layer_norm(xr, (H,), gr, br, 1e-12)
+    yr.backward(dy.float())
+    tol = dict(rtol=2e-2, atol=2e-2) if dtype == torch.bfloat16 else dict(rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(y.float().cpu(), yr, **tol)
+    torch.testing.assert_close(xc.grad.float().cpu(), xr.grad, **tol)
+    # parameter gradients are accumulated in fp32 from the given inputs: tight in both dtypes
+    torch.testing.assert_close(gc.grad.cpu(), gr.grad, rtol=1e-4, atol=1e-3 * float(gr.grad.abs().max()))
+    torch.testing.assert_close(bc.grad.cpu(), br.grad, rtol=1e-4, atol=1e-3 * float(br.grad.abs().max()))
+
+
+def test_fused_backbone_matches_unfused(ops):
+    from sparse_b200.scripts import synthetic
+    V = 2000
+    kw = dict(vocab_size=V, seed=1, dropout=0.0, bias_shift=-0.2)
+    fused = synthetic.build_sparse_model("mini", fuse_body=True, **kw).cuda()
+    plain = synthetic.build_sparse_model("mini", fuse_body=False, **kw).cuda()
+    assert fused.fused_layers == 14 and plain.fused_layers == 0
+    assert fused.state_dict().keys() == plain.state_dict().keys()
+    plain.load_state_dict(fused.state_dict())
+    feats = synthetic.token_batch(6, 64, seed=2, vocab_size=V, device="cuda")
+    outs = []
+    for m in (fused, plain):
+        m.zero_grad()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            rep = m(inf_free=False, **feats)
+        rep.sum().backward()
+        outs.append((rep.detach().float().cpu(), m.backbone.bert.embeddings.LayerNorm.weight.grad.float().cpu()))
+    # bf16 activations differ in rounding points (torch normalises in fp32 and rounds later): loose tolerance
+    torch.testing.assert_close(outs[0][0], outs[1][0], rtol=5e-2, atol=5e-2)
+    cos = torch.nn.functional.cosine_similarity(outs[0][1], outs[1][1], dim=0)
+    assert float(cos) > 0.99
