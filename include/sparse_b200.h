@@ -180,6 +180,13 @@ int sb200_layer_norm_bwd(const void* x, const void* dy, int elem_bytes, const fl
                          const float* rstd, int R, int H, void* dx, float* dgamma, float* dbeta, void* workspace,
                          size_t workspace_bytes, sb200_stream_t stream);
 
+/* Column sums of a row-major [R, N] matrix (bf16 or fp32): out[c] = sum_r dy[r,c]. The bias gradient of the body's
+ * Linear layers (replaces the torch reduce kernel behind addmm's backward). N % 8 == 0, N <= 4096. */
+int sb200_colsum_supported(int N);
+size_t sb200_colsum_workspace_bytes(int R, int N);
+int sb200_colsum(const void* dy, int elem_bytes, int R, int N, float* out, void* workspace, size_t workspace_bytes,
+                 sb200_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -28,7 +28,7 @@ bool device_flag_test_and_set(int slot) {
     static std::atomic<unsigned> flags[64];
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return false;
-    const unsigned bit = 1u << (slot & 7);
+    const unsigned bit = 1u << (slot & 31);
     return (flags[dev].fetch_or(bit) & bit) != 0;
 }
 

@@ -45,7 +45,8 @@ inline void count_launch(unsigned n = 1) { g_launches.fetch_add(n, std::memory_o
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 int num_sms();  // SM count of the current device (cached per device)
-// Per-device one-shot flags (slot in [0, 8)): returns the previous value and sets the flag.
+// Per-device one-shot flags (slot in [0, 32)): returns the previous value and sets the flag.
+// Slots: 0/5 head_fwd<1/2>, 1-4 bwd_dw<NCHUNK>, 6/7 score row kernels, 8-24 colsum<NV>.
 bool device_flag_test_and_set(int slot);
 
 }  // namespace sb200

@@ -260,3 +260,145 @@ extern "C" int sb200_layer_norm_bwd(const void* x, const void* dy, int elem_byte
     SB200_CHECK_LAUNCH("ln_bwd_finish_kernel");
     return SB200_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ bias gradient
+// db[c] = sum_r dy[r, c] for a row-major [R, N] gradient (bf16 or fp32): the bias gradient of every Linear of the body.
+// PyTorch's generic reduce kernel took 58 us per call on [40960, 384..1536] bf16 (11.6 % of the C2 step after the
+// LayerNorm fusion); this is one streaming pass with 16-byte loads, per-block partial rows and a fixed-order finish.
+namespace sb200 {
+namespace {
+
+constexpr int kCsWarps = 8;
+constexpr int kCsMaxVec = 16;  // N <= 16 * 256 = 4096 columns
+
+template <typename T> struct Vec8;
+template <> struct Vec8<__nv_bfloat16> {
+    static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
+        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(p));
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 f = __bfloat1622float2(h[i]);
+            v[2 * i] = f.x;
+            v[2 * i + 1] = f.y;
+        }
+    }
+};
+template <> struct Vec8<float> {
+    static __device__ __forceinline__ void load(const float* p, float (&v)[8]) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+};
+
+template <typename T, int NV>
+__global__ void __launch_bounds__(kCsWarps * 32)
+colsum_partial_kernel(const T* __restrict__ dy, int R, int N, float* __restrict__ partial /* [gridDim.x][N] */) {
+    extern __shared__ float red[];  // [kCsWarps][N]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nvec = N >> 3;
+    float acc[NV][8];
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[k][i] = 0.f;
+    for (int r = blockIdx.x * kCsWarps + warp; r < R; r += gridDim.x * kCsWarps) {
+        const T* row = dy + size_t(r) * N;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const int vc = lane + 32 * k;
+            if (vc < nvec) {
+                float v[8];
+                Vec8<T>::load(row + vc * 8, v);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[k][i] += v[i];
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const int vc = lane + 32 * k;
+        if (vc < nvec)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) red[warp * N + vc * 8 + i] = acc[k][i];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < N; c += kCsWarps * 32) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < kCsWarps; ++w) s += red[w * N + c];
+        partial[size_t(blockIdx.x) * N + c] = s;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+colsum_finish_kernel(const float* __restrict__ partial, int nblocks, int N, float* __restrict__ out) {
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c >= N) return;
+    float s = 0.f;
+    for (int b = 0; b < nblocks; ++b) s += __ldg(partial + size_t(b) * N + c);
+    out[c] = s;
+}
+
+int colsum_grid(int R) {
+    int g = 2 * num_sms();
+    const int need = (R + kCsWarps - 1) / kCsWarps;
+    return g < need ? g : need;
+}
+
+template <typename T>
+int launch_colsum(const void* dy, int R, int N, float* partial, int grid, cudaStream_t stream) {
+    const T* p = static_cast<const T*>(dy);
+    const size_t smem = size_t(kCsWarps) * N * sizeof(float);
+    const int nv = (N / 8 + 31) / 32;
+#define SB200_CS_CASE(NV_)                                                                                          \
+    case NV_:                                                                                                       \
+        if (smem > 48 * 1024 && !device_flag_test_and_set(8 + NV_))                                                       \
+            SB200_CUDA(cudaFuncSetAttribute(colsum_partial_kernel<T, NV_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                            int(kCsWarps * 4096 * sizeof(float))));                                 \
+        colsum_partial_kernel<T, NV_><<<grid, kCsWarps * 32, smem, stream>>>(p, R, N, partial);                     \
+        break;
+    switch (nv) {
+        SB200_CS_CASE(1) SB200_CS_CASE(2) SB200_CS_CASE(3) SB200_CS_CASE(4) SB200_CS_CASE(6) SB200_CS_CASE(8)
+        SB200_CS_CASE(12) SB200_CS_CASE(16)
+        default: return fail(SB200_ERR_ARG, "colsum: unsupported N=%d", N);
+    }
+#undef SB200_CS_CASE
+    SB200_CHECK_LAUNCH("colsum_partial_kernel");
+    return SB200_OK;
+}
+
+bool colsum_supported(int N) {
+    if (N < 8 || N % 8 != 0 || N > 4096) return false;
+    const int nv = (N / 8 + 31) / 32;
+    return nv == 1 || nv == 2 || nv == 3 || nv == 4 || nv == 6 || nv == 8 || nv == 12 || nv == 16;
+}
+
+}  // namespace
+}  // namespace sb200
+
+extern "C" int sb200_colsum_supported(int N) { return sb200::colsum_supported(N) ? 1 : 0; }
+
+extern "C" size_t sb200_colsum_workspace_bytes(int R, int N) {
+    if (R <= 0 || N <= 0) return 0;
+    return size_t(sb200::colsum_grid(R)) * N * sizeof(float);
+}
+
+extern "C" int sb200_colsum(const void* dy, int elem_bytes, int R, int N, float* out, void* workspace,
+                            size_t workspace_bytes, sb200_stream_t stream_) {
+    using namespace sb200;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    SB200_REQUIRE(dy && out, "colsum: null pointer");
+    SB200_REQUIRE(R >= 1 && colsum_supported(N), "colsum: unsupported shape R=%d N=%d", R, N);
+    SB200_REQUIRE(elem_bytes == 2 || elem_bytes == 4, "colsum: elem_bytes=%d", elem_bytes);
+    if (workspace == nullptr || workspace_bytes < sb200_colsum_workspace_bytes(R, N))
+        return fail(SB200_ERR_WORKSPACE, "colsum: workspace too small");
+    const int grid = colsum_grid(R);
+    float* partial = static_cast<float*>(workspace);
+    const int rc = elem_bytes == 2 ? launch_colsum<__nv_bfloat16>(dy, R, N, partial, grid, stream)
+                                   : launch_colsum<float>(dy, R, N, partial, grid, stream);
+    if (rc != SB200_OK) return rc;
+    colsum_finish_kernel<<<(N + 255) / 256, 256, 0, stream>>>(partial, grid, N, out);
+    SB200_CHECK_LAUNCH("colsum_finish_kernel");
+    return SB200_OK;
+}

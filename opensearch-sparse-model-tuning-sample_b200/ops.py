@@ -435,3 +435,54 @@ class LayerNormFunction(torch.autograd.Function):
 
 def layer_norm(x, gamma, beta, eps=1e-12):
     return LayerNormFunction.apply(x, gamma, beta, eps)
+
+
+# --------------------------------------------------------------------------------------------- encoder body: Linear
+def colsum_supported(n):
+    return bool(_lib.load().sb200_colsum_supported(int(n)))
+
+
+def colsum(dy):
+    """Column sums of a 2-D bf16/fp32 matrix in fp32 (the bias gradient of a Linear layer)."""
+    _need_cuda(dy)
+    if dy.dtype not in (torch.bfloat16, torch.float32):
+        dy = dy.float()
+    dy = dy.contiguous()
+    R, N = dy.shape
+    out = torch.empty(N, dtype=torch.float32, device=dy.device)
+    lib = _lib.load()
+    ws = _workspace(lib.sb200_colsum_workspace_bytes(R, N), dy.device)
+    with torch.cuda.device(dy.device):
+        code = lib.sb200_colsum(_ptr(dy), dy.element_size(), R, N, _ptr(out), _ptr(ws), ws.numel(), _stream())
+    _lib.check(code, "sb200_colsum")
+    return out
+
+
+class LinearFunction(torch.autograd.Function):
+    """y = x W^T + b with the library GEMMs of torch (cuBLAS) and the fused column-sum kernel for the bias gradient.
+    Under autocast the operands are cast like torch.nn.functional.linear would (custom_fwd)."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.bfloat16)
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return torch.nn.functional.linear(x, weight, bias)
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        dy2 = dy.reshape(-1, dy.shape[-1])
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = (dy2 @ weight).view(x.shape)
+        if ctx.needs_input_grad[1]:
+            dw = dy2.t() @ x.reshape(-1, x.shape[-1])
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = colsum(dy2)
+        return dx, dw, db
+
+
+def linear(x, weight, bias):
+    return LinearFunction.apply(x, weight, bias)

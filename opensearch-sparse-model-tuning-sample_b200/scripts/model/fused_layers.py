@@ -20,11 +20,34 @@ class FusedLayerNorm(torch.nn.LayerNorm):
         return super().forward(x)
 
 
+class FusedLinear(torch.nn.Linear):
+    """torch.nn.Linear whose bias gradient comes from the fused column-sum kernel (the GEMMs stay with cuBLAS)."""
+
+    def forward(self, x):
+        if x.is_cuda and self.bias is not None and torch.is_grad_enabled() and self.bias.requires_grad:
+            return ops.linear(x, self.weight, self.bias)
+        return super().forward(x)
+
+
+def _skip_linear(module, backbone):
+    """The vocabulary decoder is never run as a Linear (the fused head consumes its parameters directly)."""
+    out = backbone.get_output_embeddings() if hasattr(backbone, "get_output_embeddings") else None
+    return out is not None and module is out
+
+
 def fuse_backbone(backbone):
     """In place; returns the number of modules replaced."""
     swapped = 0
     for parent in backbone.modules():
         for name, child in list(parent.named_children()):
+            if type(child) is torch.nn.Linear and child.bias is not None and not _skip_linear(child, backbone) \
+                    and ops.colsum_supported(child.out_features):
+                fused = FusedLinear(child.in_features, child.out_features, bias=True, device="meta")
+                fused.weight, fused.bias = child.weight, child.bias
+                fused.train(child.training)
+                setattr(parent, name, fused)
+                swapped += 1
+                continue
             if type(child) is torch.nn.LayerNorm and len(child.normalized_shape) == 1 and child.elementwise_affine \
                     and child.bias is not None and ops.layer_norm_supported(child.normalized_shape[0]):
                 fused = FusedLayerNorm(child.normalized_shape, eps=child.eps)

@@ -385,7 +385,7 @@ def test_fused_backbone_matches_unfused(ops):
     kw = dict(vocab_size=V, seed=1, dropout=0.0, bias_shift=-0.2)
     fused = synthetic.build_sparse_model("mini", fuse_body=True, **kw).cuda()
     plain = synthetic.build_sparse_model("mini", fuse_body=False, **kw).cuda()
-    assert fused.fused_layers == 14 and plain.fused_layers == 0
+    assert fused.fused_layers == 14 + 37 and plain.fused_layers == 0  # LayerNorms + Linears of the body
     assert fused.state_dict().keys() == plain.state_dict().keys()
     plain.load_state_dict(fused.state_dict())
     feats = synthetic.token_batch(6, 64, seed=2, vocab_size=V, device="cuda")
@@ -400,3 +400,33 @@ def test_fused_backbone_matches_unfused(ops):
     torch.testing.assert_close(outs[0][0], outs[1][0], rtol=5e-2, atol=5e-2)
     cos = torch.nn.functional.cosine_similarity(outs[0][1], outs[1][1], dim=0)
     assert float(cos) > 0.99
+
+
+@pytest.mark.parametrize("R,N", [(40960, 384), (1000, 1536), (77, 3072), (5, 8), (3000, 768), (513, 4096)])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_colsum_bias_gradient(ops, R, N, dtype):
+    g = torch.Generator().manual_seed(R + N)
+    dy = torch.randn(R, N, generator=g).to(dtype)
+    got = ops.colsum(cuda(dy))
+    want = dy.double().sum(0).float()
+    torch.testing.assert_close(got.cpu(), want, rtol=1e-4, atol=1e-3)
+
+
+def test_fused_linear_matches_torch(ops):
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(6, 50, 384, generator=g)
+    w = torch.randn(1536, 384, generator=g) * 0.05
+    b = torch.randn(1536, generator=g)
+    dy = torch.randn(6, 50, 1536, generator=g)
+    outs = []
+    for fn in (ops.linear, torch.nn.functional.linear):
+        xc, wc, bc = cuda(x).requires_grad_(True), cuda(w).requires_grad_(True), cuda(b).requires_grad_(True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            y = fn(xc, wc, bc)
+        assert y.dtype == torch.bfloat16
+        y.backward(cuda(dy).bfloat16())
+        outs.append((y.float().cpu(), xc.grad.cpu(), wc.grad.cpu(), bc.grad.cpu()))
+    for a, r in zip(outs[0], outs[1]):
+        torch.testing.assert_close(a, r, rtol=2e-2, atol=2e-2)
+    # the bias gradient itself is an fp32 sum of the bf16 gradient: much tighter than torch's bf16 reduction
+    torch.testing.assert_close(outs[0][3], dy.bfloat16().float().sum((0, 1)), rtol=1e-4, atol=1e-3)
