@@ -353,7 +353,7 @@ int launch_colsum(const void* dy, int R, int N, float* partial, int grid, cudaSt
     const int nv = (N / 8 + 31) / 32;
 #define SB200_CS_CASE(NV_)                                                                                          \
     case NV_:                                                                                                       \
-        if (smem > 48 * 1024 && !device_flag_test_and_set(8 + NV_))                                                       \
+        if (smem > 48 * 1024 && !device_flag_test_and_set(8 + (NV_ == 16 ? 1 : 0) + (sizeof(T) == 4 ? 2 : 0)))                                                       \
             SB200_CUDA(cudaFuncSetAttribute(colsum_partial_kernel<T, NV_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                             int(kCsWarps * 4096 * sizeof(float))));                                 \
         colsum_partial_kernel<T, NV_><<<grid, kCsWarps * 32, smem, stream>>>(p, R, N, partial);                     \
