@@ -160,15 +160,34 @@ ln_bwd_kernel(const T* __restrict__ x, const T* __restrict__ g, const float* __r
     }
 }
 
-// dgamma[c] = sum_b partial[b][0][c], dbeta[c] = sum_b partial[b][1][c]   (fixed order)
+// out[c] = sum_b partial[b][c] over nblocks partial rows of ncols columns, fixed summation order. 32 columns per
+// block, 8 row groups per column with 4 independent accumulators each (the naive one-thread-per-column loop is a serial
+// chain of nblocks dependent loads: 47 us for 592 partial rows).
 __global__ void __launch_bounds__(256)
-ln_bwd_finish_kernel(const float* __restrict__ partial, int nblocks, int H, float* __restrict__ dgamma,
-                     float* __restrict__ dbeta) {
-    const int c = blockIdx.x * 256 + threadIdx.x;
-    if (c >= 2 * H) return;
-    float s = 0.f;
-    for (int b = 0; b < nblocks; ++b) s += __ldg(partial + size_t(b) * 2 * H + c);
-    if (c < H) dgamma[c] = s; else dbeta[c - H] = s;
+partial_reduce_kernel(const float* __restrict__ partial, int nblocks, int ncols, float* __restrict__ out0,
+                      float* __restrict__ out1, int split) {
+    __shared__ float red[8][33];
+    const int cl = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cl;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    if (c < ncols) {
+        int b = grp;
+        for (; b + 24 < nblocks; b += 32) {
+            a0 += __ldg(partial + size_t(b) * ncols + c);
+            a1 += __ldg(partial + size_t(b + 8) * ncols + c);
+            a2 += __ldg(partial + size_t(b + 16) * ncols + c);
+            a3 += __ldg(partial + size_t(b + 24) * ncols + c);
+        }
+        for (; b < nblocks; b += 8) a0 += __ldg(partial + size_t(b) * ncols + c);
+    }
+    red[grp][cl] = (a0 + a1) + (a2 + a3);
+    __syncthreads();
+    if (grp == 0 && c < ncols) {
+        float s = 0.f;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) s += red[g][cl];
+        if (c < split) out0[c] = s; else out1[c - split] = s;
+    }
 }
 
 int ln_grid(int R) {
@@ -256,8 +275,8 @@ extern "C" int sb200_layer_norm_bwd(const void* x, const void* dy, int elem_byte
     int rc = elem_bytes == 2 ? launch_bwd<__nv_bfloat16>(x, dy, gamma, mean, rstd, R, H, dx, partial, grid, stream)
                              : launch_bwd<float>(x, dy, gamma, mean, rstd, R, H, dx, partial, grid, stream);
     if (rc != SB200_OK) return rc;
-    ln_bwd_finish_kernel<<<(2 * H + 255) / 256, 256, 0, stream>>>(partial, grid, H, dgamma, dbeta);
-    SB200_CHECK_LAUNCH("ln_bwd_finish_kernel");
+    partial_reduce_kernel<<<(2 * H + 31) / 32, 256, 0, stream>>>(partial, grid, 2 * H, dgamma, dbeta, H);
+    SB200_CHECK_LAUNCH("partial_reduce_kernel");
     return SB200_OK;
 }
 
@@ -302,18 +321,31 @@ colsum_partial_kernel(const T* __restrict__ dy, int R, int N, float* __restrict_
     for (int k = 0; k < NV; ++k)
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[k][i] = 0.f;
-    for (int r = blockIdx.x * kCsWarps + warp; r < R; r += gridDim.x * kCsWarps) {
-        const T* row = dy + size_t(r) * N;
+    const int stride = gridDim.x * kCsWarps;
+    constexpr int U = NV <= 2 ? 4 : (NV <= 4 ? 2 : 1);  // rows in flight per warp (register budget)
+    for (int r = blockIdx.x * kCsWarps + warp; r < R; r += U * stride) {
+        // U independent rows per iteration keep U*NV 16-byte loads in flight per lane
+        float v[U][NV][8];
 #pragma unroll
-        for (int k = 0; k < NV; ++k) {
-            const int vc = lane + 32 * k;
-            if (vc < nvec) {
-                float v[8];
-                Vec8<T>::load(row + vc * 8, v);
+        for (int u = 0; u < U; ++u) {
+            const int rr = r + u * stride;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) acc[k][i] += v[i];
+            for (int k = 0; k < NV; ++k) {
+                const int vc = lane + 32 * k;
+                if (rr < R && vc < nvec) {
+                    Vec8<T>::load(dy + size_t(rr) * N + vc * 8, v[u][k]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[u][k][i] = 0.f;
+                }
             }
         }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int k = 0; k < NV; ++k)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[k][i] += v[u][k][i];
     }
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
@@ -329,15 +361,6 @@ colsum_partial_kernel(const T* __restrict__ dy, int R, int N, float* __restrict_
         for (int w = 0; w < kCsWarps; ++w) s += red[w * N + c];
         partial[size_t(blockIdx.x) * N + c] = s;
     }
-}
-
-__global__ void __launch_bounds__(256)
-colsum_finish_kernel(const float* __restrict__ partial, int nblocks, int N, float* __restrict__ out) {
-    const int c = blockIdx.x * 256 + threadIdx.x;
-    if (c >= N) return;
-    float s = 0.f;
-    for (int b = 0; b < nblocks; ++b) s += __ldg(partial + size_t(b) * N + c);
-    out[c] = s;
 }
 
 int colsum_grid(int R) {
@@ -398,7 +421,7 @@ extern "C" int sb200_colsum(const void* dy, int elem_bytes, int R, int N, float*
     const int rc = elem_bytes == 2 ? launch_colsum<__nv_bfloat16>(dy, R, N, partial, grid, stream)
                                    : launch_colsum<float>(dy, R, N, partial, grid, stream);
     if (rc != SB200_OK) return rc;
-    colsum_finish_kernel<<<(N + 255) / 256, 256, 0, stream>>>(partial, grid, N, out);
-    SB200_CHECK_LAUNCH("colsum_finish_kernel");
+    partial_reduce_kernel<<<(N + 31) / 32, 256, 0, stream>>>(partial, grid, N, out, out, N);
+    SB200_CHECK_LAUNCH("partial_reduce_kernel");
     return SB200_OK;
 }

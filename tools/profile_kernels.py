@@ -25,6 +25,14 @@ def run(B, L, H, V, G, nq, regime_shift):
     loss = ops.rank_loss(S, None, "infonce", G, True)
     loss.backward()
     ops.compact_rows(rep)
+    # encoder-body kernels on the step's activation shape [B*L, H]
+    x = hidden.reshape(-1, H).clone().requires_grad_(True)
+    gamma = torch.ones(H, device="cuda", requires_grad=True)
+    beta = torch.zeros(H, device="cuda", requires_grad=True)
+    y = ops.layer_norm(x, gamma, beta, 1e-12)
+    y.backward(torch.ones_like(y))
+    ops.colsum(hidden.reshape(-1, H))
+    ops.colsum(torch.randn(B * L, 4 * H, device="cuda").bfloat16())
     torch.cuda.synchronize()
 
 if __name__ == "__main__":
