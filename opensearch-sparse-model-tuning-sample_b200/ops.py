@@ -236,6 +236,7 @@ class FlopsFunction(torch.autograd.Function):
         ctx.save_for_backward(rep32, colsum, rowmask)
         ctx.group_num = group_num
         ctx.rep_dtype = rep.dtype
+        ctx.grad_rows = getattr(rep, "_sb200_grad_rows", None)  # set by gather_rep: only these rows carry grad
         return value
 
     @staticmethod
@@ -244,9 +245,10 @@ class FlopsFunction(torch.autograd.Function):
         rows, V = rep.shape
         G = ctx.group_num
         g = g.detach().float().reshape(1).contiguous()
-        d_rep = torch.empty_like(rep)
+        lo, hi = ctx.grad_rows if ctx.grad_rows is not None else (0, rows)
+        d_rep = torch.empty_like(rep) if (lo, hi) == (0, rows) else torch.zeros_like(rep)
         with torch.cuda.device(rep.device):
-            code = _lib.load().sb200_flops_bwd(_ptr(rep), _ptr(colsum), _ptr(rowmask), _ptr(g), rows // G, G, V, 0, rows,
+            code = _lib.load().sb200_flops_bwd(_ptr(rep), _ptr(colsum), _ptr(rowmask), _ptr(g), rows // G, G, V, lo, hi,
                                                0, _ptr(d_rep), _stream())
         _lib.check(code, "sb200_flops_bwd")
         return d_rep.to(ctx.rep_dtype), None, None
@@ -255,7 +257,8 @@ class FlopsFunction(torch.autograd.Function):
 def flops_value(rep, group_num=1, threshold=None):
     """trainer.py:61-73"""
     shape_v = rep.shape[-1]
-    return FlopsFunction.apply(rep.reshape(-1, shape_v), int(group_num), threshold)
+    flat = rep if rep.dim() == 2 else rep.reshape(-1, shape_v)
+    return FlopsFunction.apply(flat, int(group_num), threshold)
 
 
 # --------------------------------------------------------------------------------------------- scores + losses
@@ -289,6 +292,8 @@ class ScoresFunction(torch.autograd.Function):
         S, ws = scores_forward(q32, d32, in_batch, return_workspace=True)
         ctx.save_for_backward(q32, d32)
         ctx.ws = ws  # thresholded query lists, reused by the backward kernels
+        ctx.q_rows = getattr(q, "_sb200_grad_rows", None)  # set by gather_rep: only these rows carry grad
+        ctx.d_rows = getattr(d, "_sb200_grad_rows", None)
         ctx.in_batch = bool(in_batch)
         ctx.dtypes = (q.dtype, d.dtype)
         return S
@@ -300,13 +305,15 @@ class ScoresFunction(torch.autograd.Function):
         dS = dS.float().contiguous()
         Nq, V = q.shape
         Nd = d.shape[0]
-        d_q = torch.empty_like(q) if need_q else None
-        d_d = torch.empty_like(d) if need_d else None
+        q_lo, q_hi = ctx.q_rows if ctx.q_rows is not None else (0, Nq)
+        d_lo, d_hi = ctx.d_rows if ctx.d_rows is not None else (0, Nd)
+        d_q = (torch.empty_like(q) if (q_lo, q_hi) == (0, Nq) else torch.zeros_like(q)) if need_q else None
+        d_d = (torch.empty_like(d) if (d_lo, d_hi) == (0, Nd) else torch.zeros_like(d)) if need_d else None
         ws = ctx.ws
         with torch.cuda.device(q.device):
-            code = _lib.load().sb200_scores_bwd(_ptr(dS), _ptr(q), _ptr(d), Nq, Nd, V, 1 if ctx.in_batch else 0, 0, Nq, 0,
-                                                Nd, 0, _ptr(d_q), _ptr(d_d), _ptr(ws), 0 if ws is None else ws.numel(),
-                                                _stream())
+            code = _lib.load().sb200_scores_bwd(_ptr(dS), _ptr(q), _ptr(d), Nq, Nd, V, 1 if ctx.in_batch else 0, q_lo, q_hi,
+                                                d_lo, d_hi, 0, _ptr(d_q), _ptr(d_d), _ptr(ws),
+                                                0 if ws is None else ws.numel(), _stream())
         _lib.check(code, "sb200_scores_bwd")
         return (d_q.to(ctx.dtypes[0]) if need_q else None, d_d.to(ctx.dtypes[1]) if need_d else None, None)
 

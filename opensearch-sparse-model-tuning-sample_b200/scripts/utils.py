@@ -24,7 +24,12 @@ class _GatherKeepLocalGrad(torch.autograd.Function):
     def forward(ctx, rep, env):
         ctx.env = env
         ctx.rows = rep.shape[0]
-        return env.gather(rep.detach())
+        out = env.gather(rep.detach())
+        # consumers that know about it (ops.FlopsFunction / ops.ScoresFunction) only compute the gradient rows that
+        # survive this function's backward -- the local slice -- instead of all world_size * n rows
+        lo = env.local_process_index * ctx.rows
+        out._sb200_grad_rows = (lo, lo + ctx.rows)
+        return out
 
     @staticmethod
     def backward(ctx, grad_all):

@@ -430,3 +430,29 @@ def test_fused_linear_matches_torch(ops):
         torch.testing.assert_close(a, r, rtol=2e-2, atol=2e-2)
     # the bias gradient itself is an fp32 sum of the bf16 gradient: much tighter than torch's bf16 reduction
     torch.testing.assert_close(outs[0][3], dy.bfloat16().float().sum((0, 1)), rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("in_batch", [False, True])
+def test_local_row_backward_matches_full_backward(ops, in_batch):
+    """After gather_rep only the local slice of the gathered reps carries gradient; the loss/regulariser backward
+    kernels then compute just those rows. They must equal the corresponding rows of the full backward."""
+    from sparse_b200.scripts.train.loss import LOSS_CLS_MAP
+    Nq, G, V = 8, 3, 5000
+    g = torch.Generator().manual_seed(1)
+    q = torch.relu(torch.randn(Nq, V, generator=g)) * (torch.rand(Nq, V, generator=g) > 0.99)
+    d = torch.relu(torch.randn(Nq * G, V, generator=g)) * (torch.rand(Nq * G, V, generator=g) > 0.9)
+    teacher = torch.randn(Nq, Nq * G if in_batch else G, generator=g)
+    fn = LOSS_CLS_MAP["kldiv"](use_in_batch_negatives=in_batch, temperature=2.0)
+    grads = []
+    for rows_q, rows_d in ((None, None), ((2, 4), (6, 12))):
+        qc, dc = cuda(q).requires_grad_(True), cuda(d).requires_grad_(True)
+        if rows_q is not None:
+            qc._sb200_grad_rows, dc._sb200_grad_rows = rows_q, rows_d
+        loss = fn.get_loss(qc, dc, {"scores": cuda(teacher)}) + 0.3 * ops.flops_value(dc, G, 20) + 0.1 * ops.flops_value(qc)
+        loss.backward()
+        grads.append((qc.grad.cpu(), dc.grad.cpu()))
+    (fq, fd), (lq, ld) = grads
+    torch.testing.assert_close(lq[2:4], fq[2:4], rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(ld[6:12], fd[6:12], rtol=1e-5, atol=1e-7)
+    assert float(lq[:2].abs().max()) == 0 and float(lq[4:].abs().max()) == 0
+    assert float(ld[:6].abs().max()) == 0 and float(ld[12:].abs().max()) == 0
