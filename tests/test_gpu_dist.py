@@ -1,0 +1,104 @@
+"""2-GPU NCCL test of the data-parallel training path (skipped on a single-GPU box): every rank evaluates the global
+loss from gathered reps (compact id exchange for inf-free queries, dense all-gather for docs), loss x world + DDP mean
+must reproduce the single-process global-batch loss and parameter gradients."""
+import os
+import socket
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _build(V, loss, in_batch, inf_free):
+    import sparse_b200  # noqa: F401
+    from sparse_b200.scripts import synthetic
+    from sparse_b200.scripts.args import DataTrainingArguments, ModelArguments, TrainingArguments
+    from sparse_b200.scripts.train.loss import LOSS_CLS_MAP
+    from sparse_b200.scripts.train.trainer import SparseModelTrainer
+    idf = torch.rand(V, generator=torch.Generator().manual_seed(3)) * 5
+    model = synthetic.build_sparse_model("tiny", idf_vector=idf, vocab_size=V, seed=0, bias_shift=-0.1, dropout=0.0).cuda()
+    margs = ModelArguments(inf_free=inf_free)
+    dargs = DataTrainingArguments(loss_types=[loss], use_in_batch_negatives=in_batch, flops_d_lambda=0.05, flops_d_T=50,
+                                  flops_q_lambda=0.02, flops_q_T=30)
+    targs = TrainingArguments(bf16=True, logging_steps=10 ** 9, max_grad_norm=None)
+    fns = [LOSS_CLS_MAP[loss](use_in_batch_negatives=in_batch, temperature=1.0)]
+    return SparseModelTrainer(margs, dargs, fns, model=model, args=targs)
+
+
+def _worker(rank, world, port, loss, in_batch, inf_free, out):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from sparse_b200.scripts import synthetic
+        V, nq, G = 1500, 4, 3
+        tr = _build(V, loss, in_batch, inf_free)
+        assert tr.accelerator.num_processes == world
+        batches = [synthetic.train_batch(nq, G, 40, query_len=12, vocab_size=V, seed=70 + r, device="cuda",
+                                         with_scores=None if loss == "infonce" else G) for r in range(world)]
+
+        def run(student):
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                return tr.model(student)
+        loss_v = tr.compute_loss(run, dict(batches[rank]))
+        loss_v.backward()  # DDP averages the gradients
+        grads = {n: p.grad.detach().float().clone() for n, p in tr.model_wrapper.named_parameters() if p.grad is not None}
+        if rank == 0:
+            # single-process global batch with the same weights
+            ref = _build(V, loss, in_batch, inf_free)
+            ref.accelerator.num_processes = 1
+            ref.model_wrapper.load_state_dict(tr.model_wrapper.state_dict())
+
+            def cat(key, idx):
+                return torch.cat([b[key][0][idx] for b in batches], 0)
+            gb = {"query": [{"input_ids": cat("query", "input_ids"), "attention_mask": cat("query", "attention_mask")}],
+                  "docs": [{"input_ids": cat("docs", "input_ids"), "attention_mask": cat("docs", "attention_mask")}]}
+            if loss != "infonce":
+                gb["scores"] = torch.cat([b["scores"] for b in batches], 0)
+
+            def run_ref(student):
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    return ref.model(student)
+            ref_loss = ref.compute_loss(run_ref, gb)
+            ref_loss.backward()
+            torch.testing.assert_close(loss_v.detach() / world, ref_loss.detach(), rtol=1e-4, atol=1e-5)
+            worst = 0.0
+            for n, p in ref.model_wrapper.named_parameters():
+                if p.grad is None:
+                    continue
+                a, b = grads[n], p.grad.float()
+                denom = float(b.abs().max()) + 1e-12
+                worst = max(worst, float((a - b).abs().max()) / denom)
+            assert worst < 3e-2, worst  # bf16 activations; gradients agree to bf16 resolution
+        out.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        import traceback
+        out.put((rank, traceback.format_exc()[-1500:]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("loss,in_batch,inf_free", [("infonce", True, True), ("kldiv", False, False)])
+def test_two_gpu_global_loss_and_gradients(loss, in_batch, inf_free):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, loss, in_batch, inf_free, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [out.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(results) == [(0, "ok"), (1, "ok")], results
