@@ -16,12 +16,16 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _build(V, loss, in_batch, inf_free):
+def _build(V, loss, in_batch, inf_free, single_process=False):
     import sparse_b200  # noqa: F401
     from sparse_b200.scripts import synthetic
     from sparse_b200.scripts.args import DataTrainingArguments, ModelArguments, TrainingArguments
     from sparse_b200.scripts.train.loss import LOSS_CLS_MAP
     from sparse_b200.scripts.train.trainer import SparseModelTrainer
+    from sparse_b200.scripts.utils import DistEnv
+    env = DistEnv()
+    if single_process:  # reference run on one rank: no DDP wrapper, no collectives
+        env.num_processes, env.process_index, env.local_process_index = 1, 0, 0
     idf = torch.rand(V, generator=torch.Generator().manual_seed(3)) * 5
     model = synthetic.build_sparse_model("tiny", idf_vector=idf, vocab_size=V, seed=0, bias_shift=-0.1, dropout=0.0).cuda()
     margs = ModelArguments(inf_free=inf_free)
@@ -29,7 +33,7 @@ def _build(V, loss, in_batch, inf_free):
                                   flops_q_lambda=0.02, flops_q_T=30)
     targs = TrainingArguments(bf16=True, logging_steps=10 ** 9, max_grad_norm=None)
     fns = [LOSS_CLS_MAP[loss](use_in_batch_negatives=in_batch, temperature=1.0)]
-    return SparseModelTrainer(margs, dargs, fns, model=model, args=targs)
+    return SparseModelTrainer(margs, dargs, fns, model=model, args=targs, accelerator=env)
 
 
 def _worker(rank, world, port, loss, in_batch, inf_free, out):
@@ -54,8 +58,7 @@ def _worker(rank, world, port, loss, in_batch, inf_free, out):
         grads = {n: p.grad.detach().float().clone() for n, p in tr.model_wrapper.named_parameters() if p.grad is not None}
         if rank == 0:
             # single-process global batch with the same weights
-            ref = _build(V, loss, in_batch, inf_free)
-            ref.accelerator.num_processes = 1
+            ref = _build(V, loss, in_batch, inf_free, single_process=True)
             ref.model_wrapper.load_state_dict(tr.model_wrapper.state_dict())
 
             def cat(key, idx):
@@ -98,7 +101,7 @@ def test_two_gpu_global_loss_and_gradients(loss, in_batch, inf_free):
     procs = [ctx.Process(target=_worker, args=(r, 2, port, loss, in_batch, inf_free, out)) for r in range(2)]
     for p in procs:
         p.start()
-    results = [out.get(timeout=300) for _ in procs]
+    results = [out.get(timeout=120) for _ in procs]
     for p in procs:
         p.join(timeout=60)
     assert sorted(results) == [(0, "ok"), (1, "ok")], results
