@@ -74,14 +74,20 @@ def _worker(rank, world, port, loss, in_batch, inf_free, out):
             ref_loss = ref.compute_loss(run_ref, gb)
             ref_loss.backward()
             torch.testing.assert_close(loss_v.detach() / world, ref_loss.detach(), rtol=1e-4, atol=1e-5)
-            worst = 0.0
+            # bf16 activations with different batch compositions: compare the whole gradient in L2 and every sizeable
+            # parameter by direction
+            num = den = 0.0
+            big = max(float(p.grad.float().norm()) for _, p in ref.model_wrapper.named_parameters() if p.grad is not None)
             for n, p in ref.model_wrapper.named_parameters():
                 if p.grad is None:
                     continue
-                a, b = grads[n], p.grad.float()
-                denom = float(b.abs().max()) + 1e-12
-                worst = max(worst, float((a - b).abs().max()) / denom)
-            assert worst < 3e-2, worst  # bf16 activations; gradients agree to bf16 resolution
+                a, b = grads[n].flatten(), p.grad.float().flatten()
+                num += float((a - b).pow(2).sum())
+                den += float(b.pow(2).sum())
+                if float(b.norm()) > 1e-2 * big:
+                    cos = float(torch.nn.functional.cosine_similarity(a, b, dim=0))
+                    assert cos > 0.995, (n, cos)
+            assert (num / den) ** 0.5 < 3e-2, (num / den) ** 0.5
         out.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         import traceback
