@@ -160,32 +160,28 @@ ln_bwd_kernel(const T* __restrict__ x, const T* __restrict__ g, const float* __r
     }
 }
 
-// out[c] = sum_b partial[b][c] over nblocks partial rows of ncols columns, fixed summation order. 32 columns per
-// block, 8 row groups per column with 4 independent accumulators each (the naive one-thread-per-column loop is a serial
-// chain of nblocks dependent loads: 47 us for 592 partial rows).
+// out[c] = sum_b partial[b][c] over nblocks partial rows of ncols columns, fixed summation order. The work is tiny
+// (1-2 MB) and purely latency-bound, so it is spread wide: 8 columns per block, 32 row groups per column (one per lane
+// of a warp after the transpose below), 4 independent accumulators per thread, warp-shuffle finish.
 __global__ void __launch_bounds__(256)
 partial_reduce_kernel(const float* __restrict__ partial, int nblocks, int ncols, float* __restrict__ out0,
                       float* __restrict__ out1, int split) {
-    __shared__ float red[8][33];
-    const int cl = threadIdx.x & 31, grp = threadIdx.x >> 5;
-    const int c = blockIdx.x * 32 + cl;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = blockIdx.x * 8 + warp;  // one warp per column, lanes stride over the partial rows
+    if (c >= ncols) return;
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    if (c < ncols) {
-        int b = grp;
-        for (; b + 24 < nblocks; b += 32) {
-            a0 += __ldg(partial + size_t(b) * ncols + c);
-            a1 += __ldg(partial + size_t(b + 8) * ncols + c);
-            a2 += __ldg(partial + size_t(b + 16) * ncols + c);
-            a3 += __ldg(partial + size_t(b + 24) * ncols + c);
-        }
-        for (; b < nblocks; b += 8) a0 += __ldg(partial + size_t(b) * ncols + c);
+    int b = lane;
+    for (; b + 96 < nblocks; b += 128) {
+        a0 += __ldg(partial + size_t(b) * ncols + c);
+        a1 += __ldg(partial + size_t(b + 32) * ncols + c);
+        a2 += __ldg(partial + size_t(b + 64) * ncols + c);
+        a3 += __ldg(partial + size_t(b + 96) * ncols + c);
     }
-    red[grp][cl] = (a0 + a1) + (a2 + a3);
-    __syncthreads();
-    if (grp == 0 && c < ncols) {
-        float s = 0.f;
+    for (; b < nblocks; b += 32) a0 += __ldg(partial + size_t(b) * ncols + c);
+    float s = (a0 + a1) + (a2 + a3);
 #pragma unroll
-        for (int g = 0; g < 8; ++g) s += red[g][cl];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
         if (c < split) out0[c] = s; else out1[c - split] = s;
     }
 }
@@ -275,7 +271,7 @@ extern "C" int sb200_layer_norm_bwd(const void* x, const void* dy, int elem_byte
     int rc = elem_bytes == 2 ? launch_bwd<__nv_bfloat16>(x, dy, gamma, mean, rstd, R, H, dx, partial, grid, stream)
                              : launch_bwd<float>(x, dy, gamma, mean, rstd, R, H, dx, partial, grid, stream);
     if (rc != SB200_OK) return rc;
-    partial_reduce_kernel<<<(2 * H + 31) / 32, 256, 0, stream>>>(partial, grid, 2 * H, dgamma, dbeta, H);
+    partial_reduce_kernel<<<(2 * H + 7) / 8, 256, 0, stream>>>(partial, grid, 2 * H, dgamma, dbeta, H);
     SB200_CHECK_LAUNCH("partial_reduce_kernel");
     return SB200_OK;
 }
@@ -421,7 +417,7 @@ extern "C" int sb200_colsum(const void* dy, int elem_bytes, int R, int N, float*
     const int rc = elem_bytes == 2 ? launch_colsum<__nv_bfloat16>(dy, R, N, partial, grid, stream)
                                    : launch_colsum<float>(dy, R, N, partial, grid, stream);
     if (rc != SB200_OK) return rc;
-    partial_reduce_kernel<<<(N + 31) / 32, 256, 0, stream>>>(partial, grid, N, out, out, N);
+    partial_reduce_kernel<<<(N + 7) / 8, 256, 0, stream>>>(partial, grid, N, out, out, N);
     SB200_CHECK_LAUNCH("partial_reduce_kernel");
     return SB200_OK;
 }
