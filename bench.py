@@ -287,7 +287,11 @@ def run_ours(args):
             "eager": {"ms_per_step": round(ms_eager, 4), "clocks": clocks_eager},
             "roofline": {"kernel": "head_fwd_kernel (fused vocab GEMM + mask + max-pool + log1p)", "bound": "tensor",
                          "achieved": round(achieved, 1), "peak": peak, "unit": "TFLOP/s",
-                         "frac": round(achieved / peak, 4), "traffic": None,
+                         "frac": round(achieved / peak, 4),
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this shape, from the committed
+                         # `ncu --set full` capture (profiles/r01_ncu_full_body_kernels_c2.txt); the algorithmic minimum
+                         # is hidden 31.5 MB + W 23.4 MB + three [B,V] outputs 58.6 MB (part of which is still in L2)
+                         "traffic": 88.0e6 if (wl["shape"] == "mini" and wl["doc_len"] == 256) else None,
                          "peak_source": f"MEASURED_PEAKS.json bf16_tflops burst ({peaks['source']}); sustained figure "
                                         f"{peaks['bf16_tflops_sustained']}",
                          "avg_launch_ms": round(fwd_avg, 4), "flops_per_launch": head_flops,
