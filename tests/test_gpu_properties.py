@@ -28,7 +28,7 @@ def _ops_mod():
     return _OPS["ops"]
 
 
-@settings(max_examples=25, deadline=None)
+@settings(max_examples=25, deadline=None, derandomize=True)
 @given(B=st.integers(1, 9), L=st.integers(1, 300), Hm=st.integers(1, 12), V=st.integers(1, 700), seed=st.integers(0, 10 ** 6),
        mask_kind=st.sampled_from(["prefix", "random", "full", "holes"]), l0=st.booleans(), quantised=st.booleans())
 def test_head_forward_random_shapes_masks_and_ties(ops, B, L, Hm, V, seed, mask_kind, l0, quantised):
@@ -68,7 +68,7 @@ def test_head_forward_random_shapes_masks_and_ties(ops, B, L, Hm, V, seed, mask_
         assert torch.equal(amax.long().cpu()[active], where[active])
 
 
-@settings(max_examples=25, deadline=None)
+@settings(max_examples=25, deadline=None, derandomize=True)
 @given(Nq=st.integers(1, 40), Lq=st.integers(1, 70), V=st.integers(8, 4000), seed=st.integers(0, 10 ** 6))
 def test_idf_query_bit_exact_random(ops, Nq, Lq, V, seed):
     g = torch.Generator().manual_seed(seed)
@@ -79,7 +79,7 @@ def test_idf_query_bit_exact_random(ops, Nq, Lq, V, seed):
     assert torch.equal(got.cpu(), R.idf_query(ids, idf, special))
 
 
-@settings(max_examples=20, deadline=None)
+@settings(max_examples=20, deadline=None, derandomize=True)
 @given(N=st.integers(1, 12), G=st.integers(1, 5), V=st.integers(1, 1500), seed=st.integers(0, 10 ** 6),
        thr=st.one_of(st.none(), st.integers(0, 200)))
 def test_flops_random(ops, N, G, V, seed, thr):
@@ -95,7 +95,7 @@ def test_flops_random(ops, N, G, V, seed, thr):
     torch.testing.assert_close(x.grad.cpu(), xr.grad, rtol=1e-4, atol=1e-7)
 
 
-@settings(max_examples=20, deadline=None)
+@settings(max_examples=20, deadline=None, derandomize=True)
 @given(Nq=st.integers(1, 20), G=st.integers(1, 6), V=st.integers(2, 3000), seed=st.integers(0, 10 ** 6),
        name=st.sampled_from(["infonce", "kldiv", "marginmse"]), in_batch=st.booleans(), dense_q=st.booleans())
 def test_losses_random(ops, Nq, G, V, seed, name, in_batch, dense_q):
@@ -123,7 +123,7 @@ def test_losses_random(ops, Nq, G, V, seed, name, in_batch, dense_q):
     torch.testing.assert_close(dc.grad.cpu(), dr.grad, rtol=1e-3, atol=1e-5 * gs)
 
 
-@settings(max_examples=15, deadline=None)
+@settings(max_examples=15, deadline=None, derandomize=True)
 @given(B=st.integers(1, 20), V=st.integers(1, 5000), seed=st.integers(0, 10 ** 6), density=st.floats(0.0, 1.0))
 def test_compaction_random(ops, B, V, seed, density):
     g = torch.Generator().manual_seed(seed)
