@@ -120,7 +120,8 @@ def build_trainer(wl, regime, device):
                             weight_decay=targs.weight_decay, fused=True, capturable=True)
     sched = torch.optim.lr_scheduler.LambdaLR(
         opt, lambda s: min(1.0, (s + 1) / targs.warmup_steps) * max(0.0, (targs.max_steps - s) / targs.max_steps))
-    return SparseModelTrainer(model_args, data_args, losses, model=model, args=targs, optimizers=(opt, sched))
+    return SparseModelTrainer(model_args, data_args, losses, model=model, args=targs, optimizers=(opt, sched),
+                              grad_sync=getattr(build_trainer, "grad_sync", "ddp"))
 
 
 def host_batch(wl, rank, step):
@@ -165,6 +166,7 @@ def run_ours(args):
     wl = WORKLOADS[args.workload]
     peaks = load_peaks()
     build_trainer.no_fused_body = args.no_fused_body
+    build_trainer.grad_sync = "flat" if args.graph else "ddp"
     trainer = build_trainer(wl, args.regime, device)
     n_pool = 4
     hosts = [host_batch(wl, rank, i) for i in range(n_pool)]
@@ -205,7 +207,7 @@ def run_ours(args):
 
     # ---------------- CUDA-graph capture of the whole step (forward, loss, backward, optimizer)
     graphed = False
-    if args.graph and world == 1:
+    if args.graph:
         trainer.enable_cuda_graph(hosts[0], warmup_steps=3)
         graphed = True
         for i in range(3):
@@ -277,7 +279,9 @@ def run_ours(args):
                        "backbone": f"random-init BertForMaskedLM {wl['shape']} (PyTorch body, bf16 autocast, "
                                    f"{trainer.model_wrapper.sparse_model.fused_layers} LayerNorms on fused sm_100a kernels)",
                        "l2": "no explicit flush: one step touches > 126 MB (activations, fp32 params, AdamW state)",
-                       "launch": "whole step replayed as one CUDA graph" if graphed else "eager launches"},
+                       "launch": ("CUDA graph replay" + (" (fwd+bwd captured, flat grad all-reduce + optimizer after)"
+                                                         if world > 1 else " (whole step)")) if graphed
+                       else "eager launches", "grad_sync": trainer.grad_sync},
             "e2e": {"value": round(e2e, 2), "unit": "samples/s", "h2d_bytes_per_step": batch_bytes(hosts[0]),
                     "d2h_bytes_per_step": 4},
             "gpu_launches": int(round(launches_per_step * args.steps)),
@@ -463,6 +467,9 @@ def run_reference(args):
 
 
 def main():
+    if os.environ.get("SB200_FAULT_TIMEOUT"):
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["SB200_FAULT_TIMEOUT"]), exit=True)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -473,8 +480,8 @@ def main():
                     help="dense = random-init decoder (about all 30522 columns active per doc); trained = decoder bias "
                          "shifted so that a few hundred columns are active, like a trained checkpoint")
     ap.add_argument("--graph", action="store_true",
-                    help="replay the whole step as one CUDA graph (single GPU only; default is eager launches so that "
-                         "every GPU count runs the same code path)")
+                    help="replay the step as a CUDA graph: the whole step on one GPU; forward + backward (incl. the NCCL "
+                         "all-gathers) on several GPUs, followed by one flat gradient all-reduce and the optimizer")
     ap.add_argument("--no-fused-body", action="store_true",
                     help="keep torch.nn.LayerNorm in the backbone (A/B of the fused LayerNorm kernels)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

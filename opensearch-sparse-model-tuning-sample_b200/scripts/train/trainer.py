@@ -49,7 +49,10 @@ class ModelWrapper(torch.nn.Module):
 
 class SparseModelTrainer:
     def __init__(self, model_args, data_args, loss_functions, model=None, args=None, train_dataset=None,
-                 data_collator=None, optimizers=(None, None), accelerator=None, **unused):
+                 data_collator=None, optimizers=(None, None), accelerator=None, grad_sync="ddp", **unused):
+        """grad_sync: "ddp" (torch DistributedDataParallel, bucketed all-reduce overlapped with backward; eager launches)
+        or "flat" (gradients live in one flat fp32 buffer that is all-reduced with a single NCCL call after backward;
+        this is the mode whose forward+backward can be captured in a CUDA graph on several GPUs)."""
         self.model_args = model_args
         self.data_args = data_args
         self.loss_functions = loss_functions
@@ -65,10 +68,14 @@ class SparseModelTrainer:
         wrapper = ModelWrapper(model, model_args.inf_free)
         self.model_wrapper = wrapper
         self.model = wrapper
-        if self.accelerator.num_processes > 1 and next(wrapper.parameters()).is_cuda:
+        self.grad_sync = grad_sync if self.accelerator.num_processes > 1 else "none"
+        self._flat_grads = None
+        if self.grad_sync == "ddp" and next(wrapper.parameters()).is_cuda:
             dev = next(wrapper.parameters()).device
             self.model = torch.nn.parallel.DistributedDataParallel(wrapper, device_ids=[dev.index],
                                                                    gradient_as_bucket_view=True)
+        elif self.grad_sync == "flat":
+            self._setup_flat_grads()
         self.scaler = None
         if args is not None and getattr(args, "fp16", False):
             self.scaler = torch.amp.GradScaler("cuda")
@@ -77,6 +84,7 @@ class SparseModelTrainer:
         self._static_inputs = None
         self._static_loss = None
         self._step_t = None
+        self._after_replay = lambda: None
 
     # ------------------------------------------------------------------ reference attribute, without a per-step sync
     @property
@@ -173,14 +181,43 @@ class SparseModelTrainer:
             return torch.autocast("cuda", dtype=torch.float16)
         return torch.autocast("cuda", dtype=torch.bfloat16)
 
-    def _eager_step_body(self, inputs):
-        """forward (autocast) + loss + backward + optimizer.step, no scheduler / bookkeeping."""
+    def _setup_flat_grads(self):
+        """All parameter gradients become views of one flat fp32 buffer (one all-reduce, static addresses)."""
+        params = [p for p in self.model_wrapper.parameters() if p.requires_grad]
+        total = sum(p.numel() for p in params)
+        self._flat_grads = torch.zeros(total, dtype=torch.float32, device=params[0].device)
+        off = 0
+        for p in params:
+            p.grad = self._flat_grads[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def _zero_grads(self):
+        if self._flat_grads is not None:
+            self._flat_grads.zero_()
+        else:
+            self.optimizer.zero_grad(set_to_none=True)
+
+    def _sync_flat_grads(self):
+        """One NCCL all-reduce of the flat gradient buffer; mean over ranks like DDP (the loss carries x world)."""
+        import torch.distributed as dist
+        dist.all_reduce(self._flat_grads, group=getattr(self.accelerator, "group", None))
+        self._flat_grads.div_(self.accelerator.num_processes)
+
+    def _forward_backward(self, inputs):
+        """forward (autocast) + loss + backward; gradients are left in .grad (not yet synchronised in "flat" mode)."""
         def run(student):
             with self._autocast():
                 return self.model(student)
 
         loss = self.compute_loss(run, inputs)
         loss.backward()
+        return loss
+
+    def _eager_step_body(self, inputs):
+        """forward + loss + backward + gradient sync + optimizer.step, no scheduler / bookkeeping."""
+        loss = self._forward_backward(inputs)
+        if self._flat_grads is not None:
+            self._sync_flat_grads()
         self.optimizer.step()
         return loss
 
@@ -203,9 +240,11 @@ class SparseModelTrainer:
         capturable=True whose lr is a tensor, batches padded to the shapes of `example_inputs`. The regulariser
         warm-up (get_lambda) is computed on the device from an in-graph step counter. Single process only.
         """
-        if self.accelerator.num_processes > 1:
-            raise RuntimeError("CUDA-graph mode is single-process for now: capturing the DDP all-reduce needs the DDP "
-                               "wrapper and its warm-up on the capture side stream; multi-GPU runs launch eagerly")
+        multi = self.accelerator.num_processes > 1
+        if multi and self.grad_sync != "flat":
+            raise RuntimeError('CUDA-graph mode on several GPUs needs grad_sync="flat" (forward + backward, including '
+                               "the NCCL all-gathers of the representations, are captured; the single flat gradient "
+                               "all-reduce and the optimizer step run right after the replay)")
         if self.scaler is not None:
             raise RuntimeError("CUDA-graph mode supports bf16 only (fp16 needs GradScaler's host-side decisions)")
         if self.args is not None and getattr(self.args, "max_grad_norm", None):
@@ -218,26 +257,40 @@ class SparseModelTrainer:
         if self._ema is None:
             self._ema = torch.full((), float(self._ema_host), device=device, dtype=torch.float32)
 
-        def one_step():
-            loss = self._eager_step_body(dict(self._static_inputs))
+        def captured_part():
+            # single GPU: the whole step; several GPUs: forward + backward (the all-reduce follows the replay)
+            if multi:
+                self._zero_grads()
+                loss = self._forward_backward(dict(self._static_inputs))
+            else:
+                loss = self._eager_step_body(dict(self._static_inputs))
             self._step_t += 1.0
             return loss
 
+        def after_replay():
+            if multi:
+                self._sync_flat_grads()
+                self.optimizer.step()
+
+        self._after_replay = after_replay
         side = torch.cuda.Stream(device=device)
         side.wait_stream(torch.cuda.current_stream(device))
         with torch.cuda.stream(side):
             for _ in range(warmup_steps):
-                self.optimizer.zero_grad(set_to_none=True)
-                one_step()
+                if not multi:
+                    self.optimizer.zero_grad(set_to_none=True)
+                captured_part()
+                after_replay()
                 if self.lr_scheduler is not None:
                     self.lr_scheduler.step()
                 self.state.global_step += 1
         torch.cuda.current_stream(device).wait_stream(side)
         torch.cuda.synchronize(device)
         graph = torch.cuda.CUDAGraph()
-        self.optimizer.zero_grad(set_to_none=True)
+        if not multi:
+            self.optimizer.zero_grad(set_to_none=True)
         with torch.cuda.graph(graph):
-            self._static_loss = one_step().detach()
+            self._static_loss = captured_part().detach()
         self._graph = graph
         # the capture itself does not execute; host-side counters stay where the warm-up left them
         return self
@@ -247,11 +300,14 @@ class SparseModelTrainer:
         if self._graph is not None:
             self._copy_into(self._static_inputs, inputs)
             self._graph.replay()
+            self._after_replay()
             if self.lr_scheduler is not None:
                 self.lr_scheduler.step()
             self.state.global_step += 1
             return self._static_loss
         self.model.train()
+        if self._flat_grads is not None:
+            self._flat_grads.zero_()
 
         def run(student):
             with self._autocast():
@@ -260,9 +316,13 @@ class SparseModelTrainer:
         loss = self.compute_loss(run, inputs)
         if self.scaler is not None:
             self.scaler.scale(loss).backward()
+            if self._flat_grads is not None:
+                self._sync_flat_grads()
             self.scaler.unscale_(self.optimizer)
         else:
             loss.backward()
+            if self._flat_grads is not None:
+                self._sync_flat_grads()
         max_norm = getattr(self.args, "max_grad_norm", None) if self.args is not None else None
         if max_norm:
             torch.nn.utils.clip_grad_norm_(self.model.parameters(), max_norm)
@@ -273,7 +333,8 @@ class SparseModelTrainer:
             self.optimizer.step()
         if self.lr_scheduler is not None:
             self.lr_scheduler.step()
-        self.optimizer.zero_grad(set_to_none=True)
+        if self._flat_grads is None:
+            self.optimizer.zero_grad(set_to_none=True)
         self.state.global_step += 1
         return loss.detach()
 
