@@ -208,10 +208,14 @@ def run_ours(args):
     # ---------------- CUDA-graph capture of the whole step (forward, loss, backward, optimizer)
     graphed = False
     if args.graph:
-        trainer.enable_cuda_graph(hosts[0], warmup_steps=3)
-        graphed = True
+        try:
+            trainer.enable_cuda_graph(hosts[0], warmup_steps=3)
+            graphed = True
+        except Exception as exc:  # capture refused (e.g. driver / NCCL combination): keep launching eagerly
+            print(f"[bench] CUDA-graph capture failed, staying eager: {exc!r}", file=sys.stderr, flush=True)
+            trainer._graph = None
         for i in range(3):
-            trainer.training_step(resident[i % n_pool])
+            trainer.training_step(resident[i % n_pool] if graphed else clone_inputs(resident[i % n_pool]))
         barrier()
 
     # ---------------- timed region A: inputs resident in HBM ("value")
@@ -316,6 +320,13 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
+        torch.cuda.synchronize()
+        if graphed:
+            # destroy_process_group() blocks while a CUDA graph that captured NCCL work is alive; the line is out,
+            # every rank is past the barrier: leave without the teardown
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
         dist.destroy_process_group()
 
 
@@ -479,9 +490,11 @@ def main():
     ap.add_argument("--regime", default="dense", choices=["dense", "trained"],
                     help="dense = random-init decoder (about all 30522 columns active per doc); trained = decoder bias "
                          "shifted so that a few hundred columns are active, like a trained checkpoint")
-    ap.add_argument("--graph", action="store_true",
-                    help="replay the step as a CUDA graph: the whole step on one GPU; forward + backward (incl. the NCCL "
-                         "all-gathers) on several GPUs, followed by one flat gradient all-reduce and the optimizer")
+    ap.add_argument("--no-graph", dest="graph", action="store_false",
+                    help="launch every kernel eagerly (torch DDP for the gradients). Default: the step is replayed as a "
+                         "CUDA graph -- the whole step on one GPU; forward + backward (incl. the NCCL all-gathers) on "
+                         "several GPUs, followed by one flat gradient all-reduce and the optimizer")
+    ap.set_defaults(graph=True)
     ap.add_argument("--no-fused-body", action="store_true",
                     help="keep torch.nn.LayerNorm in the backbone (A/B of the fused LayerNorm kernels)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
