@@ -16,7 +16,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _build(V, loss, in_batch, inf_free, single_process=False):
+def _build(V, loss, in_batch, inf_free, single_process=False, grad_sync="ddp", capturable=False):
     import sparse_b200  # noqa: F401
     from sparse_b200.scripts import synthetic
     from sparse_b200.scripts.args import DataTrainingArguments, ModelArguments, TrainingArguments
@@ -33,10 +33,14 @@ def _build(V, loss, in_batch, inf_free, single_process=False):
                                   flops_q_lambda=0.02, flops_q_T=30)
     targs = TrainingArguments(bf16=True, logging_steps=10 ** 9, max_grad_norm=None)
     fns = [LOSS_CLS_MAP[loss](use_in_batch_negatives=in_batch, temperature=1.0)]
-    return SparseModelTrainer(margs, dargs, fns, model=model, args=targs, accelerator=env)
+    opt = None
+    if capturable:
+        opt = torch.optim.AdamW(model.parameters(), lr=torch.tensor(1e-5, device="cuda"), fused=True, capturable=True)
+    return SparseModelTrainer(margs, dargs, fns, model=model, args=targs, accelerator=env, grad_sync=grad_sync,
+                              optimizers=(opt, None))
 
 
-def _worker(rank, world, port, loss, in_batch, inf_free, out):
+def _worker(rank, world, port, loss, in_batch, inf_free, out, grad_sync="ddp"):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
                       LOCAL_RANK=str(rank))
@@ -45,8 +49,8 @@ def _worker(rank, world, port, loss, in_batch, inf_free, out):
     try:
         from sparse_b200.scripts import synthetic
         V, nq, G = 1500, 4, 3
-        tr = _build(V, loss, in_batch, inf_free)
-        assert tr.accelerator.num_processes == world
+        tr = _build(V, loss, in_batch, inf_free, grad_sync=grad_sync, capturable=grad_sync == "flat")
+        assert tr.accelerator.num_processes == world and tr.grad_sync == grad_sync
         batches = [synthetic.train_batch(nq, G, 40, query_len=12, vocab_size=V, seed=70 + r, device="cuda",
                                          with_scores=None if loss == "infonce" else G) for r in range(world)]
 
@@ -55,6 +59,8 @@ def _worker(rank, world, port, loss, in_batch, inf_free, out):
                 return tr.model(student)
         loss_v = tr.compute_loss(run, dict(batches[rank]))
         loss_v.backward()  # DDP averages the gradients
+        if grad_sync == "flat":
+            tr._sync_flat_grads()  # one all-reduce of the flat buffer, mean over ranks
         grads = {n: p.grad.detach().float().clone() for n, p in tr.model_wrapper.named_parameters() if p.grad is not None}
         if rank == 0:
             # single-process global batch with the same weights
@@ -88,23 +94,38 @@ def _worker(rank, world, port, loss, in_batch, inf_free, out):
                     cos = float(torch.nn.functional.cosine_similarity(a, b, dim=0))
                     assert cos > 0.995, (n, cos)
             assert (num / den) ** 0.5 < 3e-2, (num / den) ** 0.5
+        if grad_sync == "flat":
+            # CUDA-graph replay of forward + backward (NCCL all-gathers captured) against eager steps of a twin trainer
+            twin = _build(V, loss, in_batch, inf_free, grad_sync="flat", capturable=True)
+            twin.model_wrapper.load_state_dict(tr.model_wrapper.state_dict())
+            tr.enable_cuda_graph(batches[rank], warmup_steps=2)
+            for _ in range(2):
+                twin.training_step(dict(batches[rank]))
+            for _ in range(3):
+                lg = float(tr.training_step(batches[rank]))
+                le = float(twin.training_step(dict(batches[rank])))
+                assert abs(lg - le) <= 2e-3 * abs(le) + 1e-4, (lg, le)
+            tr._graph = None
         out.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         import traceback
         out.put((rank, traceback.format_exc()[-1500:]))
     finally:
+        if grad_sync == "flat":
+            os._exit(0)  # a process that captured NCCL work in a CUDA graph must not run the NCCL teardown
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("loss,in_batch,inf_free", [("infonce", True, True), ("kldiv", False, False)])
-def test_two_gpu_global_loss_and_gradients(loss, in_batch, inf_free):
+@pytest.mark.parametrize("loss,in_batch,inf_free,grad_sync", [("infonce", True, True, "ddp"), ("kldiv", False, False, "ddp"),
+                                                              ("infonce", True, True, "flat")])
+def test_two_gpu_global_loss_and_gradients(loss, in_batch, inf_free, grad_sync):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, loss, in_batch, inf_free, out)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, loss, in_batch, inf_free, out, grad_sync)) for r in range(2)]
     for p in procs:
         p.start()
     results = [out.get(timeout=120) for _ in procs]
