@@ -237,7 +237,8 @@ class SparseModelTrainer:
 
         The PyTorch backbone issues ~1000 small launches per step and is host-bound in eager mode; replaying a graph
         removes that. Requirements: bf16 (no GradScaler), no gradient clipping, an optimizer built with
-        capturable=True whose lr is a tensor, batches padded to the shapes of `example_inputs`. The regulariser
+        capturable=True whose lr is a tensor, batches padded to the shapes of `example_inputs`, and no live reference
+        to a loss / autograd graph of an earlier eager step (its AccumulateGrad nodes belong to the default stream). The regulariser
         warm-up (get_lambda) is computed on the device from an in-graph step counter. Single process only.
         """
         multi = self.accelerator.num_processes > 1
