@@ -62,8 +62,9 @@ struct HeadFwdParams {
     int LC, S, NC, N;          // chunk length, sequences per tile, chunks per sequence, S*LC
     int n_vtiles, n_groups, kblocks;   // n_vtiles counts tiles of 128 * kCG vocab rows
     int l0;
-    int dbg;                   // bring-up experiments only (0 in production)
-    int b_l_off, b_s_off;      // CTA pair: token / sequence offset of the second CTA's half of the B tile
+    int dbg;                   // bring-up experiments only, 0 in production (flags >> 8: 1 = epilogue loads TMEM but
+                               // skips the arithmetic, 2 = no padded-column skipping); see DESIGN.md 4.1
+    int b_s_off;               // CTA pair, S >= 2: sequence offset of the second CTA's half of the token tile
 };
 
 // Packs the attention mask into per-tile column bitmaps and per-sequence padding info.
@@ -516,10 +517,11 @@ extern "C" int sb200_head_fwd(const void* hidden, const void* W, const float* bi
     if (encode == nullptr) return fail(SB200_ERR_CUDA, "head_fwd: cuTensorMapEncodeTiled unavailable");
 
     // the B box is what ONE CTA loads per stage: the whole token tile, or (CTA pair) half of it
-    int box_l = t.LC, box_s = t.S, b_l_off = 0, b_s_off = 0;
+    // (one sequence per tile: half of the chunk per CTA, the second half's start is chosen per tile in the kernel)
+    int box_l = t.LC, box_s = t.S, b_s_off = 0;
     if (cg == 2) {
         if (t.S >= 2) { box_s = t.S / 2; b_s_off = t.S / 2; }
-        else          { box_l = t.LC / 2; b_l_off = t.LC / 2; }
+        else          { box_l = t.LC / 2; }
     }
     CUtensorMap tmap_w, tmap_h;
     {
@@ -566,7 +568,6 @@ extern "C" int sb200_head_fwd(const void* hidden, const void* W, const float* bi
     p.kblocks = (H + kBlockK - 1) / kBlockK;
     p.l0 = (flags & SB200_HEAD_L0) ? 1 : 0;
     p.dbg = (flags >> 8) & 0xff;
-    p.b_l_off = b_l_off;
     p.b_s_off = b_s_off;
 
     const long long total_units = (long long)p.n_vtiles * p.n_groups;

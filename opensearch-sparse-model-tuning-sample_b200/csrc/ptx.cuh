@@ -1,5 +1,5 @@
 // Thin inline-PTX wrappers for sm_100a: mbarrier, TMA (cp.async.bulk.tensor), tcgen05 (MMA/TMEM).
-// Nothing here is generic; every wrapper is used by head_fwd.cu.
+// Nothing here is generic: the wrappers are exactly what head_fwd.cu (and the bulk row copy of score_loss.cu) use.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -8,16 +8,6 @@ namespace sb200 {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile(
-        "{\n\t.reg .pred P;\n\t"
-        "elect.sync _|P, 0xffffffff;\n\t"
-        "selp.u32 %0, 1, 0, P;\n\t}"
-        : "=r"(pred));
-    return pred != 0;
 }
 
 // ---------------------------------------------------------------- mbarrier
@@ -142,10 +132,7 @@ __host__ __device__ inline uint32_t umma_idesc_bf16(int M, int N) {
     return d;
 }
 
-}  // namespace sb200
-
 // ---------------------------------------------------------------- cluster / cta_group::2 variants
-namespace sb200 {
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
