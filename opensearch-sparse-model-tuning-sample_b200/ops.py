@@ -467,17 +467,15 @@ def colsum(dy):
 
 class LinearFunction(torch.autograd.Function):
     """y = x W^T + b with the library GEMMs of torch (cuBLAS) and the fused column-sum kernel for the bias gradient.
-    Under autocast the operands are cast like torch.nn.functional.linear would (custom_fwd)."""
+    Operands arrive already in the compute dtype (see `linear`)."""
 
     @staticmethod
-    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.bfloat16)
     def forward(ctx, x, weight, bias):
         ctx.save_for_backward(x, weight)
         ctx.has_bias = bias is not None
         return torch.nn.functional.linear(x, weight, bias)
 
     @staticmethod
-    @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, dy):
         x, weight = ctx.saved_tensors
         dy2 = dy.reshape(-1, dy.shape[-1])
@@ -487,9 +485,17 @@ class LinearFunction(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             dw = dy2.t() @ x.reshape(-1, x.shape[-1])
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = colsum(dy2)
+            db = colsum(dy2).to(dy.dtype)
         return dx, dw, db
 
 
 def linear(x, weight, bias):
+    """torch.nn.functional.linear semantics, including autocast: under autocast the operands are cast to the active
+    autocast dtype (bf16 or fp16) exactly like the stock op, and the matmuls run outside the autocast region."""
+    if torch.is_autocast_enabled("cuda"):
+        dt = torch.get_autocast_dtype("cuda")
+        x, weight = x.to(dt), weight.to(dt)
+        bias = None if bias is None else bias.to(dt)
+        with torch.autocast("cuda", enabled=False):
+            return LinearFunction.apply(x, weight, bias)
     return LinearFunction.apply(x, weight, bias)

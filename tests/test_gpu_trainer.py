@@ -214,3 +214,27 @@ def test_sparse_encoder_encode_output_and_flops_metric():
     fl, ql, dl = flops_metric(enc.count_tensor, 6, enc.count_tensor, 6)
     assert fl == pytest.approx(R.search_flops(enc.count_tensor.cpu(), 6, enc.count_tensor.cpu(), 6), rel=1e-6)
     assert dl == pytest.approx(float((rep > 0).sum()) / 6, rel=1e-6) and ql == dl
+
+
+def test_fp16_autocast_training_step_runs():
+    """The reference configs train with fp16 + GradScaler: the same path (fp16 autocast, scaled loss through the custom
+    backward kernels, unscale, step) must run and produce finite parameters."""
+    import sparse_b200  # noqa: F401
+    from sparse_b200.scripts import synthetic
+    from sparse_b200.scripts.args import DataTrainingArguments, ModelArguments, TrainingArguments
+    from sparse_b200.scripts.train.loss import LOSS_CLS_MAP
+    from sparse_b200.scripts.train.trainer import SparseModelTrainer
+    V = 2000
+    model = synthetic.build_sparse_model("mini", vocab_size=V, bias_shift=-0.1, dropout=0.1).cuda()
+    targs = TrainingArguments(fp16=True, learning_rate=1e-4, logging_steps=10 ** 9, max_grad_norm=1.0, max_steps=10)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4)
+    tr = SparseModelTrainer(ModelArguments(inf_free=True), DataTrainingArguments(loss_types=["infonce"], use_in_batch_negatives=True,
+                                                                                 flops_d_lambda=0.05, flops_d_T=10),
+                            [LOSS_CLS_MAP["infonce"](use_in_batch_negatives=True)], model=model, args=targs, optimizers=(opt, None))
+    assert tr.scaler is not None
+    losses = []
+    for i in range(3):
+        batch = synthetic.train_batch(4, 3, 64, query_len=12, vocab_size=V, seed=200 + i, device="cuda")
+        losses.append(float(tr.training_step(batch)))
+    assert all(l == l and abs(l) < 1e6 for l in losses), losses
+    assert all(torch.isfinite(p).all() for p in model.parameters())
