@@ -473,7 +473,8 @@ class LinearFunction(torch.autograd.Function):
     def forward(ctx, x, weight, bias):
         ctx.save_for_backward(x, weight)
         ctx.has_bias = bias is not None
-        return torch.nn.functional.linear(x, weight, bias)
+        # the bias keeps its own (fp32) dtype as an autograd input so that its gradient stays the fp32 column sum
+        return torch.nn.functional.linear(x, weight, None if bias is None else bias.to(x.dtype))
 
     @staticmethod
     def backward(ctx, dy):
@@ -485,7 +486,7 @@ class LinearFunction(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             dw = dy2.t() @ x.reshape(-1, x.shape[-1])
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = colsum(dy2).to(dy.dtype)
+            db = colsum(dy2)
         return dx, dw, db
 
 
@@ -495,7 +496,6 @@ def linear(x, weight, bias):
     if torch.is_autocast_enabled("cuda"):
         dt = torch.get_autocast_dtype("cuda")
         x, weight = x.to(dt), weight.to(dt)
-        bias = None if bias is None else bias.to(dt)
         with torch.autocast("cuda", enabled=False):
             return LinearFunction.apply(x, weight, bias)
     return LinearFunction.apply(x, weight, bias)
