@@ -105,7 +105,8 @@ def build_trainer(wl, regime, device):
 
     shift = TRAINED_BIAS_SHIFT[wl["shape"]] if regime == "trained" else 0.0
     model = synthetic.build_sparse_model(wl["shape"], idf_vector=idf_vector(), use_l0=wl["use_l0"], bias_shift=shift,
-                                         fuse_body=not getattr(build_trainer, "no_fused_body", False))
+                                         fuse_body=not getattr(build_trainer, "no_fused_body", False),
+                                         unpad_capacity=getattr(build_trainer, "unpad_capacity", None))
     model.to(device)
     model_args = ModelArguments(inf_free=True, use_l0=wl["use_l0"])
     data_args = DataTrainingArguments(loss_types=[wl["loss"]], use_in_batch_negatives=wl["in_batch"],
@@ -167,6 +168,7 @@ def run_ours(args):
     peaks = load_peaks()
     build_trainer.no_fused_body = args.no_fused_body
     build_trainer.grad_sync = "flat" if args.graph else "ddp"
+    build_trainer.unpad_capacity = args.unpad_capacity if args.unpad_capacity > 0 else None
     trainer = build_trainer(wl, args.regime, device)
     n_pool = 4
     hosts = [host_batch(wl, rank, i) for i in range(n_pool)]
@@ -274,6 +276,9 @@ def run_ours(args):
         # maximum clock: the matching denominator is the burst cuBLAS figure (kernel timed alone), not the sustained one
         peak = peaks["bf16_tflops"]
         stats = trainer.last_stats
+        overflows = trainer.model_wrapper.sparse_model.unpad_overflows()
+        if overflows:
+            raise SystemExit(f"{overflows} batches did not fit --unpad-capacity {args.unpad_capacity}: numbers invalid")
         line = {
             "metric": "infonce_train_samples_per_sec", "value": round(value, 2), "unit": "samples/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": round(ms_resident / args.steps, 4),
@@ -282,6 +287,7 @@ def run_ours(args):
                        "global_queries": world * nq, "parallelism": f"dp{world}",
                        "backbone": f"random-init BertForMaskedLM {wl['shape']} (PyTorch body, bf16 autocast, "
                                    f"{trainer.model_wrapper.sparse_model.fused_layers} LayerNorms on fused sm_100a kernels)",
+                       "unpad_capacity": args.unpad_capacity if trainer.model_wrapper.sparse_model.__dict__.get("_packed") else None,
                        "l2": "no explicit flush: one step touches > 126 MB (activations, fp32 params, AdamW state)",
                        "launch": ("CUDA graph replay" + (" (fwd+bwd captured, flat grad all-reduce + optimizer after)"
                                                          if world > 1 else " (whole step)")) if graphed
@@ -495,6 +501,9 @@ def main():
                          "CUDA graph -- the whole step on one GPU; forward + backward (incl. the NCCL all-gathers) on "
                          "several GPUs, followed by one flat gradient all-reduce and the optimizer")
     ap.set_defaults(graph=True)
+    ap.add_argument("--unpad-capacity", type=float, default=0.85,
+                    help="padding-free encoder body: real tokens are packed into ceil(capacity * B * L) rows (the synthetic "
+                         "lengths are uniform in [L/2, L], mean 0.75; overflows are counted and fail the run). 0 = padded")
     ap.add_argument("--no-fused-body", action="store_true",
                     help="keep torch.nn.LayerNorm in the backbone (A/B of the fused LayerNorm kernels)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

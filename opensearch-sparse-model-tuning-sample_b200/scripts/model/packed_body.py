@@ -1,0 +1,127 @@
+"""Padding-free execution of a HuggingFace BERT body (the third-party encoder body).
+
+The reference pads every batch to its longest text and runs the whole encoder on the padding (``collator.py:34-41``,
+``sparse_encoders.py:108``). Here the real tokens are packed into one ``[T_cap, H]`` matrix, every row-wise op
+(Linear / GELU / LayerNorm / dropout, incl. the fused sm_100a kernels of ``fused_layers``) runs on packed rows only,
+and attention runs per sequence with the variable-length FlashAttention kernel of the ``flash_attn`` library (library
+code for this task, like cuBLAS). The packed result is scattered back to ``[B, L, H]`` for the fused sparse head.
+The module re-uses the backbone's own sub-modules and parameters: nothing is copied, ``state_dict`` is unchanged.
+
+Shapes are static (CUDA-graph friendly, no host synchronisation): ``T_cap = ceil(capacity * B * L)`` rows; tokens are
+placed with device-side index arithmetic; the filler rows ``[T, T_cap)`` form dummy sequences so that every row stays
+finite. ``capacity = 1.0`` can never overflow; a smaller capacity (chosen from the length distribution of the data)
+also shrinks the GEMMs/elementwise work. An overflow (more real tokens than rows) cannot be handled on the fly without
+a sync: it is recorded in ``overflow_count`` (device counter) and must be checked by the caller (the trainer does at
+its logging steps, ``bench.py`` after the timed region).
+"""
+import math
+
+import torch
+
+try:  # library kernel, optional: without it the padded path of transformers is used
+    from flash_attn import flash_attn_varlen_func
+except Exception:  # pragma: no cover
+    flash_attn_varlen_func = None
+
+
+class _Repad(torch.autograd.Function):
+    """padded[b*L + l] = packed[dest[b, l]]; the backward is a gather through the inverse map (no atomics)."""
+
+    @staticmethod
+    def forward(ctx, packed, dest, src_of, row_valid):
+        ctx.save_for_backward(src_of, row_valid)
+        return packed.index_select(0, dest)
+
+    @staticmethod
+    def backward(ctx, g):
+        src_of, row_valid = ctx.saved_tensors
+        return g.index_select(0, src_of) * row_valid.to(g.dtype).unsqueeze(-1), None, None, None
+
+
+class PackedBertBody:
+    """Callable like ``backbone.bert(input_ids=..., attention_mask=...)[0]`` but padding-free inside. A plain object
+    (not an nn.Module) so that the backbone's parameters are not registered twice."""
+
+    def __init__(self, bert, capacity=1.0):
+        self.bert = bert
+        self.capacity = float(capacity)
+        cfg = bert.config
+        self.num_heads = cfg.num_attention_heads
+        self.head_dim = cfg.hidden_size // cfg.num_attention_heads
+        self.attn_dropout = float(cfg.attention_probs_dropout_prob)
+        self.overflow_count = None  # device int64 counter, created on first use
+
+    @staticmethod
+    def supported(backbone):
+        bert = getattr(backbone, "bert", None)
+        if flash_attn_varlen_func is None or bert is None:
+            return False
+        cfg = bert.config
+        ok_cfg = getattr(cfg, "position_embedding_type", "absolute") == "absolute" and not getattr(cfg, "is_decoder", False)
+        layer = bert.encoder.layer[0]
+        return ok_cfg and hasattr(layer.attention, "self") and hasattr(layer.attention.self, "query") \
+            and (cfg.hidden_size // cfg.num_attention_heads) in (32, 64, 96, 128, 192, 256)
+
+    # ------------------------------------------------------------------------------------------------------------
+    def _plan(self, attention_mask):
+        """Device-side placement of the real tokens: no host sync, static shapes."""
+        B, L = attention_mask.shape
+        t_cap = int(math.ceil(self.capacity * B * L / 8.0) * 8)
+        t_cap = max(8, min(t_cap, B * L))
+        keep = attention_mask.reshape(-1) != 0
+        rank_in_pack = torch.cumsum(keep.to(torch.int32), 0, dtype=torch.int32) - 1       # [B*L]
+        total = rank_in_pack[-1] + 1                                                       # device scalar T
+        fits = keep & (rank_in_pack < t_cap)
+        dest = torch.where(fits, rank_in_pack, torch.full_like(rank_in_pack, t_cap)).long()  # dummy slot t_cap
+        if self.overflow_count is None or self.overflow_count.device != keep.device:
+            self.overflow_count = torch.zeros((), dtype=torch.int64, device=keep.device)
+        self.overflow_count += (total > t_cap).to(torch.int64)
+        # inverse map packed row -> padded position (filler rows point at 0 and are flagged invalid)
+        flat = torch.arange(B * L, device=keep.device)
+        src_of = torch.zeros(t_cap + 1, dtype=torch.long, device=keep.device).scatter_(0, dest, flat)[:t_cap]
+        row_valid = torch.arange(t_cap, device=keep.device) < total
+        # cumulative sequence lengths: B real sequences, then dummy sequences of <= L tokens covering the filler rows
+        lens = attention_mask.ne(0).sum(1, dtype=torch.int32)
+        cu_real = torch.cumsum(lens, 0, dtype=torch.int32).clamp_max(t_cap)
+        n_dummy = (t_cap + L - 1) // L
+        steps = torch.arange(1, n_dummy + 1, device=keep.device, dtype=torch.int32) * L
+        cu_dummy = (torch.minimum(total, torch.tensor(t_cap, device=keep.device, dtype=torch.int32)) + steps).clamp_max(t_cap)
+        cu = torch.cat([torch.zeros(1, dtype=torch.int32, device=keep.device), cu_real, cu_dummy])
+        return t_cap, dest, src_of, row_valid, cu
+
+    def __call__(self, input_ids=None, attention_mask=None, token_type_ids=None, **unused):
+        B, L = input_ids.shape
+        t_cap, dest, src_of, row_valid, cu = self._plan(attention_mask)
+        emb = self.bert.embeddings
+        flat_ids = input_ids.reshape(-1)
+        pos = torch.arange(L, device=input_ids.device).repeat(B)
+        ids_p = torch.zeros(t_cap + 1, dtype=flat_ids.dtype, device=flat_ids.device).scatter_(0, dest, flat_ids)[:t_cap]
+        pos_p = torch.zeros(t_cap + 1, dtype=pos.dtype, device=pos.device).scatter_(0, dest, pos)[:t_cap]
+        if token_type_ids is None:
+            typ_p = torch.zeros_like(ids_p)
+        else:
+            flat_t = token_type_ids.reshape(-1)
+            typ_p = torch.zeros(t_cap + 1, dtype=flat_t.dtype, device=flat_t.device).scatter_(0, dest, flat_t)[:t_cap]
+        x = emb.word_embeddings(ids_p) + emb.token_type_embeddings(typ_p) + emb.position_embeddings(pos_p)
+        x = emb.dropout(emb.LayerNorm(x))
+
+        h, d = self.num_heads, self.head_dim
+        p_drop = self.attn_dropout if self.bert.training else 0.0
+        scale = 1.0 / math.sqrt(d)
+        for layer in self.bert.encoder.layer:
+            att = layer.attention
+            q = att.self.query(x).view(t_cap, h, d)
+            k = att.self.key(x).view(t_cap, h, d)
+            v = att.self.value(x).view(t_cap, h, d)
+            ctx = flash_attn_varlen_func(q, k, v, cu, cu, L, L, dropout_p=p_drop, softmax_scale=scale, causal=False)
+            y = att.output.dropout(att.output.dense(ctx.reshape(t_cap, h * d)))
+            x = att.output.LayerNorm(y + x)
+            y = layer.intermediate(x)
+            y = layer.output.dropout(layer.output.dense(y))
+            x = layer.output.LayerNorm(y + x)
+        return x, (dest.clamp_max(t_cap - 1), src_of, row_valid, (B, L))
+
+    @staticmethod
+    def repad(packed, plan):
+        dest, src_of, row_valid, (B, L) = plan
+        return _Repad.apply(packed, dest, src_of, row_valid).view(B, L, packed.shape[-1])

@@ -102,10 +102,12 @@ class _PruneFunction(torch.autograd.Function):
 
 class SparseModel(torch.nn.Module):
     def __init__(self, model_id, idf=None, tokenizer_id=None, idf_requires_grad=False, prune_ratio=None,
-                 preprocess_func=None, use_l0=True, backbone=None, tokenizer=None, fuse_body=True):
+                 preprocess_func=None, use_l0=True, backbone=None, tokenizer=None, fuse_body=True, unpad_capacity=None):
         """Arguments as in the reference (:43-52). ``backbone``/``tokenizer`` may be passed pre-built (offline use:
         random-init architectures, tests, benchmarks); otherwise they are loaded with transformers as upstream.
-        ``fuse_body`` swaps the backbone's LayerNorm modules for the fused sm_100a kernels (same parameters)."""
+        ``fuse_body`` swaps the backbone's LayerNorm / Linear modules for the fused sm_100a kernels (same parameters).
+        ``unpad_capacity`` (None = off) runs a BERT body padding-free under autocast: real tokens are packed into
+        ceil(capacity * B * L) rows (see packed_body.py; 1.0 never overflows, smaller values must cover the data)."""
         super().__init__()
         import transformers
         if backbone is None:
@@ -117,6 +119,11 @@ class SparseModel(torch.nn.Module):
         if fuse_body:
             from .fused_layers import fuse_backbone
             self.fused_layers = fuse_backbone(self.backbone)
+        self.__dict__["_packed"] = None  # kept out of the module tree: it only references the backbone's modules
+        if unpad_capacity is not None:
+            from .packed_body import PackedBertBody
+            if PackedBertBody.supported(self.backbone):
+                self.__dict__["_packed"] = PackedBertBody(self.backbone.bert, unpad_capacity)
         self.tokenizer = tokenizer
         if preprocess_func is not None:
             func = getattr(TextPreProcessors, preprocess_func)
@@ -159,8 +166,20 @@ class SparseModel(torch.nn.Module):
         """Runs the backbone up to the decoder input: -> (hidden [B,L,H], decoder Linear)."""
         if self._split is None:
             self._split = _split_mlm_backbone(self.backbone)
+        packed = self.__dict__.get("_packed")
+        ids = features.get("input_ids")
+        if packed is not None and ids is not None and ids.is_cuda and torch.is_autocast_enabled("cuda"):
+            from .packed_body import PackedBertBody
+            x, plan = packed(**features)                       # [T_cap, H] real tokens only
+            hidden = self._split.transform(x)                  # head transform on packed rows
+            return PackedBertBody.repad(hidden, plan), self._split.decoder
         seq = self._split.body(**features)[0]
         return self._split.transform(seq), self._split.decoder
+
+    def unpad_overflows(self):
+        """Number of batches whose real tokens did not fit the packed capacity so far (synchronises); 0 when off."""
+        packed = self.__dict__.get("_packed")
+        return 0 if packed is None or packed.overflow_count is None else int(packed.overflow_count)
 
     # -- reference API -------------------------------------------------------------------------------------------
     def forward(self, inf_free=False, **kwargs):

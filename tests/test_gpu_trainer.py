@@ -238,3 +238,42 @@ def test_fp16_autocast_training_step_runs():
         losses.append(float(tr.training_step(batch)))
     assert all(l == l and abs(l) < 1e6 for l in losses), losses
     assert all(torch.isfinite(p).all() for p in model.parameters())
+
+
+@pytest.mark.parametrize("capacity,mask_kind", [(1.0, "prefix"), (0.9, "prefix"), (1.0, "holes")])
+def test_padding_free_body_matches_padded_body(capacity, mask_kind):
+    """The packed (unpadded, flash-attn varlen) body gives the same sparse vectors and gradients as the padded
+    transformers body on the real tokens."""
+    import sparse_b200  # noqa: F401
+    from sparse_b200.scripts import synthetic
+    V = 2000
+    kw = dict(vocab_size=V, seed=1, dropout=0.0, bias_shift=-0.2)
+    packed = synthetic.build_sparse_model("mini", unpad_capacity=capacity, **kw).cuda()
+    padded = synthetic.build_sparse_model("mini", **kw).cuda()
+    if packed.__dict__["_packed"] is None:
+        pytest.skip("flash_attn varlen kernels unavailable")
+    assert packed.state_dict().keys() == padded.state_dict().keys()
+    padded.load_state_dict(packed.state_dict())
+    feats = synthetic.token_batch(12, 96, seed=2, vocab_size=V, device="cuda")
+    if mask_kind == "holes":
+        feats["attention_mask"][:, 5::7] = 0
+    g = torch.Generator(device="cuda").manual_seed(0)
+    w = torch.randn(12, V, device="cuda", generator=g)
+    outs = []
+    for m in (packed, padded):
+        m.zero_grad()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            rep = m(inf_free=False, **feats)
+        (rep * w).sum().backward()
+        outs.append((rep.detach().float().cpu(), m.backbone.bert.encoder.layer[0].intermediate.dense.weight.grad.float().cpu(),
+                     m.backbone.bert.embeddings.word_embeddings.weight.grad.float().cpu()))
+    assert packed.unpad_overflows() == 0
+    torch.testing.assert_close(outs[0][0], outs[1][0], rtol=5e-2, atol=5e-2)   # bf16 bodies, different attention kernels
+    for a, b in zip(outs[0][1:], outs[1][1:]):
+        cos = torch.nn.functional.cosine_similarity(a.flatten(), b.flatten(), dim=0)
+        assert float(cos) > 0.99, float(cos)
+    # a capacity that is too small is detected, not silently accepted
+    tight = synthetic.build_sparse_model("mini", unpad_capacity=0.3, **kw).cuda()
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        tight(inf_free=False, **feats)
+    assert tight.unpad_overflows() == 1
