@@ -85,7 +85,7 @@ class PackedBertBody:
         cu_real = torch.cumsum(lens, 0, dtype=torch.int32).clamp_max(t_cap)
         n_dummy = (t_cap + L - 1) // L
         steps = torch.arange(1, n_dummy + 1, device=keep.device, dtype=torch.int32) * L
-        cu_dummy = (torch.minimum(total, torch.tensor(t_cap, device=keep.device, dtype=torch.int32)) + steps).clamp_max(t_cap)
+        cu_dummy = (total.clamp_max(t_cap) + steps).clamp_max(t_cap)   # (no host scalar -> tensor copies: graph capture)
         cu = torch.cat([torch.zeros(1, dtype=torch.int32, device=keep.device), cu_real, cu_dummy])
         return t_cap, dest, src_of, row_valid, cu
 
