@@ -180,6 +180,28 @@ int sb200_layer_norm_bwd(const void* x, const void* dy, int elem_bytes, const fl
                          const float* rstd, int R, int H, void* dx, float* dgamma, float* dbeta, void* workspace,
                          size_t workspace_bytes, sb200_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Residual tail of a transformer block: out = LayerNorm(dropout(y) + resid), delivered as fp32 and as bf16.
+ *   replaces transformers BertSelfOutput.forward / BertOutput.forward (dropout, residual add, LayerNorm) as run by
+ *   the backbone call at scripts/model/sparse_encoders.py:108 under bf16 autocast, plus the fp32->bf16 casts autocast
+ *   inserts in front of the following Linear layers, and the matching autograd chain.
+ *   y        bf16 [R, H]   branch output (before dropout)
+ *   resid    f32  [R, H]   residual stream, or NULL (plain LayerNorm of dropout(y))
+ *   drop_seed  device pointer to one 64-bit seed, or NULL / drop_p == 0 for no dropout. The keep mask is a pure
+ *            function of (seed, element index) (Philox4x32-10) and is regenerated by the backward call: pass the
+ *            same seed and drop_p.
+ *   out_f32 / out_bf16   either may be NULL (not both); out_bf16 = round-to-nearest of out_f32
+ *   mean, rstd  f32 [R]    saved statistics
+ * Backward: g_f32 / g_bf16 = gradients w.r.t. the two outputs (either NULL, summed in fp32); writes d_y (bf16),
+ * d_resid (f32, may be NULL), dgamma / dbeta (f32 [H], deterministic order); workspace as sb200_layer_norm_bwd. */
+int sb200_add_layer_norm_fwd(const void* y, const float* resid, const float* gamma, const float* beta, int R, int H,
+                             float eps, const void* drop_seed, float drop_p, float* out_f32, void* out_bf16,
+                             float* mean, float* rstd, sb200_stream_t stream);
+int sb200_add_layer_norm_bwd(const void* y, const float* resid, const float* g_f32, const void* g_bf16,
+                             const float* gamma, const float* mean, const float* rstd, int R, int H,
+                             const void* drop_seed, float drop_p, void* d_y, float* d_resid, float* dgamma,
+                             float* dbeta, void* workspace, size_t workspace_bytes, sb200_stream_t stream);
+
 /* Column sums of a row-major [R, N] matrix (bf16 or fp32): out[c] = sum_r dy[r,c]. The bias gradient of the body's
  * Linear layers (replaces the torch reduce kernel behind addmm's backward). N % 8 == 0, N <= 4096. */
 int sb200_colsum_supported(int N);

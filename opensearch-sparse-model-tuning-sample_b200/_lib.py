@@ -46,6 +46,9 @@ _PROTOTYPES = {
     "sb200_layer_norm_fwd": (_c_int, [_vp, _c_int, _vp, _vp, _c_int, _c_int, _c_f, _vp, _vp, _vp, _vp]),
     "sb200_layer_norm_bwd_workspace_bytes": (_sz, [_c_int, _c_int]),
     "sb200_layer_norm_bwd": (_c_int, [_vp, _vp, _c_int, _vp, _vp, _vp, _c_int, _c_int, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "sb200_add_layer_norm_fwd": (_c_int, [_vp, _vp, _vp, _vp, _c_int, _c_int, _c_f, _vp, _c_f, _vp, _vp, _vp, _vp, _vp]),
+    "sb200_add_layer_norm_bwd": (_c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _vp, _c_f, _vp, _vp, _vp,
+                                          _vp, _vp, _sz, _vp]),
     "sb200_colsum_supported": (_c_int, [_c_int]),
     "sb200_colsum_workspace_bytes": (_sz, [_c_int, _c_int]),
     "sb200_colsum": (_c_int, [_vp, _c_int, _c_int, _c_int, _vp, _vp, _sz, _vp]),

@@ -230,6 +230,219 @@ int launch_bwd(const void* x, const void* g, const float* gamma, const float* me
     return SB200_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ residual tail
+// out = LayerNorm(dropout(y) + resid) of a transformer block, with the activation delivered twice: fp32 (the residual
+// stream autocast keeps in fp32) and bf16 (the operand of the next GEMM). Replaces, per block tail, five PyTorch
+// kernels forward (dropout, bf16+fp32 add, LayerNorm, up to three fp32->bf16 casts of the same activation) and the
+// matching backward chain (cast-backs, gradient adds, LayerNorm backward, dropout mask multiply). Values are those
+// of the stock autocast sequence: dropout result rounded to bf16, add / statistics / affine in fp32, bf16 copy =
+// round-to-nearest of the fp32 output. The dropout mask is never stored: Philox4x32-10 keyed by a device-resident
+// 64-bit seed and the element index regenerates it in the backward pass.
+struct Philox {
+    uint32_t k0, k1;
+    __device__ __forceinline__ void operator()(uint32_t c0, uint32_t c1, uint32_t (&out)[4]) const {
+        uint32_t c2 = 0u, c3 = 0u, a = k0, b = k1;
+#pragma unroll
+        for (int round = 0; round < 10; ++round) {
+            const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+            const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+            c0 = hi1 ^ c1 ^ a; c1 = lo1; c2 = hi0 ^ c3 ^ b; c3 = lo0;
+            a += 0x9E3779B9u; b += 0xBB67AE85u;
+        }
+        out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+    }
+};
+
+__device__ __forceinline__ float round_bf16(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+struct DropCfg {
+    const unsigned long long* seed;  // device pointer, nullptr = no dropout
+    uint32_t threshold;              // drop when the 32-bit draw < threshold (= p * 2^32)
+    float scale;                     // 1 / (1 - p)
+};
+
+// branch row r, vector k of this lane: s = dropout(y) + resid (fp32)
+template <int NV>
+__device__ __forceinline__ void load_branch_sum(const __nv_bfloat16* __restrict__ y, const float* __restrict__ resid, int r,
+                                                int lane, bool drop, const Philox& rng, const DropCfg& dc,
+                                                float (&s)[NV][4], uint32_t& keep_bits) {
+    constexpr int H = NV * 128;
+    keep_bits = 0xffffffffu;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const int c = (lane + 32 * k) * 4;
+        Vec4<__nv_bfloat16>::load(y + size_t(r) * H + c, s[k]);
+        if (drop) {
+            uint32_t rnd[4];
+            const unsigned long long e = (static_cast<unsigned long long>(r) * H + c) >> 2;
+            rng(static_cast<uint32_t>(e), static_cast<uint32_t>(e >> 32), rnd);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const bool keep = rnd[i] >= dc.threshold;
+                if (!keep) keep_bits &= ~(1u << (k * 4 + i));
+                s[k][i] = keep ? round_bf16(s[k][i] * dc.scale) : 0.f;
+            }
+        }
+        if (resid != nullptr) {
+            float x[4];
+            Vec4<float>::load(resid + size_t(r) * H + c, x);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) s[k][i] += x[i];
+        }
+    }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(kLnThreads)
+add_ln_fwd_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ resid, const float* __restrict__ gamma,
+                  const float* __restrict__ beta, int R, float eps, DropCfg dc, float* __restrict__ out32,
+                  __nv_bfloat16* __restrict__ out16, float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+    constexpr int H = NV * 128;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float gm[NV][4], bt[NV][4];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        Vec4<float>::load(gamma + (lane + 32 * k) * 4, gm[k]);
+        Vec4<float>::load(beta + (lane + 32 * k) * 4, bt[k]);
+    }
+    const bool drop = dc.seed != nullptr;
+    Philox rng{0u, 0u};
+    if (drop) {
+        const unsigned long long sd = __ldg(dc.seed);
+        rng.k0 = static_cast<uint32_t>(sd);
+        rng.k1 = static_cast<uint32_t>(sd >> 32);
+    }
+    for (int r = blockIdx.x * kLnWarps + warp; r < R; r += gridDim.x * kLnWarps) {
+        float v[NV][4];
+        uint32_t keep_bits;
+        load_branch_sum<NV>(y, resid, r, lane, drop, rng, dc, v, keep_bits);
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) s += (v[k][0] + v[k][1]) + (v[k][2] + v[k][3]);
+        const float mean = warp_sum(s) * (1.f / H);
+        float q = 0.f;
+#pragma unroll
+        for (int k = 0; k < NV; ++k)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float dlt = v[k][i] - mean;
+                q = fmaf(dlt, dlt, q);
+            }
+        const float rstd = rsqrtf(warp_sum(q) * (1.f / H) + eps);
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            float o[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o[i] = fmaf((v[k][i] - mean) * rstd, gm[k][i], bt[k][i]);
+            const size_t off = size_t(r) * H + (lane + 32 * k) * 4;
+            if (out32 != nullptr) Vec4<float>::store(out32 + off, o);
+            if (out16 != nullptr) Vec4<__nv_bfloat16>::store(out16 + off, o);
+        }
+        if (lane == 0) {
+            mean_out[r] = mean;
+            rstd_out[r] = rstd;
+        }
+    }
+}
+
+// Gradient of the tail. g32 / g16 are the gradients that arrived at the fp32 and the bf16 copy of the output (either
+// may be null); they are summed in fp32. ds (gradient of dropout(y) + resid) leaves as d_resid (fp32) and, through
+// the regenerated dropout mask, as d_y (bf16).
+template <int NV>
+__global__ void __launch_bounds__(kLnThreads)
+add_ln_bwd_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ resid, const float* __restrict__ g32,
+                  const __nv_bfloat16* __restrict__ g16, const float* __restrict__ gamma,
+                  const float* __restrict__ mean_in, const float* __restrict__ rstd_in, int R, DropCfg dc,
+                  __nv_bfloat16* __restrict__ dy, float* __restrict__ dresid, float* __restrict__ partial) {
+    constexpr int H = NV * 128;
+    __shared__ float red[kLnWarps][H];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float gm[NV][4], dg[NV][4], db[NV][4];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        Vec4<float>::load(gamma + (lane + 32 * k) * 4, gm[k]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dg[k][i] = db[k][i] = 0.f;
+    }
+    const bool drop = dc.seed != nullptr;
+    Philox rng{0u, 0u};
+    if (drop) {
+        const unsigned long long sd = __ldg(dc.seed);
+        rng.k0 = static_cast<uint32_t>(sd);
+        rng.k1 = static_cast<uint32_t>(sd >> 32);
+    }
+    for (int r = blockIdx.x * kLnWarps + warp; r < R; r += gridDim.x * kLnWarps) {
+        const float mean = __ldg(mean_in + r), rstd = __ldg(rstd_in + r);
+        float xh[NV][4], gy[NV][4];
+        uint32_t keep_bits;
+        load_branch_sum<NV>(y, resid, r, lane, drop, rng, dc, xh, keep_bits);
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const size_t off = size_t(r) * H + (lane + 32 * k) * 4;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) gy[k][i] = 0.f;
+            if (g32 != nullptr) Vec4<float>::load(g32 + off, gy[k]);
+            if (g16 != nullptr) {
+                float t[4];
+                Vec4<__nv_bfloat16>::load(g16 + off, t);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) gy[k][i] += t[i];
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                xh[k][i] = (xh[k][i] - mean) * rstd;
+                dg[k][i] = fmaf(gy[k][i], xh[k][i], dg[k][i]);
+                db[k][i] += gy[k][i];
+                gy[k][i] *= gm[k][i];
+                s1 += gy[k][i];
+                s2 = fmaf(gy[k][i], xh[k][i], s2);
+            }
+        }
+        s1 = warp_sum(s1) * (1.f / H);
+        s2 = warp_sum(s2) * (1.f / H);
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const size_t off = size_t(r) * H + (lane + 32 * k) * 4;
+            float o[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o[i] = rstd * (gy[k][i] - s1 - xh[k][i] * s2);
+            if (dresid != nullptr) Vec4<float>::store(dresid + off, o);
+            if (drop) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    o[i] = ((keep_bits >> (k * 4 + i)) & 1u) ? round_bf16(o[i]) * dc.scale : 0.f;
+            }
+            Vec4<__nv_bfloat16>::store(dy + off, o);
+        }
+    }
+    float* out = partial + size_t(blockIdx.x) * 2 * H;
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < NV; ++k)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) red[warp][(lane + 32 * k) * 4 + i] = pass == 0 ? dg[k][i] : db[k][i];
+        __syncthreads();
+        for (int c = threadIdx.x; c < H; c += kLnThreads) {
+            float s = 0.f;
+#pragma unroll
+            for (int w = 0; w < kLnWarps; ++w) s += red[w][c];
+            out[pass * H + c] = s;
+        }
+    }
+}
+
+DropCfg make_drop(const void* seed, float p) {
+    DropCfg dc;
+    dc.seed = (seed != nullptr && p > 0.f) ? static_cast<const unsigned long long*>(seed) : nullptr;
+    const double t = double(p) * 4294967296.0;
+    dc.threshold = t >= 4294967295.0 ? 0xffffffffu : static_cast<uint32_t>(t);
+    dc.scale = p < 1.f ? 1.f / (1.f - p) : 0.f;
+    return dc;
+}
+
 bool ln_supported(int H) {
     const int nv = H / 128;
     return H % 128 == 0 && (nv == 1 || nv == 2 || nv == 3 || nv == 4 || nv == 6 || nv == 8);
@@ -271,6 +484,63 @@ extern "C" int sb200_layer_norm_bwd(const void* x, const void* dy, int elem_byte
     int rc = elem_bytes == 2 ? launch_bwd<__nv_bfloat16>(x, dy, gamma, mean, rstd, R, H, dx, partial, grid, stream)
                              : launch_bwd<float>(x, dy, gamma, mean, rstd, R, H, dx, partial, grid, stream);
     if (rc != SB200_OK) return rc;
+    partial_reduce_kernel<<<(2 * H + 7) / 8, 256, 0, stream>>>(partial, grid, 2 * H, dgamma, dbeta, H);
+    SB200_CHECK_LAUNCH("partial_reduce_kernel");
+    return SB200_OK;
+}
+
+extern "C" int sb200_add_layer_norm_fwd(const void* y, const float* resid, const float* gamma, const float* beta, int R,
+                                        int H, float eps, const void* drop_seed, float drop_p, float* out_f32,
+                                        void* out_bf16, float* mean, float* rstd, sb200_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    SB200_REQUIRE(y && gamma && beta && mean && rstd && (out_f32 || out_bf16), "add_layer_norm_fwd: null pointer");
+    SB200_REQUIRE(R >= 1 && ln_supported(H), "add_layer_norm_fwd: unsupported shape R=%d H=%d", R, H);
+    SB200_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "add_layer_norm_fwd: drop_p=%f", double(drop_p));
+    const DropCfg dc = make_drop(drop_seed, drop_p);
+    const __nv_bfloat16* yi = static_cast<const __nv_bfloat16*>(y);
+    __nv_bfloat16* o16 = static_cast<__nv_bfloat16*>(out_bf16);
+    const int grid = ln_grid(R);
+#define SB200_ALN_CASE(NV_)                                                                                           \
+    case NV_:                                                                                                         \
+        add_ln_fwd_kernel<NV_><<<grid, kLnThreads, 0, stream>>>(yi, resid, gamma, beta, R, eps, dc, out_f32, o16, mean, rstd); \
+        break;
+    switch (H / 128) {
+        SB200_ALN_CASE(1) SB200_ALN_CASE(2) SB200_ALN_CASE(3) SB200_ALN_CASE(4) SB200_ALN_CASE(6) SB200_ALN_CASE(8)
+        default: return fail(SB200_ERR_ARG, "add_layer_norm_fwd: unsupported H=%d", H);
+    }
+#undef SB200_ALN_CASE
+    SB200_CHECK_LAUNCH("add_ln_fwd_kernel");
+    return SB200_OK;
+}
+
+extern "C" int sb200_add_layer_norm_bwd(const void* y, const float* resid, const float* g_f32, const void* g_bf16,
+                                        const float* gamma, const float* mean, const float* rstd, int R, int H,
+                                        const void* drop_seed, float drop_p, void* d_y, float* d_resid, float* dgamma,
+                                        float* dbeta, void* workspace, size_t workspace_bytes, sb200_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    SB200_REQUIRE(y && gamma && mean && rstd && d_y && dgamma && dbeta && (g_f32 || g_bf16),
+                  "add_layer_norm_bwd: null pointer");
+    SB200_REQUIRE(R >= 1 && ln_supported(H), "add_layer_norm_bwd: unsupported shape R=%d H=%d", R, H);
+    SB200_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "add_layer_norm_bwd: drop_p=%f", double(drop_p));
+    if (workspace == nullptr || workspace_bytes < sb200_layer_norm_bwd_workspace_bytes(R, H))
+        return fail(SB200_ERR_WORKSPACE, "add_layer_norm_bwd: workspace too small");
+    const DropCfg dc = make_drop(drop_seed, drop_p);
+    const __nv_bfloat16* yi = static_cast<const __nv_bfloat16*>(y);
+    const __nv_bfloat16* g16 = static_cast<const __nv_bfloat16*>(g_bf16);
+    __nv_bfloat16* dyo = static_cast<__nv_bfloat16*>(d_y);
+    float* partial = static_cast<float*>(workspace);
+    const int grid = ln_grid(R);
+#define SB200_ALN_CASE(NV_)                                                                                           \
+    case NV_:                                                                                                         \
+        add_ln_bwd_kernel<NV_><<<grid, kLnThreads, 0, stream>>>(yi, resid, g_f32, g16, gamma, mean, rstd, R, dc, dyo, \
+                                                                d_resid, partial);                                    \
+        break;
+    switch (H / 128) {
+        SB200_ALN_CASE(1) SB200_ALN_CASE(2) SB200_ALN_CASE(3) SB200_ALN_CASE(4) SB200_ALN_CASE(6) SB200_ALN_CASE(8)
+        default: return fail(SB200_ERR_ARG, "add_layer_norm_bwd: unsupported H=%d", H);
+    }
+#undef SB200_ALN_CASE
+    SB200_CHECK_LAUNCH("add_ln_bwd_kernel");
     partial_reduce_kernel<<<(2 * H + 7) / 8, 256, 0, stream>>>(partial, grid, 2 * H, dgamma, dbeta, H);
     SB200_CHECK_LAUNCH("partial_reduce_kernel");
     return SB200_OK;
@@ -359,6 +629,15 @@ colsum_partial_kernel(const T* __restrict__ dy, int R, int N, float* __restrict_
     }
 }
 
+// 16-byte vectors per lane: the smallest instantiated count that covers N columns (lanes past N/8 are masked)
+int colsum_nv(int N) {
+    const int need = (N / 8 + 31) / 32;
+    const int have[] = {1, 2, 3, 4, 6, 8, 12, 16};
+    for (int v : have)
+        if (v >= need) return v;
+    return 0;
+}
+
 int colsum_grid(int R) {
     int g = 2 * num_sms();
     const int need = (R + kCsWarps - 1) / kCsWarps;
@@ -369,10 +648,10 @@ template <typename T>
 int launch_colsum(const void* dy, int R, int N, float* partial, int grid, cudaStream_t stream) {
     const T* p = static_cast<const T*>(dy);
     const size_t smem = size_t(kCsWarps) * N * sizeof(float);
-    const int nv = (N / 8 + 31) / 32;
+    const int nv = colsum_nv(N);
 #define SB200_CS_CASE(NV_)                                                                                          \
     case NV_:                                                                                                       \
-        if (smem > 48 * 1024 && !device_flag_test_and_set(8 + (NV_ == 16 ? 1 : 0) + (sizeof(T) == 4 ? 2 : 0)))                                                       \
+        if (smem > 48 * 1024 && !device_flag_test_and_set(8 + (NV_ == 16 ? 2 : (NV_ == 12 ? 1 : 0)) + (sizeof(T) == 4 ? 3 : 0)))                                                       \
             SB200_CUDA(cudaFuncSetAttribute(colsum_partial_kernel<T, NV_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                             int(kCsWarps * 4096 * sizeof(float))));                                 \
         colsum_partial_kernel<T, NV_><<<grid, kCsWarps * 32, smem, stream>>>(p, R, N, partial);                     \
@@ -388,9 +667,7 @@ int launch_colsum(const void* dy, int R, int N, float* partial, int grid, cudaSt
 }
 
 bool colsum_supported(int N) {
-    if (N < 8 || N % 8 != 0 || N > 4096) return false;
-    const int nv = (N / 8 + 31) / 32;
-    return nv == 1 || nv == 2 || nv == 3 || nv == 4 || nv == 6 || nv == 8 || nv == 12 || nv == 16;
+    return N >= 8 && N % 8 == 0 && N <= 4096;
 }
 
 }  // namespace

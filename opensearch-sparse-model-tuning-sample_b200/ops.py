@@ -444,6 +444,83 @@ def layer_norm(x, gamma, beta, eps=1e-12):
     return LayerNormFunction.apply(x, gamma, beta, eps)
 
 
+def add_layer_norm_forward(y, resid, gamma, beta, eps, seed=None, p=0.0, want_f32=True, want_bf16=True):
+    """Raw forward of the fused block tail LayerNorm(dropout(y) + resid): returns (out_f32, out_bf16, mean, rstd).
+    y bf16 [..., H]; resid fp32 or None; seed: int64 device tensor (1 element) or None."""
+    _need_cuda(y, resid, gamma, beta, seed)
+    H = y.shape[-1]
+    R = y.numel() // H
+    dev = y.device
+    out32 = torch.empty(y.shape, dtype=torch.float32, device=dev) if want_f32 else None
+    out16 = torch.empty(y.shape, dtype=torch.bfloat16, device=dev) if want_bf16 else None
+    mean = torch.empty(R, dtype=torch.float32, device=dev)
+    rstd = torch.empty(R, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        code = _lib.load().sb200_add_layer_norm_fwd(_ptr(y), _ptr(resid), _ptr(gamma), _ptr(beta), R, H, float(eps),
+                                                    _ptr(seed), float(p), _ptr(out32), _ptr(out16), _ptr(mean),
+                                                    _ptr(rstd), _stream())
+    _lib.check(code, "sb200_add_layer_norm_fwd")
+    return out32, out16, mean, rstd
+
+
+class AddLayerNormFunction(torch.autograd.Function):
+    """(out_f32, out_bf16) = LayerNorm(dropout(y) + resid): the tail of a BERT attention / feed-forward block
+    (transformers BertSelfOutput / BertOutput) under bf16 autocast, with the next GEMM's bf16 operand produced by
+    the same kernel. The dropout mask is regenerated from `seed` in the backward pass."""
+
+    @staticmethod
+    def forward(ctx, y, resid, gamma, beta, eps, seed, p, want_f32):
+        ctx.set_materialize_grads(False)
+        yc = y.detach()
+        if yc.dtype != torch.bfloat16:
+            raise TypeError("add_layer_norm: the branch output must be bf16 (run the body under bf16 autocast)")
+        yc = yc.contiguous()
+        rc = None if resid is None else resid.detach().float().contiguous()
+        g32 = gamma.detach().float().contiguous()
+        b32 = beta.detach().float().contiguous()
+        out32, out16, mean, rstd = add_layer_norm_forward(yc, rc, g32, b32, eps, seed, p, want_f32=want_f32)
+        ctx.save_for_backward(yc, rc, g32, mean, rstd, seed)
+        ctx.p = float(p)
+        ctx.dtypes = (gamma.dtype, beta.dtype, None if resid is None else resid.dtype)
+        return out32, out16
+
+    @staticmethod
+    def backward(ctx, g32_out, g16_out):
+        yc, rc, gam, mean, rstd, seed = ctx.saved_tensors
+        if g32_out is None and g16_out is None:
+            return (None,) * 8
+        H = yc.shape[-1]
+        R = yc.numel() // H
+        dev = yc.device
+        if g32_out is not None:
+            g32_out = g32_out.float().contiguous()
+        if g16_out is not None:
+            g16_out = g16_out.to(torch.bfloat16).contiguous()
+        dy = torch.empty_like(yc)
+        dres = torch.empty(yc.shape, dtype=torch.float32, device=dev) if rc is not None else None
+        dgamma = torch.empty(H, dtype=torch.float32, device=dev)
+        dbeta = torch.empty(H, dtype=torch.float32, device=dev)
+        lib = _lib.load()
+        ws = _workspace(lib.sb200_layer_norm_bwd_workspace_bytes(R, H), dev)
+        with torch.cuda.device(dev):
+            code = lib.sb200_add_layer_norm_bwd(_ptr(yc), _ptr(rc), _ptr(g32_out), _ptr(g16_out), _ptr(gam), _ptr(mean),
+                                                _ptr(rstd), R, H, _ptr(seed), ctx.p, _ptr(dy), _ptr(dres), _ptr(dgamma),
+                                                _ptr(dbeta), _ptr(ws), ws.numel(), _stream())
+        _lib.check(code, "sb200_add_layer_norm_bwd")
+        gd, bd, rd = ctx.dtypes
+        return dy, (None if dres is None else dres.to(rd)), dgamma.to(gd), dbeta.to(bd), None, None, None, None
+
+
+def add_layer_norm(y, resid, gamma, beta, eps=1e-12, p=0.0, training=False, want_f32=True):
+    """LayerNorm(dropout(y, p) + resid) -> (fp32 output or None, bf16 output). Dropout only when training and p > 0:
+    a fresh 64-bit seed is drawn on the device from torch's CUDA generator (CUDA-graph safe: the generator's
+    offset is advanced by the graph on every replay)."""
+    seed = None
+    if training and p > 0.0:
+        seed = torch.randint(-2 ** 62, 2 ** 62, (1,), dtype=torch.int64, device=y.device)
+    return AddLayerNormFunction.apply(y, resid, gamma, beta, eps, seed, float(p) if seed is not None else 0.0, want_f32)
+
+
 # --------------------------------------------------------------------------------------------- encoder body: Linear
 def colsum_supported(n):
     return bool(_lib.load().sb200_colsum_supported(int(n)))

@@ -4,7 +4,8 @@ The reference pads every batch to its longest text and runs the whole encoder on
 ``sparse_encoders.py:108``). Here the real tokens are packed into one ``[T_cap, H]`` matrix, every row-wise op
 (Linear / GELU / LayerNorm / dropout, incl. the fused sm_100a kernels of ``fused_layers``) runs on packed rows only,
 and attention runs per sequence with the variable-length FlashAttention kernel of the ``flash_attn`` library (library
-code for this task, like cuBLAS). The packed result is scattered back to ``[B, L, H]`` for the fused sparse head.
+code for this task, like cuBLAS). Each block tail (dropout + residual add + LayerNorm + the bf16 cast for the next GEMM) is one sm_100a kernel
+(``ops.add_layer_norm``). The packed result is scattered back to ``[B, L, H]`` for the fused sparse head.
 The module re-uses the backbone's own sub-modules and parameters: nothing is copied, ``state_dict`` is unchanged.
 
 Shapes are static (CUDA-graph friendly, no host synchronisation): ``T_cap = ceil(capacity * B * L)`` rows; tokens are
@@ -18,10 +19,12 @@ import math
 
 import torch
 
+from ... import ops
+
 try:  # library kernel, optional: without it the padded path of transformers is used
-    from flash_attn import flash_attn_varlen_func
+    from flash_attn import flash_attn_varlen_qkvpacked_func
 except Exception:  # pragma: no cover
-    flash_attn_varlen_func = None
+    flash_attn_varlen_qkvpacked_func = None
 
 
 class _Repad(torch.autograd.Function):
@@ -54,13 +57,14 @@ class PackedBertBody:
     @staticmethod
     def supported(backbone):
         bert = getattr(backbone, "bert", None)
-        if flash_attn_varlen_func is None or bert is None:
+        if flash_attn_varlen_qkvpacked_func is None or bert is None:
             return False
         cfg = bert.config
         ok_cfg = getattr(cfg, "position_embedding_type", "absolute") == "absolute" and not getattr(cfg, "is_decoder", False)
         layer = bert.encoder.layer[0]
         return ok_cfg and hasattr(layer.attention, "self") and hasattr(layer.attention.self, "query") \
-            and (cfg.hidden_size // cfg.num_attention_heads) in (32, 64, 96, 128, 192, 256)
+            and (cfg.hidden_size // cfg.num_attention_heads) in (32, 64, 96, 128, 192, 256) \
+            and ops.layer_norm_supported(cfg.hidden_size)
 
     # ------------------------------------------------------------------------------------------------------------
     def _plan(self, attention_mask):
@@ -89,7 +93,12 @@ class PackedBertBody:
         cu = torch.cat([torch.zeros(1, dtype=torch.int32, device=keep.device), cu_real, cu_dummy])
         return t_cap, dest, src_of, row_valid, cu
 
-    def __call__(self, input_ids=None, attention_mask=None, token_type_ids=None, **unused):
+    def __call__(self, input_ids=None, attention_mask=None, token_type_ids=None, head_transform=None, **unused):
+        """Returns (bf16 [T_cap, H] packed activations, plan). With `head_transform` (transformers
+        BertPredictionHeadTransform) the MLM head transform (dense + activation + LayerNorm) is applied as well.
+        Must run under bf16 autocast. Per block: one QKV GEMM on the concatenated projection weights, varlen
+        FlashAttention on the packed qkv, and the fused dropout + residual + LayerNorm tail of `ops.add_layer_norm`
+        that hands the next GEMM its bf16 operand (no separate cast / add / dropout kernels)."""
         B, L = input_ids.shape
         t_cap, dest, src_of, row_valid, cu = self._plan(attention_mask)
         emb = self.bert.embeddings
@@ -102,24 +111,34 @@ class PackedBertBody:
         else:
             flat_t = token_type_ids.reshape(-1)
             typ_p = torch.zeros(t_cap + 1, dtype=flat_t.dtype, device=flat_t.device).scatter_(0, dest, flat_t)[:t_cap]
-        x = emb.word_embeddings(ids_p) + emb.token_type_embeddings(typ_p) + emb.position_embeddings(pos_p)
-        x = emb.dropout(emb.LayerNorm(x))
+        x32 = emb.word_embeddings(ids_p) + emb.token_type_embeddings(typ_p) + emb.position_embeddings(pos_p)
+        x32 = emb.dropout(emb.LayerNorm(x32)).float()
+        x16 = x32.to(torch.bfloat16)
 
         h, d = self.num_heads, self.head_dim
-        p_drop = self.attn_dropout if self.bert.training else 0.0
+        training = self.bert.training
+        p_att = self.attn_dropout if training else 0.0
         scale = 1.0 / math.sqrt(d)
-        for layer in self.bert.encoder.layer:
-            att = layer.attention
-            q = att.self.query(x).view(t_cap, h, d)
-            k = att.self.key(x).view(t_cap, h, d)
-            v = att.self.value(x).view(t_cap, h, d)
-            ctx = flash_attn_varlen_func(q, k, v, cu, cu, L, L, dropout_p=p_drop, softmax_scale=scale, causal=False)
-            y = att.output.dropout(att.output.dense(ctx.reshape(t_cap, h * d)))
-            x = att.output.LayerNorm(y + x)
-            y = layer.intermediate(x)
-            y = layer.output.dropout(layer.output.dense(y))
-            x = layer.output.LayerNorm(y + x)
-        return x, (dest.clamp_max(t_cap - 1), src_of, row_valid, (B, L))
+        layers = self.bert.encoder.layer
+        for li, layer in enumerate(layers):
+            att, sa = layer.attention, layer.attention.self
+            w_qkv = torch.cat([sa.query.weight, sa.key.weight, sa.value.weight], 0)
+            b_qkv = torch.cat([sa.query.bias, sa.key.bias, sa.value.bias], 0)
+            qkv = ops.linear(x16, w_qkv, b_qkv).view(t_cap, 3, h, d)
+            ctx = flash_attn_varlen_qkvpacked_func(qkv, cu, L, dropout_p=p_att, softmax_scale=scale, causal=False)
+            y = att.output.dense(ctx.reshape(t_cap, h * d))
+            ln = att.output.LayerNorm
+            x32, x16 = ops.add_layer_norm(y, x32, ln.weight, ln.bias, ln.eps, p=att.output.dropout.p, training=training)
+            y = layer.output.dense(layer.intermediate(x16))
+            ln = layer.output.LayerNorm
+            last = li == len(layers) - 1           # nothing reads the fp32 stream after the last block
+            x32, x16 = ops.add_layer_norm(y, x32, ln.weight, ln.bias, ln.eps, p=layer.output.dropout.p,
+                                          training=training, want_f32=not last)
+        if head_transform is not None:
+            y = head_transform.transform_act_fn(head_transform.dense(x16))
+            ln = head_transform.LayerNorm
+            _, x16 = ops.add_layer_norm(y, None, ln.weight, ln.bias, ln.eps, want_f32=False)
+        return x16, (dest.clamp_max(t_cap - 1), src_of, row_valid, (B, L))
 
     @staticmethod
     def repad(packed, plan):

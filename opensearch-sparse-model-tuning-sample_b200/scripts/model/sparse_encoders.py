@@ -168,10 +168,11 @@ class SparseModel(torch.nn.Module):
             self._split = _split_mlm_backbone(self.backbone)
         packed = self.__dict__.get("_packed")
         ids = features.get("input_ids")
-        if packed is not None and ids is not None and ids.is_cuda and torch.is_autocast_enabled("cuda"):
+        if packed is not None and ids is not None and ids.is_cuda and torch.is_autocast_enabled("cuda") \
+                and torch.get_autocast_dtype("cuda") == torch.bfloat16:
             from .packed_body import PackedBertBody
-            x, plan = packed(**features)                       # [T_cap, H] real tokens only
-            hidden = self._split.transform(x)                  # head transform on packed rows
+            # [T_cap, H] bf16, real tokens only, MLM head transform included
+            hidden, plan = packed(head_transform=self.backbone.cls.predictions.transform, **features)
             return PackedBertBody.repad(hidden, plan), self._split.decoder
         seq = self._split.body(**features)[0]
         return self._split.transform(seq), self._split.decoder

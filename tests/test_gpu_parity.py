@@ -379,6 +379,88 @@ def test_fused_layer_norm_vs_torch(ops, R, H, dtype):
     torch.testing.assert_close(bc.grad.cpu(), br.grad, rtol=1e-4, atol=1e-3 * float(br.grad.abs().max()))
 
 
+@pytest.mark.parametrize("R,H,with_resid", [(37, 128, True), (4096, 384, True), (1000, 768, True), (513, 1024, False),
+                                            (8, 256, True), (300, 512, False)])
+def test_add_layer_norm_vs_torch(ops, R, H, with_resid):
+    """Fused block tail without dropout against the stock autocast sequence (bf16 branch + fp32 residual -> fp32
+    LayerNorm -> bf16 copy), forward and backward with gradients arriving at both copies."""
+    g = torch.Generator().manual_seed(R * 7 + H)
+    y = (torch.randn(R, H, generator=g) * 1.5).bfloat16()
+    resid = torch.randn(R, H, generator=g) * 2 + 0.5 if with_resid else None
+    gamma = torch.randn(H, generator=g) * 0.5 + 1
+    beta = torch.randn(H, generator=g) * 0.3
+    g32 = torch.randn(R, H, generator=g)
+    g16 = torch.randn(R, H, generator=g).bfloat16()
+    yc = cuda(y).requires_grad_(True)
+    rc = cuda(resid).requires_grad_(True) if with_resid else None
+    gc, bc = cuda(gamma).requires_grad_(True), cuda(beta).requires_grad_(True)
+    o32, o16 = ops.add_layer_norm(yc, rc, gc, bc, 1e-12)
+    assert o32.dtype == torch.float32 and o16.dtype == torch.bfloat16
+    assert torch.equal(o16, o32.bfloat16())
+    torch.autograd.backward([o32, o16], [cuda(g32), cuda(g16)])
+    yr = y.float().requires_grad_(True)
+    rr = resid.clone().requires_grad_(True) if with_resid else None
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    outr = torch.nn.functional.layer_norm(yr + rr if with_resid else yr, (H,), gr, br, 1e-12)
+    outr.backward(g32 + g16.float())
+    torch.testing.assert_close(o32.cpu(), outr, rtol=1e-5, atol=1e-5)
+    assert yc.grad.dtype == torch.bfloat16
+    torch.testing.assert_close(yc.grad.float().cpu(), yr.grad.bfloat16().float(), rtol=1e-2, atol=1e-5)  # 1 bf16 ulp
+    if with_resid:
+        torch.testing.assert_close(rc.grad.cpu(), rr.grad, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(gc.grad.cpu(), gr.grad, rtol=1e-4, atol=1e-3 * float(gr.grad.abs().max()))
+    torch.testing.assert_close(bc.grad.cpu(), br.grad, rtol=1e-4, atol=1e-3 * float(br.grad.abs().max()))
+    # only one of the two copies consumed (the other gradient is absent, not zero-filled)
+    for which in (0, 1):
+        yc.grad = None
+        outs = ops.add_layer_norm(yc, rc, gc, bc, 1e-12)
+        outs[which].backward(cuda(g32) if which == 0 else cuda(g16))
+        yr.grad = None
+        outr = torch.nn.functional.layer_norm(yr + rr if with_resid else yr, (H,), gr, br, 1e-12)
+        outr.backward(g32 if which == 0 else g16.float())
+        torch.testing.assert_close(yc.grad.float().cpu(), yr.grad.bfloat16().float(), rtol=1e-2, atol=1e-5)
+    # bf16-only output
+    none32, only16 = ops.add_layer_norm(yc, rc, gc, bc, 1e-12, want_f32=False)
+    assert none32 is None and torch.equal(only16, o16)
+
+
+@pytest.mark.parametrize("p", [0.1, 0.5])
+def test_add_layer_norm_dropout(ops, p):
+    """In-kernel Philox dropout: keep rate, scaling, rounding like torch's bf16 dropout, and a backward pass that
+    regenerates exactly the forward mask."""
+    R, H = 2048, 384
+    g = torch.Generator().manual_seed(5)
+    y = (torch.randn(R, H, generator=g) + 3.0).bfloat16()          # far from zero: the mask is readable from the sum
+    gamma = torch.randn(H, generator=g) * 0.5 + 1
+    beta = torch.randn(H, generator=g) * 0.3
+    seed = torch.tensor([123456789012345], dtype=torch.int64, device="cuda")
+    yc, gc, bc = cuda(y), cuda(gamma), cuda(beta)
+    o32, o16, mean, rstd = ops.add_layer_norm_forward(yc, None, gc, bc, 1e-12, seed=seed, p=p)
+    s = (o32 - bc) / gc / rstd[:, None] + mean[:, None]             # dropout(y) recovered from the output
+    keep = s.abs() > 0.5
+    rate = float(keep.float().mean())
+    assert abs(rate - (1 - p)) < 4 * (p * (1 - p) / (R * H)) ** 0.5 + 1e-3, rate
+    expect = torch.where(keep, (yc.float() / (1 - p)).bfloat16().float(), torch.zeros_like(s))
+    torch.testing.assert_close(s, expect, rtol=2e-3, atol=2e-3)
+    # rows and columns are not correlated (a counter bug would repeat the mask)
+    assert float((keep[0] == keep[1]).float().mean()) < 0.95 if p == 0.5 else True
+    # same seed -> same mask; different seed -> different mask
+    again = ops.add_layer_norm_forward(yc, None, gc, bc, 1e-12, seed=seed, p=p)[0]
+    assert torch.equal(again, o32)
+    other = ops.add_layer_norm_forward(yc, None, gc, bc, 1e-12, seed=seed + 1, p=p)[0]
+    assert not torch.equal(other, o32)
+    # backward against autograd through the recovered mask
+    g16 = cuda(torch.randn(R, H, generator=g).bfloat16())
+    yg = yc.clone().requires_grad_(True)
+    out = ops.AddLayerNormFunction.apply(yg, None, gc, bc, 1e-12, seed, p, False)[1]
+    out.backward(g16)
+    yr = yc.float().requires_grad_(True)
+    outr = torch.nn.functional.layer_norm(yr * keep / (1 - p), (H,), gc, bc, 1e-12)
+    outr.backward(g16.float())
+    assert torch.equal(yg.grad == 0, ~keep | (yr.grad == 0))
+    torch.testing.assert_close(yg.grad.float(), yr.grad, rtol=2e-2, atol=1e-4)
+
+
 def test_fused_backbone_matches_unfused(ops):
     from sparse_b200.scripts import synthetic
     V = 2000
