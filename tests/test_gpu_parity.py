@@ -430,7 +430,7 @@ def test_add_layer_norm_dropout(ops, p):
     regenerates exactly the forward mask."""
     R, H = 2048, 384
     g = torch.Generator().manual_seed(5)
-    y = (torch.randn(R, H, generator=g) + 3.0).bfloat16()          # far from zero: the mask is readable from the sum
+    y = (torch.randn(R, H, generator=g) * 0.3 + 3.0).bfloat16()    # far from zero: the mask is readable from the sum
     gamma = torch.randn(H, generator=g) * 0.5 + 1
     beta = torch.randn(H, generator=g) * 0.3
     seed = torch.tensor([123456789012345], dtype=torch.int64, device="cuda")
@@ -455,10 +455,10 @@ def test_add_layer_norm_dropout(ops, p):
     out = ops.AddLayerNormFunction.apply(yg, None, gc, bc, 1e-12, seed, p, False)[1]
     out.backward(g16)
     yr = yc.float().requires_grad_(True)
-    outr = torch.nn.functional.layer_norm(yr * keep / (1 - p), (H,), gc, bc, 1e-12)
+    outr = torch.nn.functional.layer_norm((yr / (1 - p)).bfloat16().float() * keep, (H,), gc, bc, 1e-12)
     outr.backward(g16.float())
     assert torch.equal(yg.grad == 0, ~keep | (yr.grad == 0))
-    torch.testing.assert_close(yg.grad.float(), yr.grad, rtol=2e-2, atol=1e-4)
+    torch.testing.assert_close(yg.grad.float(), yr.grad, rtol=2e-2, atol=2e-4)
 
 
 def test_fused_backbone_matches_unfused(ops):
