@@ -202,6 +202,30 @@ int sb200_add_layer_norm_bwd(const void* y, const float* resid, const float* g_f
                              const void* drop_seed, float drop_p, void* d_y, float* d_resid, float* dgamma,
                              float* dbeta, void* workspace, size_t workspace_bytes, sb200_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Exact GELU y = x * Phi(x) on bf16 and its backward fused with the bias gradient of the Linear in front of it:
+ *   replaces transformers BertIntermediate.intermediate_act_fn / BertPredictionHeadTransform.transform_act_fn
+ *   (torch.nn.functional.gelu) inside the backbone call at scripts/model/sparse_encoders.py:108, its autograd
+ *   backward, and the bias-gradient reduction of the preceding torch.nn.Linear.
+ *   x, y, dy, dx  bf16 [R, N] (gelu_fwd: any n % 8 == 0 elements);  colsum f32 [N] = sum_r dx[r, :] or NULL.
+ *   N % 8 == 0, N <= 4096 for the backward. Phi via erfc (Abramowitz-Stegun 7.1.26, |error| <= 1.5e-7). */
+int sb200_gelu_fwd(const void* x, size_t n, void* y, sb200_stream_t stream);
+size_t sb200_gelu_bwd_workspace_bytes(int R, int N);
+int sb200_gelu_bwd(const void* x, const void* dy, int R, int N, void* dx, float* colsum, void* workspace,
+                   size_t workspace_bytes, sb200_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Input embeddings of the body on (packed) token rows and the gradient scatter into the three tables:
+ *   replaces transformers BertEmbeddings.forward (word + token-type + position lookups and their sum) inside the
+ *   backbone call at scripts/model/sparse_encoders.py:108 and the three embedding_dense_backward pipelines.
+ *   ids, pos, typ  int64 [n] (clamped to the table sizes);  W [nW, H], P [nP, H], T [nT, H] fp32;  out, g fp32 [n, H]
+ *   out[t] = (W[ids[t]] + T[typ[t]]) + P[pos[t]].   Backward ADDS into dW / dP / dT (caller zeroes them); tokens with
+ *   ids == pad_idx (torch.nn.Embedding padding_idx, -1 = none) leave dW untouched. H % 4 == 0. */
+int sb200_embed_sum_fwd(const int64_t* ids, const int64_t* pos, const int64_t* typ, const float* W, const float* P,
+                        const float* T, int n, int H, int nW, int nP, int nT, float* out, sb200_stream_t stream);
+int sb200_embed_sum_bwd(const int64_t* ids, const int64_t* pos, const int64_t* typ, const float* g, int n, int H,
+                        int nW, int nP, int nT, int pad_idx, float* dW, float* dP, float* dT, sb200_stream_t stream);
+
 /* Column sums of a row-major [R, N] matrix (bf16 or fp32): out[c] = sum_r dy[r,c]. The bias gradient of the body's
  * Linear layers (replaces the torch reduce kernel behind addmm's backward). N % 8 == 0, N <= 4096. */
 int sb200_colsum_supported(int N);

@@ -49,6 +49,11 @@ _PROTOTYPES = {
     "sb200_add_layer_norm_fwd": (_c_int, [_vp, _vp, _vp, _vp, _c_int, _c_int, _c_f, _vp, _c_f, _vp, _vp, _vp, _vp, _vp]),
     "sb200_add_layer_norm_bwd": (_c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _vp, _c_f, _vp, _vp, _vp,
                                           _vp, _vp, _sz, _vp]),
+    "sb200_gelu_fwd": (_c_int, [_vp, _sz, _vp, _vp]),
+    "sb200_gelu_bwd_workspace_bytes": (_sz, [_c_int, _c_int]),
+    "sb200_gelu_bwd": (_c_int, [_vp, _vp, _c_int, _c_int, _vp, _vp, _vp, _sz, _vp]),
+    "sb200_embed_sum_fwd": (_c_int, [_vp] * 6 + [_c_int] * 5 + [_vp, _vp]),
+    "sb200_embed_sum_bwd": (_c_int, [_vp] * 4 + [_c_int] * 6 + [_vp] * 4),
     "sb200_colsum_supported": (_c_int, [_c_int]),
     "sb200_colsum_workspace_bytes": (_sz, [_c_int, _c_int]),
     "sb200_colsum": (_c_int, [_vp, _c_int, _c_int, _c_int, _vp, _vp, _sz, _vp]),

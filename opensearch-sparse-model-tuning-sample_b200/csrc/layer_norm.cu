@@ -293,7 +293,7 @@ __device__ __forceinline__ void load_branch_sum(const __nv_bfloat16* __restrict_
 }
 
 template <int NV>
-__global__ void __launch_bounds__(kLnThreads)
+__global__ void __launch_bounds__(kLnThreads, NV <= 3 ? 4 : (NV <= 4 ? 3 : 2))
 add_ln_fwd_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ resid, const float* __restrict__ gamma,
                   const float* __restrict__ beta, int R, float eps, DropCfg dc, float* __restrict__ out32,
                   __nv_bfloat16* __restrict__ out16, float* __restrict__ mean_out, float* __restrict__ rstd_out) {
@@ -349,7 +349,7 @@ add_ln_fwd_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__
 // may be null); they are summed in fp32. ds (gradient of dropout(y) + resid) leaves as d_resid (fp32) and, through
 // the regenerated dropout mask, as d_y (bf16).
 template <int NV>
-__global__ void __launch_bounds__(kLnThreads)
+__global__ void __launch_bounds__(kLnThreads, NV <= 3 ? 3 : (NV <= 4 ? 2 : 1))
 add_ln_bwd_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ resid, const float* __restrict__ g32,
                   const __nv_bfloat16* __restrict__ g16, const float* __restrict__ gamma,
                   const float* __restrict__ mean_in, const float* __restrict__ rstd_in, int R, DropCfg dc,
@@ -434,6 +434,13 @@ add_ln_bwd_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__
     }
 }
 
+// one wave of resident blocks (the kernels are latency-bound: every resident warp counts, a second wave only adds a tail)
+int tail_grid(int R, int blocks_per_sm) {
+    const int g = blocks_per_sm * num_sms();
+    const int need = (R + kLnWarps - 1) / kLnWarps;
+    return g < need ? g : need;
+}
+
 DropCfg make_drop(const void* seed, float p) {
     DropCfg dc;
     dc.seed = (seed != nullptr && p > 0.f) ? static_cast<const unsigned long long*>(seed) : nullptr;
@@ -499,7 +506,7 @@ extern "C" int sb200_add_layer_norm_fwd(const void* y, const float* resid, const
     const DropCfg dc = make_drop(drop_seed, drop_p);
     const __nv_bfloat16* yi = static_cast<const __nv_bfloat16*>(y);
     __nv_bfloat16* o16 = static_cast<__nv_bfloat16*>(out_bf16);
-    const int grid = ln_grid(R);
+    const int grid = tail_grid(R, H / 128 <= 3 ? 4 : (H / 128 <= 4 ? 3 : 2));
 #define SB200_ALN_CASE(NV_)                                                                                           \
     case NV_:                                                                                                         \
         add_ln_fwd_kernel<NV_><<<grid, kLnThreads, 0, stream>>>(yi, resid, gamma, beta, R, eps, dc, out_f32, o16, mean, rstd); \
@@ -529,7 +536,7 @@ extern "C" int sb200_add_layer_norm_bwd(const void* y, const float* resid, const
     const __nv_bfloat16* g16 = static_cast<const __nv_bfloat16*>(g_bf16);
     __nv_bfloat16* dyo = static_cast<__nv_bfloat16*>(d_y);
     float* partial = static_cast<float*>(workspace);
-    const int grid = ln_grid(R);
+    const int grid = tail_grid(R, H / 128 <= 3 ? 3 : (H / 128 <= 4 ? 2 : 1));  // <= ln_grid(R): workspace rows
 #define SB200_ALN_CASE(NV_)                                                                                           \
     case NV_:                                                                                                         \
         add_ln_bwd_kernel<NV_><<<grid, kLnThreads, 0, stream>>>(yi, resid, g_f32, g16, gamma, mean, rstd, R, dc, dyo, \
@@ -696,5 +703,205 @@ extern "C" int sb200_colsum(const void* dy, int elem_bytes, int R, int N, float*
     if (rc != SB200_OK) return rc;
     partial_reduce_kernel<<<(N + 7) / 8, 256, 0, stream>>>(partial, grid, N, out, out, N);
     SB200_CHECK_LAUNCH("partial_reduce_kernel");
+    return SB200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ GELU
+// y = x * Phi(x) (the exact "gelu" of transformers' BertIntermediate / BertPredictionHeadTransform) on bf16 rows, and
+// its backward fused with the bias gradient of the Linear in front of it: dx = dy * (Phi(x) + x * phi(x)),
+// db[c] = sum_r dx[r, c]. Phi through erfc by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below bf16
+// resolution; one ex2 and one rcp per element instead of erff's long polynomial, which keeps both kernels
+// HBM-bound: forward 4 B/element, backward 6 B/element).
+namespace sb200 {
+namespace {
+
+// ~15 issue slots per element (the first version, with __expf / __frcp_rn and their special-case paths, needed 37
+// and made both kernels issue-bound at the speed of PyTorch's erff kernels: 53.5 M elements per call).
+__device__ __forceinline__ float ex2_approx(float v) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ float rcp_approx(float v) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+
+__device__ __forceinline__ void gelu_terms(float x, float& cdf, float& pdf_x) {
+    const float e = ex2_approx(x * x * -0.72134752044448170f);               // exp(-x^2 / 2)
+    const float t = rcp_approx(fmaf(0.23164189798f, fabsf(x), 1.f));         // 1 / (1 + 0.3275911 * |x| / sqrt 2)
+    float p = fmaf(0.5307027145f, t, -0.7265760135f);                        // 0.5 * A&S coefficients
+    p = fmaf(p, t, 0.7107068705f);
+    p = fmaf(p, t, -0.142248368f);
+    p = fmaf(p, t, 0.127414796f);
+    const float half_erfc = p * t * e;                                       // 0.5 * erfc(|x| / sqrt 2)
+    cdf = 0.5f + copysignf(0.5f - half_erfc, x);                             // Phi(x) = 1 - Phi(-x)
+    pdf_x = x * e * 0.39894228040143268f;                                    // x * phi(x)
+}
+
+__device__ __forceinline__ void unpack8(const uint4& raw, float (&v)[8]) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 f = __bfloat1622float2(h[i]);
+        v[2 * i] = f.x;
+        v[2 * i + 1] = f.y;
+    }
+}
+__device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
+    uint4 raw;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    return raw;
+}
+
+constexpr int kGeluThreads = 256;
+constexpr int kGeluUnroll = 4;  // 16-byte vectors in flight per thread
+
+__global__ void __launch_bounds__(kGeluThreads)
+gelu_fwd_kernel(const uint4* __restrict__ x, size_t nvec, uint4* __restrict__ y) {
+    const size_t stride = size_t(gridDim.x) * kGeluThreads;
+    for (size_t base = size_t(blockIdx.x) * kGeluThreads + threadIdx.x; base < nvec; base += stride * kGeluUnroll) {
+        uint4 raw[kGeluUnroll];
+#pragma unroll
+        for (int u = 0; u < kGeluUnroll; ++u)
+            if (base + u * stride < nvec) raw[u] = __ldg(x + base + u * stride);
+#pragma unroll
+        for (int u = 0; u < kGeluUnroll; ++u) {
+            if (base + u * stride >= nvec) continue;
+            float v[8];
+            unpack8(raw[u], v);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float cdf, px;
+                gelu_terms(v[i], cdf, px);
+                v[i] *= cdf;
+            }
+            y[base + u * stride] = pack8(v);
+        }
+    }
+}
+
+// Each warp owns one 256-column slab (blockIdx.y; a lane's 16-byte vector = 8 columns) and walks rows with kGbRows
+// of them in flight: few registers (8 bias-gradient accumulators per lane), all blocks resident, 2*kGbRows 16-byte
+// loads outstanding per lane. (A first version with one warp per full row kept N/32 accumulators per lane: 104
+// registers, 25 % occupancy, 3.4 TB/s.)
+constexpr int kGbRows = 4;
+
+template <bool kColsum>
+__global__ void __launch_bounds__(kCsWarps * 32, 4)
+gelu_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy, int R, int N,
+                __nv_bfloat16* __restrict__ dx, float* __restrict__ partial /* [gridDim.x][N] */) {
+    __shared__ float red[kCsWarps][256];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int col = blockIdx.y * 256 + lane * 8;
+    const bool live = col < N;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    const int stride = gridDim.x * kCsWarps;
+    for (int r = blockIdx.x * kCsWarps + warp; r < R; r += kGbRows * stride) {
+        uint4 xr[kGbRows], gr[kGbRows];
+#pragma unroll
+        for (int u = 0; u < kGbRows; ++u) {
+            const int rr = r + u * stride;
+            const bool ok = live && rr < R;
+            xr[u] = ok ? __ldg(reinterpret_cast<const uint4*>(x + size_t(rr) * N + col)) : make_uint4(0u, 0u, 0u, 0u);
+            gr[u] = ok ? __ldg(reinterpret_cast<const uint4*>(dy + size_t(rr) * N + col)) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int u = 0; u < kGbRows; ++u) {
+            const int rr = r + u * stride;
+            float xv[8], gv[8];
+            unpack8(xr[u], xv);
+            unpack8(gr[u], gv);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float cdf, px;
+                gelu_terms(xv[i], cdf, px);
+                gv[i] *= cdf + px;
+            }
+            const uint4 out = pack8(gv);
+            if (live && rr < R) *reinterpret_cast<uint4*>(dx + size_t(rr) * N + col) = out;
+            if (kColsum) {
+                // the bias gradient sums the bf16 values the GEMMs will read, like the unfused path
+                // (rows past R contribute gelu'(0) * 0 = 0)
+                unpack8(out, gv);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[i] += gv[i];
+            }
+        }
+    }
+    if (!kColsum) return;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[warp][lane * 8 + i] = acc[i];
+    __syncthreads();
+    const int c = threadIdx.x;  // 256 threads = 256 columns of the slab
+    if (blockIdx.y * 256 + c < N) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < kCsWarps; ++w) s += red[w][c];
+        partial[size_t(blockIdx.x) * N + blockIdx.y * 256 + c] = s;
+    }
+}
+
+int gelu_bwd_row_blocks(int R, int N) {
+    const int nslab = (N + 255) / 256;
+    int gx = (4 * num_sms() + nslab - 1) / nslab;          // ~4 resident blocks per SM in total
+    const int need = (R + kCsWarps - 1) / kCsWarps;
+    if (gx > need) gx = need;
+    const int cap = colsum_grid(R);                          // the workspace is sized for this many partial rows
+    return gx < cap ? (gx < 1 ? 1 : gx) : cap;
+}
+
+}  // namespace
+}  // namespace sb200
+
+extern "C" int sb200_gelu_fwd(const void* x, size_t n, void* y, sb200_stream_t stream_) {
+    using namespace sb200;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    SB200_REQUIRE(x && y, "gelu_fwd: null pointer");
+    SB200_REQUIRE(n >= 8 && n % 8 == 0, "gelu_fwd: n=%zu must be a positive multiple of 8", n);
+    const size_t nvec = n / 8;
+    const size_t per_block = size_t(kGeluThreads) * kGeluUnroll;
+    size_t grid = (nvec + per_block - 1) / per_block;
+    const size_t cap = size_t(num_sms()) * 8;
+    if (grid > cap) grid = cap;
+    gelu_fwd_kernel<<<int(grid), kGeluThreads, 0, stream>>>(static_cast<const uint4*>(x), nvec, static_cast<uint4*>(y));
+    SB200_CHECK_LAUNCH("gelu_fwd_kernel");
+    return SB200_OK;
+}
+
+extern "C" size_t sb200_gelu_bwd_workspace_bytes(int R, int N) { return sb200_colsum_workspace_bytes(R, N); }
+
+extern "C" int sb200_gelu_bwd(const void* x, const void* dy, int R, int N, void* dx, float* colsum, void* workspace,
+                              size_t workspace_bytes, sb200_stream_t stream_) {
+    using namespace sb200;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    SB200_REQUIRE(x && dy && dx, "gelu_bwd: null pointer");
+    SB200_REQUIRE(R >= 1 && colsum_supported(N), "gelu_bwd: unsupported shape R=%d N=%d", R, N);
+    float* partial = nullptr;
+    if (colsum != nullptr) {
+        if (workspace == nullptr || workspace_bytes < sb200_gelu_bwd_workspace_bytes(R, N))
+            return fail(SB200_ERR_WORKSPACE, "gelu_bwd: workspace too small");
+        partial = static_cast<float*>(workspace);
+    }
+    const int gx = gelu_bwd_row_blocks(R, N);
+    const dim3 grid3(gx, (N + 255) / 256);
+    const int grid = gx;
+    const __nv_bfloat16* xi = static_cast<const __nv_bfloat16*>(x);
+    const __nv_bfloat16* gi = static_cast<const __nv_bfloat16*>(dy);
+    __nv_bfloat16* dxo = static_cast<__nv_bfloat16*>(dx);
+    if (partial != nullptr)
+        gelu_bwd_kernel<true><<<grid3, kCsWarps * 32, 0, stream>>>(xi, gi, R, N, dxo, partial);
+    else
+        gelu_bwd_kernel<false><<<grid3, kCsWarps * 32, 0, stream>>>(xi, gi, R, N, dxo, nullptr);
+    SB200_CHECK_LAUNCH("gelu_bwd_kernel");
+    if (partial != nullptr) {
+        partial_reduce_kernel<<<(N + 7) / 8, 256, 0, stream>>>(partial, grid, N, colsum, colsum, N);
+        SB200_CHECK_LAUNCH("partial_reduce_kernel");
+    }
     return SB200_OK;
 }

@@ -521,6 +521,49 @@ def add_layer_norm(y, resid, gamma, beta, eps=1e-12, p=0.0, training=False, want
     return AddLayerNormFunction.apply(y, resid, gamma, beta, eps, seed, float(p) if seed is not None else 0.0, want_f32)
 
 
+# --------------------------------------------------------------------------------------------- encoder body: embeddings
+class EmbedSumFunction(torch.autograd.Function):
+    """(W[ids] + T[typ]) + P[pos] on token rows, fp32 tables (transformers BertEmbeddings lookups); the backward
+    scatters the gradient into the three dense table gradients with vector reductions (summation order is not
+    deterministic, like the head backward)."""
+
+    @staticmethod
+    def forward(ctx, ids, pos, typ, W, P, T, padding_idx):
+        _need_cuda(ids, pos, typ, W, P, T)
+        if not (W.dtype == P.dtype == T.dtype == torch.float32):
+            raise TypeError("embed_sum: fp32 embedding tables required")
+        ids, pos, typ = (t.to(torch.int64).contiguous() for t in (ids, pos, typ))
+        Wc, Pc, Tc = W.detach().contiguous(), P.detach().contiguous(), T.detach().contiguous()
+        n, H = ids.numel(), W.shape[1]
+        out = torch.empty(n, H, dtype=torch.float32, device=W.device)
+        with torch.cuda.device(W.device):
+            code = _lib.load().sb200_embed_sum_fwd(_ptr(ids), _ptr(pos), _ptr(typ), _ptr(Wc), _ptr(Pc), _ptr(Tc), n, H,
+                                                   W.shape[0], P.shape[0], T.shape[0], _ptr(out), _stream())
+        _lib.check(code, "sb200_embed_sum_fwd")
+        ctx.save_for_backward(ids, pos, typ)
+        ctx.shapes = (W.shape, P.shape, T.shape)
+        ctx.padding_idx = -1 if padding_idx is None else int(padding_idx)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        ids, pos, typ = ctx.saved_tensors
+        sw, sp, st = ctx.shapes
+        g = g.float().contiguous()
+        dW = torch.zeros(sw, dtype=torch.float32, device=g.device)
+        dP = torch.zeros(sp, dtype=torch.float32, device=g.device)
+        dT = torch.zeros(st, dtype=torch.float32, device=g.device)
+        with torch.cuda.device(g.device):
+            code = _lib.load().sb200_embed_sum_bwd(_ptr(ids), _ptr(pos), _ptr(typ), _ptr(g), ids.numel(), sw[1], sw[0],
+                                                   sp[0], st[0], ctx.padding_idx, _ptr(dW), _ptr(dP), _ptr(dT), _stream())
+        _lib.check(code, "sb200_embed_sum_bwd")
+        return None, None, None, dW, dP, dT, None
+
+
+def embed_sum(ids, pos, typ, word_table, pos_table, type_table, padding_idx=None):
+    return EmbedSumFunction.apply(ids, pos, typ, word_table, pos_table, type_table, padding_idx)
+
+
 # --------------------------------------------------------------------------------------------- encoder body: Linear
 def colsum_supported(n):
     return bool(_lib.load().sb200_colsum_supported(int(n)))
@@ -542,16 +585,29 @@ def colsum(dy):
     return out
 
 
+def _weight_grad(dy2, x2, w_dtype):
+    """dy2^T @ x2 in the dtype of the weight the gradient belongs to."""
+    if dy2.dtype != x2.dtype:
+        dy2 = dy2.to(x2.dtype)
+    if w_dtype == torch.float32 and x2.dtype in (torch.bfloat16, torch.float16):
+        return torch.mm(dy2.t(), x2, out_dtype=torch.float32)
+    return (dy2.t() @ x2).to(w_dtype)
+
+
 class LinearFunction(torch.autograd.Function):
     """y = x W^T + b with the library GEMMs of torch (cuBLAS) and the fused column-sum kernel for the bias gradient.
     Operands arrive already in the compute dtype (see `linear`)."""
 
     @staticmethod
     def forward(ctx, x, weight, bias):
-        ctx.save_for_backward(x, weight)
+        # the fp32 master weight is the autograd input: its gradient leaves the weight-gradient GEMM in fp32
+        # (bf16 operands, fp32 output) instead of being rounded to bf16 and cast back
+        w = weight if weight.dtype == x.dtype else weight.to(x.dtype)
+        ctx.save_for_backward(x, w)
         ctx.has_bias = bias is not None
+        ctx.w_dtype = weight.dtype
         # the bias keeps its own (fp32) dtype as an autograd input so that its gradient stays the fp32 column sum
-        return torch.nn.functional.linear(x, weight, None if bias is None else bias.to(x.dtype))
+        return torch.nn.functional.linear(x, w, None if bias is None else bias.to(x.dtype))
 
     @staticmethod
     def backward(ctx, dy):
@@ -561,10 +617,79 @@ class LinearFunction(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = (dy2 @ weight).view(x.shape)
         if ctx.needs_input_grad[1]:
-            dw = dy2.t() @ x.reshape(-1, x.shape[-1])
+            dw = _weight_grad(dy2, x.reshape(-1, x.shape[-1]), ctx.w_dtype)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = colsum(dy2)
         return dx, dw, db
+
+
+def gelu_forward(x):
+    """Exact GELU of a bf16 tensor (numel % 8 == 0) on the sm_100a kernel."""
+    _need_cuda(x)
+    if x.dtype != torch.bfloat16 or x.numel() % 8 != 0 or x.numel() == 0:
+        raise TypeError("gelu: bf16 input with a positive multiple of 8 elements required")
+    x = x.contiguous()
+    y = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        code = _lib.load().sb200_gelu_fwd(_ptr(x), x.numel(), _ptr(y), _stream())
+    _lib.check(code, "sb200_gelu_fwd")
+    return y
+
+
+def gelu_backward(x, dy, want_colsum=True):
+    """(dx bf16 [R, N], colsum fp32 [N] or None) for y = gelu(x); colsum = column sums of dx (bias gradient)."""
+    _need_cuda(x, dy)
+    N = x.shape[-1]
+    R = x.numel() // N
+    x = x.contiguous()
+    dy = dy.to(torch.bfloat16).contiguous()
+    dx = torch.empty_like(x)
+    lib = _lib.load()
+    cs = torch.empty(N, dtype=torch.float32, device=x.device) if want_colsum else None
+    ws = _workspace(lib.sb200_gelu_bwd_workspace_bytes(R, N), x.device) if want_colsum else None
+    with torch.cuda.device(x.device):
+        code = lib.sb200_gelu_bwd(_ptr(x), _ptr(dy), R, N, _ptr(dx), _ptr(cs), _ptr(ws), 0 if ws is None else ws.numel(),
+                                  _stream())
+    _lib.check(code, "sb200_gelu_bwd")
+    return dx, cs
+
+
+class LinearGeluFunction(torch.autograd.Function):
+    """gelu(x W^T + b) for bf16 operands (transformers BertIntermediate, BertPredictionHeadTransform.dense + act):
+    cuBLAS GEMMs, GELU forward kernel, and one backward kernel that produces the pre-activation gradient and the
+    bias gradient together."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        w = weight if weight.dtype == x.dtype else weight.to(x.dtype)
+        pre = torch.nn.functional.linear(x, w, None if bias is None else bias.to(x.dtype))
+        ctx.save_for_backward(x, w, pre)
+        ctx.has_bias = bias is not None
+        ctx.w_dtype = weight.dtype
+        return gelu_forward(pre)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, pre = ctx.saved_tensors
+        N = pre.shape[-1]
+        want_db = ctx.has_bias and ctx.needs_input_grad[2]
+        dpre, db = gelu_backward(pre.view(-1, N), dy.reshape(-1, N), want_colsum=want_db)
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = (dpre @ weight).view(x.shape)
+        if ctx.needs_input_grad[1]:
+            dw = _weight_grad(dpre, x.reshape(-1, x.shape[-1]), ctx.w_dtype)
+        return dx, dw, db
+
+
+def linear_gelu(x, weight, bias):
+    """gelu(linear(x)) under bf16 autocast (or with bf16 operands); raises otherwise (bf16-only kernels)."""
+    if torch.is_autocast_enabled("cuda") and torch.get_autocast_dtype("cuda") == torch.bfloat16:
+        with torch.autocast("cuda", enabled=False):
+            return LinearGeluFunction.apply(x.to(torch.bfloat16), weight, bias)
+    if x.dtype != torch.bfloat16:
+        raise TypeError("linear_gelu: bf16 operands or bf16 autocast required")
+    return LinearGeluFunction.apply(x, weight, bias)
 
 
 def linear(x, weight, bias):
@@ -572,7 +697,6 @@ def linear(x, weight, bias):
     autocast dtype (bf16 or fp16) exactly like the stock op, and the matmuls run outside the autocast region."""
     if torch.is_autocast_enabled("cuda"):
         dt = torch.get_autocast_dtype("cuda")
-        x, weight = x.to(dt), weight.to(dt)
         with torch.autocast("cuda", enabled=False):
-            return LinearFunction.apply(x, weight, bias)
+            return LinearFunction.apply(x.to(dt), weight, bias)
     return LinearFunction.apply(x, weight, bias)

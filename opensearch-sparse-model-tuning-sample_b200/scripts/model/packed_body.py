@@ -111,7 +111,11 @@ class PackedBertBody:
         else:
             flat_t = token_type_ids.reshape(-1)
             typ_p = torch.zeros(t_cap + 1, dtype=flat_t.dtype, device=flat_t.device).scatter_(0, dest, flat_t)[:t_cap]
-        x32 = emb.word_embeddings(ids_p) + emb.token_type_embeddings(typ_p) + emb.position_embeddings(pos_p)
+        tables = (emb.word_embeddings.weight, emb.position_embeddings.weight, emb.token_type_embeddings.weight)
+        if all(t.dtype == torch.float32 for t in tables):
+            x32 = ops.embed_sum(ids_p, pos_p, typ_p, *tables, padding_idx=emb.word_embeddings.padding_idx)
+        else:
+            x32 = emb.word_embeddings(ids_p) + emb.token_type_embeddings(typ_p) + emb.position_embeddings(pos_p)
         x32 = emb.dropout(emb.LayerNorm(x32)).float()
         x16 = x32.to(torch.bfloat16)
 
@@ -129,16 +133,26 @@ class PackedBertBody:
             y = att.output.dense(ctx.reshape(t_cap, h * d))
             ln = att.output.LayerNorm
             x32, x16 = ops.add_layer_norm(y, x32, ln.weight, ln.bias, ln.eps, p=att.output.dropout.p, training=training)
-            y = layer.output.dense(layer.intermediate(x16))
+            y = layer.output.dense(self._dense_act(layer.intermediate.dense, layer.intermediate.intermediate_act_fn, x16))
             ln = layer.output.LayerNorm
             last = li == len(layers) - 1           # nothing reads the fp32 stream after the last block
             x32, x16 = ops.add_layer_norm(y, x32, ln.weight, ln.bias, ln.eps, p=layer.output.dropout.p,
                                           training=training, want_f32=not last)
         if head_transform is not None:
-            y = head_transform.transform_act_fn(head_transform.dense(x16))
+            y = self._dense_act(head_transform.dense, head_transform.transform_act_fn, x16)
             ln = head_transform.LayerNorm
             _, x16 = ops.add_layer_norm(y, None, ln.weight, ln.bias, ln.eps, want_f32=False)
         return x16, (dest.clamp_max(t_cap - 1), src_of, row_valid, (B, L))
+
+    @staticmethod
+    def _dense_act(dense, act, x16):
+        """act(dense(x)); the exact GELU of BERT runs on the fused sm_100a kernels (bias gradient included)."""
+        exact_gelu = act is torch.nn.functional.gelu or (type(act).__name__ == "GELUActivation"
+                                                         and getattr(act, "act", None) is torch.nn.functional.gelu)
+        if exact_gelu and dense.out_features % 8 == 0 \
+                and dense.out_features <= 4096:
+            return ops.linear_gelu(x16, dense.weight, dense.bias)
+        return act(dense(x16))
 
     @staticmethod
     def repad(packed, plan):

@@ -461,6 +461,92 @@ def test_add_layer_norm_dropout(ops, p):
     torch.testing.assert_close(yg.grad.float(), yr.grad, rtol=2e-2, atol=2e-4)
 
 
+@pytest.mark.parametrize("R,N", [(64, 8), (1000, 384), (4096, 1536), (513, 3072), (77, 4096), (300, 1152), (5, 40)])
+def test_gelu_kernels_vs_torch(ops, R, N):
+    """Exact-GELU forward / backward (+ fused bias gradient) against torch's erf GELU evaluated in fp32."""
+    g = torch.Generator().manual_seed(R + N)
+    x = (torch.randn(R, N, generator=g) * 2.5).bfloat16()
+    x[0, :8] = torch.tensor([-12.0, -6.0, -4.0, -0.0, 0.0, 4.0, 6.0, 12.0]).bfloat16()
+    dy = torch.randn(R, N, generator=g).bfloat16()
+    xc = cuda(x)
+    y = ops.gelu_forward(xc)
+    xr = x.float().requires_grad_(True)
+    yr = torch.nn.functional.gelu(xr)
+    yr.backward(dy.float())
+    # one bf16 ulp; tiny negative-tail values (|y| < 1e-4) only to absolute accuracy
+    torch.testing.assert_close(y.float().cpu(), yr.detach().bfloat16().float(), rtol=8e-3, atol=2e-6)
+    if R * N > 100000:   # nearly all results are bit-equal to torch's (the rest sit on a bf16 rounding boundary)
+        assert float((y.float().cpu() != yr.detach().bfloat16().float()).float().mean()) < 0.03
+    dx, db = ops.gelu_backward(xc, cuda(dy))
+    torch.testing.assert_close(dx.float().cpu(), xr.grad.bfloat16().float(), rtol=8e-3, atol=2e-6)
+    torch.testing.assert_close(db.cpu(), dx.float().sum(0).cpu(), rtol=1e-5, atol=1e-4)
+    dx2, none = ops.gelu_backward(xc, cuda(dy), want_colsum=False)
+    assert none is None and torch.equal(dx2, dx)
+
+
+def test_linear_gelu_function(ops):
+    g = torch.Generator().manual_seed(0)
+    x = (torch.randn(640, 384, generator=g)).bfloat16()
+    w = (torch.randn(1536, 384, generator=g) * 0.05)
+    b = torch.randn(1536, generator=g) * 0.1
+    dy = torch.randn(640, 1536, generator=g).bfloat16()
+    xc, wc, bc = cuda(x).requires_grad_(True), cuda(w).requires_grad_(True), cuda(b).requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y = ops.linear_gelu(xc, wc, bc)
+    y.backward(cuda(dy))
+    xr, wr, br = cuda(x).requires_grad_(True), cuda(w).requires_grad_(True), cuda(b).requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        yr = torch.nn.functional.gelu(torch.nn.functional.linear(xr, wr, br))
+    yr.backward(cuda(dy))
+    assert y.dtype == torch.bfloat16 and wc.grad.dtype == torch.float32 and bc.grad.dtype == torch.float32
+    torch.testing.assert_close(y.float(), yr.float(), rtol=1.6e-2, atol=1e-3)
+    torch.testing.assert_close(xc.grad.float(), xr.grad.float(), rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(wc.grad, wr.grad, rtol=2e-2, atol=5e-2)
+    torch.testing.assert_close(bc.grad, br.grad, rtol=2e-2, atol=5e-2)
+
+
+@pytest.mark.parametrize("n,H", [(1000, 384), (37, 64), (4096, 768)])
+def test_embed_sum_vs_torch(ops, n, H):
+    g = torch.Generator().manual_seed(n + H)
+    nW, nP, nT = 3000, 512, 2
+    W, P, T = (cuda(torch.randn(k, H, generator=g)).requires_grad_(True) for k in (nW, nP, nT))
+    ids = cuda(torch.randint(0, nW, (n,), generator=g))
+    ids[::5] = 7        # a hot row
+    ids[1::9] = 0       # the padding row
+    pos = cuda(torch.randint(0, nP, (n,), generator=g))
+    typ = cuda(torch.randint(0, nT, (n,), generator=g))
+    dy = cuda(torch.randn(n, H, generator=g))
+    out = ops.embed_sum(ids, pos, typ, W, P, T, padding_idx=0)
+    out.backward(dy)
+    got = [t.grad.clone() for t in (W, P, T)]
+    for t in (W, P, T):
+        t.grad = None
+    F = torch.nn.functional
+    ref = (F.embedding(ids, W, padding_idx=0) + F.embedding(typ, T)) + F.embedding(pos, P)
+    ref.backward(dy)
+    assert torch.equal(out, ref)
+    for a, t in zip(got, (W, P, T)):
+        torch.testing.assert_close(a, t.grad, rtol=1e-4, atol=1e-4 * float(t.grad.abs().max()))
+    assert float(got[0][0].abs().max()) == 0.0
+
+
+def test_linear_weight_grad_is_fp32_gemm_output(ops):
+    """Under bf16 autocast the weight gradient comes out of the GEMM in fp32 (no bf16 rounding of dW)."""
+    g = torch.Generator().manual_seed(3)
+    x = cuda(torch.randn(4096, 384, generator=g))
+    w = cuda(torch.randn(384, 384, generator=g) * 0.05).requires_grad_(True)
+    b = cuda(torch.randn(384, generator=g)).requires_grad_(True)
+    dy = cuda(torch.randn(4096, 384, generator=g)).bfloat16()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y = ops.linear(x, w, b)
+    y.backward(dy)
+    exact = dy.float().t() @ x.bfloat16().float()
+    assert w.grad.dtype == torch.float32
+    err_fp32_out = float((w.grad - exact).abs().max())
+    err_bf16_out = float((exact.bfloat16().float() - exact).abs().max())
+    assert err_fp32_out < 0.25 * err_bf16_out, (err_fp32_out, err_bf16_out)
+
+
 def test_fused_backbone_matches_unfused(ops):
     from sparse_b200.scripts import synthetic
     V = 2000

@@ -33,6 +33,17 @@ def run(B, L, H, V, G, nq, regime_shift):
     y.backward(torch.ones_like(y))
     ops.colsum(hidden.reshape(-1, H))
     ops.colsum(torch.randn(B * L, 4 * H, device="cuda").bfloat16())
+    # fused block tail and GELU kernels on the packed activation shape (85 % of B*L rows)
+    T = int(B * L * 0.85) // 8 * 8
+    yb = torch.randn(T, H, device="cuda").bfloat16().requires_grad_(True)
+    res = torch.randn(T, H, device="cuda", requires_grad=True)
+    for _ in range(2):
+        o32, o16 = ops.add_layer_norm(yb, res, gamma, beta, 1e-12, p=0.1, training=True)
+        torch.autograd.backward([o32, o16], [torch.randn_like(o32), torch.randn_like(o16)])
+    pre = torch.randn(T, 4 * H, device="cuda").bfloat16()
+    for _ in range(2):
+        ops.gelu_forward(pre)
+        ops.gelu_backward(pre, torch.randn_like(pre))
     torch.cuda.synchronize()
 
 if __name__ == "__main__":

@@ -7,7 +7,7 @@ import bench
 from torch.profiler import profile, ProfilerActivity
 
 
-def run(capacity, top=28):
+def run(capacity, top=90):
     wl = bench.WORKLOADS["c2"]
     bench.build_trainer.unpad_capacity = capacity if capacity > 0 else None
     bench.build_trainer.grad_sync = "ddp"
