@@ -285,8 +285,12 @@ def run_ours(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": wl["name"], "regime": args.regime, "per_gpu_queries": nq, "per_gpu_docs": nd,
                        "global_queries": world * nq, "parallelism": f"dp{world}",
-                       "backbone": f"random-init BertForMaskedLM {wl['shape']} (PyTorch body, bf16 autocast, "
-                                   f"{trainer.model_wrapper.sparse_model.fused_layers} LayerNorms on fused sm_100a kernels)",
+                       "backbone": f"random-init BertForMaskedLM {wl['shape']}, bf16 autocast; "
+                                   + ("padding-free body: cuBLAS GEMMs + flash_attn varlen (library), embeddings / "
+                                      "block tails (dropout+residual+LayerNorm) / GELU / bias gradients on this "
+                                      "repo's sm_100a kernels" if trainer.model_wrapper.sparse_model.__dict__.get("_packed")
+                                      else f"padded transformers body, {trainer.model_wrapper.sparse_model.fused_layers} "
+                                           "LayerNorm/Linear modules on this repo's sm_100a kernels"),
                        "unpad_capacity": args.unpad_capacity if trainer.model_wrapper.sparse_model.__dict__.get("_packed") else None,
                        "l2": "no explicit flush: one step touches > 126 MB (activations, fp32 params, AdamW state)",
                        "launch": ("CUDA graph replay" + (" (fwd+bwd captured, flat grad all-reduce + optimizer after)"

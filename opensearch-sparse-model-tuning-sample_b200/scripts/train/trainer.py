@@ -372,12 +372,24 @@ class SparseModelTrainer:
                 loader.sampler.set_epoch(epoch)
             for batch in loader:
                 self.training_step(self._to_device(batch, device))
+                if self.state.global_step % max(1, self.args.logging_steps) == 0:
+                    self._check_unpad()
                 if self.args.save_strategy == "steps" and self.state.global_step % self.args.save_steps == 0:
                     self._save(os.path.join(self.args.output_dir, f"checkpoint-{self.state.global_step}"))
                 if self.state.global_step >= self.args.max_steps:
                     break
             epoch += 1
+        self._check_unpad()
         return self.state.global_step
+
+    def _check_unpad(self):
+        """The padding-free body packs a batch into a fixed number of rows (SparseModel(unpad_capacity=...)); a batch
+        with more real tokens than that cannot be detected without a host sync, so it is counted on the device and
+        checked here, at logging cadence. Training on truncated batches is never silently accepted."""
+        n = self.model_wrapper.sparse_model.unpad_overflows()
+        if n:
+            raise RuntimeError(f"{n} batch(es) held more real tokens than unpad_capacity allows: raise unpad_capacity "
+                               "(1.0 can never overflow) and restart from the last checkpoint")
 
     def _save(self, output_dir=None, state_dict=None):
         """reference :145-156 -- main process only, ModelWrapper.save layout."""

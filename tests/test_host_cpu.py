@@ -88,3 +88,34 @@ def test_synthetic_batches_layout():
     assert ((docs["input_ids"] == 0) == (docs["attention_mask"] == 0)).all()
     tok = synthetic.SyntheticTokenizer()
     assert sorted(tok.vocab[t] for t in tok.special_tokens_map.values()) == [0, 100, 101, 102, 103]
+
+
+def test_packed_body_plan_and_repad_cpu():
+    """Host-side logic of the padding-free body: device-free placement plan (holes, empty rows, overflow) and the
+    scatter back to [B, L, H] with its gradient."""
+    from sparse_b200.scripts.model.packed_body import PackedBertBody, _Repad
+    body = PackedBertBody.__new__(PackedBertBody)
+    body.capacity, body.overflow_count = 1.0, None
+    mask = torch.tensor([[1, 1, 1, 0], [1, 0, 1, 1], [0, 0, 0, 0], [1, 1, 1, 1]])
+    t_cap, dest, src_of, row_valid, cu = body._plan(mask)
+    assert t_cap == 16 and int(body.overflow_count) == 0
+    kept = mask.reshape(-1).nonzero().flatten()
+    assert dest[kept].tolist() == list(range(10)) and set(dest[mask.reshape(-1) == 0].tolist()) == {16}
+    assert src_of[:10].tolist() == kept.tolist() and row_valid.tolist() == [True] * 10 + [False] * 6
+    assert cu.tolist() == [0, 3, 6, 6, 10, 14, 16, 16, 16]          # real sequences, then dummy ones over the filler rows
+    packed = torch.arange(16.0).unsqueeze(1).repeat(1, 2).requires_grad_(True)
+    plan = (dest.clamp_max(t_cap - 1), src_of, row_valid, (4, 4))
+    padded = PackedBertBody.repad(packed, plan)
+    assert padded.shape == (4, 4, 2)
+    assert padded.reshape(16, 2)[kept, 0].tolist() == list(range(10))
+    w = torch.arange(1.0, 17.0).unsqueeze(1).repeat(1, 2)
+    (padded.reshape(16, 2) * w).sum().backward()
+    assert packed.grad[:10, 0].tolist() == (kept + 1).float().tolist()   # gradient of the padded position it fed
+    assert packed.grad[10:].abs().sum() == 0                              # filler rows get none
+    # capacity below the token count: counted, tokens past the capacity are dropped into the dummy slot
+    body.capacity, body.overflow_count = 0.5, None
+    t_cap, dest, src_of, row_valid, cu = body._plan(mask)
+    assert t_cap == 8 and int(body.overflow_count) == 1
+    assert dest[kept].tolist() == list(range(8)) + [8, 8] and int(cu.max()) == 8 and cu.tolist() == sorted(cu.tolist())
+    body._plan(mask[:2])
+    assert int(body.overflow_count) == 1                                  # 6 tokens fit the 8 rows: counter unchanged
