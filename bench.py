@@ -159,6 +159,9 @@ def run_ours(args):
     torch.cuda.set_device(device)
     if world > 1:
         os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")  # required for NCCL inside CUDA graphs
+        # stdout carries exactly one JSON line: NCCL's own banner ("NCCL version ...", printed when NCCL_DEBUG is set
+        # on the box) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=device)
     import sparse_b200
     from sparse_b200 import ops

@@ -20,7 +20,15 @@ def main(path):
     tot = sum(v for _, v in rows)
     agg = collections.defaultdict(lambda: [0, 0.0])
     for name, v in rows:
-        short = re.sub(r"<.*", "", name)[:70]
+        short = name.replace("(anonymous namespace)::", "").replace("<unnamed>::", "")
+        short = re.sub(r"^void ", "", short)
+        short = re.sub(r"\(.*", "", short)                  # drop the argument list
+        short = re.sub(r"<(?!\d+(, *\w+)*>).*", "", short)  # keep small integer template arguments only
+        if "elementwise_kernel" in short:                    # PyTorch's generic kernels: add the functor name
+            inner = re.findall(r"native::(?:<unnamed>::)?(\w+)", name.replace("(anonymous namespace)::", ""))
+            if len(inner) > 1:
+                short += "[" + inner[1] + "]"
+        short = short[:70]
         agg[short][0] += 1
         agg[short][1] += v
     print(f"{len(rows)} launches, {tot/1e3:.3f} ms total device time (serialised, cold-cache)")
