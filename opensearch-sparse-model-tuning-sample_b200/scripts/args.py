@@ -58,6 +58,9 @@ class ModelArguments:
     prune_ratio: Optional[float] = None
     preprocess_func: Optional[str] = None
     use_l0: bool = False
+    # B200 extensions (absent from the reference's ModelArguments; defaults keep its behaviour)
+    fuse_body: bool = True                    # backbone LayerNorm / Linear modules on the fused sm_100a kernels
+    unpad_capacity: Optional[float] = None    # padding-free BERT body: rows = ceil(capacity * B * L); 1.0 never overflows
 
     def __post_init__(self):
         if self.tokenizer_name is None:

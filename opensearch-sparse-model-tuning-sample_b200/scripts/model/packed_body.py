@@ -100,6 +100,8 @@ class PackedBertBody:
         FlashAttention on the packed qkv, and the fused dropout + residual + LayerNorm tail of `ops.add_layer_norm`
         that hands the next GEMM its bf16 operand (no separate cast / add / dropout kernels)."""
         B, L = input_ids.shape
+        if attention_mask is None:
+            attention_mask = torch.ones_like(input_ids)
         t_cap, dest, src_of, row_valid, cu = self._plan(attention_mask)
         emb = self.bert.embeddings
         flat_ids = input_ids.reshape(-1)

@@ -97,4 +97,5 @@ def get_model(model_args, backbone=None, tokenizer=None):
     return SparseModel(model_args.model_name_or_path, idf=idf, tokenizer_id=model_args.tokenizer_name,
                        idf_requires_grad=model_args.idf_requires_grad, prune_ratio=model_args.prune_ratio,
                        preprocess_func=model_args.preprocess_func, use_l0=model_args.use_l0, backbone=backbone,
-                       tokenizer=tokenizer)
+                       tokenizer=tokenizer, fuse_body=getattr(model_args, "fuse_body", True),
+                       unpad_capacity=getattr(model_args, "unpad_capacity", None))
