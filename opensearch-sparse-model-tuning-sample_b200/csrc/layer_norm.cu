@@ -261,20 +261,46 @@ struct DropCfg {
     float scale;                     // 1 / (1 - p)
 };
 
+// Row layout of the tail kernels: a row of H = NVL * WPR * 128 columns is owned by WPR warps (1 for H <= 512, 2 above:
+// with one warp per 768/1024-wide row the backward needs 215-255 registers, one block per SM, 12 % occupancy).
+// Warp `half` of the row group holds NVL four-wide vectors per lane: vector k covers columns
+// ((half * NVL + k) * 32 + lane) * 4 .. +3. Row statistics of a split row are combined through shared memory and a
+// 64-thread named barrier.
+template <int NVL, int WPR>
+struct RowGeom {
+    static constexpr int H = NVL * WPR * 128;
+    static constexpr int kRowsPerBlock = kLnWarps / WPR;
+    static __device__ __forceinline__ int col(int half, int lane, int k) { return ((half * NVL + k) * 32 + lane) * 4; }
+};
+
+// sum of (a, b) over the WPR warps of a row group; xchg = [2][kLnWarps] float2 slots, buf toggles per call
+template <int WPR>
+__device__ __forceinline__ void row_sum2(float& a, float& b, float2* xchg, int& buf, int warp, int lane) {
+    a = warp_sum(a);
+    b = warp_sum(b);
+    if (WPR == 1) return;
+    if (lane == 0) xchg[buf * kLnWarps + warp] = make_float2(a, b);
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + (warp >> 1)) : "memory");
+    const float2 o = xchg[buf * kLnWarps + (warp ^ 1)];
+    buf ^= 1;  // the next exchange uses the other slot set: a slow reader of this one is never overwritten
+    a += o.x;
+    b += o.y;
+}
+
 // branch row r, vector k of this lane: s = dropout(y) + resid (fp32)
-template <int NV>
+template <int NVL, int WPR>
 __device__ __forceinline__ void load_branch_sum(const __nv_bfloat16* __restrict__ y, const float* __restrict__ resid, int r,
-                                                int lane, bool drop, const Philox& rng, const DropCfg& dc,
-                                                float (&s)[NV][4], uint32_t& keep_bits) {
-    constexpr int H = NV * 128;
+                                                int half, int lane, bool drop, const Philox& rng, const DropCfg& dc,
+                                                float (&s)[NVL][4], uint32_t& keep_bits) {
+    using G = RowGeom<NVL, WPR>;
     keep_bits = 0xffffffffu;
 #pragma unroll
-    for (int k = 0; k < NV; ++k) {
-        const int c = (lane + 32 * k) * 4;
-        Vec4<__nv_bfloat16>::load(y + size_t(r) * H + c, s[k]);
+    for (int k = 0; k < NVL; ++k) {
+        const int c = G::col(half, lane, k);
+        Vec4<__nv_bfloat16>::load(y + size_t(r) * G::H + c, s[k]);
         if (drop) {
             uint32_t rnd[4];
-            const unsigned long long e = (static_cast<unsigned long long>(r) * H + c) >> 2;
+            const unsigned long long e = (static_cast<unsigned long long>(r) * G::H + c) >> 2;
             rng(static_cast<uint32_t>(e), static_cast<uint32_t>(e >> 32), rnd);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -285,25 +311,29 @@ __device__ __forceinline__ void load_branch_sum(const __nv_bfloat16* __restrict_
         }
         if (resid != nullptr) {
             float x[4];
-            Vec4<float>::load(resid + size_t(r) * H + c, x);
+            Vec4<float>::load(resid + size_t(r) * G::H + c, x);
 #pragma unroll
             for (int i = 0; i < 4; ++i) s[k][i] += x[i];
         }
     }
 }
 
-template <int NV>
-__global__ void __launch_bounds__(kLnThreads, NV <= 3 ? 4 : (NV <= 4 ? 3 : 2))
+template <int NVL, int WPR>
+__global__ void __launch_bounds__(kLnThreads, NVL <= 3 ? 4 : 3)
 add_ln_fwd_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ resid, const float* __restrict__ gamma,
                   const float* __restrict__ beta, int R, float eps, DropCfg dc, float* __restrict__ out32,
                   __nv_bfloat16* __restrict__ out16, float* __restrict__ mean_out, float* __restrict__ rstd_out) {
-    constexpr int H = NV * 128;
+    using G = RowGeom<NVL, WPR>;
+    constexpr int H = G::H;
+    __shared__ float2 xchg[2 * kLnWarps];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float gm[NV][4], bt[NV][4];
+    const int half = warp % WPR, slot = warp / WPR;
+    int buf = 0;
+    float gm[NVL][4], bt[NVL][4];
 #pragma unroll
-    for (int k = 0; k < NV; ++k) {
-        Vec4<float>::load(gamma + (lane + 32 * k) * 4, gm[k]);
-        Vec4<float>::load(beta + (lane + 32 * k) * 4, bt[k]);
+    for (int k = 0; k < NVL; ++k) {
+        Vec4<float>::load(gamma + G::col(half, lane, k), gm[k]);
+        Vec4<float>::load(beta + G::col(half, lane, k), bt[k]);
     }
     const bool drop = dc.seed != nullptr;
     Philox rng{0u, 0u};
@@ -312,33 +342,36 @@ add_ln_fwd_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__
         rng.k0 = static_cast<uint32_t>(sd);
         rng.k1 = static_cast<uint32_t>(sd >> 32);
     }
-    for (int r = blockIdx.x * kLnWarps + warp; r < R; r += gridDim.x * kLnWarps) {
-        float v[NV][4];
+    for (int r = blockIdx.x * G::kRowsPerBlock + slot; r < R; r += gridDim.x * G::kRowsPerBlock) {
+        float v[NVL][4];
         uint32_t keep_bits;
-        load_branch_sum<NV>(y, resid, r, lane, drop, rng, dc, v, keep_bits);
-        float s = 0.f;
+        load_branch_sum<NVL, WPR>(y, resid, r, half, lane, drop, rng, dc, v, keep_bits);
+        float s = 0.f, unused = 0.f;
 #pragma unroll
-        for (int k = 0; k < NV; ++k) s += (v[k][0] + v[k][1]) + (v[k][2] + v[k][3]);
-        const float mean = warp_sum(s) * (1.f / H);
+        for (int k = 0; k < NVL; ++k) s += (v[k][0] + v[k][1]) + (v[k][2] + v[k][3]);
+        row_sum2<WPR>(s, unused, xchg, buf, warp, lane);
+        const float mean = s * (1.f / H);
         float q = 0.f;
 #pragma unroll
-        for (int k = 0; k < NV; ++k)
+        for (int k = 0; k < NVL; ++k)
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const float dlt = v[k][i] - mean;
                 q = fmaf(dlt, dlt, q);
             }
-        const float rstd = rsqrtf(warp_sum(q) * (1.f / H) + eps);
+        unused = 0.f;
+        row_sum2<WPR>(q, unused, xchg, buf, warp, lane);
+        const float rstd = rsqrtf(q * (1.f / H) + eps);
 #pragma unroll
-        for (int k = 0; k < NV; ++k) {
+        for (int k = 0; k < NVL; ++k) {
             float o[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) o[i] = fmaf((v[k][i] - mean) * rstd, gm[k][i], bt[k][i]);
-            const size_t off = size_t(r) * H + (lane + 32 * k) * 4;
+            const size_t off = size_t(r) * H + G::col(half, lane, k);
             if (out32 != nullptr) Vec4<float>::store(out32 + off, o);
             if (out16 != nullptr) Vec4<__nv_bfloat16>::store(out16 + off, o);
         }
-        if (lane == 0) {
+        if (lane == 0 && half == 0) {
             mean_out[r] = mean;
             rstd_out[r] = rstd;
         }
@@ -348,19 +381,23 @@ add_ln_fwd_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__
 // Gradient of the tail. g32 / g16 are the gradients that arrived at the fp32 and the bf16 copy of the output (either
 // may be null); they are summed in fp32. ds (gradient of dropout(y) + resid) leaves as d_resid (fp32) and, through
 // the regenerated dropout mask, as d_y (bf16).
-template <int NV>
-__global__ void __launch_bounds__(kLnThreads, NV <= 3 ? 3 : (NV <= 4 ? 2 : 1))
+template <int NVL, int WPR>
+__global__ void __launch_bounds__(kLnThreads, NVL <= 3 ? 3 : 2)
 add_ln_bwd_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ resid, const float* __restrict__ g32,
                   const __nv_bfloat16* __restrict__ g16, const float* __restrict__ gamma,
                   const float* __restrict__ mean_in, const float* __restrict__ rstd_in, int R, DropCfg dc,
                   __nv_bfloat16* __restrict__ dy, float* __restrict__ dresid, float* __restrict__ partial) {
-    constexpr int H = NV * 128;
-    __shared__ float red[kLnWarps][H];
+    using G = RowGeom<NVL, WPR>;
+    constexpr int H = G::H;
+    __shared__ float red[G::kRowsPerBlock][H];
+    __shared__ float2 xchg[2 * kLnWarps];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float gm[NV][4], dg[NV][4], db[NV][4];
+    const int half = warp % WPR, slot = warp / WPR;
+    int buf = 0;
+    float gm[NVL][4], dg[NVL][4], db[NVL][4];
 #pragma unroll
-    for (int k = 0; k < NV; ++k) {
-        Vec4<float>::load(gamma + (lane + 32 * k) * 4, gm[k]);
+    for (int k = 0; k < NVL; ++k) {
+        Vec4<float>::load(gamma + G::col(half, lane, k), gm[k]);
 #pragma unroll
         for (int i = 0; i < 4; ++i) dg[k][i] = db[k][i] = 0.f;
     }
@@ -371,15 +408,15 @@ add_ln_bwd_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__
         rng.k0 = static_cast<uint32_t>(sd);
         rng.k1 = static_cast<uint32_t>(sd >> 32);
     }
-    for (int r = blockIdx.x * kLnWarps + warp; r < R; r += gridDim.x * kLnWarps) {
+    for (int r = blockIdx.x * G::kRowsPerBlock + slot; r < R; r += gridDim.x * G::kRowsPerBlock) {
         const float mean = __ldg(mean_in + r), rstd = __ldg(rstd_in + r);
-        float xh[NV][4], gy[NV][4];
+        float xh[NVL][4], gy[NVL][4];
         uint32_t keep_bits;
-        load_branch_sum<NV>(y, resid, r, lane, drop, rng, dc, xh, keep_bits);
+        load_branch_sum<NVL, WPR>(y, resid, r, half, lane, drop, rng, dc, xh, keep_bits);
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-        for (int k = 0; k < NV; ++k) {
-            const size_t off = size_t(r) * H + (lane + 32 * k) * 4;
+        for (int k = 0; k < NVL; ++k) {
+            const size_t off = size_t(r) * H + G::col(half, lane, k);
 #pragma unroll
             for (int i = 0; i < 4; ++i) gy[k][i] = 0.f;
             if (g32 != nullptr) Vec4<float>::load(g32 + off, gy[k]);
@@ -399,11 +436,12 @@ add_ln_bwd_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__
                 s2 = fmaf(gy[k][i], xh[k][i], s2);
             }
         }
-        s1 = warp_sum(s1) * (1.f / H);
-        s2 = warp_sum(s2) * (1.f / H);
+        row_sum2<WPR>(s1, s2, xchg, buf, warp, lane);
+        s1 *= (1.f / H);
+        s2 *= (1.f / H);
 #pragma unroll
-        for (int k = 0; k < NV; ++k) {
-            const size_t off = size_t(r) * H + (lane + 32 * k) * 4;
+        for (int k = 0; k < NVL; ++k) {
+            const size_t off = size_t(r) * H + G::col(half, lane, k);
             float o[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) o[i] = rstd * (gy[k][i] - s1 - xh[k][i] * s2);
@@ -421,23 +459,23 @@ add_ln_bwd_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__
     for (int pass = 0; pass < 2; ++pass) {
         __syncthreads();
 #pragma unroll
-        for (int k = 0; k < NV; ++k)
+        for (int k = 0; k < NVL; ++k)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) red[warp][(lane + 32 * k) * 4 + i] = pass == 0 ? dg[k][i] : db[k][i];
+            for (int i = 0; i < 4; ++i) red[slot][G::col(half, lane, k) + i] = pass == 0 ? dg[k][i] : db[k][i];
         __syncthreads();
         for (int c = threadIdx.x; c < H; c += kLnThreads) {
             float s = 0.f;
 #pragma unroll
-            for (int w = 0; w < kLnWarps; ++w) s += red[w][c];
+            for (int w = 0; w < G::kRowsPerBlock; ++w) s += red[w][c];
             out[pass * H + c] = s;
         }
     }
 }
 
 // one wave of resident blocks (the kernels are latency-bound: every resident warp counts, a second wave only adds a tail)
-int tail_grid(int R, int blocks_per_sm) {
+int tail_grid(int R, int blocks_per_sm, int rows_per_block) {
     const int g = blocks_per_sm * num_sms();
-    const int need = (R + kLnWarps - 1) / kLnWarps;
+    const int need = (R + rows_per_block - 1) / rows_per_block;
     return g < need ? g : need;
 }
 
@@ -506,13 +544,14 @@ extern "C" int sb200_add_layer_norm_fwd(const void* y, const float* resid, const
     const DropCfg dc = make_drop(drop_seed, drop_p);
     const __nv_bfloat16* yi = static_cast<const __nv_bfloat16*>(y);
     __nv_bfloat16* o16 = static_cast<__nv_bfloat16*>(out_bf16);
-    const int grid = tail_grid(R, H / 128 <= 3 ? 4 : (H / 128 <= 4 ? 3 : 2));
-#define SB200_ALN_CASE(NV_)                                                                                           \
+#define SB200_ALN_CASE(NV_, NVL_, WPR_)                                                                               \
     case NV_:                                                                                                         \
-        add_ln_fwd_kernel<NV_><<<grid, kLnThreads, 0, stream>>>(yi, resid, gamma, beta, R, eps, dc, out_f32, o16, mean, rstd); \
+        add_ln_fwd_kernel<NVL_, WPR_><<<tail_grid(R, NVL_ <= 3 ? 4 : 3, kLnWarps / WPR_), kLnThreads, 0, stream>>>(   \
+            yi, resid, gamma, beta, R, eps, dc, out_f32, o16, mean, rstd);                                            \
         break;
     switch (H / 128) {
-        SB200_ALN_CASE(1) SB200_ALN_CASE(2) SB200_ALN_CASE(3) SB200_ALN_CASE(4) SB200_ALN_CASE(6) SB200_ALN_CASE(8)
+        SB200_ALN_CASE(1, 1, 1) SB200_ALN_CASE(2, 2, 1) SB200_ALN_CASE(3, 3, 1) SB200_ALN_CASE(4, 4, 1)
+        SB200_ALN_CASE(6, 3, 2) SB200_ALN_CASE(8, 4, 2)
         default: return fail(SB200_ERR_ARG, "add_layer_norm_fwd: unsupported H=%d", H);
     }
 #undef SB200_ALN_CASE
@@ -536,14 +575,16 @@ extern "C" int sb200_add_layer_norm_bwd(const void* y, const float* resid, const
     const __nv_bfloat16* g16 = static_cast<const __nv_bfloat16*>(g_bf16);
     __nv_bfloat16* dyo = static_cast<__nv_bfloat16*>(d_y);
     float* partial = static_cast<float*>(workspace);
-    const int grid = tail_grid(R, H / 128 <= 3 ? 3 : (H / 128 <= 4 ? 2 : 1));  // <= ln_grid(R): workspace rows
-#define SB200_ALN_CASE(NV_)                                                                                           \
+    int grid = 0;  // <= ln_grid(R) blocks: the workspace holds one partial row per block
+#define SB200_ALN_CASE(NV_, NVL_, WPR_)                                                                               \
     case NV_:                                                                                                         \
-        add_ln_bwd_kernel<NV_><<<grid, kLnThreads, 0, stream>>>(yi, resid, g_f32, g16, gamma, mean, rstd, R, dc, dyo, \
-                                                                d_resid, partial);                                    \
+        grid = tail_grid(R, NVL_ <= 3 ? 3 : 2, kLnWarps / WPR_);                                                      \
+        add_ln_bwd_kernel<NVL_, WPR_><<<grid, kLnThreads, 0, stream>>>(yi, resid, g_f32, g16, gamma, mean, rstd, R,   \
+                                                                       dc, dyo, d_resid, partial);                    \
         break;
     switch (H / 128) {
-        SB200_ALN_CASE(1) SB200_ALN_CASE(2) SB200_ALN_CASE(3) SB200_ALN_CASE(4) SB200_ALN_CASE(6) SB200_ALN_CASE(8)
+        SB200_ALN_CASE(1, 1, 1) SB200_ALN_CASE(2, 2, 1) SB200_ALN_CASE(3, 3, 1) SB200_ALN_CASE(4, 4, 1)
+        SB200_ALN_CASE(6, 3, 2) SB200_ALN_CASE(8, 4, 2)
         default: return fail(SB200_ERR_ARG, "add_layer_norm_bwd: unsupported H=%d", H);
     }
 #undef SB200_ALN_CASE
