@@ -512,7 +512,11 @@ extern "C" int sb200_layer_norm_fwd(const void* x, int elem_bytes, const float* 
 
 extern "C" size_t sb200_layer_norm_bwd_workspace_bytes(int R, int H) {
     if (R <= 0 || H <= 0) return 0;
-    return size_t(ln_grid(R)) * 2 * H * sizeof(float);
+    // one partial (dgamma, dbeta) row per block of any backward variant: at most 4 blocks per SM, and never more
+    // blocks than row groups (>= 4 rows per block: the split-row tail kernels hold kLnWarps / 2 rows per block)
+    const int by_rows = (R + kLnWarps / 2 - 1) / (kLnWarps / 2);
+    const int cap = 4 * num_sms();
+    return size_t(by_rows < cap ? by_rows : cap) * 2 * H * sizeof(float);
 }
 
 extern "C" int sb200_layer_norm_bwd(const void* x, const void* dy, int elem_bytes, const float* gamma, const float* mean,
@@ -579,6 +583,8 @@ extern "C" int sb200_add_layer_norm_bwd(const void* y, const float* resid, const
 #define SB200_ALN_CASE(NV_, NVL_, WPR_)                                                                               \
     case NV_:                                                                                                         \
         grid = tail_grid(R, NVL_ <= 3 ? 3 : 2, kLnWarps / WPR_);                                                      \
+        if (size_t(grid) * 2 * H * sizeof(float) > workspace_bytes)                                                   \
+            return fail(SB200_ERR_WORKSPACE, "add_layer_norm_bwd: workspace too small for %d blocks", grid);          \
         add_ln_bwd_kernel<NVL_, WPR_><<<grid, kLnThreads, 0, stream>>>(yi, resid, g_f32, g16, gamma, mean, rstd, R,   \
                                                                        dc, dyo, d_resid, partial);                    \
         break;
