@@ -25,6 +25,33 @@ def test_library_exports_every_declared_symbol():
     assert lib.sb200_head_bwd_workspace_bytes(160, 256, 384, 30522) >= 160 * 30522 * 8
 
 
+def test_ctypes_prototypes_match_the_header():
+    """Every ctypes prototype of _lib.py has the argument count and the scalar/pointer kinds of its declaration in
+    include/sparse_b200.h (a mismatch would corrupt the stack silently, and no CPU test calls the kernels)."""
+    import ctypes
+    header = open(os.path.join(ROOT, "include", "sparse_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    protos = dict(re.findall(r"\b(sb200_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", header, flags=re.S))
+    assert set(protos) == set(_lib._PROTOTYPES)
+    for name, params in protos.items():
+        params = " ".join(params.split())
+        args = [] if params in ("", "void") else [a.strip() for a in params.split(",")]
+        restype, argtypes = _lib._PROTOTYPES[name]
+        assert len(args) == len(argtypes), (name, args, argtypes)
+        for a, t in zip(args, argtypes):
+            is_ptr = "*" in a or a.startswith("sb200_stream_t")
+            if is_ptr:
+                assert t is ctypes.c_void_p, (name, a, t)
+            elif a.startswith("float"):
+                assert t is ctypes.c_float, (name, a, t)
+            elif a.startswith("size_t"):
+                assert t is ctypes.c_size_t, (name, a, t)
+            elif a.startswith("int ") or a.startswith("int32_t"):
+                assert t is ctypes.c_int, (name, a, t)
+            else:
+                raise AssertionError(f"{name}: unclassified parameter {a!r}")
+
+
 def test_argument_errors_are_reported_not_crashes():
     lib = _lib.load()
     code = lib.sb200_head_fwd(0, 0, 0, 0, 8, 1, 1, 8, 1, 0, 0, 0, 0, 0, 0, 0)
