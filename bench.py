@@ -159,9 +159,6 @@ def run_ours(args):
     torch.cuda.set_device(device)
     if world > 1:
         os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")  # required for NCCL inside CUDA graphs
-        # stdout carries exactly one JSON line: NCCL's own banner ("NCCL version ...", printed when NCCL_DEBUG is set
-        # on the box) goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=device)
     import sparse_b200
     from sparse_b200 import ops
@@ -330,7 +327,7 @@ def run_ours(args):
             line["cpu_baseline"] = cpu_baseline(wl, args.regime, seconds=args.cpu_seconds)
         if not args.no_extras and world == 1:
             line["extras"] = extras(trainer, wl, device, peaks)
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         torch.cuda.synchronize()
@@ -479,7 +476,7 @@ def run_reference(args):
     value = steps * n_queries / dt
     sample = (f"each step = {n_queries} queries x {wl['docs_per_query']} docs (seq {wl['doc_len']}) of the workload, fp32 "
               f"torch CPU, {torch.get_num_threads()} threads")
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "infonce_train_samples_per_sec", "value": round(value, 3), "unit": "samples/s",
         "n_gpus": world, "steps": steps, "warmup": 1, "ms_per_step": round(dt / steps * 1e3, 2),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -487,10 +484,30 @@ def run_reference(args):
         "cpu_baseline": {"value": round(value, 3), "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
                          "sample": sample},
         "e2e": {"value": round(value, 3), "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }), flush=True)
+    })
+
+
+_RESULT_OUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly one JSON line. Libraries write banners to fd 1 (NCCL prints "NCCL version ..." there when
+    NCCL_DEBUG is set on the box): keep a private duplicate of the original stdout for the result and point fd 1 at
+    stderr for everything else."""
+    global _RESULT_OUT
+    sys.stdout.flush()
+    _RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    out = _RESULT_OUT if _RESULT_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
+    claim_stdout()
     if os.environ.get("SB200_FAULT_TIMEOUT"):
         import faulthandler
         faulthandler.dump_traceback_later(int(os.environ["SB200_FAULT_TIMEOUT"]), exit=True)
