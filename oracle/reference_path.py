@@ -12,7 +12,6 @@ outputs of the reference's own modules, generated in the build container by ``or
 
 Every function names the reference lines it follows (paths relative to the reference root).
 """
-import math
 
 import torch
 

@@ -120,7 +120,7 @@ def test_synthetic_batches_layout():
 def test_packed_body_plan_and_repad_cpu():
     """Host-side logic of the padding-free body: device-free placement plan (holes, empty rows, overflow) and the
     scatter back to [B, L, H] with its gradient."""
-    from sparse_b200.scripts.model.packed_body import PackedBertBody, _Repad
+    from sparse_b200.scripts.model.packed_body import PackedBertBody
     body = PackedBertBody.__new__(PackedBertBody)
     body.capacity, body.overflow_count = 1.0, None
     mask = torch.tensor([[1, 1, 1, 0], [1, 0, 1, 1], [0, 0, 0, 0], [1, 1, 1, 1]])
