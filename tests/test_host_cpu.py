@@ -146,3 +146,15 @@ def test_packed_body_plan_and_repad_cpu():
     assert dest[kept].tolist() == list(range(8)) + [8, 8] and int(cu.max()) == 8 and cu.tolist() == sorted(cu.tolist())
     body._plan(mask[:2])
     assert int(body.overflow_count) == 1                                  # 6 tokens fit the 8 rows: counter unchanged
+
+
+def test_trainer_refuses_overflowed_packed_batches():
+    """A batch that did not fit unpad_capacity is reported at logging cadence, never trained on silently."""
+    from types import SimpleNamespace
+    from sparse_b200.scripts.train.trainer import SparseModelTrainer
+    t = SparseModelTrainer.__new__(SparseModelTrainer)
+    t.model_wrapper = SimpleNamespace(sparse_model=SimpleNamespace(unpad_overflows=lambda: 0))
+    t._check_unpad()
+    t.model_wrapper.sparse_model.unpad_overflows = lambda: 2
+    with pytest.raises(RuntimeError, match="unpad_capacity"):
+        t._check_unpad()
