@@ -167,7 +167,7 @@ def run_ours(args):
     wl = WORKLOADS[args.workload]
     peaks = load_peaks()
     build_trainer.no_fused_body = args.no_fused_body
-    build_trainer.grad_sync = "flat" if args.graph else "ddp"
+    build_trainer.grad_sync = args.grad_sync if args.grad_sync != "auto" else ("flat" if args.graph else "ddp")
     build_trainer.unpad_capacity = args.unpad_capacity if args.unpad_capacity > 0 else None
     trainer = build_trainer(wl, args.regime, device)
     n_pool = 4
@@ -525,6 +525,9 @@ def main():
                          "CUDA graph -- the whole step on one GPU; forward + backward (incl. the NCCL all-gathers) on "
                          "several GPUs, followed by one flat gradient all-reduce and the optimizer")
     ap.set_defaults(graph=True)
+    ap.add_argument("--grad-sync", default="auto", choices=["auto", "ddp", "flat", "flat_overlap"],
+                    help="gradient synchronisation on several GPUs: auto = flat (one all-reduce after the backward pass) "
+                         "with the CUDA graph, ddp without; flat_overlap = bucketed all-reduces issued during backward")
     ap.add_argument("--unpad-capacity", type=float, default=0.85,
                     help="padding-free encoder body: real tokens are packed into ceil(capacity * B * L) rows (the synthetic "
                          "lengths are uniform in [L/2, L], mean 0.75; overflows are counted and fail the run). 0 = padded")

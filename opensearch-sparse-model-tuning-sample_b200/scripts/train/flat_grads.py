@@ -1,0 +1,104 @@
+"""Flat gradient buffer with bucketed all-reduce overlapped with the backward pass (data-parallel training, the
+gradient all-reduce of the reference's DDP wrapper: HF Trainer / accelerate around ``scripts/train/trainer.py``).
+
+All parameter gradients are views of one flat fp32 buffer (static addresses: CUDA-graph friendly). The buffer is cut
+into contiguous buckets; a post-accumulate hook per parameter counts a bucket down and, when its last gradient has
+been accumulated, issues the bucket's all-reduce on a side stream, so that the transfer runs while the backward pass
+of the earlier layers is still computing. ``finish()`` issues whatever is left and makes the compute stream wait for
+the side stream. Inside a CUDA-graph capture the side stream is forked from and joined back into the capturing
+stream, so the collectives become nodes of the same graph. The mean over ranks is taken by NCCL (``ReduceOp.AVG``).
+
+On CPU tensors (gloo, tests) the same bookkeeping runs without streams.
+"""
+import torch
+import torch.distributed as dist
+
+
+class FlatGradBuckets:
+    def __init__(self, params, num_processes, group=None, bucket_bytes=24 << 20, overlap=True):
+        self.params = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("FlatGradBuckets: no trainable parameters")
+        self.world = int(num_processes)
+        self.group = group
+        dev = self.params[0].device
+        self.device = dev
+        total = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        spans, off = [], 0
+        for p in self.params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            spans.append((off, off + p.numel()))
+            off += p.numel()
+        # buckets are cut from the END of the buffer: the gradients of the last layers are produced first
+        per_bucket = max(1, int(bucket_bytes) // 4)
+        self.bounds, self.bucket_of = [], [0] * len(self.params)
+        hi, i = total, len(self.params) - 1
+        while i >= 0:
+            lo = hi
+            while i >= 0 and (hi - lo < per_bucket or lo == hi):
+                lo = spans[i][0]
+                self.bucket_of[i] = len(self.bounds)
+                i -= 1
+            self.bounds.append((lo, hi))
+            hi = lo
+        self._count = [0] * len(self.bounds)
+        for b in self.bucket_of:
+            self._count[b] += 1
+        self._left = list(self._count)
+        self._launched = [False] * len(self.bounds)
+        self.comm_stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
+        self._use_avg = dev.type == "cuda" and dist.is_initialized() and dist.get_backend(group) == "nccl"
+        self._handles = []
+        if overlap:
+            for idx, p in enumerate(self.params):
+                self._handles.append(p.register_post_accumulate_grad_hook(self._make_hook(idx)))
+
+    def _make_hook(self, idx):
+        def hook(param):
+            b = self.bucket_of[idx]
+            self._left[b] -= 1
+            if self._left[b] == 0:
+                self._launch(b)
+        return hook
+
+    def _all_reduce(self, t):
+        if self.world <= 1 or not dist.is_initialized():
+            return
+        if self._use_avg:
+            dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.group)
+        else:
+            dist.all_reduce(t, group=self.group)
+            t.div_(self.world)
+
+    def _launch(self, b):
+        if self._launched[b]:
+            return
+        self._launched[b] = True
+        lo, hi = self.bounds[b]
+        t = self.flat[lo:hi]
+        if self.comm_stream is None:
+            self._all_reduce(t)
+            return
+        # the gradient was accumulated on the stream that is current inside the hook (the autograd engine sets it)
+        self.comm_stream.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.comm_stream):
+            self._all_reduce(t)
+
+    def zero(self):
+        self.flat.zero_()
+
+    def finish(self):
+        """After backward: all-reduce the buckets whose hooks did not complete (parameters without a gradient in this
+        step), in bucket order on every rank, then make the current stream wait for the communication stream."""
+        for b in range(len(self.bounds)):
+            self._launch(b)
+        if self.comm_stream is not None:
+            torch.cuda.current_stream(self.device).wait_stream(self.comm_stream)
+        self._left = list(self._count)
+        self._launched = [False] * len(self.bounds)
+
+    def remove_hooks(self):
+        for h in self._handles:
+            h.remove()
+        self._handles = []

@@ -52,7 +52,9 @@ class SparseModelTrainer:
                  data_collator=None, optimizers=(None, None), accelerator=None, grad_sync="ddp", **unused):
         """grad_sync: "ddp" (torch DistributedDataParallel, bucketed all-reduce overlapped with backward; eager launches)
         or "flat" (gradients live in one flat fp32 buffer that is all-reduced with a single NCCL call after backward;
-        this is the mode whose forward+backward can be captured in a CUDA graph on several GPUs)."""
+        this is the mode whose forward+backward can be captured in a CUDA graph on several GPUs), or "flat_overlap"
+        (same buffer, cut into buckets whose all-reduces are issued from gradient hooks on a side stream while the
+        backward pass is still running -- flat_grads.FlatGradBuckets; graph-capturable as well)."""
         self.model_args = model_args
         self.data_args = data_args
         self.loss_functions = loss_functions
@@ -70,12 +72,18 @@ class SparseModelTrainer:
         self.model = wrapper
         self.grad_sync = grad_sync if self.accelerator.num_processes > 1 else "none"
         self._flat_grads = None
+        self._buckets = None
         if self.grad_sync == "ddp" and next(wrapper.parameters()).is_cuda:
             dev = next(wrapper.parameters()).device
             self.model = torch.nn.parallel.DistributedDataParallel(wrapper, device_ids=[dev.index],
                                                                    gradient_as_bucket_view=True)
         elif self.grad_sync == "flat":
             self._setup_flat_grads()
+        elif self.grad_sync == "flat_overlap":
+            from .flat_grads import FlatGradBuckets
+            self._buckets = FlatGradBuckets(self.model_wrapper.parameters(), self.accelerator.num_processes,
+                                            group=getattr(self.accelerator, "group", None))
+            self._flat_grads = self._buckets.flat
         self.scaler = None
         if args is not None and getattr(args, "fp16", False):
             self.scaler = torch.amp.GradScaler("cuda")
@@ -199,6 +207,9 @@ class SparseModelTrainer:
 
     def _sync_flat_grads(self):
         """One NCCL all-reduce of the flat gradient buffer; mean over ranks like DDP (the loss carries x world)."""
+        if self._buckets is not None:   # "flat_overlap": most buckets are already in flight; issue the rest and join
+            self._buckets.finish()
+            return
         import torch.distributed as dist
         dist.all_reduce(self._flat_grads, group=getattr(self.accelerator, "group", None))
         self._flat_grads.div_(self.accelerator.num_processes)
@@ -242,7 +253,7 @@ class SparseModelTrainer:
         warm-up (get_lambda) is computed on the device from an in-graph step counter. Single process only.
         """
         multi = self.accelerator.num_processes > 1
-        if multi and self.grad_sync != "flat":
+        if multi and self.grad_sync not in ("flat", "flat_overlap"):
             raise RuntimeError('CUDA-graph mode on several GPUs needs grad_sync="flat" (forward + backward, including '
                                "the NCCL all-gathers of the representations, are captured; the single flat gradient "
                                "all-reduce and the optimizer step run right after the replay)")
@@ -263,6 +274,9 @@ class SparseModelTrainer:
             if multi:
                 self._zero_grads()
                 loss = self._forward_backward(dict(self._static_inputs))
+                if self._buckets is not None:
+                    # bucket all-reduces were forked onto the side stream during backward: join them inside the capture
+                    self._sync_flat_grads()
             else:
                 loss = self._eager_step_body(dict(self._static_inputs))
             self._step_t += 1.0
@@ -270,7 +284,8 @@ class SparseModelTrainer:
 
         def after_replay():
             if multi:
-                self._sync_flat_grads()
+                if self._buckets is None:
+                    self._sync_flat_grads()
                 self.optimizer.step()
 
         self._after_replay = after_replay

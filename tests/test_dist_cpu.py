@@ -77,3 +77,68 @@ def test_gather_rep_single_process_is_identity():
     from sparse_b200.scripts.utils import DistEnv, gather_rep
     x = torch.randn(3, 5, requires_grad=True)
     assert gather_rep(x, DistEnv()) is x
+
+
+def _bucket_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import sparse_b200  # noqa: F401
+        from sparse_b200.scripts.train.flat_grads import FlatGradBuckets
+
+        def build():
+            torch.manual_seed(7)
+            emb = torch.nn.Embedding(50, 16)
+            body = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.Tanh(), torch.nn.Linear(32, 16))
+            dec = torch.nn.Linear(16, 50)
+            dec.weight = emb.weight                      # tied, like the MLM decoder
+            unused = torch.nn.Linear(4, 4)               # never reached by the loss
+            return torch.nn.ModuleList([emb, body, dec, unused])
+
+        def loss_of(m, step):
+            g = torch.Generator().manual_seed(1000 * step + rank)
+            ids = torch.randint(0, 50, (6, 5), generator=g)
+            return m[2](m[1](m[0](ids))).logsumexp(-1).mean() * world
+
+        ref, net = build(), build()
+        buckets = FlatGradBuckets(net.parameters(), world, bucket_bytes=2048)
+        assert len(buckets.bounds) >= 3
+        for step in range(3):
+            # reference: plain backward, one all-reduce per parameter, mean
+            for p in ref.parameters():
+                p.grad = None
+            loss_of(ref, step).backward()
+            want = []
+            for p in ref.parameters():
+                g = torch.zeros_like(p) if p.grad is None else p.grad.clone()
+                dist.all_reduce(g)
+                want.append(g / world)
+            buckets.zero()
+            loss_of(net, step).backward()
+            assert any(buckets._launched), "no bucket was reduced during backward"
+            buckets.finish()
+            assert buckets._left == buckets._count and not any(buckets._launched)
+            for p, w in zip(net.parameters(), want):
+                assert p.grad.data_ptr() >= buckets.flat.data_ptr()          # still a view of the flat buffer
+                torch.testing.assert_close(p.grad, w, rtol=1e-6, atol=1e-7)
+        out.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        import traceback
+        out.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_bucketed_flat_gradients_match_plain_allreduce_world2():
+    """flat_grads.FlatGradBuckets: hooks reduce buckets during backward (tied weights, a parameter without gradient,
+    several steps); result = mean over ranks of the plain gradients."""
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_bucket_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [out.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(results) == [(0, "ok"), (1, "ok")], results
