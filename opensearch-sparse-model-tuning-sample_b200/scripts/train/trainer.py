@@ -211,8 +211,12 @@ class SparseModelTrainer:
             self._buckets.finish()
             return
         import torch.distributed as dist
-        dist.all_reduce(self._flat_grads, group=getattr(self.accelerator, "group", None))
-        self._flat_grads.div_(self.accelerator.num_processes)
+        group = getattr(self.accelerator, "group", None)
+        if self._flat_grads.is_cuda and dist.get_backend(group) == "nccl":
+            dist.all_reduce(self._flat_grads, op=dist.ReduceOp.AVG, group=group)   # mean taken inside NCCL
+        else:
+            dist.all_reduce(self._flat_grads, group=group)
+            self._flat_grads.div_(self.accelerator.num_processes)
 
     def _forward_backward(self, inputs):
         """forward (autocast) + loss + backward; gradients are left in .grad (not yet synchronised in "flat" mode)."""
