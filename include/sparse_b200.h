@@ -90,15 +90,15 @@ int sb200_prune_rows(float* rep, int B, int V, float ratio, sb200_stream_t strea
 
 /* ---------------------------------------------------------------------------------------------
  * (3) Inf-free IDF query encoding.   Replaces sparse_encoders.py:121-127.
- *   ids      i64 [Nq, Lq]   token ids (attention mask is ignored, as in the reference)
+ *   ids      i64 or i32 [Nq, Lq] token ids, ids_elem_bytes = 8 or 4 (attention mask is ignored, as in the reference)
  *   idf      f32 [V]        idf_vector parameter
  *   special  i32 [n_special] token ids forced to zero
  *   q        f32 [Nq, V]    out: relu(idf[v]) where v occurs in row and is not special, else 0
  * Bit-exact with the reference.  Ids outside [0, V) are an error in the reference (index error);
  * here they are ignored and counted in *bad_ids (device i32, nullable).
  * ------------------------------------------------------------------------------------------- */
-int sb200_idf_query(const int64_t* ids, const float* idf, const int32_t* special, int n_special, int Nq, int Lq, int V,
-                    float* q, int32_t* bad_ids, sb200_stream_t stream);
+int sb200_idf_query(const void* ids, int ids_elem_bytes, const float* idf, const int32_t* special, int n_special, int Nq,
+                    int Lq, int V, float* q, int32_t* bad_ids, sb200_stream_t stream);
 /* d_idf[v] = sum_b d_q[b,v] * [q[b,v] > 0]   (gradient of the above w.r.t. idf; idf_requires_grad) */
 int sb200_idf_query_bwd(const float* d_q, const float* q, int Nq, int V, float* d_idf, sb200_stream_t stream);
 

@@ -30,7 +30,7 @@ _PROTOTYPES = {
     "sb200_head_bwd": (_c_int, [_vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp,
                                 _sz, _vp]),
     "sb200_prune_rows": (_c_int, [_vp, _c_int, _c_int, _c_f, _vp]),
-    "sb200_idf_query": (_c_int, [_vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp]),
+    "sb200_idf_query": (_c_int, [_vp, _c_int, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp]),
     "sb200_idf_query_bwd": (_c_int, [_vp, _vp, _c_int, _c_int, _vp, _vp]),
     "sb200_flops_fwd": (_c_int, [_vp, _c_int, _c_int, _c_int, _c_f, _vp, _vp, _vp, _vp, _vp]),
     "sb200_flops_bwd": (_c_int, [_vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp]),
@@ -83,8 +83,6 @@ def load():
         try:
             fn = getattr(lib, name)
         except AttributeError:
-            if os.environ.get("SB200_ALLOW_PARTIAL") == "1":  # kernel bring-up only
-                continue
             raise SparseB200Error(f"{LIB_PATH} does not export {name}; rebuild the library") from None
         fn.restype = res
         fn.argtypes = args

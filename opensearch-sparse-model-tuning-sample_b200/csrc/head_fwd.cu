@@ -62,8 +62,6 @@ struct HeadFwdParams {
     int LC, S, NC, N;          // chunk length, sequences per tile, chunks per sequence, S*LC
     int n_vtiles, n_groups, kblocks;   // n_vtiles counts tiles of 128 * kCG vocab rows
     int l0;
-    int dbg;                   // bring-up experiments only, 0 in production (flags >> 8: 1 = epilogue loads TMEM but
-                               // skips the arithmetic, 2 = no padded-column skipping); see DESIGN.md 4.1
     int b_s_off;               // CTA pair, S >= 2: sequence offset of the second CTA's half of the token tile
 };
 
@@ -111,7 +109,7 @@ __global__ void head_prep_kernel(const void* __restrict__ mask, int elem_bytes, 
 // Token columns a tile really needs (S == 1: one sequence per tile): padding beyond the last real token of the
 // chunk is neither multiplied nor read back. Multiple of 16, at least 16.
 __device__ __forceinline__ int tile_columns(const HeadFwdParams& p, int g, int c) {
-    if (p.S != 1 || (p.dbg & 2)) return p.N;
+    if (p.S != 1) return p.N;
     const int extent = __ldg(p.seqinfo + g).z - c * p.LC;
     const int n = (min(max(extent, 1), p.LC) + 15) & ~15;
     return n;
@@ -314,13 +312,6 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
                 if (hi != 0) tmem_ld16(tmem_acc + n1, rb);
                 if ((lo | hi) != 0) tmem_ld_wait();
                 const int l0 = l_begin + (n0 - n_begin);
-                if (p.dbg & 1) {  // experiment: TMEM loads only
-                    uint32_t acc = 0;
-                    if (lo != 0) for (int i = 0; i < 16; ++i) acc |= ra[i];
-                    if (hi != 0) for (int i = 0; i < 16; ++i) acc |= rb[i];
-                    if (acc == 0x12345678u) idx = 1;
-                    continue;
-                }
                 if (!want_arg) {
                     if (lo == 0xffffu) block16_value(ra, lo, std::false_type{});
                     else if (lo != 0) block16_value(ra, lo, std::true_type{});
@@ -567,7 +558,6 @@ extern "C" int sb200_head_fwd(const void* hidden, const void* W, const float* bi
     p.n_groups = t.n_groups;
     p.kblocks = (H + kBlockK - 1) / kBlockK;
     p.l0 = (flags & SB200_HEAD_L0) ? 1 : 0;
-    p.dbg = (flags >> 8) & 0xff;
     p.b_s_off = b_s_off;
 
     const long long total_units = (long long)p.n_vtiles * p.n_groups;

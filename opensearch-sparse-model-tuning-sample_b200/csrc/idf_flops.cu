@@ -20,33 +20,27 @@ __device__ __forceinline__ float warp_max(float x) {
 }
 
 // ------------------------------------------------------------------------------------------ IDF query
-// grid (slabs, Nq): a block zero-fills its slab of the row, barriers, then stores relu(idf[id]) for the ids of the
-// row that fall into the slab. Duplicate ids store the same value (idempotent), specials and bad ids are skipped.
+// grid (slabs of kIdfSlab columns, Nq): the block builds its slab of the row in shared memory (zero-fill, then
+// relu(idf[id]) for the row's ids that fall into the slab; duplicate ids store the same value, specials and ids outside
+// [0, V) are skipped) and streams it out once with 16-byte stores. Every output byte is written exactly once; many
+// small blocks keep all SMs busy whatever Nq is (the whole kernel is a Nq*V*4-byte write).
 constexpr int kIdfThreads = 256;
+constexpr int kIdfSlab = 4096;
 
+template <typename IdT>
 __global__ void __launch_bounds__(kIdfThreads)
-idf_query_kernel(const int64_t* __restrict__ ids, const float* __restrict__ idf, const int32_t* __restrict__ special,
-                 int n_special, int Lq, int V, int slab, float* __restrict__ q, int32_t* __restrict__ bad_ids) {
+idf_query_kernel(const IdT* __restrict__ ids, const float* __restrict__ idf, const int32_t* __restrict__ special,
+                 int n_special, int Lq, int V, float* __restrict__ q, int32_t* __restrict__ bad_ids) {
+    __shared__ __align__(16) float slab[kIdfSlab];
     const int b = blockIdx.y;
-    const int s0 = blockIdx.x * slab;
-    const int s1 = min(V, s0 + slab);
-    float* row = q + size_t(b) * V;
-    // zero fill [s0, s1): scalar head up to 16-byte alignment, float4 body, scalar tail
-    {
-        const uintptr_t addr = reinterpret_cast<uintptr_t>(row + s0);
-        int head = int(((16 - (addr & 15)) & 15) >> 2);
-        head = min(head, s1 - s0);
-        const int body4 = (s1 - s0 - head) >> 2;
-        const int tail0 = s0 + head + body4 * 4;
-        if (int(threadIdx.x) < head) row[s0 + threadIdx.x] = 0.f;
-        float4* p4 = reinterpret_cast<float4*>(row + s0 + head);
-        for (int i = threadIdx.x; i < body4; i += kIdfThreads) p4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (tail0 + int(threadIdx.x) < s1) row[tail0 + threadIdx.x] = 0.f;
-    }
+    const int s0 = blockIdx.x * kIdfSlab;
+    const int s1 = min(V, s0 + kIdfSlab);
+    for (int i = threadIdx.x; i < kIdfSlab / 4; i += kIdfThreads)
+        reinterpret_cast<float4*>(slab)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
     int bad = 0;
     for (int l = threadIdx.x; l < Lq; l += kIdfThreads) {
-        const int64_t id = __ldg(ids + size_t(b) * Lq + l);
+        const long long id = static_cast<long long>(__ldg(ids + size_t(b) * Lq + l));
         if (id < 0 || id >= V) {
             ++bad;
             continue;
@@ -54,9 +48,22 @@ idf_query_kernel(const int64_t* __restrict__ ids, const float* __restrict__ idf,
         if (id < s0 || id >= s1) continue;
         bool is_special = false;
         for (int k = 0; k < n_special; ++k) is_special |= (__ldg(special + k) == int32_t(id));
-        if (!is_special) row[id] = fmaxf(__ldg(idf + id), 0.f);
+        if (!is_special) slab[int(id) - s0] = fmaxf(__ldg(idf + id), 0.f);
     }
     if (bad_ids != nullptr && blockIdx.x == 0 && bad > 0) atomicAdd(bad_ids, bad);
+    __syncthreads();
+    // stream the slab out: scalar head up to 16-byte alignment of the destination, float4 body, scalar tail
+    float* dst = q + size_t(b) * V + s0;
+    const int n = s1 - s0;
+    const int head = min(n, int(((16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15) >> 2));
+    const int body4 = (n - head) >> 2;
+    if (int(threadIdx.x) < head) dst[threadIdx.x] = slab[threadIdx.x];
+    for (int i = threadIdx.x; i < body4; i += kIdfThreads) {
+        const float* sp = slab + head + 4 * i;
+        reinterpret_cast<float4*>(dst + head)[i] = make_float4(sp[0], sp[1], sp[2], sp[3]);
+    }
+    const int tail0 = head + 4 * body4;
+    if (tail0 + int(threadIdx.x) < n) dst[tail0 + threadIdx.x] = slab[tail0 + threadIdx.x];
 }
 
 // d_idf[v] = sum_b d_q[b,v] * [q[b,v] > 0]
@@ -191,19 +198,20 @@ flops_bwd_kernel(const float* __restrict__ rep, const float* __restrict__ colsum
 
 using namespace sb200;
 
-extern "C" int sb200_idf_query(const int64_t* ids, const float* idf, const int32_t* special, int n_special, int Nq,
-                               int Lq, int V, float* q, int32_t* bad_ids, sb200_stream_t stream_) {
+extern "C" int sb200_idf_query(const void* ids, int ids_elem_bytes, const float* idf, const int32_t* special, int n_special,
+                               int Nq, int Lq, int V, float* q, int32_t* bad_ids, sb200_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     SB200_REQUIRE(ids && idf && q && (special || n_special == 0), "idf_query: null pointer");
+    SB200_REQUIRE(ids_elem_bytes == 8 || ids_elem_bytes == 4, "idf_query: ids_elem_bytes=%d", ids_elem_bytes);
     SB200_REQUIRE(Nq >= 1 && Lq >= 1 && V >= 1 && n_special >= 0 && Nq <= 65535, "idf_query: bad shape");
-    // enough blocks to fill the machine: Nq rows x slabs
-    int slabs = (2 * num_sms() + Nq - 1) / Nq;
-    if (slabs < 1) slabs = 1;
-    int slab = (V + slabs - 1) / slabs;
-    slab = int(align_up(size_t(slab), 1024));
-    slabs = (V + slab - 1) / slab;
     if (bad_ids != nullptr) SB200_CUDA(cudaMemsetAsync(bad_ids, 0, sizeof(int32_t), stream));
-    idf_query_kernel<<<dim3(slabs, Nq), kIdfThreads, 0, stream>>>(ids, idf, special, n_special, Lq, V, slab, q, bad_ids);
+    const dim3 grid((V + kIdfSlab - 1) / kIdfSlab, Nq);
+    if (ids_elem_bytes == 8)
+        idf_query_kernel<int64_t><<<grid, kIdfThreads, 0, stream>>>(static_cast<const int64_t*>(ids), idf, special,
+                                                                    n_special, Lq, V, q, bad_ids);
+    else
+        idf_query_kernel<int32_t><<<grid, kIdfThreads, 0, stream>>>(static_cast<const int32_t*>(ids), idf, special,
+                                                                    n_special, Lq, V, q, bad_ids);
     SB200_CHECK_LAUNCH("idf_query_kernel");
     return SB200_OK;
 }

@@ -28,9 +28,6 @@ def _workspace(nbytes, device):
     return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
 
 
-import os as _os
-_DEBUG_FLAGS = int(_os.environ.get("SB200_HEAD_DEBUG", "0")) << 8  # kernel bring-up experiments only
-
 # Optional per-call CUDA-event timing of named C-ABI calls (used by bench.py for the live roofline numbers).
 _PROFILE = None
 
@@ -101,7 +98,7 @@ def head_forward(hidden, weight, bias, attention_mask, use_l0=False, want_aux=Tr
     ws = _workspace(ws_bytes, dev)
     with torch.cuda.device(dev), _timed("head_fwd"):
         code = lib.sb200_head_fwd(_ptr(hidden), _ptr(weight), _ptr(bias), _ptr(mask), mask.element_size(), B, L, H, V,
-                                  (_lib.HEAD_L0 if use_l0 else 0) | _DEBUG_FLAGS, _ptr(rep), _ptr(xmax), _ptr(argmax),
+                                  (_lib.HEAD_L0 if use_l0 else 0), _ptr(rep), _ptr(xmax), _ptr(argmax),
                                   _ptr(ws), ws.numel(), _stream())
     _lib.check(code, "sb200_head_fwd")
     return rep, xmax, argmax
@@ -169,17 +166,30 @@ def sparse_head(hidden, weight, bias, attention_mask, use_l0=False):
 
 
 # --------------------------------------------------------------------------------------------- inf-free query
-def idf_query_forward(input_ids, idf_vector, special_ids):
+def idf_query_forward(input_ids, idf_vector, special_ids, check_ids=None):
+    """q[b, v] = relu(idf[v]) for the non-special token ids of row b (sparse_encoders.py:121-127), bit-exact.
+    Token ids outside [0, V) make the reference raise an index error; here they are counted on the device and, when
+    `check_ids` is true (default: whenever gradients are off, i.e. encode / eval, and no stream capture is running),
+    the count is read back and an IndexError is raised. The training step skips the read-back (it would be a host
+    synchronisation per step) -- such ids contribute nothing there."""
     _need_cuda(input_ids, idf_vector, special_ids)
-    ids = input_ids.to(torch.int64).contiguous()
+    ids = input_ids
+    if ids.dtype not in (torch.int64, torch.int32):
+        ids = ids.to(torch.int64)
+    ids = ids.contiguous()
     Nq, Lq = ids.shape
     idf = idf_vector.detach().float().contiguous()
     V = idf.numel()
     q = torch.empty(Nq, V, dtype=torch.float32, device=ids.device)
+    if check_ids is None:
+        check_ids = not torch.is_grad_enabled() and not torch.cuda.is_current_stream_capturing()
+    bad = torch.empty(1, dtype=torch.int32, device=ids.device) if check_ids else None
     with torch.cuda.device(ids.device):
-        code = _lib.load().sb200_idf_query(_ptr(ids), _ptr(idf), _ptr(special_ids), int(special_ids.numel()), Nq, Lq, V,
-                                           _ptr(q), 0, _stream())
+        code = _lib.load().sb200_idf_query(_ptr(ids), ids.element_size(), _ptr(idf), _ptr(special_ids),
+                                           int(special_ids.numel()), Nq, Lq, V, _ptr(q), _ptr(bad), _stream())
     _lib.check(code, "sb200_idf_query")
+    if bad is not None and int(bad) != 0:
+        raise IndexError(f"idf_query: {int(bad)} token id(s) outside [0, {V})")
     return q
 
 

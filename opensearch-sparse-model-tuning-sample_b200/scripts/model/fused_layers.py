@@ -11,22 +11,26 @@ from ... import ops
 
 
 class FusedLayerNorm(torch.nn.LayerNorm):
-    """Drop-in torch.nn.LayerNorm over the last dimension, sm_100a kernels for CUDA tensors."""
+    """Drop-in torch.nn.LayerNorm over the last dimension on the sm_100a kernels. CUDA tensors only: like the rest of
+    the package there is no eager / CPU path (fuse_backbone only swaps modules the kernel supports; fp16 activations
+    are normalised in fp32, which is also what autocast does for torch's LayerNorm)."""
 
     def forward(self, x):
-        if (x.is_cuda and self.elementwise_affine and self.bias is not None and len(self.normalized_shape) == 1
-                and x.dtype in (torch.bfloat16, torch.float32)):
-            return ops.layer_norm(x, self.weight, self.bias, self.eps)
-        return super().forward(x)
+        if x.dtype not in (torch.bfloat16, torch.float32):
+            return ops.layer_norm(x.float(), self.weight, self.bias, self.eps).to(x.dtype)
+        return ops.layer_norm(x, self.weight, self.bias, self.eps)
 
 
 class FusedLinear(torch.nn.Linear):
-    """torch.nn.Linear whose bias gradient comes from the fused column-sum kernel (the GEMMs stay with cuBLAS)."""
+    """torch.nn.Linear whose bias gradient comes from the fused column-sum kernel. The GEMMs themselves are cuBLAS
+    (library) in both branches: with gradients off there is no bias gradient to fuse and the stock op is called."""
 
     def forward(self, x):
-        if x.is_cuda and self.bias is not None and torch.is_grad_enabled() and self.bias.requires_grad:
+        if not x.is_cuda:
+            raise ops._lib.SparseB200Error("FusedLinear runs on CUDA tensors only (no CPU path)")
+        if torch.is_grad_enabled() and self.bias.requires_grad:
             return ops.linear(x, self.weight, self.bias)
-        return super().forward(x)
+        return torch.nn.functional.linear(x, self.weight, self.bias)
 
 
 def _skip_linear(module, backbone):

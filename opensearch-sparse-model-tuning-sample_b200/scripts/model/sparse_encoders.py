@@ -182,6 +182,22 @@ class SparseModel(torch.nn.Module):
         packed = self.__dict__.get("_packed")
         return 0 if packed is None or packed.overflow_count is None else int(packed.overflow_count)
 
+    def unpad_counter(self):
+        """The device-side overflow counter (int64 scalar tensor) or None."""
+        packed = self.__dict__.get("_packed")
+        return None if packed is None else packed.overflow_count
+
+    def unpad_step_flag(self):
+        """fp32 [1] device flag: 1.0 if a forward since the last unpad_step_reset() overflowed the packed capacity.
+        None when the packed body is off or its capacity (>= 1.0) can never overflow."""
+        packed = self.__dict__.get("_packed")
+        return None if packed is None or packed.capacity >= 1.0 else packed.step_overflow
+
+    def unpad_step_reset(self):
+        packed = self.__dict__.get("_packed")
+        if packed is not None and packed.step_overflow is not None:
+            packed.step_overflow.zero_()
+
     # -- reference API -------------------------------------------------------------------------------------------
     def forward(self, inf_free=False, **kwargs):
         return self._encode_inf_free(**kwargs) if inf_free else self._encode(**kwargs)

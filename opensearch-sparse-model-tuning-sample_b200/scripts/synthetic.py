@@ -13,6 +13,8 @@ MODEL_SHAPES = {
     "mini": dict(hidden_size=384, num_hidden_layers=6, num_attention_heads=12, intermediate_size=1536),
     # BERT-base (co-condenser-marco, opensearch-neural-sparse-encoding-v1)
     "base": dict(hidden_size=768, num_hidden_layers=12, num_attention_heads=12, intermediate_size=3072),
+    # kd-ensemble dense teacher stand-in (Alibaba-NLP/gte-large-en-v1.5 scale: 24 layers x 1024)
+    "large": dict(hidden_size=1024, num_hidden_layers=24, num_attention_heads=16, intermediate_size=4096),
     "tiny": dict(hidden_size=64, num_hidden_layers=2, num_attention_heads=4, intermediate_size=128),
 }
 
@@ -87,10 +89,13 @@ def token_batch(batch, seq_len, seed, vocab_size=VOCAB_SIZE, full_length=False, 
 
 
 def train_batch(n_queries, docs_per_query, doc_len, query_len=32, seed=1234, vocab_size=VOCAB_SIZE, device="cpu",
-                with_scores=None):
-    """The dict layout compute_loss expects (reference collator.py:23-57, 146-177): lists, element 0 = student."""
-    batch = {"query": [token_batch(n_queries, query_len, seed, vocab_size, device=device)],
-             "docs": [token_batch(n_queries * docs_per_query, doc_len, seed + 1, vocab_size, device=device)]}
+                with_scores=None, n_feature_sets=1):
+    """The dict layout compute_loss expects (reference collator.py:23-57, 146-177): lists, element 0 = student,
+    elements 1.. = the same texts tokenised for each kd-ensemble teacher (here: copies of the student's ids)."""
+    q = token_batch(n_queries, query_len, seed, vocab_size, device=device)
+    d = token_batch(n_queries * docs_per_query, doc_len, seed + 1, vocab_size, device=device)
+    batch = {"query": [q] + [{k: v.clone() for k, v in q.items()} for _ in range(n_feature_sets - 1)],
+             "docs": [d] + [{k: v.clone() for k, v in d.items()} for _ in range(n_feature_sets - 1)]}
     if with_scores is not None:
         g = torch.Generator().manual_seed(seed + 11)
         batch["scores"] = (torch.randn(n_queries, with_scores, generator=g) * 3).to(device)

@@ -7,6 +7,8 @@ own minimal data-parallel loop: one process per GPU, torch DDP (NCCL) for the gr
 for the representation all-gather, bf16/fp16 autocast around the model forward, AdamW + linear warm-up as built by
 train_ir.py.
 """
+import contextlib
+import gc
 import json
 import logging
 import os
@@ -92,7 +94,8 @@ class SparseModelTrainer:
         self._static_inputs = None
         self._static_loss = None
         self._step_t = None
-        self._after_replay = lambda: None
+        self._ovf_host = None
+        self._ovf_event = None
 
     # ------------------------------------------------------------------ reference attribute, without a per-step sync
     @property
@@ -123,8 +126,10 @@ class SparseModelTrainer:
     def compute_loss(self, model, inputs, return_outputs=False, num_items_in_batch=None):
         """reference :81-143"""
         if hasattr(self, "bi_encoder_teacher"):
-            inputs["scores"] = self.bi_encoder_teacher.get_scores_batch(q_features_list=inputs["query"][1:],
-                                                                        d_features_list=inputs["docs"][1:])
+            # HF Trainer runs compute_loss inside its autocast context, so the reference's teachers run in half precision
+            with self._autocast():
+                inputs["scores"] = self.bi_encoder_teacher.get_scores_batch(q_features_list=inputs["query"][1:],
+                                                                            d_features_list=inputs["docs"][1:])
         student = {"q_input_ids": inputs["query"][0]["input_ids"],
                    "q_attention_mask": inputs["query"][0]["attention_mask"],
                    "input_ids": inputs["docs"][0]["input_ids"],
@@ -168,9 +173,28 @@ class SparseModelTrainer:
         sm = self.model_wrapper.sparse_model
         if (env.num_processes > 1 and self.model_args.inf_free and not sm.idf_requires_grad and q_rep.is_cuda
                 and hasattr(env, "gather")):
-            all_ids = env.gather(q_input_ids.contiguous())
+            # The collator pads to the longest text of the LOCAL batch (collator.py:34-41), so Lq differs between ranks
+            # while all_gather_into_tensor needs equal shapes: every rank right-pads its ids to max_seq_length (the
+            # collator truncates there, so no batch is longer) with a special-token id, which the IDF kernel ignores
+            # exactly like the reference zeroes the special columns -- the rebuilt vectors stay bit-exact.
+            width = int(getattr(self.data_args, "max_seq_length", 0) or 0)
+            ids = q_input_ids
+            if ids.shape[1] > width:
+                width = self._agree_on_width(ids.shape[1])
+            if ids.shape[1] < width:
+                pad = ids.new_full((ids.shape[0], width - ids.shape[1]), int(sm.special_token_ids[0]))
+                ids = torch.cat([ids, pad], dim=1)
+            all_ids = env.gather(ids.to(torch.int32).contiguous())
             return ops.idf_query(all_ids, sm.idf_vector, sm._special_ids_on(all_ids.device))
         return gather_rep(q_rep, env)
+
+    def _agree_on_width(self, local_width):
+        """max over ranks of a host integer (queries longer than max_seq_length: one small all-reduce + sync)."""
+        import torch.distributed as dist
+        dev = next(self.model_wrapper.parameters()).device
+        t = torch.tensor([int(local_width)], device=dev, dtype=torch.int64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=getattr(self.accelerator, "group", None))
+        return int(t.item())
 
     def _log_step(self, d_rep, d_flops, flops_loss):
         with torch.no_grad():
@@ -185,9 +209,13 @@ class SparseModelTrainer:
 
     # ------------------------------------------------------------------ step / loop
     def _autocast(self):
+        """fp16 / bf16 autocast exactly when the training arguments ask for it; fp32 otherwise, like the reference.
+        (The fused head always multiplies half-precision operands: bf16 unless fp16 autocast is active.)"""
         if self.args is not None and getattr(self.args, "fp16", False):
             return torch.autocast("cuda", dtype=torch.float16)
-        return torch.autocast("cuda", dtype=torch.bfloat16)
+        if self.args is None or getattr(self.args, "bf16", False):
+            return torch.autocast("cuda", dtype=torch.bfloat16)
+        return contextlib.nullcontext()
 
     def _setup_flat_grads(self):
         """All parameter gradients become views of one flat fp32 buffer (one all-reduce, static addresses)."""
@@ -224,23 +252,53 @@ class SparseModelTrainer:
             with self._autocast():
                 return self.model(student)
 
+        self.model_wrapper.sparse_model.unpad_step_reset()
         loss = self.compute_loss(run, inputs)
-        loss.backward()
+        if self.scaler is not None:
+            flag = self.model_wrapper.sparse_model.unpad_step_flag()
+            if flag is not None:   # fp16: poison the loss so that GradScaler skips the step of an overflowed batch
+                loss = loss + torch.where(flag > 0, torch.full_like(flag, float("inf")), torch.zeros_like(flag)).sum()
+            self.scaler.scale(loss).backward()
+        else:
+            loss.backward()
         return loss
+
+    def _optimizer_step(self):
+        """optimizer.step(), skipped ON THE DEVICE for a batch that overflowed the packed-body capacity: the fused
+        AdamW kernels take the same `found_inf` flag GradScaler uses for fp16 overflows, so the weights, the moments
+        and the step count stay untouched and a truncated batch can never leak into the model (it is counted, and
+        check_unpad() raises)."""
+        if self.scaler is not None:
+            self.scaler.step(self.optimizer)
+            self.scaler.update()
+            return
+        flag = self.model_wrapper.sparse_model.unpad_step_flag()
+        if flag is not None:
+            if not getattr(self.optimizer, "_step_supports_amp_scaling", False):
+                raise RuntimeError("unpad_capacity < 1 needs an optimizer that can skip a step on a device flag "
+                                   "(torch.optim.AdamW(..., fused=True)); use that or unpad_capacity=1.0")
+            self.optimizer.grad_scale = None
+            self.optimizer.found_inf = flag
+        self.optimizer.step()
 
     def _eager_step_body(self, inputs):
         """forward + loss + backward + gradient sync + optimizer.step, no scheduler / bookkeeping."""
         loss = self._forward_backward(inputs)
         if self._flat_grads is not None:
             self._sync_flat_grads()
-        self.optimizer.step()
+        if self.scaler is not None:
+            self.scaler.unscale_(self.optimizer)
+        max_norm = getattr(self.args, "max_grad_norm", None) if self.args is not None else None
+        if max_norm:
+            torch.nn.utils.clip_grad_norm_(self.model.parameters(), max_norm)
+        self._optimizer_step()
         return loss
 
     @staticmethod
     def _copy_into(dst, src):
         if torch.is_tensor(dst):
             dst.copy_(src, non_blocking=True)
-        elif isinstance(dst, dict):
+        elif hasattr(dst, "items"):
             for k in dst:
                 SparseModelTrainer._copy_into(dst[k], src[k])
         else:
@@ -248,19 +306,21 @@ class SparseModelTrainer:
                 SparseModelTrainer._copy_into(a, b)
 
     def enable_cuda_graph(self, example_inputs, warmup_steps=3):
-        """Captures forward + loss + backward + optimizer step as ONE CUDA graph (fixed batch shapes).
+        """Captures the WHOLE step as one CUDA graph (fixed batch shapes): forward + loss + backward + optimizer, and on
+        several GPUs also every collective -- the all-gathers of the representations, the gradient all-reduce(s)
+        (bucketed and overlapped with backward in "flat_overlap" mode) -- so a step is a single graph launch.
 
         The PyTorch backbone issues ~1000 small launches per step and is host-bound in eager mode; replaying a graph
         removes that. Requirements: bf16 (no GradScaler), no gradient clipping, an optimizer built with
-        capturable=True whose lr is a tensor, batches padded to the shapes of `example_inputs`, and no live reference
-        to a loss / autograd graph of an earlier eager step (its AccumulateGrad nodes belong to the default stream). The regulariser
-        warm-up (get_lambda) is computed on the device from an in-graph step counter. Single process only.
+        capturable=True whose lr is a tensor, batches padded to the shapes of `example_inputs`, no live reference to a
+        loss / autograd graph of an earlier eager step, and grad_sync "flat" / "flat_overlap" on several GPUs. The
+        regulariser warm-up (get_lambda) is computed on the device from an in-graph step counter. Call
+        release_graph() before tearing the process group down.
         """
         multi = self.accelerator.num_processes > 1
         if multi and self.grad_sync not in ("flat", "flat_overlap"):
-            raise RuntimeError('CUDA-graph mode on several GPUs needs grad_sync="flat" (forward + backward, including '
-                               "the NCCL all-gathers of the representations, are captured; the single flat gradient "
-                               "all-reduce and the optimizer step run right after the replay)")
+            raise RuntimeError('CUDA-graph mode on several GPUs needs grad_sync="flat" or "flat_overlap" (gradients in '
+                               "one flat buffer with static addresses)")
         if self.scaler is not None:
             raise RuntimeError("CUDA-graph mode supports bf16 only (fp16 needs GradScaler's host-side decisions)")
         if self.args is not None and getattr(self.args, "max_grad_norm", None):
@@ -273,90 +333,66 @@ class SparseModelTrainer:
         if self._ema is None:
             self._ema = torch.full((), float(self._ema_host), device=device, dtype=torch.float32)
 
-        def captured_part():
-            # single GPU: the whole step; several GPUs: forward + backward (the all-reduce follows the replay)
-            if multi:
+        def whole_step():
+            if self._flat_grads is not None:
                 self._zero_grads()
-                loss = self._forward_backward(dict(self._static_inputs))
-                if self._buckets is not None:
-                    # bucket all-reduces were forked onto the side stream during backward: join them inside the capture
-                    self._sync_flat_grads()
-            else:
-                loss = self._eager_step_body(dict(self._static_inputs))
+            loss = self._eager_step_body(dict(self._static_inputs))
             self._step_t += 1.0
             return loss
 
-        def after_replay():
-            if multi:
-                if self._buckets is None:
-                    self._sync_flat_grads()
-                self.optimizer.step()
-
-        self._after_replay = after_replay
         side = torch.cuda.Stream(device=device)
         side.wait_stream(torch.cuda.current_stream(device))
         with torch.cuda.stream(side):
             for _ in range(warmup_steps):
-                if not multi:
+                if self._flat_grads is None:
                     self.optimizer.zero_grad(set_to_none=True)
-                captured_part()
-                after_replay()
+                whole_step()
                 if self.lr_scheduler is not None:
                     self.lr_scheduler.step()
                 self.state.global_step += 1
         torch.cuda.current_stream(device).wait_stream(side)
         torch.cuda.synchronize(device)
         graph = torch.cuda.CUDAGraph()
-        if not multi:
+        if self._flat_grads is None:
             self.optimizer.zero_grad(set_to_none=True)
         with torch.cuda.graph(graph):
-            self._static_loss = captured_part().detach()
+            self._static_loss = whole_step().detach()
         self._graph = graph
         # the capture itself does not execute; host-side counters stay where the warm-up left them
         return self
 
+    def release_graph(self):
+        """Drops the captured graph (and with it the captured NCCL work) so that the process group can be destroyed."""
+        if self._graph is None:
+            return
+        dev = next(self.model_wrapper.parameters()).device
+        torch.cuda.synchronize(dev)
+        self._graph = None
+        self._static_loss = None
+        self._static_inputs = None
+        self._step_t = None
+        gc.collect()
+        torch.cuda.synchronize(dev)
+
     def training_step(self, inputs):
         """forward (autocast) + loss + backward + optimizer step; returns the detached loss tensor (no sync)."""
+        self._poll_unpad()
         if self._graph is not None:
             self._copy_into(self._static_inputs, inputs)
             self._graph.replay()
-            self._after_replay()
-            if self.lr_scheduler is not None:
-                self.lr_scheduler.step()
-            self.state.global_step += 1
-            return self._static_loss
-        self.model.train()
-        if self._flat_grads is not None:
-            self._flat_grads.zero_()
-
-        def run(student):
-            with self._autocast():
-                return self.model(student)
-
-        loss = self.compute_loss(run, inputs)
-        if self.scaler is not None:
-            self.scaler.scale(loss).backward()
-            if self._flat_grads is not None:
-                self._sync_flat_grads()
-            self.scaler.unscale_(self.optimizer)
+            loss = self._static_loss
         else:
-            loss.backward()
+            self.model.train()
             if self._flat_grads is not None:
-                self._sync_flat_grads()
-        max_norm = getattr(self.args, "max_grad_norm", None) if self.args is not None else None
-        if max_norm:
-            torch.nn.utils.clip_grad_norm_(self.model.parameters(), max_norm)
-        if self.scaler is not None:
-            self.scaler.step(self.optimizer)
-            self.scaler.update()
-        else:
-            self.optimizer.step()
+                self._flat_grads.zero_()
+            loss = self._eager_step_body(inputs).detach()
+            if self._flat_grads is None:
+                self.optimizer.zero_grad(set_to_none=True)
         if self.lr_scheduler is not None:
             self.lr_scheduler.step()
-        if self._flat_grads is None:
-            self.optimizer.zero_grad(set_to_none=True)
         self.state.global_step += 1
-        return loss.detach()
+        self._post_unpad()
+        return loss
 
     def get_train_dataloader(self):
         if self.train_dataset is None:
@@ -376,42 +412,67 @@ class SparseModelTrainer:
     def _to_device(obj, device):
         if torch.is_tensor(obj):
             return obj.to(device, non_blocking=True)
-        if isinstance(obj, dict):
+        if hasattr(obj, "items"):   # dict or a tokenizer's BatchEncoding
             return {k: SparseModelTrainer._to_device(v, device) for k, v in obj.items()}
         if isinstance(obj, (list, tuple)):
             return type(obj)(SparseModelTrainer._to_device(v, device) for v in obj)
         return obj
 
     def train(self):
+        if self.args is not None and int(getattr(self.args, "gradient_accumulation_steps", 1) or 1) != 1:
+            raise NotImplementedError("gradient_accumulation_steps != 1 is not supported by this trainer")
         device = next(self.model_wrapper.parameters()).device
         loader = self.get_train_dataloader()
+        if device.type == "cuda":
+            from ..dataset.collator import PrefetchLoader
+            loader = PrefetchLoader(loader, device)   # pinned host batch -> H2D on a side stream, one step ahead
         epoch = 0
         while self.state.global_step < self.args.max_steps:
             if hasattr(loader.sampler, "set_epoch"):
                 loader.sampler.set_epoch(epoch)
             for batch in loader:
                 self.training_step(self._to_device(batch, device))
-                if self.state.global_step % max(1, self.args.logging_steps) == 0:
-                    self._check_unpad()
                 if self.args.save_strategy == "steps" and self.state.global_step % self.args.save_steps == 0:
                     self._save(os.path.join(self.args.output_dir, f"checkpoint-{self.state.global_step}"))
                 if self.state.global_step >= self.args.max_steps:
                     break
             epoch += 1
-        self._check_unpad()
+        self.check_unpad()
         return self.state.global_step
 
-    def _check_unpad(self):
-        """The padding-free body packs a batch into a fixed number of rows (SparseModel(unpad_capacity=...)); a batch
-        with more real tokens than that cannot be detected without a host sync, so it is counted on the device and
-        checked here, at logging cadence. Training on truncated batches is never silently accepted."""
+    # ------------------------------------------------------------------ packed-body overflow (unpad_capacity < 1)
+    # A batch with more real tokens than the packed capacity cannot be seen on the host without a sync. It is handled
+    # in three layers: (1) on the device, in the same step, the optimizer update of such a batch is skipped
+    # (_optimizer_step), so the weights never see it; (2) after every step the overflow counter is copied to pinned host
+    # memory asynchronously and the NEXT step raises as soon as that copy has landed; (3) check_unpad() synchronises and
+    # raises -- called before every checkpoint and at the end of train().
+    def _post_unpad(self):
+        sm = self.model_wrapper.sparse_model
+        counter = sm.unpad_counter()
+        if counter is None:
+            return
+        if self._ovf_host is None:
+            self._ovf_host = torch.zeros((), dtype=torch.int64).pin_memory()
+            self._ovf_event = torch.cuda.Event()
+        self._ovf_host.copy_(counter, non_blocking=True)
+        self._ovf_event.record()
+
+    def _poll_unpad(self):
+        if self._ovf_event is not None and self._ovf_event.query() and int(self._ovf_host) > 0:
+            self.check_unpad()
+
+    def check_unpad(self):
         n = self.model_wrapper.sparse_model.unpad_overflows()
         if n:
-            raise RuntimeError(f"{n} batch(es) held more real tokens than unpad_capacity allows: raise unpad_capacity "
-                               "(1.0 can never overflow) and restart from the last checkpoint")
+            raise RuntimeError(f"{n} batch(es) held more real tokens than unpad_capacity allows; their optimizer updates "
+                               "were skipped on the device (the weights are intact). Raise unpad_capacity (1.0 can never "
+                               "overflow) and resume.")
+
+    _check_unpad = check_unpad
 
     def _save(self, output_dir=None, state_dict=None):
         """reference :145-156 -- main process only, ModelWrapper.save layout."""
+        self.check_unpad()
         output_dir = output_dir if output_dir is not None else self.args.output_dir
         os.makedirs(output_dir, exist_ok=True)
         logger.info("Saving model checkpoint to %s", output_dir)

@@ -67,10 +67,9 @@ def test_head_forward_vs_oracle(ops, B, L, H, V, mode, use_l0):
     # fp32 accumulation in a different order than the CPU GEMM: rel 1e-4 / abs 2e-5 (north_star allows 1e-3)
     assert_close(rep, want, 1e-4, 2e-5, "rep")
     assert_close(xmax, values, 1e-4, 2e-5, "xmax")
+    # identical arg-max up to documented tie handling: check_argmax requires EVERY reported position to hold the
+    # maximum within 2e-5, so a position that differs from the oracle's can only be a value tie
     check_argmax(hidden, W, bias, mask, values, amax)
-    active = want > 1e-4
-    agree = (amax.long().cpu() == where)[active].float().mean() if active.any() else torch.tensor(1.0)
-    assert float(agree) > 0.999
 
 
 def test_head_forward_mask_dtypes_and_no_bias(ops):

@@ -154,3 +154,26 @@ def test_idf_vector_fixture(idf_vector):
     for tok, (idx, val) in probe["tokens"].items():
         assert float(idf_vector[idx]) == pytest.approx(val, rel=1e-7), tok
     assert float(idf_vector.min()) > 0 and float(idf_vector.max()) < 16
+
+
+def test_port_step_matches_reference_modules_step():
+    """bench.py's CPU arm: the oracle port and the reference's own modules (when the tree is present in this
+    container) run the same tiny training step to the same losses, for the three workload kinds."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import pytest
+    from oracle import reference_runner as RR
+    if not RR.reference_available():
+        pytest.skip("reference tree not present")
+    import bench
+    for name, extra in (("c2", {}), ("c3", {}), ("c4", {"teachers": [("dense", "tiny"), ("sparse", "tiny")]})):
+        wl = dict(bench.WORKLOADS[name])
+        wl.update(shape="tiny", n_queries=3, doc_len=24, query_len=8, **extra)
+        losses = {}
+        for prefer in (True, False):
+            step, kind, _ = RR.make_cpu_step(wl, 0.0, bench.idf_vector(), prefer_reference=prefer)
+            losses[kind] = [step(), step()]
+        assert set(losses) == {"reference", "port"}
+        for a, b in zip(losses["reference"], losses["port"]):
+            assert abs(a - b) <= 1e-5 * max(1.0, abs(a)), (name, losses)
