@@ -541,9 +541,9 @@ def extras(trainer, wl, args, device, peaks, hosts):
         add("flops_fwd_l0_threshold", lambda: ops.flops_forward(d_rep, G, 150), 2 * nd * V * 4)
         add("scores_fwd_in_batch", lambda: ops.scores_forward(q_rep, d_rep, True), (nq + nd) * V * 4)
         add("scores_fwd_in_batch_dense_queries", lambda: ops.scores_forward(q_dense, d_rep, True), (nq + nd) * V * 4)
-        if hasattr(ops, "score_loss_forward"):   # scores + infoNCE loss in one pass (2 launches)
-            add("score_loss_fwd_infonce_in_batch",
-                lambda: ops.score_loss_forward(q_rep, d_rep, None, "infonce", nd // nq, True), (nq + nd) * V * 4)
+        # scores + infoNCE loss + dS in one call (2 launches: query lists, persistent cooperative row kernel)
+        add("score_loss_fwd_infonce_in_batch",
+            lambda: ops.score_loss_forward(q_rep, d_rep, None, "infonce", nd // nq, True, q_nnz_bound=lq), (nq + nd) * V * 4)
         add("idf_query", lambda: ops.idf_query_forward(ids, model.idf_vector, sp), nq * lq * 12 + nq * V * 4)
         add("compact_rows", lambda: ops.compact_rows(d_rep), 2 * nd * V * 4)
         out[tag] = res

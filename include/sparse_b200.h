@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SB200_ABI_VERSION 1
+#define SB200_ABI_VERSION 2
 
 enum {
     SB200_OK = 0,
@@ -108,13 +108,17 @@ int sb200_idf_query_bwd(const float* d_q, const float* q, int Nq, int V, float* 
  *   threshold < 0: plain FLOPS  sum_{g,v} (mean_n |rep|)^2
  *   threshold >= 0: only rows with nnz(row) > threshold contribute to the mean (mean still over N)
  *   colsum   f32 [G, V]  out: sum_n rowmask*|rep|  (saved for backward)
- *   rowmask  f32 [N*G]   out: 1/0 row mask (all ones when threshold < 0)
+ *   rowmask  f32 [N*G]   out: 1/0 row mask; written only with a threshold or stats (may be NULL otherwise; the
+ *                        backward treats a NULL rowmask as all ones)
  *   value    f32 [1]     out
  *   stats    f32 [4]     out (nullable): total nnz, sum of positive entries, max entry, unused
+ *   workspace: sb200_flops_workspace_bytes(N, G, V). Plain FLOPS is ONE launch (row-split clusters, DSMEM reduction,
+ *   deterministic last-block sum); the thresholded variant adds the row pass.
  * Backward: d_rep[n,g,v] (+)= gscale * 2*colsum[g,v]/N^2 * sign(rep) * rowmask   (gscale read on device)
  * ------------------------------------------------------------------------------------------- */
+size_t sb200_flops_workspace_bytes(int N, int G, int V);
 int sb200_flops_fwd(const float* rep, int N, int G, int V, float threshold, float* colsum, float* rowmask,
-                    float* value, float* stats, sb200_stream_t stream);
+                    float* value, float* stats, void* workspace, size_t workspace_bytes, sb200_stream_t stream);
 int sb200_flops_bwd(const float* rep, const float* colsum, const float* rowmask, const float* gscale, int N, int G,
                     int V, int row_begin, int row_end, int accumulate, float* d_rep, sb200_stream_t stream);
 
@@ -125,18 +129,22 @@ int sb200_flops_bwd(const float* rep, const float* colsum, const float* rowmask,
  *   against its own docs i*G .. i*G+G-1.
  * ------------------------------------------------------------------------------------------- */
 size_t sb200_scores_workspace_bytes(int Nq, int Nd, int V, int in_batch);
-/* With a workspace (in_batch only) the query rows are thresholded (!= 0) into (column, value) lists and every document
- * row is staged in shared memory once and gathered by all query lists: one HBM pass over d, no atomics. If a query row
- * has more than 512 non-zeros a device-side flag routes the work to the dense fp32 tile kernel instead (no host sync).
- * Without a workspace only the dense kernel runs. */
+/* in_batch with a workspace: the query rows are thresholded (!= 0) into ordered (column, value) lists (one block per
+ * query, no atomics) and every document row is streamed through shared memory once (ring of bulk-async-copied row parts,
+ * any V) and gathered by all query lists: one HBM pass over d, no atomics, deterministic. Lists of up to 1024 entries
+ * per query are supported (short ones live in registers, longer ones are streamed from L2); beyond that a device-side
+ * flag routes the work to the dense fp32 tile kernel (no host sync). Without a workspace only the dense kernel runs.
+ * in_batch == 0: one cluster of CTAs per query (DSMEM reduction), no workspace needed. */
 int sb200_scores_fwd(const float* q, const float* d, int Nq, int Nd, int V, int in_batch, float* S, void* workspace,
                      size_t workspace_bytes, sb200_stream_t stream);
-/* d_q[i,:] = sum_j dS[i,j] d[j,:] (rows q_begin..q_end) ; d_d[j,:] = sum_i dS[i,j] q[i,:] (rows d_begin..d_end).
- * Either output may be NULL.  accumulate != 0 adds into the outputs. Outputs are full-size [Nq,V] / [Nd,V].
- * fwd_workspace (nullable): the workspace sb200_scores_fwd filled for the same q; enables the sparse-query path. */
-int sb200_scores_bwd(const float* dS, const float* q, const float* d, int Nq, int Nd, int V, int in_batch,
-                     int q_begin, int q_end, int d_begin, int d_end, int accumulate, float* d_q, float* d_d,
-                     const void* fwd_workspace, size_t workspace_bytes, sb200_stream_t stream);
+/* d_q[i,:] = gs * sum_j dS[i,j] d[j,:] (rows q_begin..q_end) ; d_d[j,:] = gs * sum_i dS[i,j] q[i,:] (rows
+ * d_begin..d_end); gs = *gscale (device scalar, nullable = 1): the upstream gradient of a scalar loss, so that no
+ * separate dS * g pass is needed. Either output may be NULL. accumulate != 0 adds into the outputs. Outputs are
+ * full-size [Nq,V] / [Nd,V]. fwd_workspace (nullable): the workspace the forward call filled for the same q; enables
+ * the sparse-query path. */
+int sb200_scores_bwd(const float* dS, const float* gscale, const float* q, const float* d, int Nq, int Nd, int V,
+                     int in_batch, int q_begin, int q_end, int d_begin, int d_end, int accumulate, float* d_q,
+                     float* d_d, const void* fwd_workspace, size_t workspace_bytes, sb200_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * (6) Ranking losses on a score matrix.   Replaces loss.py:33-42 (KLDiv), 64-76 (MarginMSE),
@@ -145,9 +153,23 @@ int sb200_scores_bwd(const float* dS, const float* q, const float* d, int Nq, in
  *   teacher  f32 [Nq, C]   (kldiv / marginmse; NULL for infonce)
  *   G        docs per query (positive first); in_batch infonce drops other queries' positives
  *   loss     f32 [1] out ;  dS f32 [Nq, C] out (nullable): d loss / d S
+ *   workspace: sb200_rank_loss_workspace_bytes(Nq) (row losses; the last block adds them in row order: deterministic)
  * ------------------------------------------------------------------------------------------- */
+size_t sb200_rank_loss_workspace_bytes(int Nq);
 int sb200_rank_loss(int mode, const float* S, const float* teacher, int Nq, int C, int G, int in_batch,
-                    float temperature, float* loss, float* dS, sb200_stream_t stream);
+                    float temperature, float* loss, float* dS, void* workspace, size_t workspace_bytes,
+                    sb200_stream_t stream);
+
+/* (5)+(6) in one call: S = q.d^T, loss = ranking loss(S [, teacher]) and dS = d loss / d S, i.e. what
+ * LOSS_CLS_MAP[name](...).__call__(q_rep, d_rep, inputs) computes (loss.py:25-43, 57-77, 86-107), Nd == Nq * G.
+ * in_batch: 2 launches (query lists + one persistent cooperative kernel: document rows -> grid barrier -> loss rows
+ * spread over the CTAs -> last block sums). own docs: 1 launch (cluster per query). q_nnz_bound > 0 promises that no
+ * query row has more non-zeros than that (inf-free queries: the token count); 0 = unknown, the dense fallback kernels
+ * are then enqueued behind a device-side flag. workspace: sb200_scores_workspace_bytes(Nq, Nd, V, in_batch); pass the
+ * same workspace to sb200_scores_bwd. */
+int sb200_score_loss_fwd(int mode, const float* q, const float* d, const float* teacher, int Nq, int Nd, int V, int G,
+                         int in_batch, float temperature, int q_nnz_bound, float* S, float* loss, float* dS,
+                         void* workspace, size_t workspace_bytes, sb200_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * (7) "next" rows: encode output path (sparse_encoders.py:137-150, 178-179) and the teacher

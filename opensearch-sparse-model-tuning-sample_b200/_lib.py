@@ -32,13 +32,17 @@ _PROTOTYPES = {
     "sb200_prune_rows": (_c_int, [_vp, _c_int, _c_int, _c_f, _vp]),
     "sb200_idf_query": (_c_int, [_vp, _c_int, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp]),
     "sb200_idf_query_bwd": (_c_int, [_vp, _vp, _c_int, _c_int, _vp, _vp]),
-    "sb200_flops_fwd": (_c_int, [_vp, _c_int, _c_int, _c_int, _c_f, _vp, _vp, _vp, _vp, _vp]),
+    "sb200_flops_workspace_bytes": (_sz, [_c_int, _c_int, _c_int]),
+    "sb200_flops_fwd": (_c_int, [_vp, _c_int, _c_int, _c_int, _c_f, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "sb200_flops_bwd": (_c_int, [_vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp]),
     "sb200_scores_workspace_bytes": (_sz, [_c_int, _c_int, _c_int, _c_int]),
     "sb200_scores_fwd": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp, _vp, _sz, _vp]),
-    "sb200_scores_bwd": (_c_int, [_vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
+    "sb200_scores_bwd": (_c_int, [_vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
                                   _c_int, _vp, _vp, _vp, _sz, _vp]),
-    "sb200_rank_loss": (_c_int, [_c_int, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_f, _vp, _vp, _vp]),
+    "sb200_rank_loss_workspace_bytes": (_sz, [_c_int]),
+    "sb200_rank_loss": (_c_int, [_c_int, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_f, _vp, _vp, _vp, _sz, _vp]),
+    "sb200_score_loss_fwd": (_c_int, [_c_int, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_f, _c_int, _vp,
+                                      _vp, _vp, _vp, _sz, _vp]),
     "sb200_compact_workspace_bytes": (_sz, [_c_int, _c_int]),
     "sb200_compact_rows": (_c_int, [_vp, _c_int, _c_int, _c_int, _vp, _vp, _vp, _c_int, _vp, _vp, _sz, _vp]),
     "sb200_minmax_accumulate": (_c_int, [_vp, _c_int, _c_int, _c_f, _c_int, _vp, _vp]),
@@ -86,7 +90,7 @@ def load():
             raise SparseB200Error(f"{LIB_PATH} does not export {name}; rebuild the library") from None
         fn.restype = res
         fn.argtypes = args
-    if lib.sb200_abi_version() != 1:
+    if lib.sb200_abi_version() != 2:
         raise SparseB200Error("libsparse_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -1,9 +1,12 @@
 // HBM-bound vector kernels of the training step: inf-free IDF query lookup (sparse_encoders.py:121-127)
 // and the FLOPS / L0-thresholded FLOPS regulariser (trainer.py:61-73), forward and backward.
 // All are streaming passes with 128-bit accesses where alignment allows, warp-shuffle reductions, no tensor cores.
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
 #include "common.h"
+
+namespace cg = cooperative_groups;
 
 namespace sb200 {
 namespace {
@@ -80,20 +83,33 @@ idf_query_bwd_kernel(const float* __restrict__ d_q, const float* __restrict__ q,
 }
 
 // ------------------------------------------------------------------------------------------ FLOPS regulariser
-// Pass 1 (threshold >= 0 or stats wanted): one block per row -> nnz, rowmask, stats.
+// Row pass (only for the L0-thresholded variant or when logging stats are wanted): one block per row -> nnz, rowmask,
+// stats. 8-byte loads when the row is 8-byte aligned.
 __global__ void __launch_bounds__(256)
 flops_rowstat_kernel(const float* __restrict__ rep, int V, float threshold, float* __restrict__ rowmask,
                      float* __restrict__ stats) {
     __shared__ float red[3][8];
     const float* row = rep + size_t(blockIdx.x) * V;
     float nnz = 0.f, psum = 0.f, pmax = 0.f;
-    for (int v = threadIdx.x; v < V; v += 256) {
-        const float x = __ldg(row + v);
+    auto take = [&](float x) {
         nnz += (x != 0.f) ? 1.f : 0.f;
         if (x > 0.f) {
             psum += x;
             pmax = fmaxf(pmax, x);
         }
+    };
+    if ((reinterpret_cast<uintptr_t>(row) & 7) == 0) {
+        const int n2 = V >> 1;
+        const float2* r2 = reinterpret_cast<const float2*>(row);
+#pragma unroll 4
+        for (int v = threadIdx.x; v < n2; v += 256) {
+            const float2 x = __ldg(r2 + v);
+            take(x.x);
+            take(x.y);
+        }
+        if ((V & 1) && threadIdx.x == 0) take(__ldg(row + V - 1));
+    } else {
+        for (int v = threadIdx.x; v < V; v += 256) take(__ldg(row + v));
     }
     nnz = warp_sum(nnz);
     psum = warp_sum(psum);
@@ -123,23 +139,33 @@ flops_rowstat_kernel(const float* __restrict__ rep, int V, float threshold, floa
     }
 }
 
-// Pass 2: colsum[g,v] = sum_n rowmask[n*G+g] * |rep[n,g,v]| and value += sum_c (colsum[c]/N)^2, one pass over rep.
-// Each thread owns VEC adjacent columns and walks all N rows (8 independent 16-byte loads in flight per thread,
-// enough to cover the HBM latency-bandwidth product with G*V/VEC threads).
+// Column pass: colsum[g,v] = sum_n rowmask[n*G+g] * |rep[n,g,v]| and value = sum_c (colsum[c]/N)^2, ONE pass over rep,
+// one launch. Each thread owns VEC adjacent columns; the N rows are split over the CTAs of a thread-block CLUSTER
+// (cluster dimension y), so that every thread has its whole row range in flight at once and G*V/VEC*RS threads cover
+// the latency-bandwidth product even for small batches. The partial column sums meet in the leader CTA's registers
+// through distributed shared memory (fixed order: deterministic), the leader writes colsum and its share of the value,
+// and the last leader to finish adds the per-block shares in block order (no atomics on floats, no memset).
+constexpr int kColThreads = 128;
+__device__ unsigned int g_ticket_flops = 0;
+
 template <int VEC>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kColThreads)
 flops_colsum_kernel(const float* __restrict__ rep, const float* __restrict__ rowmask, int N, int GV, int G, int V,
-                    float invN, float* __restrict__ colsum, float* __restrict__ value) {
-    __shared__ float red[4];
-    const int col = (blockIdx.x * 128 + threadIdx.x) * VEC;
-    float sq = 0.f;
+                    float invN, float* __restrict__ colsum, float* __restrict__ partial, float* __restrict__ value) {
+    __shared__ float part[kColThreads * VEC];
+    __shared__ float red[kColThreads / 32];
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned int rs = cluster.num_blocks(), rr = cluster.block_rank();
+    const int col = (blockIdx.x * kColThreads + threadIdx.x) * VEC;
+    const int rows_per = (N + int(rs) - 1) / int(rs);
+    const int n0 = min(N, int(rr) * rows_per), n1 = min(N, n0 + rows_per);
+    float acc[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
     if (col < GV) {
         const int g = col / V;
-        float acc[VEC];
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
 #pragma unroll 8
-        for (int n = 0; n < N; ++n) {
+        for (int n = n0; n < n1; ++n) {
             const float mk = (rowmask != nullptr) ? __ldg(rowmask + size_t(n) * G + g) : 1.f;
             const float* p = rep + size_t(n) * GV + col;
             if (VEC == 4) {
@@ -156,6 +182,25 @@ flops_colsum_kernel(const float* __restrict__ rep, const float* __restrict__ row
                 acc[0] += mk * fabsf(__ldg(p));
             }
         }
+    }
+    if (rs > 1) {
+        if (rr != 0) {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) part[threadIdx.x * VEC + i] = acc[i];
+        }
+        cluster.sync();
+        if (rr == 0) {
+            for (unsigned int r = 1; r < rs; ++r) {
+                const float* remote = cluster.map_shared_rank(part, r);
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) acc[i] += remote[threadIdx.x * VEC + i];
+            }
+        }
+        cluster.sync();   // the peers' shared memory stays alive until the leader has read it
+        if (rr != 0) return;
+    }
+    float sq = 0.f;
+    if (col < GV) {
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
             colsum[col + i] = acc[i];
@@ -166,30 +211,61 @@ flops_colsum_kernel(const float* __restrict__ rep, const float* __restrict__ row
     sq = warp_sum(sq);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sq;
     __syncthreads();
-    if (threadIdx.x == 0) atomicAdd(value, red[0] + red[1] + red[2] + red[3]);
+    __shared__ int is_last;
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int i = 0; i < kColThreads / 32; ++i) s += red[i];
+        partial[blockIdx.x] = s;
+        __threadfence();
+        is_last = (atomicAdd(&g_ticket_flops, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    float s = 0.f;
+    for (int i = threadIdx.x; i < int(gridDim.x); i += kColThreads) s += __ldcg(partial + i);
+    s = warp_sum(s);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < kColThreads / 32; ++i) t += red[i];
+        *value = t;
+        g_ticket_flops = 0u;
+    }
 }
 
-__global__ void fill_ones_kernel(float* __restrict__ p, int n) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = 1.f;
-}
-
-// d_rep[row, v] (+)= gscale * 2*colsum[g,v]/N^2 * sign(rep) * rowmask[row], rows [row_begin, row_end)
+// d_rep[row, v] (+)= gscale * 2*colsum[g,v]/N^2 * sign(rep) * rowmask[row], rows [row_begin, row_end); rowmask may be
+// null (= all ones). 8-byte accesses when everything is 8-byte aligned.
+template <int VEC>
 __global__ void __launch_bounds__(256)
 flops_bwd_kernel(const float* __restrict__ rep, const float* __restrict__ colsum, const float* __restrict__ rowmask,
                  const float* __restrict__ gscale, int G, int V, int row_begin, float k, int accumulate,
                  float* __restrict__ d_rep) {
     const int row = row_begin + blockIdx.y;
     const int g = row % G;
-    const float s = __ldg(gscale) * k * __ldg(rowmask + row);
+    const float s = __ldg(gscale) * k * (rowmask != nullptr ? __ldg(rowmask + row) : 1.f);
     const float* r = rep + size_t(row) * V;
     const float* cs = colsum + size_t(g) * V;
     float* o = d_rep + size_t(row) * V;
-    for (int v = blockIdx.x * 256 + threadIdx.x; v < V; v += gridDim.x * 256) {
-        const float x = __ldg(r + v);
+    auto one = [&](float x, float c, float prev) {
         const float sg = (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f);
-        const float gval = s * __ldg(cs + v) * sg;
-        o[v] = accumulate ? (o[v] + gval) : gval;
+        const float gval = s * c * sg;
+        return accumulate ? (prev + gval) : gval;
+    };
+    if (VEC == 2) {
+        const int n2 = V >> 1;
+        for (int v = blockIdx.x * 256 + threadIdx.x; v < n2; v += gridDim.x * 256) {
+            const float2 x = __ldg(reinterpret_cast<const float2*>(r) + v);
+            const float2 c = __ldg(reinterpret_cast<const float2*>(cs) + v);
+            float2 prev = make_float2(0.f, 0.f);
+            if (accumulate) prev = reinterpret_cast<const float2*>(o)[v];
+            reinterpret_cast<float2*>(o)[v] = make_float2(one(x.x, c.x, prev.x), one(x.y, c.y, prev.y));
+        }
+    } else {
+        for (int v = blockIdx.x * 256 + threadIdx.x; v < V; v += gridDim.x * 256)
+            o[v] = one(__ldg(r + v), __ldg(cs + v), accumulate ? o[v] : 0.f);
     }
 }
 
@@ -224,53 +300,81 @@ extern "C" int sb200_idf_query_bwd(const float* d_q, const float* q, int Nq, int
     return SB200_OK;
 }
 
+extern "C" size_t sb200_flops_workspace_bytes(int N, int G, int V) {
+    if (N <= 0 || G <= 0 || V <= 0) return 0;
+    return align_up(size_t((size_t(G) * V + kColThreads - 1) / kColThreads) * sizeof(float), 256);   // per-block shares
+}
+
+template <int VEC>
+static int launch_colsum(const float* rep, const float* mask_in, int N, int GV, int G, int V, float* colsum,
+                         float* partial, float* value, cudaStream_t stream) {
+    const int blocks = (GV / VEC + kColThreads - 1) / kColThreads;
+    // row split (cluster size): enough CTAs for ~8 per SM, at least 8 rows per CTA, a power of two <= 8
+    int rs = 1;
+    while (rs < 8 && blocks * rs < 8 * num_sms() && N / (rs * 2) >= 8) rs *= 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(unsigned(blocks), unsigned(rs));
+    cfg.blockDim = dim3(kColThreads);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = unsigned(rs);
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SB200_CUDA(cudaLaunchKernelEx(&cfg, flops_colsum_kernel<VEC>, rep, mask_in, N, GV, G, V, 1.f / float(N), colsum,
+                                  partial, value));
+    SB200_CHECK_LAUNCH("flops_colsum_kernel");
+    return SB200_OK;
+}
+
 extern "C" int sb200_flops_fwd(const float* rep, int N, int G, int V, float threshold, float* colsum, float* rowmask,
-                               float* value, float* stats, sb200_stream_t stream_) {
+                               float* value, float* stats, void* workspace, size_t workspace_bytes,
+                               sb200_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    SB200_REQUIRE(rep && colsum && rowmask && value, "flops_fwd: null pointer");
+    SB200_REQUIRE(rep && colsum && value, "flops_fwd: null pointer");
     SB200_REQUIRE(N >= 1 && G >= 1 && V >= 1, "flops_fwd: bad shape");
     const long long rows = (long long)N * G;
     const long long GV = (long long)G * V;
     SB200_REQUIRE(rows <= 0x7fffffffLL && GV <= 0x7fffffffLL, "flops_fwd: shape too large");
-    SB200_CUDA(cudaMemsetAsync(value, 0, sizeof(float), stream));
-    if (threshold >= 0.f || stats != nullptr) {
-        // row pass: nnz per row -> L0 row mask (+ logging stats). Only the thresholded variant needs it.
+    if (workspace == nullptr || workspace_bytes < sb200_flops_workspace_bytes(N, G, V))
+        return fail(SB200_ERR_WORKSPACE, "flops_fwd: workspace too small");
+    const bool row_pass = threshold >= 0.f || stats != nullptr;
+    SB200_REQUIRE(!row_pass || rowmask != nullptr, "flops_fwd: rowmask required with a threshold or stats");
+    if (row_pass) {
+        // row pass: nnz per row -> L0 row mask (+ logging stats). The plain regulariser does not need it.
         if (stats != nullptr) SB200_CUDA(cudaMemsetAsync(stats, 0, 4 * sizeof(float), stream));
         flops_rowstat_kernel<<<int(rows), 256, 0, stream>>>(rep, V, threshold, rowmask, stats);
         SB200_CHECK_LAUNCH("flops_rowstat_kernel");
-    } else {
-        fill_ones_kernel<<<int((rows + 255) / 256), 256, 0, stream>>>(rowmask, int(rows));
-        SB200_CHECK_LAUNCH("fill_ones_kernel");
     }
     const float* mask_in = (threshold >= 0.f) ? rowmask : nullptr;
     const bool a16 = (reinterpret_cast<uintptr_t>(rep) & 15) == 0;
-    const int vec = (a16 && V % 4 == 0) ? 4 : ((a16 && V % 2 == 0) ? 2 : 1);
-    const int blocks = int((GV / vec + 127) / 128);
-    const float invN = 1.f / float(N);
-    if (vec == 4)
-        flops_colsum_kernel<4><<<blocks, 128, 0, stream>>>(rep, mask_in, N, int(GV), G, V, invN, colsum, value);
-    else if (vec == 2)
-        flops_colsum_kernel<2><<<blocks, 128, 0, stream>>>(rep, mask_in, N, int(GV), G, V, invN, colsum, value);
-    else
-        flops_colsum_kernel<1><<<blocks, 128, 0, stream>>>(rep, mask_in, N, int(GV), G, V, invN, colsum, value);
-    SB200_CHECK_LAUNCH("flops_colsum_kernel");
-    return SB200_OK;
+    float* partial = static_cast<float*>(workspace);
+    if (a16 && V % 4 == 0) return launch_colsum<4>(rep, mask_in, N, int(GV), G, V, colsum, partial, value, stream);
+    if (a16 && V % 2 == 0) return launch_colsum<2>(rep, mask_in, N, int(GV), G, V, colsum, partial, value, stream);
+    return launch_colsum<1>(rep, mask_in, N, int(GV), G, V, colsum, partial, value, stream);
 }
 
 extern "C" int sb200_flops_bwd(const float* rep, const float* colsum, const float* rowmask, const float* gscale, int N,
                                int G, int V, int row_begin, int row_end, int accumulate, float* d_rep,
                                sb200_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    SB200_REQUIRE(rep && colsum && rowmask && gscale && d_rep, "flops_bwd: null pointer");
+    SB200_REQUIRE(rep && colsum && gscale && d_rep, "flops_bwd: null pointer");
     SB200_REQUIRE(N >= 1 && G >= 1 && V >= 1 && row_begin >= 0 && row_end <= N * G && row_begin <= row_end,
                   "flops_bwd: bad shape");
     if (row_end == row_begin) return SB200_OK;
     SB200_REQUIRE(row_end - row_begin <= 65535, "flops_bwd: too many rows");
-    int xb = (V + 255) / 256;
-    if (xb > 32) xb = 32;
     const float k = 2.f / (float(N) * float(N));
-    flops_bwd_kernel<<<dim3(xb, row_end - row_begin), 256, 0, stream>>>(rep, colsum, rowmask, gscale, G, V, row_begin, k,
-                                                                        accumulate, d_rep);
+    const bool vec2 = V % 2 == 0 && ((reinterpret_cast<uintptr_t>(rep) | reinterpret_cast<uintptr_t>(colsum) |
+                                      reinterpret_cast<uintptr_t>(d_rep)) & 7) == 0;
+    int xb = ((vec2 ? V / 2 : V) + 255) / 256;
+    if (xb > 16) xb = 16;
+    const dim3 grid(xb, row_end - row_begin);
+    if (vec2)
+        flops_bwd_kernel<2><<<grid, 256, 0, stream>>>(rep, colsum, rowmask, gscale, G, V, row_begin, k, accumulate, d_rep);
+    else
+        flops_bwd_kernel<1><<<grid, 256, 0, stream>>>(rep, colsum, rowmask, gscale, G, V, row_begin, k, accumulate, d_rep);
     SB200_CHECK_LAUNCH("flops_bwd_kernel");
     return SB200_OK;
 }

@@ -2,11 +2,14 @@
 // compaction (sparse_encoders.py:137-150, 178-179) and the teacher min-max normalisation
 // (bi_encoder_wrapper.py:133-138). fp32 CUDA-core arithmetic throughout (the reference runs these GEMMs in
 // fp32 with TF32 off); the score kernels are HBM/L2-bound: (Nq+Nd)*V*4 bytes against Nq*Nd*V*2 flop.
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
 #include "common.h"
 #include "ptx.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace sb200 {
 namespace {
@@ -43,9 +46,38 @@ __device__ __forceinline__ float block_min(float x, float* red) {
     return -block_max<THREADS>(-x, red);
 }
 
+// Deterministic "last block finishes the sum": every block publishes its partial results, takes a ticket, and the
+// block that draws the last ticket adds the n partials in a fixed order and resets the ticket for the next launch.
+// The ticket counters are per-device globals: one in-flight launch per kernel and device (stream-ordered use).
+template <int THREADS>
+__device__ __forceinline__ void finish_sum_last_block(unsigned int* ticket, unsigned int n_blocks, const float* partial,
+                                                      int n, float scale, float* out, float* red) {
+    __shared__ int is_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int t = atomicAdd(ticket, 1u);
+        is_last = (t == n_blocks - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < n; i += THREADS) acc += __ldcg(partial + i);
+    acc = block_sum<THREADS>(acc, red);
+    if (threadIdx.x == 0) {
+        *out = acc * scale;
+        *ticket = 0u;
+    }
+}
+
+__device__ unsigned int g_ticket_rank_loss = 0;
+__device__ unsigned int g_ticket_fused = 0;
+__device__ unsigned int g_ticket_group = 0;
+
 // ------------------------------------------------------------------------------------------ scores, in-batch
-// S[i,j] += sum_{k in split} q[i,k] d[j,k].  64x64 output tile per block, 4x4 per thread, K staged 32 at a time
-// through shared memory (transposed, stride 65 -> conflict-free), split-K over blockIdx.z merged with atomics.
+// Dense fallback. S[i,j] += sum_{k in split} q[i,k] d[j,k].  64x64 output tile per block, 4x4 per thread, K staged 32
+// at a time through shared memory (transposed, stride 65 -> conflict-free), split-K over blockIdx.z merged with atomics.
 constexpr int kST = 64, kSK = 32, kSStride = kST + 1;
 
 __global__ void __launch_bounds__(256)
@@ -112,19 +144,117 @@ scores_tile_kernel(const float* __restrict__ q, const float* __restrict__ d, int
     }
 }
 
-// scores, own docs only: S[i,g] = q[i,:] . d[i*G+g,:]   grid (ksplit, Nq)
+// ------------------------------------------------------------------------------------------ ranking-loss row
+// Loss contribution of query row i (already scaled by the batch mean) and, if g != nullptr, d loss / d S[i, :].
+// Result valid in thread 0. All THREADS threads of the block must call it. loss.py:33-42, 64-76, 94-106.
+template <int THREADS>
+__device__ float rank_loss_row(int mode, const float* __restrict__ s, const float* __restrict__ t, float* __restrict__ g,
+                               int i, int Nq, int C, int G, int in_batch, float invT, float* red) {
+    const float invNq = 1.f / float(Nq);
+    if (mode == SB200_LOSS_INFONCE) {
+        // selected columns: own positive + every hard negative (loss.py:90-101); own docs only when !in_batch
+        const int pos = in_batch ? i * G : 0;
+        auto selected = [&](int j) { return !in_batch || j == pos || (j % G) != 0; };
+        float m = -CUDART_INF_F;
+        for (int j = threadIdx.x; j < C; j += THREADS)
+            if (selected(j)) m = fmaxf(m, s[j]);
+        m = block_max<THREADS>(m, red);
+        float z = 0.f;
+        for (int j = threadIdx.x; j < C; j += THREADS)
+            if (selected(j)) z += expf(s[j] - m);
+        z = block_sum<THREADS>(z, red);
+        const float lse = m + logf(z);
+        if (g != nullptr) {
+            for (int j = threadIdx.x; j < C; j += THREADS) {
+                float v = 0.f;
+                if (selected(j)) v = (expf(s[j] - lse) - (j == pos ? 1.f : 0.f)) * invNq;
+                g[j] = v;
+            }
+        }
+        return (lse - s[pos]) * invNq;
+    }
+    if (mode == SB200_LOSS_KLDIV) {
+        float ms = -CUDART_INF_F, mt = -CUDART_INF_F;
+        for (int j = threadIdx.x; j < C; j += THREADS) {
+            ms = fmaxf(ms, s[j] * invT);
+            mt = fmaxf(mt, t[j] * invT);
+        }
+        ms = block_max<THREADS>(ms, red);
+        mt = block_max<THREADS>(mt, red);
+        float zs = 0.f, zt = 0.f;
+        for (int j = threadIdx.x; j < C; j += THREADS) {
+            zs += expf(s[j] * invT - ms);
+            zt += expf(t[j] * invT - mt);
+        }
+        zs = block_sum<THREADS>(zs, red);
+        zt = block_sum<THREADS>(zt, red);
+        const float lzs = logf(zs), lzt = logf(zt);
+        float acc = 0.f;
+        for (int j = threadIdx.x; j < C; j += THREADS) {
+            const float lps = s[j] * invT - ms - lzs;
+            const float lpt = t[j] * invT - mt - lzt;
+            const float pt = expf(lpt);
+            if (pt > 0.f) acc += pt * (lpt - lps);  // xlogy(t,t) - t*input
+            if (g != nullptr) g[j] = (expf(lps) - pt) * invT * invNq;
+        }
+        acc = block_sum<THREADS>(acc, red);
+        return acc * invNq;
+    }
+    // margin MSE: margins against column 0 (loss.py:52-55)
+    const float s0 = s[0] * invT, t0 = t[0] * invT;
+    const float norm = 1.f / (float(Nq) * float(C - 1));
+    float acc = 0.f, g0 = 0.f;
+    for (int j = 1 + threadIdx.x; j < C; j += THREADS) {
+        const float diff = (s0 - s[j] * invT) - (t0 - t[j] * invT);
+        acc = fmaf(diff, diff, acc);
+        const float gj = 2.f * diff * norm * invT;
+        g0 += gj;
+        if (g != nullptr) g[j] = -gj;
+    }
+    acc = block_sum<THREADS>(acc, red);
+    g0 = block_sum<THREADS>(g0, red);
+    if (threadIdx.x == 0 && g != nullptr) g[0] = g0;
+    return acc * norm;
+}
+
+// One block per query row; the last block adds the row losses in row order (deterministic, no memset).
 __global__ void __launch_bounds__(256)
-scores_group_kernel(const float* __restrict__ q, const float* __restrict__ d, int G, int V, int kchunk,
-                    float* __restrict__ S) {
+rank_loss_kernel(int mode, const float* __restrict__ S, const float* __restrict__ teacher, int Nq, int C, int G,
+                 int in_batch, float invT, float* __restrict__ loss, float* __restrict__ dS, float* __restrict__ rowloss) {
     __shared__ float red[8];
+    const int i = blockIdx.x;
+    const float v = rank_loss_row<256>(mode, S + size_t(i) * C, teacher ? teacher + size_t(i) * C : nullptr,
+                                       dS ? dS + size_t(i) * C : nullptr, i, Nq, C, G, in_batch, invT, red);
+    if (threadIdx.x == 0) rowloss[i] = v;
+    finish_sum_last_block<256>(&g_ticket_rank_loss, gridDim.x, rowloss, Nq, 1.f, loss, red);
+}
+
+// ------------------------------------------------------------------------------------------ scores, own docs only
+// S[i,g] = q[i,:] . d[i*G+g,:] and, fused, the ranking loss of row i. A thread-block CLUSTER of `KS` CTAs shares one
+// query: each CTA streams its slice of the vocabulary (q once, the G doc rows once), the partial dot products meet in
+// the leader's shared memory through DSMEM, the leader writes S[i,:], evaluates the loss row and takes part in the
+// deterministic final sum. One launch, no atomics on S, no memset.
+constexpr int kGroupThreads = 256;
+constexpr int kGroupMaxG = 64;
+
+__global__ void __launch_bounds__(kGroupThreads)
+score_group_kernel(const float* __restrict__ q, const float* __restrict__ d, int Nq, int G, int V, int mode,
+                   const float* __restrict__ teacher, float invT, float* __restrict__ S, float* __restrict__ dS,
+                   float* __restrict__ rowloss, float* __restrict__ loss) {
+    __shared__ float red[kGroupThreads / 32];
+    __shared__ float part[kGroupMaxG];        // this CTA's partial dot products
+    __shared__ float srow[kGroupMaxG];        // leader: the finished score row
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned int ks = cluster.num_blocks(), kr = cluster.block_rank();
     const int i = blockIdx.y;
-    const int k_begin = blockIdx.x * kchunk, k_end = min(V, k_begin + kchunk);
+    const int kchunk = int(align_up_sz(size_t((V + ks - 1) / ks), 4));
+    const int k_begin = min(V, int(kr) * kchunk), k_end = min(V, k_begin + kchunk);
     const float* qi = q + size_t(i) * V;
     for (int g0 = 0; g0 < G; g0 += 8) {
         float acc[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-        for (int k = k_begin + threadIdx.x; k < k_end; k += 256) {
+        for (int k = k_begin + threadIdx.x; k < k_end; k += kGroupThreads) {
             const float qv = __ldg(qi + k);
 #pragma unroll
             for (int e = 0; e < 8; ++e)
@@ -133,30 +263,54 @@ scores_group_kernel(const float* __restrict__ q, const float* __restrict__ d, in
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             if (g0 + e < G) {  // block-uniform
-                const float s = block_sum<256>(acc[e], red);
-                if (threadIdx.x == 0) {
-                    if (gridDim.x == 1) S[size_t(i) * G + g0 + e] = s;
-                    else atomicAdd(S + size_t(i) * G + g0 + e, s);
-                }
+                const float s = block_sum<kGroupThreads>(acc[e], red);
+                if (threadIdx.x == 0) part[g0 + e] = s;
             }
         }
     }
+    cluster.sync();
+    if (kr == 0) {
+        for (int g = threadIdx.x; g < G; g += kGroupThreads) {
+            float s = part[g];
+            for (unsigned int r = 1; r < ks; ++r) s += *cluster.map_shared_rank(&part[g], r);   // fixed order
+            srow[g] = s;
+            S[size_t(i) * G + g] = s;
+        }
+    }
+    cluster.sync();   // peers' shared memory must stay alive until the leader has read it
+    if (kr != 0 || mode < 0) return;
+    __syncthreads();
+    const float v = rank_loss_row<kGroupThreads>(mode, srow, teacher ? teacher + size_t(i) * G : nullptr,
+                                                 dS ? dS + size_t(i) * G : nullptr, i, Nq, G, G, 0, invT, red);
+    if (threadIdx.x == 0) rowloss[i] = v;
+    finish_sum_last_block<kGroupThreads>(&g_ticket_group, unsigned(Nq), rowloss, Nq, 1.f, loss, red);
 }
 
 // ------------------------------------------------------------------------------------------ sparse-query path
 // Queries are very sparse (inf-free: at most Lq token ids; learned: tens to hundreds of entries once trained), so
-// q.d^T = sum over the query's non-zeros of val * d[j, col]. The query rows are thresholded (!= 0) into (col, val)
-// lists once; then each DOCUMENT row is staged in shared memory (V*4 B = 122 KB) exactly once and every query's list
-// is gathered from it: HBM traffic = one pass over d, S[i,j] written once, no atomics (deterministic).
-// Dispatch is on the device: if any query row has more than kQCap non-zeros the flag is set, the sparse kernels exit
-// and the dense tile kernel (which exits when the flag is clear) does the work instead -- no host synchronisation.
-constexpr int kQCap = 512;
+// q.d^T = sum over the query's non-zeros of val * d[j, col]. The query rows are thresholded (!= 0) into ordered
+// (col, val) lists once (q_compact_kernel); then every DOCUMENT row is streamed through shared memory exactly once and
+// all query lists are gathered from it: HBM traffic = one pass over d, S[i,j] written once, no atomics (deterministic).
+//
+// The row kernel is persistent (one CTA per SM, rows round-robin) and keeps the memory pipe busy with a ring of
+// kRowStages shared-memory stages, each holding one PART of a row (a row is cut into n_parts equal column ranges so
+// that any vocabulary size fits): parts are fetched with one bulk async copy each (cp.async.bulk, mbarrier completion)
+// kRowStages parts ahead of the gather, so the next rows are in flight while the current part is consumed.
+// Two gather modes, chosen on the device from the list lengths (block-uniform):
+//   (A) registers: tpq = 512/Nq threads share a query, each keeps <= 32 entries in registers for the whole kernel;
+//   (B) streamed lists: warps walk the queries, lanes the (ascending) entries of the current part, from L2.
+// A query with more than kQCap non-zeros raises the device-side flag: the dense kernels then do the work.
+constexpr int kQCap = 1024;
 constexpr int kRowThreads = 512;
+constexpr int kEPT = 32;
+constexpr int kRowStages = 3;
+constexpr int kRowSmemBudget = 200 * 1024;   // dynamic shared memory for the stages
+constexpr int kRowMaxQ = 2048;               // mode (B): cursor + partial score per query in shared memory
 
 struct QLists {
-    int* flag;      // [1]  1 = some row overflowed -> dense path
-    int* nnz;       // [Nq]
-    int* cols;      // [Nq][kQCap]
+    int* flag;      // [1]  written by the forward row kernel: 1 = some row has more than kQCap entries -> dense path
+    int* nnz;       // [Nq] true non-zero count per query row
+    int* cols;      // [Nq][kQCap] ascending
     float* vals;    // [Nq][kQCap]
 };
 
@@ -173,98 +327,211 @@ inline QLists qlists_carve(void* ws, int Nq) {
     return q;
 }
 
-// grid (column slabs, Nq): slots are claimed with one atomic per non-zero on the row's counter (zeroed by the caller);
-// the order of a list is irrelevant. nnz[i] ends up as the true count (may exceed the capacity: then the flag is set).
-__global__ void __launch_bounds__(256)
-q_compact_kernel(const float* __restrict__ q, int V, int cap, QLists L) {
-    const int i = blockIdx.y;
+// One block per query row: ordered stream compaction (ballot + block scan), no atomics, no pre-zeroed counters.
+constexpr int kCompactThreads = 1024;
+constexpr int kCompactBatch = 8;   // independent loads in flight per thread
+
+__global__ void __launch_bounds__(kCompactThreads)
+q_compact_kernel(const float* __restrict__ q, int V, QLists L) {
+    __shared__ int warp_cnt[kCompactBatch][32];
+    const int i = blockIdx.x;
     const float* row = q + size_t(i) * V;
-    for (int v = blockIdx.x * 256 + threadIdx.x; v < V; v += gridDim.x * 256) {
-        const float x = __ldg(row + v);
-        if (x != 0.f) {
-            const int slot = atomicAdd(L.nnz + i, 1);
-            if (slot < kQCap) {
-                L.cols[size_t(i) * kQCap + slot] = v;
-                L.vals[size_t(i) * kQCap + slot] = x;
-            }
-            if (slot == cap) atomicOr(L.flag, 1);  // the row does not fit the register budget of the row kernels
-        }
-    }
-}
-
-// Asynchronous global->shared copy of src[0, n) (cp.async, no registers held): every thread issues all its
-// requests before anyone waits, so a whole slab is in flight per CTA.
-__device__ __forceinline__ void stage_async(float* __restrict__ dst, const float* __restrict__ src, int n) {
-    const uint32_t d0 = static_cast<uint32_t>(__cvta_generic_to_shared(dst));
-    if ((reinterpret_cast<uintptr_t>(src) & 7) == 0) {
-        const int n2 = n >> 1;
-        for (int t = threadIdx.x; t < n2; t += kRowThreads)
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d0 + t * 8), "l"(src + 2 * t) : "memory");
-        if ((n & 1) && threadIdx.x == 0)
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d0 + (n - 1) * 4), "l"(src + n - 1) : "memory");
-    } else {
-        for (int t = threadIdx.x; t < n; t += kRowThreads)
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d0 + t * 4), "l"(src + t) : "memory");
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-}
-__device__ __forceinline__ void stage_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
-// grid (row slots, query chunks of kRowThreads/tpq queries). Each thread keeps up to kEPT (column, value) entries of ONE
-// query in registers for the whole kernel (tpq threads share a query); a block walks document rows: the row is
-// staged in shared memory with cp.async (whole row in flight), every thread gathers its entries from it, the tpq
-// partial sums are shuffled together and S[i,j] is written once -- no atomics, deterministic, d is read from HBM once
-// per query chunk. Rows longer than the register budget (nnz > kEPT*tpq) raise the device-side flag instead.
-constexpr int kEPT = 32;
-
-__global__ void __launch_bounds__(kRowThreads, 1)
-scores_docrow_kernel(const float* __restrict__ d, int Nq, int Nd, int V, int tpq, QLists L, float* __restrict__ S) {
-    extern __shared__ __align__(128) float row_s[];
-    if (*L.flag != 0) return;  // dense path handles it
-    const int qi = blockIdx.y * (kRowThreads / tpq) + threadIdx.x / tpq;
-    const int sub = threadIdx.x % tpq;
-    int col[kEPT];
-    float val[kEPT];
-    const int n = (qi < Nq) ? min(__ldg(L.nnz + qi), kQCap) : 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int base = 0;
+    for (int v0 = 0; v0 < V; v0 += kCompactThreads * kCompactBatch) {
+        float x[kCompactBatch];
+        uint32_t bal[kCompactBatch];
 #pragma unroll
-    for (int e = 0; e < kEPT; ++e) {
-        const int k = sub + e * tpq;
-        const bool ok = k < n;
-        col[e] = ok ? __ldg(L.cols + size_t(qi) * kQCap + k) : 0;
-        val[e] = ok ? __ldg(L.vals + size_t(qi) * kQCap + k) : 0.f;
-    }
-    // rows are pulled with ONE bulk async copy each (TMA engine, completion on an mbarrier); the few floats before
-    // the first / after the last 16-byte boundary are moved by ordinary loads. `shift` keeps source and destination
-    // in the same 16-byte phase.
-    __shared__ __align__(8) uint64_t bar;
-    if (threadIdx.x == 0) {
-        mbar_init(&bar, 1);
-        fence_mbar_init();
-    }
-    __syncthreads();
-    uint32_t phase = 0;
-    for (int j = blockIdx.x; j < Nd; j += gridDim.x) {
-        const float* src = d + size_t(j) * V;
-        const int head = min(V, int(((16 - (reinterpret_cast<uintptr_t>(src) & 15)) & 15) >> 2));
-        const int shift = (4 - head) & 3;
-        const int nbulk = ((V - head) >> 2) << 2;
-        __syncthreads();  // everyone is done gathering from the previous row
-        if (threadIdx.x == 0 && nbulk > 0) {
-            mbar_arrive_expect_tx(&bar, uint32_t(nbulk) * 4u);
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(smem_u32(row_s + head + shift)), "l"(src + head), "r"(uint32_t(nbulk) * 4u), "r"(smem_u32(&bar))
-                         : "memory");
+        for (int b = 0; b < kCompactBatch; ++b) {
+            const int v = v0 + b * kCompactThreads + threadIdx.x;
+            x[b] = (v < V) ? __ldg(row + v) : 0.f;
         }
-        if (int(threadIdx.x) < head) row_s[threadIdx.x + shift] = __ldg(src + threadIdx.x);
-        for (int t = head + nbulk + threadIdx.x; t < V; t += kRowThreads) row_s[t + shift] = __ldg(src + t);
-        if (nbulk > 0) mbar_wait(&bar, phase);
-        phase ^= 1;
+#pragma unroll
+        for (int b = 0; b < kCompactBatch; ++b) {
+            bal[b] = __ballot_sync(0xffffffffu, x[b] != 0.f);
+            if (lane == 0) warp_cnt[b][warp] = __popc(bal[b]);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int b = 0; b < kCompactBatch; ++b) {
+            const int c = warp_cnt[b][lane];                 // lane w holds the count of warp w
+            int incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            const int before = __shfl_sync(0xffffffffu, incl - c, warp);   // entries of lower warps
+            const int off = base + before + __popc(bal[b] & ((1u << lane) - 1u));
+            if (x[b] != 0.f && off < kQCap) {
+                L.cols[size_t(i) * kQCap + off] = v0 + b * kCompactThreads + threadIdx.x;
+                L.vals[size_t(i) * kQCap + off] = x[b];
+            }
+            base += total;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) L.nnz[i] = base;
+}
+
+struct LossArgs {
+    int mode;                 // SB200_LOSS_* or -1: scores only
+    const float* teacher;     // [Nq, Nd] or nullptr
+    int G;
+    float invT;
+    float* loss;              // [1]
+    float* dS;                // [Nq, Nd] or nullptr
+    float* rowloss;           // [Nq] scratch
+};
+
+// Issues the fetch of part `p` of document row `j` into `stage` (called by warp 0; lane 0 drives the bulk copy, the
+// <= 3 floats in front of / behind the 16-byte aligned interior are moved by ordinary loads of lanes 1..6).
+__device__ __forceinline__ void row_part_issue(const float* __restrict__ d, int V, int j, int p, int part_len,
+                                               float* stage, uint64_t* bar, int lane) {
+    const int c0 = p * part_len;
+    const int len = min(V, c0 + part_len) - c0;
+    const float* src = d + size_t(j) * V + c0;
+    const int a = int(reinterpret_cast<uintptr_t>(src) & 15) >> 2;   // phase of the source inside a 16-byte line
+    const int head = min(len, (4 - a) & 3);
+    const int nbulk = ((len - head) >> 2) << 2;
+    const int tail0 = head + nbulk;
+    if (lane == 0) {
+        if (nbulk > 0) {
+            mbar_arrive_expect_tx(bar, uint32_t(nbulk) * 4u);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_u32(stage + head + a)), "l"(src + head), "r"(uint32_t(nbulk) * 4u), "r"(smem_u32(bar))
+                         : "memory");
+        } else {
+            mbar_arrive(bar);
+        }
+    } else if (lane <= 3) {
+        if (lane - 1 < head) stage[a + lane - 1] = __ldg(src + lane - 1);
+    } else if (lane <= 6) {
+        const int t = tail0 + lane - 4;
+        if (t < len) stage[a + t] = __ldg(src + t);
+    }
+}
+
+template <bool kFused>
+__global__ void __launch_bounds__(kRowThreads, 1)
+scores_docrow_kernel(const float* __restrict__ d, int Nq, int Nd, int V, int n_parts, int part_len, QLists L,
+                     float* __restrict__ S, LossArgs la) {
+    extern __shared__ __align__(128) float stages[];            // [kRowStages][part_len + 8]
+    __shared__ __align__(8) uint64_t full_bar[kRowStages];
+    __shared__ int cursor_s[kRowMaxQ];                          // mode (B)
+    __shared__ float acc_s[kRowMaxQ];
+    __shared__ float red[kRowThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int stage_floats = part_len + 8;
+
+    // ---- list lengths -> overflow flag and gather mode (block-uniform)
+    int mx = 0;
+    for (int i = threadIdx.x; i < Nq; i += kRowThreads) mx = max(mx, __ldg(L.nnz + i));
+    mx = int(block_max<kRowThreads>(float(mx), red));
+    const bool overflow = mx > kQCap;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *L.flag = overflow ? 1 : 0;
+    int tpq = 32;                                               // threads sharing one query in mode (A)
+    while (tpq > 1 && kRowThreads / tpq < Nq) tpq >>= 1;
+    const bool mode_a = (kRowThreads / tpq >= Nq) && (mx <= kEPT * tpq);
+    const bool mode_b_ok = Nq <= kRowMaxQ;
+    const bool work = !overflow && (mode_a || mode_b_ok);       // otherwise the dense kernels produce S
+    if (blockIdx.x == 0 && threadIdx.x == 0 && !work) *L.flag = 1;
+
+    if (work) {
+        int col[kEPT];
+        float val[kEPT];
+        const int qi = threadIdx.x / tpq, sub = threadIdx.x % tpq;
+        if (mode_a) {
+            const int n = (qi < Nq) ? __ldg(L.nnz + qi) : 0;
+#pragma unroll
+            for (int e = 0; e < kEPT; ++e) {
+                const int k = sub + e * tpq;
+                const bool ok = k < n;
+                col[e] = ok ? __ldg(L.cols + size_t(qi) * kQCap + k) : 0x7fffffff;
+                val[e] = ok ? __ldg(L.vals + size_t(qi) * kQCap + k) : 0.f;
+            }
+        }
+        if (threadIdx.x == 0) {
+            for (int s = 0; s < kRowStages; ++s) mbar_init(&full_bar[s], 1);
+            fence_mbar_init();
+        }
+        __syncthreads();
+        const int my_rows = (Nd - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
+        const int total = my_rows * n_parts;
+        if (warp == 0)
+            for (int t = 0; t < kRowStages && t < total; ++t)
+                row_part_issue(d, V, blockIdx.x + (t / n_parts) * gridDim.x, t % n_parts, part_len,
+                               stages + t * stage_floats, &full_bar[t], lane);
         __syncthreads();
         float acc = 0.f;
+        for (int t = 0; t < total; ++t) {
+            const int s = t % kRowStages;
+            const uint32_t ph = uint32_t(t / kRowStages) & 1u;
+            const int r = t / n_parts, p = t - r * n_parts;
+            const int j = blockIdx.x + r * gridDim.x;
+            const int c0 = p * part_len;
+            const int plen = min(V, c0 + part_len) - c0;
+            const float* st = stages + s * stage_floats +
+                              (int(reinterpret_cast<uintptr_t>(d + size_t(j) * V + c0) & 15) >> 2);
+            mbar_wait(&full_bar[s], ph);
+            if (mode_a) {
 #pragma unroll
-        for (int e = 0; e < kEPT; ++e) acc = fmaf(val[e], row_s[col[e] + shift], acc);
-        for (int o = tpq >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (sub == 0 && qi < Nq) S[size_t(qi) * Nd + j] = acc;
+                for (int e = 0; e < kEPT; ++e) {
+                    const unsigned int c = unsigned(col[e] - c0);
+                    if (c < unsigned(plen)) acc = fmaf(val[e], st[c], acc);
+                }
+                if (p == n_parts - 1) {
+                    for (int o = tpq >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                    if (sub == 0 && qi < Nq) S[size_t(qi) * Nd + j] = acc;
+                    acc = 0.f;
+                }
+            } else {
+                const int c1 = c0 + plen;
+                for (int i = warp; i < Nq; i += kRowThreads / 32) {
+                    const int n = min(__ldg(L.nnz + i), kQCap);
+                    int k0 = (p == 0) ? 0 : cursor_s[i];
+                    float a = 0.f;
+                    while (true) {
+                        const int k = k0 + lane;
+                        const int c = (k < n) ? __ldg(L.cols + size_t(i) * kQCap + k) : 0x7fffffff;
+                        const bool in = c < c1;
+                        if (in) a = fmaf(__ldg(L.vals + size_t(i) * kQCap + k), st[c - c0], a);
+                        const int cnt = __popc(__ballot_sync(0xffffffffu, in));
+                        k0 += cnt;
+                        if (cnt < 32) break;
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+                    if (lane == 0) {
+                        if (p > 0) a += acc_s[i];
+                        if (p == n_parts - 1) S[size_t(i) * Nd + j] = a;
+                        else { acc_s[i] = a; cursor_s[i] = k0; }
+                    }
+                }
+            }
+            __syncthreads();   // everyone is done with stage s
+            if (warp == 0 && t + kRowStages < total) {
+                const int tn = t + kRowStages;
+                row_part_issue(d, V, blockIdx.x + (tn / n_parts) * gridDim.x, tn % n_parts, part_len,
+                               stages + s * stage_floats, &full_bar[s], lane);
+            }
+        }
+    }
+    if constexpr (kFused) {
+        // ---- ranking loss on the finished score matrix: grid-wide barrier (cooperative launch), rows over blocks
+        __threadfence();
+        cg::this_grid().sync();
+        if (!work) return;     // grid-uniform: the separate dense kernels + rank_loss_kernel follow
+        for (int i = blockIdx.x; i < Nq; i += gridDim.x) {
+            const float v = rank_loss_row<kRowThreads>(la.mode, S + size_t(i) * Nd,
+                                                       la.teacher ? la.teacher + size_t(i) * Nd : nullptr,
+                                                       la.dS ? la.dS + size_t(i) * Nd : nullptr, i, Nq, Nd, la.G, 1,
+                                                       la.invT, red);
+            if (threadIdx.x == 0) la.rowloss[i] = v;
+            __syncthreads();
+        }
+        finish_sum_last_block<kRowThreads>(&g_ticket_fused, gridDim.x, la.rowloss, Nq, 1.f, la.loss, red);
     }
 }
 
@@ -273,14 +540,28 @@ __global__ void zero_if_dense_kernel(float* __restrict__ S, size_t n, const int*
     if (*dense_flag == 0) return;
     for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) S[i] = 0.f;
 }
+// dense fallback of the fused score+loss call: runs rank_loss rows only when the flag is set
+__global__ void __launch_bounds__(256)
+rank_loss_if_dense_kernel(int mode, const float* __restrict__ S, const float* __restrict__ teacher, int Nq, int C, int G,
+                          int in_batch, float invT, const int* __restrict__ dense_flag, float* __restrict__ loss,
+                          float* __restrict__ dS, float* __restrict__ rowloss) {
+    __shared__ float red[8];
+    if (*dense_flag == 0) return;
+    const int i = blockIdx.x;
+    const float v = rank_loss_row<256>(mode, S + size_t(i) * C, teacher ? teacher + size_t(i) * C : nullptr,
+                                       dS ? dS + size_t(i) * C : nullptr, i, Nq, C, G, in_batch, invT, red);
+    if (threadIdx.x == 0) rowloss[i] = v;
+    finish_sum_last_block<256>(&g_ticket_rank_loss, gridDim.x, rowloss, Nq, 1.f, loss, red);
+}
 
-// d_d[j, :] (+)= sum_i dS[i,j] * q[i,:] for rows [d_begin, d_end): same register-resident lists; the row is built in
-// shared memory (zero-fill + shared-memory atomics) and written to HBM once. Query chunks beyond the first accumulate.
+// d_d[j, :] (+)= gs * sum_i dS[i,j] * q[i,:] for rows [d_begin, d_end): the row is built in shared memory (zero-fill +
+// shared-memory atomics over the query lists) and written to HBM once. gs = *gscale (device scalar) or 1.
 __global__ void __launch_bounds__(kRowThreads, 1)
-scores_docrow_bwd_kernel(const float* __restrict__ dS, int Nq, int Nd, int V, int tpq, QLists L, int d_begin, int d_end,
-                         int accumulate, float* __restrict__ d_d) {
+scores_docrow_bwd_kernel(const float* __restrict__ dS, const float* __restrict__ gscale, int Nq, int Nd, int V, int tpq,
+                         QLists L, int d_begin, int d_end, int accumulate, float* __restrict__ d_d) {
     extern __shared__ float row_s[];
     if (*L.flag != 0) return;
+    const float gs = gscale != nullptr ? __ldg(gscale) : 1.f;
     const int per = kRowThreads / tpq;
     const int sub = threadIdx.x % tpq;
     for (int j = d_begin + blockIdx.x; j < d_end; j += gridDim.x) {
@@ -290,7 +571,7 @@ scores_docrow_bwd_kernel(const float* __restrict__ dS, int Nq, int Nd, int V, in
         for (int q0 = 0; q0 < Nq; q0 += per) {   // all query chunks by the same block: one owner per output row
             const int qi = q0 + threadIdx.x / tpq;
             if (qi < Nq) {
-                const float g = __ldg(dS + size_t(qi) * Nd + j);
+                const float g = __ldg(dS + size_t(qi) * Nd + j) * gs;
                 const int n = min(__ldg(L.nnz + qi), kQCap);
                 if (g != 0.f)
                     for (int k = sub; k < n; k += tpq)
@@ -304,16 +585,18 @@ scores_docrow_bwd_kernel(const float* __restrict__ dS, int Nq, int Nd, int V, in
 }
 
 // ------------------------------------------------------------------------------------------ scores backward
-// out[r, v] (+)= sum_k coef(r,k) * in[k, v],  coef(r,k) = dS[r*sr + k*sk];  r in [r_begin, r_end), k in [0, K).
+// out[r, v] (+)= gs * sum_k coef(r,k) * in[k, v],  coef(r,k) = dS[r*sr + k*sk];  r in [r_begin, r_end), k in [0, K).
 // 16 output rows per block, 2 columns per thread; coefficients staged in shared memory.
 constexpr int kBR = 16, kBKc = 256;
 
 template <int VECW>
 __global__ void __launch_bounds__(256)
-scores_bwd_kernel(const float* __restrict__ dS, int sr, int sk, const float* __restrict__ in, int K, int V, int r_begin,
-                  int r_end, int accumulate, const int* __restrict__ dense_flag, float* __restrict__ out) {
+scores_bwd_kernel(const float* __restrict__ dS, const float* __restrict__ gscale, int sr, int sk,
+                  const float* __restrict__ in, int K, int V, int r_begin, int r_end, int accumulate,
+                  const int* __restrict__ dense_flag, float* __restrict__ out) {
     __shared__ float coef[kBR][kBKc];
     if (dense_flag != nullptr && *dense_flag == 0) return;  // the sparse-query kernel produced the rows
+    const float gs = gscale != nullptr ? __ldg(gscale) : 1.f;
     const int r0 = r_begin + blockIdx.y * kBR;
     const int v = (blockIdx.x * 256 + threadIdx.x) * VECW;
     float acc[kBR][VECW];
@@ -326,7 +609,7 @@ scores_bwd_kernel(const float* __restrict__ dS, int sr, int sk, const float* __r
         __syncthreads();
         for (int t = threadIdx.x; t < kBR * nk; t += 256) {
             const int r = t / nk, k = t - r * nk;
-            coef[r][k] = (r0 + r < r_end) ? __ldg(dS + size_t(r0 + r) * sr + size_t(kc + k) * sk) : 0.f;
+            coef[r][k] = (r0 + r < r_end) ? __ldg(dS + size_t(r0 + r) * sr + size_t(kc + k) * sk) * gs : 0.f;
         }
         __syncthreads();
         if (v < V) {
@@ -358,13 +641,13 @@ scores_bwd_kernel(const float* __restrict__ dS, int sr, int sk, const float* __r
     }
 }
 
-// own-docs backward: d_d[i*G+g, v] (+)= dS[i,g] q[i,v]    grid (xb, rows)
+// own-docs backward: d_d[i*G+g, v] (+)= gs * dS[i,g] q[i,v]    grid (xb, rows)
 __global__ void __launch_bounds__(256)
-scores_group_bwd_d_kernel(const float* __restrict__ dS, const float* __restrict__ q, int G, int V, int d_begin,
-                          int accumulate, float* __restrict__ d_d) {
+scores_group_bwd_d_kernel(const float* __restrict__ dS, const float* __restrict__ gscale, const float* __restrict__ q,
+                          int G, int V, int d_begin, int accumulate, float* __restrict__ d_d) {
     const int row = d_begin + blockIdx.y;
     const int i = row / G;
-    const float c = __ldg(dS + row);  // dS is [Nq, G] row-major == index row
+    const float c = __ldg(dS + row) * (gscale != nullptr ? __ldg(gscale) : 1.f);  // dS is [Nq, G] row-major == index row
     const float* qi = q + size_t(i) * V;
     float* o = d_d + size_t(row) * V;
     for (int v = blockIdx.x * 256 + threadIdx.x; v < V; v += gridDim.x * 256) {
@@ -372,96 +655,18 @@ scores_group_bwd_d_kernel(const float* __restrict__ dS, const float* __restrict_
         o[v] = accumulate ? (o[v] + gval) : gval;
     }
 }
-// own-docs backward: d_q[i, v] (+)= sum_g dS[i,g] d[i*G+g, v]
+// own-docs backward: d_q[i, v] (+)= gs * sum_g dS[i,g] d[i*G+g, v]
 __global__ void __launch_bounds__(256)
-scores_group_bwd_q_kernel(const float* __restrict__ dS, const float* __restrict__ d, int G, int V, int q_begin,
-                          int accumulate, float* __restrict__ d_q) {
+scores_group_bwd_q_kernel(const float* __restrict__ dS, const float* __restrict__ gscale, const float* __restrict__ d,
+                          int G, int V, int q_begin, int accumulate, float* __restrict__ d_q) {
     const int i = q_begin + blockIdx.y;
+    const float gs = gscale != nullptr ? __ldg(gscale) : 1.f;
     float* o = d_q + size_t(i) * V;
     for (int v = blockIdx.x * 256 + threadIdx.x; v < V; v += gridDim.x * 256) {
         float acc = 0.f;
         for (int g = 0; g < G; ++g) acc = fmaf(__ldg(dS + size_t(i) * G + g), __ldg(d + (size_t(i) * G + g) * V + v), acc);
+        acc *= gs;
         o[v] = accumulate ? (o[v] + acc) : acc;
-    }
-}
-
-// ------------------------------------------------------------------------------------------ ranking losses
-// One block per query row. loss is accumulated with one atomicAdd per row (already scaled by the batch mean).
-__global__ void __launch_bounds__(256)
-rank_loss_kernel(int mode, const float* __restrict__ S, const float* __restrict__ teacher, int Nq, int C, int G,
-                 int in_batch, float invT, float* __restrict__ loss, float* __restrict__ dS) {
-    __shared__ float red[8];
-    const int i = blockIdx.x;
-    const float* s = S + size_t(i) * C;
-    float* g = dS != nullptr ? dS + size_t(i) * C : nullptr;
-    const float invNq = 1.f / float(Nq);
-
-    if (mode == SB200_LOSS_INFONCE) {
-        // selected columns: own positive + every hard negative (loss.py:90-101); own docs only when !in_batch
-        const int pos = in_batch ? i * G : 0;
-        auto selected = [&](int j) { return !in_batch || j == pos || (j % G) != 0; };
-        float m = -CUDART_INF_F;
-        for (int j = threadIdx.x; j < C; j += 256)
-            if (selected(j)) m = fmaxf(m, s[j]);
-        m = block_max<256>(m, red);
-        float z = 0.f;
-        for (int j = threadIdx.x; j < C; j += 256)
-            if (selected(j)) z += expf(s[j] - m);
-        z = block_sum<256>(z, red);
-        const float lse = m + logf(z);
-        if (threadIdx.x == 0) atomicAdd(loss, (lse - s[pos]) * invNq);
-        if (g != nullptr) {
-            for (int j = threadIdx.x; j < C; j += 256) {
-                float v = 0.f;
-                if (selected(j)) v = (expf(s[j] - lse) - (j == pos ? 1.f : 0.f)) * invNq;
-                g[j] = v;
-            }
-        }
-    } else if (mode == SB200_LOSS_KLDIV) {
-        const float* t = teacher + size_t(i) * C;
-        float ms = -CUDART_INF_F, mt = -CUDART_INF_F;
-        for (int j = threadIdx.x; j < C; j += 256) {
-            ms = fmaxf(ms, s[j] * invT);
-            mt = fmaxf(mt, t[j] * invT);
-        }
-        ms = block_max<256>(ms, red);
-        mt = block_max<256>(mt, red);
-        float zs = 0.f, zt = 0.f;
-        for (int j = threadIdx.x; j < C; j += 256) {
-            zs += expf(s[j] * invT - ms);
-            zt += expf(t[j] * invT - mt);
-        }
-        zs = block_sum<256>(zs, red);
-        zt = block_sum<256>(zt, red);
-        const float lzs = logf(zs), lzt = logf(zt);
-        float acc = 0.f;
-        for (int j = threadIdx.x; j < C; j += 256) {
-            const float lps = s[j] * invT - ms - lzs;
-            const float lpt = t[j] * invT - mt - lzt;
-            const float pt = expf(lpt);
-            if (pt > 0.f) acc += pt * (lpt - lps);  // xlogy(t,t) - t*input
-            if (g != nullptr) g[j] = (expf(lps) - pt) * invT * invNq;
-        }
-        acc = block_sum<256>(acc, red);
-        if (threadIdx.x == 0) atomicAdd(loss, acc * invNq);
-    } else {  // margin MSE: margins against column 0 (loss.py:52-55)
-        const float* t = teacher + size_t(i) * C;
-        const float s0 = s[0] * invT, t0 = t[0] * invT;
-        const float norm = 1.f / (float(Nq) * float(C - 1));
-        float acc = 0.f, g0 = 0.f;
-        for (int j = 1 + threadIdx.x; j < C; j += 256) {
-            const float diff = (s0 - s[j] * invT) - (t0 - t[j] * invT);
-            acc = fmaf(diff, diff, acc);
-            const float gj = 2.f * diff * norm * invT;
-            g0 += gj;
-            if (g != nullptr) g[j] = -gj;
-        }
-        acc = block_sum<256>(acc, red);
-        g0 = block_sum<256>(g0, red);
-        if (threadIdx.x == 0) {
-            atomicAdd(loss, acc * norm);
-            if (g != nullptr) g[0] = g0;
-        }
     }
 }
 
@@ -590,6 +795,59 @@ int pick_ksplit(int base_blocks, int V, int quantum, int* kchunk) {
     return ks;
 }
 
+struct RowPlan {
+    int n_parts, part_len;
+    size_t smem;
+};
+// smallest number of equal parts whose kRowStages stages fit the shared-memory budget
+RowPlan row_plan(int V) {
+    RowPlan p;
+    p.n_parts = 1;
+    while (true) {
+        p.part_len = int(align_up(size_t((V + p.n_parts - 1) / p.n_parts), 4));
+        p.smem = size_t(kRowStages) * size_t(p.part_len + 8) * sizeof(float);
+        if (p.smem <= size_t(kRowSmemBudget)) break;
+        ++p.n_parts;
+    }
+    if (p.n_parts == 1 && V >= 8192) {   // at least two parts per row: the gather of one overlaps the fetch of the next
+        p.n_parts = 2;
+        p.part_len = int(align_up(size_t((V + 1) / 2), 4));
+        p.smem = size_t(kRowStages) * size_t(p.part_len + 8) * sizeof(float);
+    }
+    return p;
+}
+
+int launch_q_compact(const float* q, int Nq, int V, QLists L, cudaStream_t stream) {
+    q_compact_kernel<<<Nq, kCompactThreads, 0, stream>>>(q, V, L);
+    SB200_CHECK_LAUNCH("q_compact_kernel");
+    return SB200_OK;
+}
+
+// the persistent row kernel; fused != 0 -> cooperative launch with the loss phase
+int launch_docrow(const float* d, int Nq, int Nd, int V, QLists L, float* S, const LossArgs& la, bool fused,
+                  cudaStream_t stream) {
+    const RowPlan plan = row_plan(V);
+    int grid = num_sms();
+    if (grid > Nd) grid = Nd;
+    if (!device_flag_test_and_set(6)) {
+        SB200_CUDA(cudaFuncSetAttribute(scores_docrow_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        kRowSmemBudget));
+        SB200_CUDA(cudaFuncSetAttribute(scores_docrow_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        kRowSmemBudget));
+    }
+    int n_parts = plan.n_parts, part_len = plan.part_len;
+    if (fused) {
+        void* args[] = {(void*)&d, (void*)&Nq, (void*)&Nd, (void*)&V, (void*)&n_parts, (void*)&part_len, (void*)&L,
+                        (void*)&S, (void*)&la};
+        SB200_CUDA(cudaLaunchCooperativeKernel((const void*)scores_docrow_kernel<true>, dim3(grid), dim3(kRowThreads), args,
+                                               plan.smem, stream));
+    } else {
+        scores_docrow_kernel<false><<<grid, kRowThreads, plan.smem, stream>>>(d, Nq, Nd, V, n_parts, part_len, L, S, la);
+    }
+    SB200_CHECK_LAUNCH("scores_docrow_kernel");
+    return SB200_OK;
+}
+
 }  // namespace
 }  // namespace sb200
 
@@ -597,8 +855,9 @@ using namespace sb200;
 
 extern "C" size_t sb200_scores_workspace_bytes(int Nq, int Nd, int V, int in_batch) {
     (void)Nd; (void)V;
-    if (!in_batch || Nq <= 0) return 0;
-    return qlists_bytes(Nq);  // thresholded query lists (+ dispatch flag); reused by sb200_scores_bwd
+    if (Nq <= 0) return 0;
+    // in-batch: thresholded query lists (+ dispatch flag), reused by sb200_scores_bwd; both modes: Nq row losses
+    return (in_batch ? qlists_bytes(Nq) : 0) + align_up_sz(size_t(Nq) * sizeof(float), 256);
 }
 
 static int row_kernel_grid(int rows, int chunks) {
@@ -610,8 +869,57 @@ static size_t row_slab_bytes(int V) { return size_t(V + 4) * sizeof(float); }
 // threads that share one query (power of two <= 32): as many as the block allows, so short lists stay in registers
 static int threads_per_query(int Nq) {
     int tpq = 32;
-    while (tpq > 2 && kRowThreads / tpq < Nq) tpq >>= 1;  // >= 2: lists of up to 64 entries always fit
+    while (tpq > 2 && kRowThreads / tpq < Nq) tpq >>= 1;
     return tpq;
+}
+
+// dense fp32 tiles: the only path without a workspace, the fallback (device-side flag) with one
+static int launch_dense_scores(const float* q, const float* d, int Nq, int Nd, int V, const int* dense_flag, float* S,
+                               cudaStream_t stream) {
+    const int tj = (Nd + kST - 1) / kST, ti = (Nq + kST - 1) / kST;
+    SB200_REQUIRE(ti <= 65535, "scores_fwd: Nq too large");
+    int kchunk;
+    const int ks = pick_ksplit(tj * ti, V, kSK, &kchunk);
+    if (ks > 1) {
+        if (dense_flag != nullptr) {
+            zero_if_dense_kernel<<<2 * num_sms(), 256, 0, stream>>>(S, size_t(Nq) * Nd, dense_flag);
+            SB200_CHECK_LAUNCH("zero_if_dense_kernel");
+        } else {
+            SB200_CUDA(cudaMemsetAsync(S, 0, size_t(Nq) * Nd * sizeof(float), stream));
+        }
+    }
+    scores_tile_kernel<<<dim3(tj, ti, ks), 256, 0, stream>>>(q, d, Nq, Nd, V, kchunk, dense_flag, S);
+    SB200_CHECK_LAUNCH("scores_tile_kernel");
+    return SB200_OK;
+}
+
+static int launch_group(const float* q, const float* d, int Nq, int G, int V, int mode, const float* teacher, float invT,
+                        float* S, float* dS, float* rowloss, float* loss, cudaStream_t stream) {
+    SB200_REQUIRE(Nq <= 65535, "scores: Nq too large");
+    SB200_REQUIRE(G <= kGroupMaxG, "scores (own docs): G=%d exceeds %d", G, kGroupMaxG);
+    int ks = (2 * num_sms() + Nq - 1) / Nq;   // CTAs per query: fill the machine, at most a portable cluster
+    if (ks > 8) ks = 8;
+    while (ks & (ks - 1)) --ks;
+    if (ks < 1) ks = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(unsigned(ks), unsigned(Nq));
+    cfg.blockDim = dim3(kGroupThreads);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = unsigned(ks);
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SB200_CUDA(cudaLaunchKernelEx(&cfg, score_group_kernel, q, d, Nq, G, V, mode, teacher, invT, S, dS, rowloss, loss));
+    SB200_CHECK_LAUNCH("score_group_kernel");
+    return SB200_OK;
+}
+
+static float* rowloss_of(void* workspace, int Nq, int in_batch) {
+    return reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + (in_batch ? qlists_bytes(Nq) : 0));
 }
 
 extern "C" int sb200_scores_fwd(const float* q, const float* d, int Nq, int Nd, int V, int in_batch, float* S,
@@ -620,56 +928,72 @@ extern "C" int sb200_scores_fwd(const float* q, const float* d, int Nq, int Nd, 
     SB200_REQUIRE(q && d && S, "scores_fwd: null pointer");
     SB200_REQUIRE(Nq >= 1 && Nd >= 1 && V >= 1, "scores_fwd: bad shape");
     if (in_batch) {
-        const int tj = (Nd + kST - 1) / kST, ti = (Nq + kST - 1) / kST;
-        SB200_REQUIRE(ti <= 65535, "scores_fwd: Nq too large");
-        const size_t row_smem = row_slab_bytes(V);
-        const bool sparse_ok = workspace != nullptr && workspace_bytes >= qlists_bytes(Nq) && row_smem <= 200 * 1024 &&
-                               Nq <= 65535;
+        const bool sparse_ok = workspace != nullptr && workspace_bytes >= qlists_bytes(Nq) && Nq <= 65535;
         const int* dense_flag = nullptr;
         if (sparse_ok) {
             QLists L = qlists_carve(workspace, Nq);
-            // flag and the per-row counters are adjacent: one memset
-            SB200_CUDA(cudaMemsetAsync(L.flag, 0, 256 + align_up_sz(size_t(Nq) * 4, 256), stream));
-            const int tpq = threads_per_query(Nq);
-            const int per = kRowThreads / tpq, chunks = (Nq + per - 1) / per;
-            const int cap = kEPT * tpq < kQCap ? kEPT * tpq : kQCap;
-            q_compact_kernel<<<dim3(8, Nq), 256, 0, stream>>>(q, V, cap, L);
-            SB200_CHECK_LAUNCH("q_compact_kernel");
-            if (!device_flag_test_and_set(6))
-                SB200_CUDA(cudaFuncSetAttribute(scores_docrow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            scores_docrow_kernel<<<dim3(row_kernel_grid(Nd, chunks), chunks), kRowThreads, row_smem, stream>>>(d, Nq, Nd, V, tpq, L, S);
-            SB200_CHECK_LAUNCH("scores_docrow_kernel");
+            int rc = launch_q_compact(q, Nq, V, L, stream);
+            if (rc != SB200_OK) return rc;
+            LossArgs la = {};
+            la.mode = -1;
+            rc = launch_docrow(d, Nq, Nd, V, L, S, la, false, stream);
+            if (rc != SB200_OK) return rc;
             dense_flag = L.flag;
         }
-        // dense fp32 tiles: the only path without a workspace, the fallback (device-side flag) with one
-        int kchunk;
-        const int ks = pick_ksplit(tj * ti, V, kSK, &kchunk);
-        if (ks > 1) {
-            if (sparse_ok) {
-                zero_if_dense_kernel<<<2 * num_sms(), 256, 0, stream>>>(S, size_t(Nq) * Nd, dense_flag);
-                SB200_CHECK_LAUNCH("zero_if_dense_kernel");
-            } else {
-                SB200_CUDA(cudaMemsetAsync(S, 0, size_t(Nq) * Nd * sizeof(float), stream));
-            }
-        }
-        scores_tile_kernel<<<dim3(tj, ti, ks), 256, 0, stream>>>(q, d, Nq, Nd, V, kchunk, dense_flag, S);
-        SB200_CHECK_LAUNCH("scores_tile_kernel");
-    } else {
-        SB200_REQUIRE(Nd % Nq == 0, "scores_fwd: Nd=%d is not a multiple of Nq=%d", Nd, Nq);
-        SB200_REQUIRE(Nq <= 65535, "scores_fwd: Nq too large");
-        const int G = Nd / Nq;
-        int kchunk;
-        const int ks = pick_ksplit(Nq, V, 256, &kchunk);
-        if (ks > 1) SB200_CUDA(cudaMemsetAsync(S, 0, size_t(Nq) * G * sizeof(float), stream));
-        scores_group_kernel<<<dim3(ks, Nq), 256, 0, stream>>>(q, d, G, V, kchunk, S);
-        SB200_CHECK_LAUNCH("scores_group_kernel");
+        return launch_dense_scores(q, d, Nq, Nd, V, dense_flag, S, stream);
     }
+    SB200_REQUIRE(Nd % Nq == 0, "scores_fwd: Nd=%d is not a multiple of Nq=%d", Nd, Nq);
+    return launch_group(q, d, Nq, Nd / Nq, V, -1, nullptr, 1.f, S, nullptr, nullptr, nullptr, stream);
+}
+
+extern "C" int sb200_score_loss_fwd(int mode, const float* q, const float* d, const float* teacher, int Nq, int Nd, int V,
+                                    int G, int in_batch, float temperature, int q_nnz_bound, float* S, float* loss,
+                                    float* dS, void* workspace, size_t workspace_bytes, sb200_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    SB200_REQUIRE(q && d && S && loss, "score_loss_fwd: null pointer");
+    SB200_REQUIRE(Nq >= 1 && Nd >= 1 && V >= 1 && G >= 1, "score_loss_fwd: bad shape");
+    SB200_REQUIRE(mode >= SB200_LOSS_INFONCE && mode <= SB200_LOSS_MARGINMSE, "score_loss_fwd: bad mode %d", mode);
+    SB200_REQUIRE(mode == SB200_LOSS_INFONCE || teacher != nullptr, "score_loss_fwd: teacher scores required");
+    SB200_REQUIRE(temperature > 0.f, "score_loss_fwd: temperature must be positive");
+    SB200_REQUIRE(Nd == Nq * G, "score_loss_fwd: Nd=%d != Nq*G=%d", Nd, Nq * G);
+    const int C = in_batch ? Nd : G;
+    SB200_REQUIRE(mode != SB200_LOSS_MARGINMSE || C >= 2, "score_loss_fwd: marginmse needs >= 2 columns");
+    const size_t need = sb200_scores_workspace_bytes(Nq, Nd, V, in_batch);
+    if (workspace == nullptr || workspace_bytes < need)
+        return fail(SB200_ERR_WORKSPACE, "score_loss_fwd: workspace %zu < %zu", workspace_bytes, need);
+    float* rowloss = rowloss_of(workspace, Nq, in_batch);
+    const float invT = 1.f / temperature;
+    if (!in_batch)
+        return launch_group(q, d, Nq, G, V, mode, teacher, invT, S, dS, rowloss, loss, stream);
+    SB200_REQUIRE(Nq <= 65535, "score_loss_fwd: Nq too large");
+    QLists L = qlists_carve(workspace, Nq);
+    int rc = launch_q_compact(q, Nq, V, L, stream);
+    if (rc != SB200_OK) return rc;
+    LossArgs la;
+    la.mode = mode;
+    la.teacher = teacher;
+    la.G = G;
+    la.invT = invT;
+    la.loss = loss;
+    la.dS = dS;
+    la.rowloss = rowloss;
+    rc = launch_docrow(d, Nq, Nd, V, L, S, la, true, stream);
+    if (rc != SB200_OK) return rc;
+    // Caller-guaranteed bound on the non-zeros per query row (inf-free queries: the token count): the sparse kernel
+    // always does the work and nothing else is launched. Otherwise the dense kernels follow; they exit at once unless
+    // the device-side flag says a query row did not fit the lists.
+    if (q_nnz_bound > 0 && q_nnz_bound <= kQCap && Nq <= kRowMaxQ) return SB200_OK;
+    rc = launch_dense_scores(q, d, Nq, Nd, V, L.flag, S, stream);
+    if (rc != SB200_OK) return rc;
+    rank_loss_if_dense_kernel<<<Nq, 256, 0, stream>>>(mode, S, teacher, Nq, C, G, 1, invT, L.flag, loss, dS, rowloss);
+    SB200_CHECK_LAUNCH("rank_loss_if_dense_kernel");
     return SB200_OK;
 }
 
-extern "C" int sb200_scores_bwd(const float* dS, const float* q, const float* d, int Nq, int Nd, int V, int in_batch,
-                                int q_begin, int q_end, int d_begin, int d_end, int accumulate, float* d_q, float* d_d,
-                                const void* fwd_workspace, size_t workspace_bytes, sb200_stream_t stream_) {
+extern "C" int sb200_scores_bwd(const float* dS, const float* gscale, const float* q, const float* d, int Nq, int Nd,
+                                int V, int in_batch, int q_begin, int q_end, int d_begin, int d_end, int accumulate,
+                                float* d_q, float* d_d, const void* fwd_workspace, size_t workspace_bytes,
+                                sb200_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     SB200_REQUIRE(dS && q && d, "scores_bwd: null pointer");
     SB200_REQUIRE(Nq >= 1 && Nd >= 1 && V >= 1, "scores_bwd: bad shape");
@@ -682,27 +1006,27 @@ extern "C" int sb200_scores_bwd(const float* dS, const float* q, const float* d,
         if (d_d != nullptr && d_end > d_begin) {
             const size_t row_smem = row_slab_bytes(V);
             const int* dense_flag = nullptr;
-            if (fwd_workspace != nullptr && workspace_bytes >= qlists_bytes(Nq) && row_smem <= 200 * 1024) {
-                // query lists built by sb200_scores_fwd: one shared-memory row per document, written to HBM once
+            if (fwd_workspace != nullptr && workspace_bytes >= qlists_bytes(Nq) && row_smem <= size_t(kRowSmemBudget)) {
+                // query lists built by the forward call: one shared-memory row per document, written to HBM once
                 QLists L = qlists_carve(const_cast<void*>(fwd_workspace), Nq);
                 if (!device_flag_test_and_set(7))
                     SB200_CUDA(cudaFuncSetAttribute(scores_docrow_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                    200 * 1024));
+                                                    kRowSmemBudget));
                 scores_docrow_bwd_kernel<<<row_kernel_grid(d_end - d_begin, 1), kRowThreads, row_smem, stream>>>(
-                    dS, Nq, Nd, V, threads_per_query(Nq), L, d_begin, d_end, accumulate, d_d);
+                    dS, gscale, Nq, Nd, V, threads_per_query(Nq), L, d_begin, d_end, accumulate, d_d);
                 SB200_CHECK_LAUNCH("scores_docrow_bwd_kernel");
                 dense_flag = L.flag;
             }
             dim3 grid(xb, (d_end - d_begin + kBR - 1) / kBR);
             // out row r = doc j, k = query i: coef = dS[i*Nd + j]
-            if (vec2) scores_bwd_kernel<2><<<grid, 256, 0, stream>>>(dS, 1, Nd, q, Nq, V, d_begin, d_end, accumulate, dense_flag, d_d);
-            else scores_bwd_kernel<1><<<grid, 256, 0, stream>>>(dS, 1, Nd, q, Nq, V, d_begin, d_end, accumulate, dense_flag, d_d);
+            if (vec2) scores_bwd_kernel<2><<<grid, 256, 0, stream>>>(dS, gscale, 1, Nd, q, Nq, V, d_begin, d_end, accumulate, dense_flag, d_d);
+            else scores_bwd_kernel<1><<<grid, 256, 0, stream>>>(dS, gscale, 1, Nd, q, Nq, V, d_begin, d_end, accumulate, dense_flag, d_d);
             SB200_CHECK_LAUNCH("scores_bwd_kernel(d_d)");
         }
         if (d_q != nullptr && q_end > q_begin) {
             dim3 grid(xb, (q_end - q_begin + kBR - 1) / kBR);
-            if (vec2) scores_bwd_kernel<2><<<grid, 256, 0, stream>>>(dS, Nd, 1, d, Nd, V, q_begin, q_end, accumulate, nullptr, d_q);
-            else scores_bwd_kernel<1><<<grid, 256, 0, stream>>>(dS, Nd, 1, d, Nd, V, q_begin, q_end, accumulate, nullptr, d_q);
+            if (vec2) scores_bwd_kernel<2><<<grid, 256, 0, stream>>>(dS, gscale, Nd, 1, d, Nd, V, q_begin, q_end, accumulate, nullptr, d_q);
+            else scores_bwd_kernel<1><<<grid, 256, 0, stream>>>(dS, gscale, Nd, 1, d, Nd, V, q_begin, q_end, accumulate, nullptr, d_q);
             SB200_CHECK_LAUNCH("scores_bwd_kernel(d_q)");
         }
     } else {
@@ -712,20 +1036,25 @@ extern "C" int sb200_scores_bwd(const float* dS, const float* q, const float* d,
         if (xb > 32) xb = 32;
         if (d_d != nullptr && d_end > d_begin) {
             SB200_REQUIRE(d_end - d_begin <= 65535, "scores_bwd: too many rows");
-            scores_group_bwd_d_kernel<<<dim3(xb, d_end - d_begin), 256, 0, stream>>>(dS, q, G, V, d_begin, accumulate, d_d);
+            scores_group_bwd_d_kernel<<<dim3(xb, d_end - d_begin), 256, 0, stream>>>(dS, gscale, q, G, V, d_begin, accumulate, d_d);
             SB200_CHECK_LAUNCH("scores_group_bwd_d_kernel");
         }
         if (d_q != nullptr && q_end > q_begin) {
             SB200_REQUIRE(q_end - q_begin <= 65535, "scores_bwd: too many rows");
-            scores_group_bwd_q_kernel<<<dim3(xb, q_end - q_begin), 256, 0, stream>>>(dS, d, G, V, q_begin, accumulate, d_q);
+            scores_group_bwd_q_kernel<<<dim3(xb, q_end - q_begin), 256, 0, stream>>>(dS, gscale, d, G, V, q_begin, accumulate, d_q);
             SB200_CHECK_LAUNCH("scores_group_bwd_q_kernel");
         }
     }
     return SB200_OK;
 }
 
+extern "C" size_t sb200_rank_loss_workspace_bytes(int Nq) {
+    return Nq > 0 ? align_up_sz(size_t(Nq) * sizeof(float), 256) : 0;
+}
+
 extern "C" int sb200_rank_loss(int mode, const float* S, const float* teacher, int Nq, int C, int G, int in_batch,
-                               float temperature, float* loss, float* dS, sb200_stream_t stream_) {
+                               float temperature, float* loss, float* dS, void* workspace, size_t workspace_bytes,
+                               sb200_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     SB200_REQUIRE(S && loss, "rank_loss: null pointer");
     SB200_REQUIRE(mode >= SB200_LOSS_INFONCE && mode <= SB200_LOSS_MARGINMSE, "rank_loss: bad mode %d", mode);
@@ -737,8 +1066,10 @@ extern "C" int sb200_rank_loss(int mode, const float* S, const float* teacher, i
         if (in_batch) SB200_REQUIRE(C == Nq * G, "rank_loss: in-batch infonce expects C == Nq*G");
         else SB200_REQUIRE(C == G, "rank_loss: infonce expects C == G");
     }
-    SB200_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), stream));
-    rank_loss_kernel<<<Nq, 256, 0, stream>>>(mode, S, teacher, Nq, C, G, in_batch, 1.f / temperature, loss, dS);
+    if (workspace == nullptr || workspace_bytes < sb200_rank_loss_workspace_bytes(Nq))
+        return fail(SB200_ERR_WORKSPACE, "rank_loss: workspace too small");
+    rank_loss_kernel<<<Nq, 256, 0, stream>>>(mode, S, teacher, Nq, C, G, in_batch, 1.f / temperature, loss, dS,
+                                             static_cast<float*>(workspace));
     SB200_CHECK_LAUNCH("rank_loss_kernel");
     return SB200_OK;
 }

@@ -200,6 +200,8 @@ class IdfQueryFunction(torch.autograd.Function):
         if idf_vector.requires_grad:
             ctx.save_for_backward(q)
         ctx.idf_dtype = idf_vector.dtype
+        # a row holds at most one entry per token: lets the score kernels skip their dense-query fallback launches
+        q._sb200_nnz_bound = int(input_ids.shape[1])
         return q
 
     @staticmethod
@@ -219,7 +221,8 @@ def idf_query(input_ids, idf_vector, special_ids):
 
 # --------------------------------------------------------------------------------------------- FLOPS regulariser
 def flops_forward(rep, group_num=1, threshold=None, want_stats=False):
-    """-> (value [] fp32, colsum [G,V], rowmask [N*G], stats [4] | None)"""
+    """-> (value [] fp32, colsum [G,V], rowmask [N*G] | None, stats [4] | None). The row mask exists only for the
+    L0-thresholded variant (or with stats); the plain regulariser is one launch over rep."""
     _need_cuda(rep)
     rep = rep.float().contiguous()
     rows, V = rep.shape
@@ -228,12 +231,15 @@ def flops_forward(rep, group_num=1, threshold=None, want_stats=False):
     N = rows // group_num
     dev = rep.device
     colsum = torch.empty(group_num, V, dtype=torch.float32, device=dev)
-    rowmask = torch.empty(rows, dtype=torch.float32, device=dev)
+    need_rows = threshold is not None or want_stats
+    rowmask = torch.empty(rows, dtype=torch.float32, device=dev) if need_rows else None
     value = torch.empty((), dtype=torch.float32, device=dev)
     stats = torch.empty(4, dtype=torch.float32, device=dev) if want_stats else None
+    lib = _lib.load()
+    ws = _workspace(lib.sb200_flops_workspace_bytes(N, group_num, V), dev)
     with torch.cuda.device(dev):
-        code = _lib.load().sb200_flops_fwd(_ptr(rep), N, group_num, V, -1.0 if threshold is None else float(threshold),
-                                           _ptr(colsum), _ptr(rowmask), _ptr(value), _ptr(stats), _stream())
+        code = lib.sb200_flops_fwd(_ptr(rep), N, group_num, V, -1.0 if threshold is None else float(threshold),
+                                   _ptr(colsum), _ptr(rowmask), _ptr(value), _ptr(stats), _ptr(ws), ws.numel(), _stream())
     _lib.check(code, "sb200_flops_fwd")
     return value, colsum, rowmask, stats
 
@@ -272,7 +278,7 @@ def flops_value(rep, group_num=1, threshold=None):
 
 
 # --------------------------------------------------------------------------------------------- scores + losses
-def scores_forward(q, d, in_batch, return_workspace=False):
+def _check_qd(q, d, in_batch):
     _need_cuda(q, d)
     q = q.float().contiguous()
     d = d.float().contiguous()
@@ -282,16 +288,36 @@ def scores_forward(q, d, in_batch, return_workspace=False):
         raise ValueError("q and d must share the vocabulary dimension")
     if not in_batch and Nd % Nq != 0:
         raise ValueError("number of docs must be a multiple of the number of queries")
+    return q, d, Nq, Nd, V
+
+
+def scores_forward(q, d, in_batch, return_workspace=False):
+    q, d, Nq, Nd, V = _check_qd(q, d, in_batch)
     C = Nd if in_batch else Nd // Nq
     S = torch.empty(Nq, C, dtype=torch.float32, device=q.device)
     lib = _lib.load()
-    nbytes = lib.sb200_scores_workspace_bytes(Nq, Nd, V, 1 if in_batch else 0)
-    ws = _workspace(nbytes, q.device) if nbytes > 0 else None
+    ws = _workspace(lib.sb200_scores_workspace_bytes(Nq, Nd, V, 1 if in_batch else 0), q.device)
     with torch.cuda.device(q.device):
-        code = lib.sb200_scores_fwd(_ptr(q), _ptr(d), Nq, Nd, V, 1 if in_batch else 0, _ptr(S), _ptr(ws),
-                                    0 if ws is None else ws.numel(), _stream())
+        code = lib.sb200_scores_fwd(_ptr(q), _ptr(d), Nq, Nd, V, 1 if in_batch else 0, _ptr(S), _ptr(ws), ws.numel(),
+                                    _stream())
     _lib.check(code, "sb200_scores_fwd")
     return (S, ws) if return_workspace else S
+
+
+def _scores_backward(dS, gscale, q, d, in_batch, q_rows, d_rows, need_q, need_d, ws):
+    """(d_q | None, d_d | None) = gscale * (dS d, dS^T q) restricted to the row ranges that carry gradient."""
+    Nq, V = q.shape
+    Nd = d.shape[0]
+    q_lo, q_hi = q_rows if q_rows is not None else (0, Nq)
+    d_lo, d_hi = d_rows if d_rows is not None else (0, Nd)
+    d_q = (torch.empty_like(q) if (q_lo, q_hi) == (0, Nq) else torch.zeros_like(q)) if need_q else None
+    d_d = (torch.empty_like(d) if (d_lo, d_hi) == (0, Nd) else torch.zeros_like(d)) if need_d else None
+    with torch.cuda.device(q.device):
+        code = _lib.load().sb200_scores_bwd(_ptr(dS), _ptr(gscale), _ptr(q), _ptr(d), Nq, Nd, V, 1 if in_batch else 0,
+                                            q_lo, q_hi, d_lo, d_hi, 0, _ptr(d_q), _ptr(d_d), _ptr(ws),
+                                            0 if ws is None else ws.numel(), _stream())
+    _lib.check(code, "sb200_scores_bwd")
+    return d_q, d_d
 
 
 class ScoresFunction(torch.autograd.Function):
@@ -301,7 +327,7 @@ class ScoresFunction(torch.autograd.Function):
         d32 = d.detach().float().contiguous()
         S, ws = scores_forward(q32, d32, in_batch, return_workspace=True)
         ctx.save_for_backward(q32, d32)
-        ctx.ws = ws  # thresholded query lists, reused by the backward kernels
+        ctx.ws = ws if in_batch else None  # thresholded query lists, reused by the backward kernels
         ctx.q_rows = getattr(q, "_sb200_grad_rows", None)  # set by gather_rep: only these rows carry grad
         ctx.d_rows = getattr(d, "_sb200_grad_rows", None)
         ctx.in_batch = bool(in_batch)
@@ -312,19 +338,8 @@ class ScoresFunction(torch.autograd.Function):
     def backward(ctx, dS):
         q, d = ctx.saved_tensors
         need_q, need_d = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        dS = dS.float().contiguous()
-        Nq, V = q.shape
-        Nd = d.shape[0]
-        q_lo, q_hi = ctx.q_rows if ctx.q_rows is not None else (0, Nq)
-        d_lo, d_hi = ctx.d_rows if ctx.d_rows is not None else (0, Nd)
-        d_q = (torch.empty_like(q) if (q_lo, q_hi) == (0, Nq) else torch.zeros_like(q)) if need_q else None
-        d_d = (torch.empty_like(d) if (d_lo, d_hi) == (0, Nd) else torch.zeros_like(d)) if need_d else None
-        ws = ctx.ws
-        with torch.cuda.device(q.device):
-            code = _lib.load().sb200_scores_bwd(_ptr(dS), _ptr(q), _ptr(d), Nq, Nd, V, 1 if ctx.in_batch else 0, q_lo, q_hi,
-                                                d_lo, d_hi, 0, _ptr(d_q), _ptr(d_d), _ptr(ws),
-                                                0 if ws is None else ws.numel(), _stream())
-        _lib.check(code, "sb200_scores_bwd")
+        d_q, d_d = _scores_backward(dS.float().contiguous(), None, q, d, ctx.in_batch, ctx.q_rows, ctx.d_rows, need_q,
+                                    need_d, ctx.ws)
         return (d_q.to(ctx.dtypes[0]) if need_q else None, d_d.to(ctx.dtypes[1]) if need_d else None, None)
 
 
@@ -349,9 +364,11 @@ class RankLossFunction(torch.autograd.Function):
                 raise ValueError(f"teacher scores {tuple(t32.shape)} do not match student scores {(Nq, C)}")
         loss = torch.empty((), dtype=torch.float32, device=S.device)
         dS = torch.empty_like(S32) if S.requires_grad else None
+        lib = _lib.load()
+        ws = _workspace(lib.sb200_rank_loss_workspace_bytes(Nq), S.device)
         with torch.cuda.device(S.device):
-            code = _lib.load().sb200_rank_loss(_LOSS_MODES[mode], _ptr(S32), _ptr(t32), Nq, C, int(G), 1 if in_batch else 0,
-                                               float(temperature), _ptr(loss), _ptr(dS), _stream())
+            code = lib.sb200_rank_loss(_LOSS_MODES[mode], _ptr(S32), _ptr(t32), Nq, C, int(G), 1 if in_batch else 0,
+                                       float(temperature), _ptr(loss), _ptr(dS), _ptr(ws), ws.numel(), _stream())
         _lib.check(code, "sb200_rank_loss")
         if dS is not None:
             ctx.save_for_backward(dS)
@@ -366,6 +383,67 @@ class RankLossFunction(torch.autograd.Function):
 
 def rank_loss(S, teacher, mode, G, in_batch, temperature=1.0):
     return RankLossFunction.apply(S, teacher, mode, G, in_batch, temperature)
+
+
+def score_loss_forward(q, d, teacher, mode, G, in_batch, temperature=1.0, q_nnz_bound=0, want_grad=True):
+    """Scores + ranking loss in one call (sb200_score_loss_fwd): -> (loss [], S [Nq,C], dS [Nq,C] | None, workspace)."""
+    q, d, Nq, Nd, V = _check_qd(q, d, in_batch)
+    if Nd != Nq * int(G):
+        raise ValueError(f"{Nd} docs != {Nq} queries x G={G}")
+    C = Nd if in_batch else Nd // Nq
+    t32 = None
+    if teacher is not None:
+        _need_cuda(teacher)
+        t32 = teacher.detach().float().contiguous()
+        if tuple(t32.shape) != (Nq, C):
+            raise ValueError(f"teacher scores {tuple(t32.shape)} do not match student scores {(Nq, C)}")
+    S = torch.empty(Nq, C, dtype=torch.float32, device=q.device)
+    dS = torch.empty(Nq, C, dtype=torch.float32, device=q.device) if want_grad else None
+    loss = torch.empty((), dtype=torch.float32, device=q.device)
+    lib = _lib.load()
+    ws = _workspace(lib.sb200_scores_workspace_bytes(Nq, Nd, V, 1 if in_batch else 0), q.device)
+    with torch.cuda.device(q.device):
+        code = lib.sb200_score_loss_fwd(_LOSS_MODES[mode], _ptr(q), _ptr(d), _ptr(t32), Nq, Nd, V, int(G),
+                                        1 if in_batch else 0, float(temperature), int(q_nnz_bound), _ptr(S), _ptr(loss),
+                                        _ptr(dS), _ptr(ws), ws.numel(), _stream())
+    _lib.check(code, "sb200_score_loss_fwd")
+    return loss, S, dS, ws
+
+
+class ScoreLossFunction(torch.autograd.Function):
+    """loss = ranking_loss(q . d^T [, teacher]) with the score matrix, the loss and d loss / d S produced by one fused
+    forward call; the backward multiplies by the upstream scalar inside the score-backward kernels."""
+
+    @staticmethod
+    def forward(ctx, q, d, teacher, mode, G, in_batch, temperature):
+        q32 = q.detach().float().contiguous()
+        d32 = d.detach().float().contiguous()
+        want = q.requires_grad or d.requires_grad
+        loss, S, dS, ws = score_loss_forward(q32, d32, teacher, mode, G, in_batch, temperature,
+                                             q_nnz_bound=int(getattr(q, "_sb200_nnz_bound", 0) or 0), want_grad=want)
+        if want:
+            ctx.save_for_backward(q32, d32, dS)
+        ctx.ws = ws if in_batch else None
+        ctx.q_rows = getattr(q, "_sb200_grad_rows", None)
+        ctx.d_rows = getattr(d, "_sb200_grad_rows", None)
+        ctx.in_batch = bool(in_batch)
+        ctx.dtypes = (q.dtype, d.dtype)
+        ctx.mark_non_differentiable(S)
+        return loss, S
+
+    @staticmethod
+    def backward(ctx, g, _g_scores):
+        q, d, dS = ctx.saved_tensors
+        need_q, need_d = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        gscale = g.detach().float().reshape(1).contiguous()
+        d_q, d_d = _scores_backward(dS, gscale, q, d, ctx.in_batch, ctx.q_rows, ctx.d_rows, need_q, need_d, ctx.ws)
+        return (d_q.to(ctx.dtypes[0]) if need_q else None, d_d.to(ctx.dtypes[1]) if need_d else None, None, None, None,
+                None, None)
+
+
+def score_loss(q, d, teacher, mode, G, in_batch, temperature=1.0):
+    """-> scalar loss (loss.py:25-43, 57-77, 86-107 on dense q_rep / d_rep)."""
+    return ScoreLossFunction.apply(q, d, teacher, mode, int(G), bool(in_batch), float(temperature))[0]
 
 
 # --------------------------------------------------------------------------------------------- encode output path

@@ -53,7 +53,7 @@ class PackedBertBody:
         self.head_dim = cfg.hidden_size // cfg.num_attention_heads
         self.attn_dropout = float(cfg.attention_probs_dropout_prob)
         self.overflow_count = None  # device int64 counter, created on first use
-        self.step_overflow = None   # fp32 [1] device flag of the current step (the trainer resets and consumes it)
+        self.step_overflow = None   # fp32 scalar device flag of the current step (the trainer resets and consumes it)
 
     @staticmethod
     def supported(backbone):
@@ -80,7 +80,7 @@ class PackedBertBody:
         dest = torch.where(fits, rank_in_pack, torch.full_like(rank_in_pack, t_cap)).long()  # dummy slot t_cap
         if self.overflow_count is None or self.overflow_count.device != keep.device:
             self.overflow_count = torch.zeros((), dtype=torch.int64, device=keep.device)
-            self.step_overflow = torch.zeros(1, dtype=torch.float32, device=keep.device)
+            self.step_overflow = torch.zeros((), dtype=torch.float32, device=keep.device)
         over = total > t_cap
         self.overflow_count += over.to(torch.int64)
         self.step_overflow.clamp_(min=over.to(torch.float32))

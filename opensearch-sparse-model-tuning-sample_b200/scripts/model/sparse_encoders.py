@@ -188,7 +188,7 @@ class SparseModel(torch.nn.Module):
         return None if packed is None else packed.overflow_count
 
     def unpad_step_flag(self):
-        """fp32 [1] device flag: 1.0 if a forward since the last unpad_step_reset() overflowed the packed capacity.
+        """fp32 scalar (0-dim) device flag: 1.0 if a forward since the last unpad_step_reset() overflowed the packed capacity.
         None when the packed body is off or its capacity (>= 1.0) can never overflow."""
         packed = self.__dict__.get("_packed")
         return None if packed is None or packed.capacity >= 1.0 else packed.step_overflow

@@ -1,5 +1,6 @@
 """Drop-in for the reference's ``scripts/train/loss.py``: same classes, constructor arguments and ``get_loss``
-contract; the score matrix and the loss (+ its gradient) are computed by the sm_100a kernels in ``ops``.
+contract; the score matrix, the loss and its gradient come from one fused call into the sm_100a kernels
+(``ops.score_loss``: 2 launches in-batch, 1 for own-docs scoring).
 
 Layout contract (reference collator): docs are query-major with the positive first, so with G = Nd // Nq the positive
 of query i is row i*G.
@@ -22,13 +23,12 @@ class SparseTrainingLoss:
         return self.weight * self(q_rep, d_rep, inputs)
 
 
-def _student_and_teacher(q_rep, d_rep, inputs, in_batch, what):
-    teacher = inputs["scores"]
+def _teacher_scores(q_rep, inputs, in_batch, what):
     if not in_batch and q_rep.shape[0] == 1:
         # the reference squeezes the batch dimension away here and fails inside (log_)softmax(dim=1) (loss.py:33-35)
         raise IndexError(f"{what} without in-batch negatives needs a batch of at least 2 queries "
                          "(Dimension out of range in the reference)")
-    return ops.scores(q_rep, d_rep, in_batch), teacher
+    return inputs["scores"]
 
 
 class KLDivLoss(SparseTrainingLoss):
@@ -40,9 +40,9 @@ class KLDivLoss(SparseTrainingLoss):
         super().__init__(weight)
 
     def __call__(self, q_rep, d_rep, inputs):
-        S, teacher = _student_and_teacher(q_rep, d_rep, inputs, self.use_in_batch_negatives, "KLDivLoss")
+        teacher = _teacher_scores(q_rep, inputs, self.use_in_batch_negatives, "KLDivLoss")
         G = d_rep.shape[0] // q_rep.shape[0]
-        return ops.rank_loss(S, teacher, "kldiv", G, self.use_in_batch_negatives, self.temperature)
+        return ops.score_loss(q_rep, d_rep, teacher, "kldiv", G, self.use_in_batch_negatives, self.temperature)
 
 
 class MarginMSELoss(SparseTrainingLoss):
@@ -54,9 +54,9 @@ class MarginMSELoss(SparseTrainingLoss):
         super().__init__(weight)
 
     def __call__(self, q_rep, d_rep, inputs):
-        S, teacher = _student_and_teacher(q_rep, d_rep, inputs, self.use_in_batch_negatives, "MarginMSELoss")
+        teacher = _teacher_scores(q_rep, inputs, self.use_in_batch_negatives, "MarginMSELoss")
         G = d_rep.shape[0] // q_rep.shape[0]
-        return ops.rank_loss(S, teacher, "marginmse", G, self.use_in_batch_negatives, self.temperature)
+        return ops.score_loss(q_rep, d_rep, teacher, "marginmse", G, self.use_in_batch_negatives, self.temperature)
 
 
 class InfoNCELoss(SparseTrainingLoss):
@@ -69,8 +69,7 @@ class InfoNCELoss(SparseTrainingLoss):
 
     def __call__(self, q_rep, d_rep, inputs):
         G = d_rep.shape[0] // q_rep.shape[0]
-        S = ops.scores(q_rep, d_rep, self.use_in_batch_negatives)
-        return ops.rank_loss(S, None, "infonce", G, self.use_in_batch_negatives, 1.0)
+        return ops.score_loss(q_rep, d_rep, None, "infonce", G, self.use_in_batch_negatives, 1.0)
 
 
 LOSS_CLS_MAP = {"infonce": InfoNCELoss, "kldiv": KLDivLoss, "marginmse": MarginMSELoss}

@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.EXPORTED_SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.sb200_abi_version() == 1
+    assert lib.sb200_abi_version() == 2
     assert lib.sb200_head_fwd_workspace_bytes(160, 256) > 0
     assert lib.sb200_head_bwd_workspace_bytes(160, 256, 384, 30522) >= 160 * 30522 * 8
 
@@ -56,7 +56,7 @@ def test_argument_errors_are_reported_not_crashes():
     lib = _lib.load()
     code = lib.sb200_head_fwd(0, 0, 0, 0, 8, 1, 1, 8, 1, 0, 0, 0, 0, 0, 0, 0)
     assert code == 1 and b"null" in lib.sb200_last_error()
-    code = lib.sb200_rank_loss(7, 1, 0, 1, 1, 1, 0, 1.0, 1, 0, 0)
+    code = lib.sb200_rank_loss(7, 1, 0, 1, 1, 1, 0, 1.0, 1, 0, 0, 0, 0)
     assert code == 1 and b"mode" in lib.sb200_last_error()
 
 
