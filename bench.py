@@ -482,12 +482,18 @@ def ncu_traffic(wl):
 
 
 # ------------------------------------------------------------------------------------------------ extras (1 GPU)
-def _time_cuda(fn, iters, flush=None):
+def _time_cuda(fn, iters, flush=None, read_flush=False):
+    """Mean CUDA-event time of fn() in ms. L2 is flushed before every call: by WRITING a buffer larger than L2 (the
+    profiling recipe's method; it leaves the L2 full of dirty lines whose write-back then competes with the kernel's own
+    reads) or, read_flush=True, by READING one (L2 full of clean lines)."""
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     total = 0.0
     for _ in range(iters):
         if flush is not None:
-            flush.zero_()
+            if read_flush:
+                flush.view(torch.float32).sum()
+            else:
+                flush.zero_()
         e0.record()
         fn()
         e1.record()
@@ -519,7 +525,8 @@ def extras(trainer, wl, args, device, peaks, hosts):
     model.train()
     # HBM-bound kernels: at the step's shapes (launch-latency regime: a few MB per call) and at a large shape
     # (8-GPU global batch of BERT-base C3 scale) where the HBM roofline is the meaningful yardstick. L2 is flushed
-    # before every launch; bytes are the algorithmic single-pass figures of DESIGN.md section 4.3.
+    # before every launch, once by writing 256 MB (`ms`, the recipe's method) and once by reading 256 MB
+    # (`ms_clean_l2`); bytes are the algorithmic single-pass figures of DESIGN.md section 4.3.
     hbm = peaks["hbm_gbs"]
     sp = model._special_ids_on(device)
 
@@ -535,8 +542,13 @@ def extras(trainer, wl, args, device, peaks, hosts):
             for _ in range(3):
                 fn()
             ms = _time_cuda(fn, 10, flush)
-            gbs = nbytes / (ms / 1e3) / 1e9
-            res[name] = {"ms": round(ms, 4), "GB/s": round(gbs, 1), "frac_of_hbm_peak": round(gbs / hbm, 4), "bytes": nbytes}
+            ms_clean = _time_cuda(fn, 10, flush, read_flush=True)
+            gbs, gbs_clean = nbytes / (ms / 1e3) / 1e9, nbytes / (ms_clean / 1e3) / 1e9
+            res[name] = {"ms": round(ms, 4), "GB/s": round(gbs, 1), "frac_of_hbm_peak": round(gbs / hbm, 4),
+                         "ms_clean_l2": round(ms_clean, 4), "GB/s_clean_l2": round(gbs_clean, 1),
+                         "frac_of_hbm_peak_clean_l2": round(gbs_clean / hbm, 4), "bytes": nbytes}
+        # yardstick: torch's own read-only reduction over the same bytes, same two flush methods
+        add("torch_sum_read_only_yardstick", lambda: d_rep.sum(), nd * V * 4)
         add("flops_fwd", lambda: ops.flops_forward(d_rep, G, None), nd * V * 4)
         add("flops_fwd_l0_threshold", lambda: ops.flops_forward(d_rep, G, 150), 2 * nd * V * 4)
         add("scores_fwd_in_batch", lambda: ops.scores_forward(q_rep, d_rep, True), (nq + nd) * V * 4)

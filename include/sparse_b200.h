@@ -112,8 +112,8 @@ int sb200_idf_query_bwd(const float* d_q, const float* q, int Nq, int V, float* 
  *                        backward treats a NULL rowmask as all ones)
  *   value    f32 [1]     out
  *   stats    f32 [4]     out (nullable): total nnz, sum of positive entries, max entry, unused
- *   workspace: sb200_flops_workspace_bytes(N, G, V). Plain FLOPS is ONE launch (row-split clusters, DSMEM reduction,
- *   deterministic last-block sum); the thresholded variant adds the row pass.
+ *   workspace: sb200_flops_workspace_bytes(N, G, V). Plain FLOPS is ONE launch (column owners with batched row loads,
+ *   deterministic last-block sum of the value); the thresholded variant adds the row pass.
  * Backward: d_rep[n,g,v] (+)= gscale * 2*colsum[g,v]/N^2 * sign(rep) * rowmask   (gscale read on device)
  * ------------------------------------------------------------------------------------------- */
 size_t sb200_flops_workspace_bytes(int N, int G, int V);

@@ -293,9 +293,10 @@ score_group_kernel(const float* __restrict__ q, const float* __restrict__ d, int
 // all query lists are gathered from it: HBM traffic = one pass over d, S[i,j] written once, no atomics (deterministic).
 //
 // The row kernel is persistent (one CTA per SM, rows round-robin) and keeps the memory pipe busy with a ring of
-// kRowStages shared-memory stages, each holding one PART of a row (a row is cut into n_parts equal column ranges so
-// that any vocabulary size fits): parts are fetched with one bulk async copy each (cp.async.bulk, mbarrier completion)
-// kRowStages parts ahead of the gather, so the next rows are in flight while the current part is consumed.
+// shared-memory stages, each holding one PART of a row (a row is cut into n_parts equal column ranges so that any
+// vocabulary size fits): all 512 threads fetch a part with 16-byte cp.async copies (no registers held, two parts in
+// flight per SM while the current one is consumed -- measured: LSU-issued copies stream HBM at 5+ TB/s where one bulk
+// (TMA) request per part reached 3.2 TB/s).
 // Two gather modes, chosen on the device from the list lengths (block-uniform):
 //   (A) registers: tpq = 512/Nq threads share a query, each keeps <= 32 entries in registers for the whole kernel;
 //   (B) streamed lists: warps walk the queries, lanes the (ascending) entries of the current part, from L2.
@@ -385,40 +386,39 @@ struct LossArgs {
     float* rowloss;           // [Nq] scratch
 };
 
-// Issues the fetch of part `p` of document row `j` into `stage` (called by warp 0; lane 0 drives the bulk copy, the
-// <= 3 floats in front of / behind the 16-byte aligned interior are moved by ordinary loads of lanes 1..6).
+// Issues the asynchronous fetch of part `p` of document row `j` into `stage` (all threads): 16-byte cp.async for the
+// aligned interior, 4-byte cp.async for the <= 3 floats in front of / behind it. The stage keeps the source's phase
+// inside a 16-byte line (element x of the part lives at stage[a + x]), so source and destination are co-aligned.
 __device__ __forceinline__ void row_part_issue(const float* __restrict__ d, int V, int j, int p, int part_len,
-                                               float* stage, uint64_t* bar, int lane) {
+                                               float* stage) {
     const int c0 = p * part_len;
     const int len = min(V, c0 + part_len) - c0;
     const float* src = d + size_t(j) * V + c0;
-    const int a = int(reinterpret_cast<uintptr_t>(src) & 15) >> 2;   // phase of the source inside a 16-byte line
+    const int a = int(reinterpret_cast<uintptr_t>(src) & 15) >> 2;
     const int head = min(len, (4 - a) & 3);
-    const int nbulk = ((len - head) >> 2) << 2;
-    const int tail0 = head + nbulk;
-    if (lane == 0) {
-        if (nbulk > 0) {
-            mbar_arrive_expect_tx(bar, uint32_t(nbulk) * 4u);
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(smem_u32(stage + head + a)), "l"(src + head), "r"(uint32_t(nbulk) * 4u), "r"(smem_u32(bar))
-                         : "memory");
-        } else {
-            mbar_arrive(bar);
-        }
-    } else if (lane <= 3) {
-        if (lane - 1 < head) stage[a + lane - 1] = __ldg(src + lane - 1);
-    } else if (lane <= 6) {
-        const int t = tail0 + lane - 4;
-        if (t < len) stage[a + t] = __ldg(src + t);
-    }
+    const int n16 = (len - head) >> 2;
+    const uint32_t dst0 = smem_u32(stage + a + head);
+    const float* s0 = src + head;
+    for (int t = threadIdx.x; t < n16; t += kRowThreads)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + uint32_t(t) * 16u), "l"(s0 + 4 * t) : "memory");
+    const int tail0 = head + 4 * n16;
+    if (int(threadIdx.x) < head)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(stage + a + threadIdx.x)), "l"(src + threadIdx.x)
+                     : "memory");
+    else if (threadIdx.x >= 32 && int(threadIdx.x) - 32 < len - tail0)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;"
+                     ::"r"(smem_u32(stage + a + tail0 + threadIdx.x - 32)), "l"(src + tail0 + threadIdx.x - 32)
+                     : "memory");
 }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 template <bool kFused>
 __global__ void __launch_bounds__(kRowThreads, 1)
 scores_docrow_kernel(const float* __restrict__ d, int Nq, int Nd, int V, int n_parts, int part_len, QLists L,
                      float* __restrict__ S, LossArgs la) {
     extern __shared__ __align__(128) float stages[];            // [kRowStages][part_len + 8]
-    __shared__ __align__(8) uint64_t full_bar[kRowStages];
     __shared__ int cursor_s[kRowMaxQ];                          // mode (B)
     __shared__ float acc_s[kRowMaxQ];
     __shared__ float red[kRowThreads / 32];
@@ -452,29 +452,32 @@ scores_docrow_kernel(const float* __restrict__ d, int Nq, int Nd, int V, int n_p
                 val[e] = ok ? __ldg(L.vals + size_t(qi) * kQCap + k) : 0.f;
             }
         }
-        if (threadIdx.x == 0) {
-            for (int s = 0; s < kRowStages; ++s) mbar_init(&full_bar[s], 1);
-            fence_mbar_init();
-        }
-        __syncthreads();
         const int my_rows = (Nd - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
         const int total = my_rows * n_parts;
-        if (warp == 0)
-            for (int t = 0; t < kRowStages && t < total; ++t)
-                row_part_issue(d, V, blockIdx.x + (t / n_parts) * gridDim.x, t % n_parts, part_len,
-                               stages + t * stage_floats, &full_bar[t], lane);
-        __syncthreads();
+        // prologue: parts 0 .. kRowStages-2 in flight (one commit group per part, empty groups past the end)
+        for (int t = 0; t < kRowStages - 1; ++t) {
+            if (t < total)
+                row_part_issue(d, V, blockIdx.x + (t / n_parts) * gridDim.x, t % n_parts, part_len, stages + t * stage_floats);
+            cp_async_commit();
+        }
         float acc = 0.f;
         for (int t = 0; t < total; ++t) {
             const int s = t % kRowStages;
-            const uint32_t ph = uint32_t(t / kRowStages) & 1u;
             const int r = t / n_parts, p = t - r * n_parts;
             const int j = blockIdx.x + r * gridDim.x;
             const int c0 = p * part_len;
             const int plen = min(V, c0 + part_len) - c0;
             const float* st = stages + s * stage_floats +
                               (int(reinterpret_cast<uintptr_t>(d + size_t(j) * V + c0) & 15) >> 2);
-            mbar_wait(&full_bar[s], ph);
+            cp_async_wait<kRowStages - 2>();   // this thread's copies of part t have landed ...
+            __syncthreads();                   // ... and everybody's; everybody is also done gathering part t-1
+            {   // refill the stage part t-1 lived in with part t + kRowStages - 1
+                const int tn = t + kRowStages - 1;
+                if (tn < total)
+                    row_part_issue(d, V, blockIdx.x + (tn / n_parts) * gridDim.x, tn % n_parts, part_len,
+                                   stages + (tn % kRowStages) * stage_floats);
+                cp_async_commit();
+            }
             if (mode_a) {
 #pragma unroll
                 for (int e = 0; e < kEPT; ++e) {
@@ -510,13 +513,8 @@ scores_docrow_kernel(const float* __restrict__ d, int Nq, int Nd, int V, int n_p
                     }
                 }
             }
-            __syncthreads();   // everyone is done with stage s
-            if (warp == 0 && t + kRowStages < total) {
-                const int tn = t + kRowStages;
-                row_part_issue(d, V, blockIdx.x + (tn / n_parts) * gridDim.x, tn % n_parts, part_len,
-                               stages + s * stage_floats, &full_bar[s], lane);
-            }
         }
+        cp_async_wait<0>();
     }
     if constexpr (kFused) {
         // ---- ranking loss on the finished score matrix: grid-wide barrier (cooperative launch), rows over blocks
@@ -533,6 +531,108 @@ scores_docrow_kernel(const float* __restrict__ d, int Nq, int Nd, int V, int n_p
         }
         finish_sum_last_block<kRowThreads>(&g_ticket_fused, gridDim.x, la.rowloss, Nq, 1.f, la.loss, red);
     }
+}
+
+// ------------------------------------------------------------------------------------------ very sparse queries
+// Direct gather: one block per query row i, ONE launch for scores + loss + dS.
+//   (1) ordered compaction of q[i, :] into shared memory (and into the global lists the backward kernel reuses);
+//   (2) warps walk the documents j (four at a time), lanes the entries: S[i,j] = sum_k val_k * d[j, col_k], read
+//       straight from global memory -- Nq * nnz 32-byte sectors per document instead of the V * 4 bytes of streaming the
+//       row, the better deal while Nq * nnz * 8 <= V (inf-free queries of a per-GPU batch);
+//   (3) the ranking-loss row of query i from the score row held in shared memory;
+//   (4) the deterministic last-block sum of the row losses.
+constexpr int kGatherThreads = 512;
+constexpr int kGatherCap = 256;       // entries per query row kept in shared memory
+constexpr int kGatherMaxNd = 8192;    // score row kept in shared memory
+__device__ unsigned int g_ticket_gather = 0;
+
+__global__ void __launch_bounds__(kGatherThreads)
+score_gather_kernel(const float* __restrict__ q, const float* __restrict__ d, int Nq, int Nd, int V, QLists L,
+                    float* __restrict__ S, LossArgs la) {
+    __shared__ int col_s[kGatherCap];
+    __shared__ float val_s[kGatherCap];
+    __shared__ int warp_cnt[kCompactBatch][kGatherThreads / 32];
+    __shared__ float red[kGatherThreads / 32];
+    extern __shared__ float srow[];     // [Nd]
+    const int i = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int kWarps = kGatherThreads / 32;
+    // ---- (1) ordered compaction
+    const float* row = q + size_t(i) * V;
+    int base = 0;
+    for (int v0 = 0; v0 < V; v0 += kGatherThreads * kCompactBatch) {
+        float x[kCompactBatch];
+        uint32_t bal[kCompactBatch];
+#pragma unroll
+        for (int b = 0; b < kCompactBatch; ++b) {
+            const int v = v0 + b * kGatherThreads + threadIdx.x;
+            x[b] = (v < V) ? __ldg(row + v) : 0.f;
+        }
+#pragma unroll
+        for (int b = 0; b < kCompactBatch; ++b) {
+            bal[b] = __ballot_sync(0xffffffffu, x[b] != 0.f);
+            if (lane == 0) warp_cnt[b][warp] = __popc(bal[b]);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int b = 0; b < kCompactBatch; ++b) {
+            const int c = (lane < kWarps) ? warp_cnt[b][lane] : 0;
+            int incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            const int before = __shfl_sync(0xffffffffu, incl - c, warp);
+            const int off = base + before + __popc(bal[b] & ((1u << lane) - 1u));
+            if (x[b] != 0.f) {
+                const int v = v0 + b * kGatherThreads + threadIdx.x;
+                if (off < kGatherCap) {
+                    col_s[off] = v;
+                    val_s[off] = x[b];
+                }
+                if (off < kQCap) {
+                    L.cols[size_t(i) * kQCap + off] = v;
+                    L.vals[size_t(i) * kQCap + off] = x[b];
+                }
+            }
+            base += total;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        L.nnz[i] = base;
+        if (i == 0) *L.flag = 0;
+    }
+    const int n = min(base, kGatherCap);   // the host only picks this kernel when the caller's bound fits
+    // ---- (2) gather
+    for (int j0 = warp * 4; j0 < Nd; j0 += kWarps * 4) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int k = lane; k < n; k += 32) {
+            const int c = col_s[k];
+            const float w = val_s[k];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (j0 + u < Nd) acc[u] = fmaf(w, __ldg(d + size_t(j0 + u) * V + c), acc[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
+            if (lane == 0 && j0 + u < Nd) {
+                srow[j0 + u] = acc[u];
+                S[size_t(i) * Nd + j0 + u] = acc[u];
+            }
+        }
+    }
+    __syncthreads();
+    if (la.mode < 0) return;
+    // ---- (3) + (4)
+    const float v = rank_loss_row<kGatherThreads>(la.mode, srow, la.teacher ? la.teacher + size_t(i) * Nd : nullptr,
+                                                  la.dS ? la.dS + size_t(i) * Nd : nullptr, i, Nq, Nd, la.G, 1, la.invT, red);
+    if (threadIdx.x == 0) la.rowloss[i] = v;
+    finish_sum_last_block<kGatherThreads>(&g_ticket_gather, gridDim.x, la.rowloss, Nq, 1.f, la.loss, red);
 }
 
 // zero-fills S only when the dense fallback is going to accumulate split-K partials into it
@@ -799,22 +899,31 @@ struct RowPlan {
     int n_parts, part_len;
     size_t smem;
 };
-// smallest number of equal parts whose kRowStages stages fit the shared-memory budget
+// a row is cut into the smallest number (>= 2 for long rows: finer pipelining) of equal parts such that kRowStages
+// stages fit the shared-memory budget
 RowPlan row_plan(int V) {
     RowPlan p;
-    p.n_parts = 1;
+    p.n_parts = V >= 8192 ? 2 : 1;
     while (true) {
         p.part_len = int(align_up(size_t((V + p.n_parts - 1) / p.n_parts), 4));
         p.smem = size_t(kRowStages) * size_t(p.part_len + 8) * sizeof(float);
         if (p.smem <= size_t(kRowSmemBudget)) break;
         ++p.n_parts;
     }
-    if (p.n_parts == 1 && V >= 8192) {   // at least two parts per row: the gather of one overlaps the fetch of the next
-        p.n_parts = 2;
-        p.part_len = int(align_up(size_t((V + 1) / 2), 4));
-        p.smem = size_t(kRowStages) * size_t(p.part_len + 8) * sizeof(float);
-    }
     return p;
+}
+
+// Very sparse queries (caller-promised bound): gathering Nq*bound 32-byte sectors per document beats streaming its
+// V*4 bytes, and a block per query needs no grid-wide barrier for the loss -> one launch.
+bool use_gather_kernel(int Nq, int Nd, int V, int q_nnz_bound) {
+    return q_nnz_bound > 0 && q_nnz_bound <= kGatherCap && Nd <= kGatherMaxNd &&
+           (long long)Nq * q_nnz_bound * 8 <= (long long)V;
+}
+int launch_gather(const float* q, const float* d, int Nq, int Nd, int V, QLists L, float* S, const LossArgs& la,
+                  cudaStream_t stream) {
+    score_gather_kernel<<<Nq, kGatherThreads, size_t(Nd) * sizeof(float), stream>>>(q, d, Nq, Nd, V, L, S, la);
+    SB200_CHECK_LAUNCH("score_gather_kernel");
+    return SB200_OK;
 }
 
 int launch_q_compact(const float* q, int Nq, int V, QLists L, cudaStream_t stream) {
@@ -967,6 +1076,9 @@ extern "C" int sb200_score_loss_fwd(int mode, const float* q, const float* d, co
         return launch_group(q, d, Nq, G, V, mode, teacher, invT, S, dS, rowloss, loss, stream);
     SB200_REQUIRE(Nq <= 65535, "score_loss_fwd: Nq too large");
     QLists L = qlists_carve(workspace, Nq);
+    LossArgs lg;
+    lg.mode = mode; lg.teacher = teacher; lg.G = G; lg.invT = invT; lg.loss = loss; lg.dS = dS; lg.rowloss = rowloss;
+    if (use_gather_kernel(Nq, Nd, V, q_nnz_bound)) return launch_gather(q, d, Nq, Nd, V, L, S, lg, stream);
     int rc = launch_q_compact(q, Nq, V, L, stream);
     if (rc != SB200_OK) return rc;
     LossArgs la;
