@@ -140,7 +140,7 @@ def build_teachers(wl, device):
     return [m.to(device) for m in models]
 
 
-def build_trainer(wl, args, device, accelerator=None, model=None, grad_sync=None, optimizer=True):
+def build_trainer(wl, args, device, accelerator=None, model=None, grad_sync=None, optimizer=True, rep_gather="nccl"):
     import sparse_b200  # noqa: F401
     from sparse_b200.scripts import synthetic
     from sparse_b200.scripts.args import DataTrainingArguments, ModelArguments, TrainingArguments
@@ -173,7 +173,7 @@ def build_trainer(wl, args, device, accelerator=None, model=None, grad_sync=None
         sched = torch.optim.lr_scheduler.LambdaLR(
             opt, lambda s: min(1.0, (s + 1) / targs.warmup_steps) * max(0.0, (targs.max_steps - s) / targs.max_steps))
     return SparseModelTrainer(model_args, data_args, losses, model=model, args=targs, optimizers=(opt, sched),
-                              accelerator=accelerator, grad_sync=grad_sync or "ddp")
+                              accelerator=accelerator, grad_sync=grad_sync or "ddp", rep_gather=rep_gather)
 
 
 def host_batch(wl, rank, step):
@@ -287,7 +287,8 @@ def run_ours(args):
     wl = WORKLOADS[args.workload]
     peaks = load_peaks()
     grad_sync = args.grad_sync if args.grad_sync != "auto" else ("flat_overlap" if args.graph else "ddp")
-    trainer = build_trainer(wl, args, device, grad_sync=grad_sync)
+    rep_gather = args.rep_gather if args.rep_gather != "auto" else ("peer" if 1 < world <= 8 else "nccl")
+    trainer = build_trainer(wl, args, device, grad_sync=grad_sync, rep_gather=rep_gather)
     teachers = build_teachers(wl, device)
     if teachers is not None:
         trainer.set_bi_encoder_teacher(models=teachers)
@@ -461,6 +462,8 @@ def run_ours(args):
     if world > 1:
         barrier()
         trainer.release_graph()   # the captured NCCL work must be gone before the communicator is torn down
+        barrier()
+        trainer.close()           # peer-memory sinks (CUDA IPC mappings)
         barrier()
         dist.destroy_process_group()
 
@@ -803,6 +806,10 @@ def main():
     ap.add_argument("--grad-sync", default="auto", choices=["auto", "ddp", "flat", "flat_overlap"],
                     help="gradient synchronisation on several GPUs: auto = flat_overlap (bucketed all-reduces issued during "
                          "backward) with the CUDA graph, ddp without; flat = one all-reduce after the backward pass")
+    ap.add_argument("--rep-gather", default="auto", choices=["auto", "nccl", "peer"],
+                    help="exchange of the representations between ranks: peer = symmetric NVLink peer memory (the head "
+                         "kernel stores the document vectors into every rank's gathered buffer from its epilogue, flag "
+                         "barrier instead of a collective); nccl = all_gather_into_tensor. auto = peer on 2..8 GPUs")
     ap.add_argument("--unpad-capacity", type=float, default=0.85,
                     help="padding-free encoder body: real tokens are packed into ceil(capacity * B * L) rows (the synthetic "
                          "lengths are uniform in [L/2, L], mean 0.75; an overflowing batch skips its optimizer step on the "

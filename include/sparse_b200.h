@@ -64,12 +64,18 @@ unsigned long long sb200_launch_count(void);
  *   xmax    f32  [B, V]  out (nullable): the pooled pre-activation value max_l(logit*mask)
  *   argmax  i32  [B, V]  out (nullable): sequence position of that maximum (lowest l on ties, the
  *                        first masked position when the maximum is the 0 of a masked slot)
+ *   peer_rep  host array of n_peers (0..7) device pointers, or NULL: the fused all-gather of gather_rep
+ *             (scripts/utils.py:16-23). Entry k is THIS rank's [B, V] slot inside rank k's gathered buffer
+ *             (peer-mapped through sb200_peer_import); the epilogue stores every finished rep[b, v] there as
+ *             well, over NVLink, while the following tiles are being multiplied. Publish with
+ *             sb200_peer_signal, consume after sb200_peer_wait.
  *   H % 8 == 0, 1 <= L <= 4096, V >= 1.  Logits never touch HBM.
  * ------------------------------------------------------------------------------------------- */
 size_t sb200_head_fwd_workspace_bytes(int B, int L);
 int sb200_head_fwd(const void* hidden, const void* W, const float* bias, const void* mask, int mask_elem_bytes,
                    int B, int L, int H, int V, int flags, float* rep, float* xmax, int32_t* argmax,
-                   void* workspace, size_t workspace_bytes, sb200_stream_t stream);
+                   float* const* peer_rep, int n_peers, void* workspace, size_t workspace_bytes,
+                   sb200_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * (2) Sparse head backward.   Replaces the autograd backward of sparse_encoders.py:108-114
@@ -254,6 +260,30 @@ int sb200_colsum_supported(int N);
 size_t sb200_colsum_workspace_bytes(int R, int N);
 int sb200_colsum(const void* dy, int elem_bytes, int R, int N, float* out, void* workspace, size_t workspace_bytes,
                  sb200_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Symmetric peer memory over NVLink (CUDA IPC), one process per GPU: the exchange steps of data-parallel training
+ * without NCCL -- gather_rep (scripts/utils.py:16-23 = accelerate's gather), the teacher gather
+ * (bi_encoder_wrapper.py:130) and the score gather (trainer.py:101-104).
+ *   alloc / export / import / close / free: every rank allocates the same buffer (zero-filled), exports a 64-byte IPC
+ *   handle, imports its peers' handles (peer access is enabled on import).
+ *   allgather: copies `bytes` (multiple of 16) from src into slot `rank` (offset dst_byte_offset + rank * bytes) of every
+ *   rank's buffer; dst_ptrs is a HOST array of `world` (<= 16) device pointers, entry p = rank p's buffer as mapped here.
+ *   signal: epoch = ++(*send_epoch) (device counter), then flags_of_rank_p[rank] = epoch for every p (release, system
+ *   scope); flag_ptrs like dst_ptrs. wait: epoch = ++(*wait_epoch), spins until all `world` local flags reached it.
+ *   All three are kernels on the caller's stream (CUDA-graph capturable, no host synchronisation). A buffer may be
+ *   rewritten once every rank has consumed it; in the training step the gradient all-reduce between two steps orders
+ *   that. */
+int sb200_peer_alloc(size_t bytes, void** ptr);
+int sb200_peer_free(void* ptr);
+int sb200_peer_export(const void* ptr, void* handle64);
+int sb200_peer_import(const void* handle64, void** ptr);
+int sb200_peer_close(void* ptr);
+int sb200_peer_allgather(const void* src, size_t bytes, int rank, int world, void* const* dst_ptrs,
+                         size_t dst_byte_offset, sb200_stream_t stream);
+int sb200_peer_signal(uint32_t* send_epoch, int rank, int world, void* const* flag_ptrs, size_t flag_byte_offset,
+                      sb200_stream_t stream);
+int sb200_peer_wait(uint32_t* wait_epoch, const uint32_t* local_flags, int world, sb200_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -25,7 +25,7 @@ _PROTOTYPES = {
     "sb200_launch_count": (ctypes.c_ulonglong, []),
     "sb200_head_fwd_workspace_bytes": (_sz, [_c_int, _c_int]),
     "sb200_head_fwd": (_c_int, [_vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp,
-                                _vp, _sz, _vp]),
+                                _vp, _c_int, _vp, _sz, _vp]),
     "sb200_head_bwd_workspace_bytes": (_sz, [_c_int, _c_int, _c_int, _c_int]),
     "sb200_head_bwd": (_c_int, [_vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp,
                                 _sz, _vp]),
@@ -61,6 +61,14 @@ _PROTOTYPES = {
     "sb200_colsum_supported": (_c_int, [_c_int]),
     "sb200_colsum_workspace_bytes": (_sz, [_c_int, _c_int]),
     "sb200_colsum": (_c_int, [_vp, _c_int, _c_int, _c_int, _vp, _vp, _sz, _vp]),
+    "sb200_peer_alloc": (_c_int, [_sz, _vp]),
+    "sb200_peer_free": (_c_int, [_vp]),
+    "sb200_peer_export": (_c_int, [_vp, _vp]),
+    "sb200_peer_import": (_c_int, [_vp, _vp]),
+    "sb200_peer_close": (_c_int, [_vp]),
+    "sb200_peer_allgather": (_c_int, [_vp, _sz, _c_int, _c_int, _vp, _sz, _vp]),
+    "sb200_peer_signal": (_c_int, [_vp, _c_int, _c_int, _vp, _sz, _vp]),
+    "sb200_peer_wait": (_c_int, [_vp, _vp, _c_int, _vp]),
 }
 
 EXPORTED_SYMBOLS = tuple(_PROTOTYPES)

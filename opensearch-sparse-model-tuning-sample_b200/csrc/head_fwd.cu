@@ -62,6 +62,8 @@ struct HeadFwdParams {
     int LC, S, NC, N;          // chunk length, sequences per tile, chunks per sequence, S*LC
     int n_vtiles, n_groups, kblocks;   // n_vtiles counts tiles of 128 * kCG vocab rows
     int l0;
+    int n_peers;               // data-parallel all-gather fused into the epilogue: rep[b, v] is also stored into the
+    float* peer_rep[7];        // gathered buffers of up to 7 other ranks (peer-mapped pointers to THIS rank's slot)
     int b_s_off;               // CTA pair, S >= 2: sequence offset of the second CTA's half of the token tile
 };
 
@@ -338,6 +340,10 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
             float r1 = log1pf(fmaxf(x, 0.f));
             if (p.l0) r1 = log1pf(r1);
             p.rep[o] = r1;
+            // fused all-gather: the same value goes straight into every peer's gathered buffer over NVLink (a warp writes
+            // 32 consecutive floats = one 128-byte line per peer), overlapped with the MMAs of the following tiles
+#pragma unroll 1
+            for (int k = 0; k < p.n_peers; ++k) p.peer_rep[k][o] = r1;
         };
 
         // Work split of one tile over the n_wg warpgroups:
@@ -484,9 +490,12 @@ extern "C" size_t sb200_head_fwd_workspace_bytes(int B, int L) {
 
 extern "C" int sb200_head_fwd(const void* hidden, const void* W, const float* bias, const void* mask,
                               int mask_elem_bytes, int B, int L, int H, int V, int flags, float* rep, float* xmax,
-                              int32_t* argmax, void* workspace, size_t workspace_bytes, sb200_stream_t stream_) {
+                              int32_t* argmax, float* const* peer_rep, int n_peers, void* workspace,
+                              size_t workspace_bytes, sb200_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     SB200_REQUIRE(hidden && W && mask && rep, "head_fwd: null pointer");
+    SB200_REQUIRE(n_peers >= 0 && n_peers <= 7 && (n_peers == 0 || peer_rep != nullptr), "head_fwd: bad peer list (%d)",
+                  n_peers);
     SB200_REQUIRE(B >= 1 && V >= 1 && L >= 1 && L <= 4096, "head_fwd: bad shape B=%d L=%d V=%d", B, L, V);
     SB200_REQUIRE(H >= 8 && H % 8 == 0, "head_fwd: H=%d must be a positive multiple of 8", H);
     SB200_REQUIRE(mask_elem_bytes == 1 || mask_elem_bytes == 4 || mask_elem_bytes == 8, "head_fwd: mask_elem_bytes=%d",
@@ -558,6 +567,8 @@ extern "C" int sb200_head_fwd(const void* hidden, const void* W, const float* bi
     p.n_groups = t.n_groups;
     p.kblocks = (H + kBlockK - 1) / kBlockK;
     p.l0 = (flags & SB200_HEAD_L0) ? 1 : 0;
+    p.n_peers = n_peers;
+    for (int k = 0; k < 7; ++k) p.peer_rep[k] = k < n_peers ? peer_rep[k] : nullptr;
     p.b_s_off = b_s_off;
 
     const long long total_units = (long long)p.n_vtiles * p.n_groups;

@@ -330,7 +330,7 @@ inline QLists qlists_carve(void* ws, int Nq) {
 
 // One block per query row: ordered stream compaction (ballot + block scan), no atomics, no pre-zeroed counters.
 constexpr int kCompactThreads = 1024;
-constexpr int kCompactBatch = 8;   // independent loads in flight per thread
+constexpr int kCompactBatch = 16;  // independent loads in flight per thread
 
 __global__ void __launch_bounds__(kCompactThreads)
 q_compact_kernel(const float* __restrict__ q, int V, QLists L) {

@@ -64,10 +64,13 @@ class _timed:
 
 
 # --------------------------------------------------------------------------------------------- sparse head
-def head_forward(hidden, weight, bias, attention_mask, use_l0=False, want_aux=True):
+def head_forward(hidden, weight, bias, attention_mask, use_l0=False, want_aux=True, out=None, peer_ptrs=None):
     """Fused MLM-decoder GEMM + mask + max-pool + log1p(relu) (sparse_encoders.py:108-114).
 
     hidden [B,L,H] bf16, weight [V,H] bf16, bias [V] fp32 or None, attention_mask [B,L] (int64/int32/uint8/bool).
+    out: optional preallocated contiguous fp32 [B,V] result buffer (e.g. this rank's slot of a PeerSink);
+    peer_ptrs: up to 7 device pointers of the same [B,V] slot inside other ranks' gathered buffers -- the epilogue
+    stores the result there too (the fused all-gather of gather_rep).
     Returns (rep [B,V] fp32, xmax [B,V] fp32 | None, argmax [B,V] int32 | None).
     """
     _need_cuda(hidden, weight, bias, attention_mask)
@@ -91,15 +94,22 @@ def head_forward(hidden, weight, bias, attention_mask, use_l0=False, want_aux=Tr
         bias = bias.detach().float().contiguous()
     lib = _lib.load()
     dev = hidden.device
-    rep = torch.empty(B, V, dtype=torch.float32, device=dev)
+    if out is None:
+        rep = torch.empty(B, V, dtype=torch.float32, device=dev)
+    else:
+        if out.dtype != torch.float32 or tuple(out.shape) != (B, V) or not out.is_contiguous() or out.device != dev:
+            raise ValueError("head_forward: `out` must be a contiguous fp32 [B, V] tensor on the inputs' device")
+        rep = out
     xmax = torch.empty(B, V, dtype=torch.float32, device=dev) if want_aux else None
     argmax = torch.empty(B, V, dtype=torch.int32, device=dev) if want_aux else None
     ws_bytes = lib.sb200_head_fwd_workspace_bytes(B, L)
     ws = _workspace(ws_bytes, dev)
+    peers = list(peer_ptrs or [])
+    c_peers = (_lib.ctypes.c_void_p * max(1, len(peers)))(*peers) if peers else None
     with torch.cuda.device(dev), _timed("head_fwd"):
         code = lib.sb200_head_fwd(_ptr(hidden), _ptr(weight), _ptr(bias), _ptr(mask), mask.element_size(), B, L, H, V,
-                                  (_lib.HEAD_L0 if use_l0 else 0), _ptr(rep), _ptr(xmax), _ptr(argmax),
-                                  _ptr(ws), ws.numel(), _stream())
+                                  (_lib.HEAD_L0 if use_l0 else 0), _ptr(rep), _ptr(xmax), _ptr(argmax), c_peers,
+                                  len(peers), _ptr(ws), ws.numel(), _stream())
     _lib.check(code, "sb200_head_fwd")
     return rep, xmax, argmax
 
@@ -139,11 +149,15 @@ class SparseHeadFunction(torch.autograd.Function):
     """rep = head(hidden, weight, bias, mask); gradients flow to hidden, weight and bias."""
 
     @staticmethod
-    def forward(ctx, hidden, weight, bias, attention_mask, use_l0):
+    def forward(ctx, hidden, weight, bias, attention_mask, use_l0, sink=None):
         h16 = hidden.detach().to(torch.bfloat16).contiguous()
         w16 = weight.detach().to(torch.bfloat16).contiguous()
         needs_grad = any(t is not None and t.requires_grad for t in (hidden, weight, bias))
-        rep, xmax, argmax = head_forward(h16, w16, bias, attention_mask, use_l0, want_aux=needs_grad)
+        out = peers = None
+        if sink is not None and (sink.rows, sink.width) == (h16.shape[0], w16.shape[0]) and sink.world <= 8:
+            out, peers = sink.slot(), sink.remote_slots()    # fused all-gather: results land in every rank's buffer
+        rep, xmax, argmax = head_forward(h16, w16, bias, attention_mask, use_l0, want_aux=needs_grad, out=out,
+                                         peer_ptrs=peers)
         if needs_grad:
             ctx.save_for_backward(h16, w16, xmax, argmax)
         ctx.use_l0 = bool(use_l0)
@@ -158,11 +172,13 @@ class SparseHeadFunction(torch.autograd.Function):
         d_hidden, dW, dbias = head_backward(d_rep, xmax, argmax, h16, w16, ctx.use_l0, want_bias_grad=ctx.has_bias)
         hd, wd, bd = ctx.in_dtypes
         return (d_hidden.to(hd) if need_h else None, dW.to(wd) if need_w else None,
-                dbias.to(bd) if (need_b and ctx.has_bias) else None, None, None)
+                dbias.to(bd) if (need_b and ctx.has_bias) else None, None, None, None)
 
 
-def sparse_head(hidden, weight, bias, attention_mask, use_l0=False):
-    return SparseHeadFunction.apply(hidden, weight, bias, attention_mask, use_l0)
+def sparse_head(hidden, weight, bias, attention_mask, use_l0=False, sink=None):
+    """sink: an optional scripts.peer.PeerSink of shape [B, V] -- the head then writes its output rows straight into
+    every rank's gathered buffer (gather_rep fused into the GEMM epilogue); follow with peer_gather(rep, sink)."""
+    return SparseHeadFunction.apply(hidden, weight, bias, attention_mask, use_l0, sink)
 
 
 # --------------------------------------------------------------------------------------------- inf-free query

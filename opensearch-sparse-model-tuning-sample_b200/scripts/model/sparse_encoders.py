@@ -202,14 +202,17 @@ class SparseModel(torch.nn.Module):
     def forward(self, inf_free=False, **kwargs):
         return self._encode_inf_free(**kwargs) if inf_free else self._encode(**kwargs)
 
-    def _encode(self, **kwargs):
+    def _encode(self, _sink=None, **kwargs):
+        """`_sink` (B200 extension, not a tokenizer feature): a scripts.peer.PeerSink -- the head kernel then stores its
+        rows into every rank's gathered buffer as well (gather_rep fused into the GEMM epilogue)."""
         hidden, decoder = self.head_inputs(**kwargs)
-        rep = ops.sparse_head(hidden, decoder.weight, decoder.bias, kwargs.get("attention_mask"), use_l0=self.use_l0)
+        rep = ops.sparse_head(hidden, decoder.weight, decoder.bias, kwargs.get("attention_mask"), use_l0=self.use_l0,
+                              sink=_sink)
         if self.prune_ratio is None:
             return rep
         return _PruneFunction.apply(rep, float(self.prune_ratio))
 
-    def _encode_inf_free(self, **kwargs):
+    def _encode_inf_free(self, _sink=None, **kwargs):
         input_ids = kwargs.get("input_ids")
         return ops.idf_query(input_ids, self.idf_vector, self._special_ids_on(input_ids.device))
 

@@ -29,9 +29,15 @@ class ModelWrapper(torch.nn.Module):
         super().__init__()
         self.sparse_model = sparse_model
         self.inf_free = inf_free
+        self.__dict__["peer_sinks"] = None   # scripts.peer.PeerSinks, set by a multi-GPU trainer (rep_gather="peer")
 
     def forward(self, inputs):
-        d_rep = self.sparse_model(inf_free=False, input_ids=inputs["input_ids"],
+        sink = None
+        sinks = self.__dict__.get("peer_sinks")
+        if sinks is not None and self.training and self.sparse_model.prune_ratio is None:
+            # the document vectors leave the head kernel straight into every rank's gathered buffer
+            sink = sinks.get("d_rep", inputs["input_ids"].shape[0], self.sparse_model.vocab_size, torch.float32)
+        d_rep = self.sparse_model(inf_free=False, _sink=sink, input_ids=inputs["input_ids"],
                                   attention_mask=inputs["attention_mask"])
         q_rep = self.sparse_model(inf_free=self.inf_free, input_ids=inputs["q_input_ids"],
                                   attention_mask=inputs["q_attention_mask"])
@@ -51,12 +57,17 @@ class ModelWrapper(torch.nn.Module):
 
 class SparseModelTrainer:
     def __init__(self, model_args, data_args, loss_functions, model=None, args=None, train_dataset=None,
-                 data_collator=None, optimizers=(None, None), accelerator=None, grad_sync="ddp", **unused):
+                 data_collator=None, optimizers=(None, None), accelerator=None, grad_sync="ddp", rep_gather="nccl",
+                 **unused):
         """grad_sync: "ddp" (torch DistributedDataParallel, bucketed all-reduce overlapped with backward; eager launches)
         or "flat" (gradients live in one flat fp32 buffer that is all-reduced with a single NCCL call after backward;
         this is the mode whose forward+backward can be captured in a CUDA graph on several GPUs), or "flat_overlap"
         (same buffer, cut into buckets whose all-reduces are issued from gradient hooks on a side stream while the
-        backward pass is still running -- flat_grads.FlatGradBuckets; graph-capturable as well)."""
+        backward pass is still running -- flat_grads.FlatGradBuckets; graph-capturable as well).
+        rep_gather: "nccl" (all_gather_into_tensor, the reference's accelerate.gather) or "peer" (symmetric NVLink peer
+        memory, scripts/peer.py: the head kernel stores the document vectors into every rank's gathered buffer from its
+        epilogue; ids / scores / teacher vectors go through a copy kernel; flag barrier instead of a collective). "peer"
+        applies to the training step on CUDA with 2..8 ranks of one node; everything else falls back to "nccl"."""
         self.model_args = model_args
         self.data_args = data_args
         self.loss_functions = loss_functions
@@ -73,6 +84,11 @@ class SparseModelTrainer:
         self.model_wrapper = wrapper
         self.model = wrapper
         self.grad_sync = grad_sync if self.accelerator.num_processes > 1 else "none"
+        self.rep_gather = "nccl"
+        if (rep_gather == "peer" and 1 < self.accelerator.num_processes <= 8 and model is not None
+                and next(model.parameters()).is_cuda and hasattr(self.accelerator, "enable_peer_sinks")):
+            wrapper.__dict__["peer_sinks"] = self.accelerator.enable_peer_sinks(next(model.parameters()).device)
+            self.rep_gather = "peer"
         self._flat_grads = None
         self._buckets = None
         if self.grad_sync == "ddp" and next(wrapper.parameters()).is_cuda:
@@ -184,7 +200,8 @@ class SparseModelTrainer:
             if ids.shape[1] < width:
                 pad = ids.new_full((ids.shape[0], width - ids.shape[1]), int(sm.special_token_ids[0]))
                 ids = torch.cat([ids, pad], dim=1)
-            all_ids = env.gather(ids.to(torch.int32).contiguous())
+            ids = ids.to(torch.int32).contiguous()
+            all_ids = env.gather_plain(ids) if hasattr(env, "gather_plain") else env.gather(ids)
             return ops.idf_query(all_ids, sm.idf_vector, sm._special_ids_on(all_ids.device))
         return gather_rep(q_rep, env)
 
@@ -253,6 +270,8 @@ class SparseModelTrainer:
                 return self.model(student)
 
         self.model_wrapper.sparse_model.unpad_step_reset()
+        if hasattr(self.accelerator, "begin_step"):
+            self.accelerator.begin_step()      # peer-memory gather sites are numbered per step
         loss = self.compute_loss(run, inputs)
         if self.scaler is not None:
             flag = self.model_wrapper.sparse_model.unpad_step_flag()
@@ -261,6 +280,8 @@ class SparseModelTrainer:
             self.scaler.scale(loss).backward()
         else:
             loss.backward()
+        if hasattr(self.accelerator, "end_step"):
+            self.accelerator.end_step()
         return loss
 
     def _optimizer_step(self):
@@ -373,6 +394,15 @@ class SparseModelTrainer:
         self._step_t = None
         gc.collect()
         torch.cuda.synchronize(dev)
+
+    def close(self):
+        """Releases the captured graph and the peer-memory sinks (call before destroying the process group)."""
+        self.release_graph()
+        sinks = getattr(self.accelerator, "peer_sinks", None)
+        if sinks is not None:
+            sinks.close()
+            self.accelerator.peer_sinks = None
+            self.model_wrapper.__dict__["peer_sinks"] = None
 
     def training_step(self, inputs):
         """forward (autocast) + loss + backward + optimizer step; returns the detached loss tensor (no sync)."""

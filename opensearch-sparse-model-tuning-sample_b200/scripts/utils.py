@@ -38,9 +38,15 @@ class _GatherKeepLocalGrad(torch.autograd.Function):
 
 
 def gather_rep(rep, accelerator):
-    """``accelerator`` needs ``num_processes``, ``local_process_index`` and ``gather`` (DistEnv or accelerate)."""
+    """``accelerator`` needs ``num_processes``, ``local_process_index`` and ``gather`` (DistEnv or accelerate). With a
+    DistEnv whose peer sinks are enabled (trainer option rep_gather="peer") the exchange runs over symmetric NVLink peer
+    memory instead of NCCL (scripts/peer.py) -- same rows, same gradient rule."""
     if accelerator.num_processes == 1:
         return rep
+    sink = accelerator.peer_sink_for(rep) if hasattr(accelerator, "peer_sink_for") else None
+    if sink is not None:
+        from .peer import peer_gather
+        return peer_gather(rep, sink)
     return _GatherKeepLocalGrad.apply(rep, accelerator)
 
 
@@ -55,6 +61,46 @@ class DistEnv:
         # single node: the reference indexes the gathered tensor with local_process_index (utils.py:21)
         self.local_process_index = self.process_index
         self.is_main_process = self.process_index == 0
+        self.peer_sinks = None      # scripts.peer.PeerSinks once enable_peer_sinks() has been called
+        self._peer_site = 0
+
+    # ------------------------------------------------------------------ symmetric peer memory (rep_gather="peer")
+    def enable_peer_sinks(self, device):
+        from .peer import PeerSinks
+        if self.peer_sinks is None:
+            self.peer_sinks = PeerSinks(self, device)
+        return self.peer_sinks
+
+    def begin_step(self):
+        """Called by the trainer at the start of a training step: peer gathers are allowed until end_step() (the reuse of
+        a sink is ordered by the gradient all-reduce that follows every step)."""
+        self._peer_site = 0
+        self._in_step = True
+
+    def end_step(self):
+        self._in_step = False
+
+    def peer_sink_for(self, tensor):
+        """The sink a gather of `tensor` should use, or None (NCCL). A tensor the fused head already wrote into its sink is
+        recognised by address; everything else gets the next numbered site of this step (sites are created collectively
+        on first use, so every rank must issue the same gathers in the same order -- true for the training step)."""
+        if self.peer_sinks is None or not getattr(self, "_in_step", False) or not tensor.is_cuda or tensor.dim() != 2:
+            return None
+        if (tensor.shape[0] * tensor.shape[1] * tensor.element_size()) % 16 != 0:
+            return None
+        for sink in self.peer_sinks._sinks.values():
+            if sink.holds(tensor):
+                return sink
+        self._peer_site += 1
+        return self.peer_sinks.get(f"site{self._peer_site}", tensor.shape[0], tensor.shape[1], tensor.dtype)
+
+    def gather_plain(self, tensor):
+        """Gather without autograd (ids, teacher outputs): peer memory when enabled, NCCL otherwise."""
+        sink = self.peer_sink_for(tensor)
+        if sink is None:
+            return self.gather(tensor)
+        from .peer import peer_gather
+        return peer_gather(tensor, sink).detach()
 
     def gather(self, tensor):
         if self.num_processes == 1:

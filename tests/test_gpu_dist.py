@@ -16,7 +16,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _build(V, loss, in_batch, inf_free, single_process=False, grad_sync="ddp", capturable=False):
+def _build(V, loss, in_batch, inf_free, single_process=False, grad_sync="ddp", capturable=False, rep_gather="nccl"):
     import sparse_b200  # noqa: F401
     from sparse_b200.scripts import synthetic
     from sparse_b200.scripts.args import DataTrainingArguments, ModelArguments, TrainingArguments
@@ -37,10 +37,10 @@ def _build(V, loss, in_batch, inf_free, single_process=False, grad_sync="ddp", c
     if capturable:
         opt = torch.optim.AdamW(model.parameters(), lr=torch.tensor(1e-5, device="cuda"), fused=True, capturable=True)
     return SparseModelTrainer(margs, dargs, fns, model=model, args=targs, accelerator=env, grad_sync=grad_sync,
-                              optimizers=(opt, None))
+                              optimizers=(opt, None), rep_gather=rep_gather)
 
 
-def _worker(rank, world, port, loss, in_batch, inf_free, out, grad_sync="ddp"):
+def _worker(rank, world, port, loss, in_batch, inf_free, out, grad_sync="ddp", rep_gather="nccl"):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
                       LOCAL_RANK=str(rank))
@@ -49,18 +49,24 @@ def _worker(rank, world, port, loss, in_batch, inf_free, out, grad_sync="ddp"):
     try:
         from sparse_b200.scripts import synthetic
         V, nq, G = 1500, 4, 3
-        tr = _build(V, loss, in_batch, inf_free, grad_sync=grad_sync, capturable=grad_sync == "flat")
-        assert tr.accelerator.num_processes == world and tr.grad_sync == grad_sync
+        flat = grad_sync in ("flat", "flat_overlap")
+        tr = _build(V, loss, in_batch, inf_free, grad_sync=grad_sync, capturable=flat, rep_gather=rep_gather)
+        assert tr.accelerator.num_processes == world and tr.grad_sync == grad_sync and tr.rep_gather == rep_gather
+        # kd data carries the teacher scores of the query's own docs; with in-batch negatives the teachers would score
+        # every gathered doc: [nq, world * nq * G] per rank
+        n_scores = None if loss == "infonce" else (world * nq * G if in_batch else G)
         batches = [synthetic.train_batch(nq, G, 40, query_len=12, vocab_size=V, seed=70 + r, device="cuda",
-                                         with_scores=None if loss == "infonce" else G) for r in range(world)]
+                                         with_scores=n_scores) for r in range(world)]
 
         def run(student):
             with torch.autocast("cuda", dtype=torch.bfloat16):
                 return tr.model(student)
+        tr.accelerator.begin_step()   # peer-memory gather sites are numbered per step
         loss_v = tr.compute_loss(run, dict(batches[rank]))
         loss_v.backward()  # DDP averages the gradients
-        if grad_sync == "flat":
-            tr._sync_flat_grads()  # one all-reduce of the flat buffer, mean over ranks
+        tr.accelerator.end_step()
+        if flat:
+            tr._sync_flat_grads()  # all-reduce of the flat buffer (or of its remaining buckets), mean over ranks
         grads = {n: p.grad.detach().float().clone() for n, p in tr.model_wrapper.named_parameters() if p.grad is not None}
         if rank == 0:
             # single-process global batch with the same weights
@@ -95,14 +101,14 @@ def _worker(rank, world, port, loss, in_batch, inf_free, out, grad_sync="ddp"):
                     assert cos > 0.995, (n, cos)
             assert (num / den) ** 0.5 < 3e-2, (num / den) ** 0.5
             ref_loss = None
-        if grad_sync == "flat":
-            # CUDA-graph replay of forward + backward (NCCL all-gathers captured) against eager steps of a twin trainer
+        if flat:
+            # CUDA-graph replay of the whole step (collectives captured) against eager steps of a twin trainer
             # drop every reference to the eager autograd graph first: a live AccumulateGrad node created on the default
             # stream would be reused inside the capture and invalidate it
             loss_v = None
             import gc
             gc.collect()
-            twin = _build(V, loss, in_batch, inf_free, grad_sync="flat", capturable=True)
+            twin = _build(V, loss, in_batch, inf_free, grad_sync="flat", capturable=True, rep_gather=rep_gather)
             twin.model_wrapper.load_state_dict(tr.model_wrapper.state_dict())
             tr.enable_cuda_graph(batches[rank], warmup_steps=2)
             for _ in range(2):
@@ -111,33 +117,39 @@ def _worker(rank, world, port, loss, in_batch, inf_free, out, grad_sync="ddp"):
                 lg = float(tr.training_step(batches[rank]))
                 le = float(twin.training_step(dict(batches[rank])))
                 assert abs(lg - le) <= 2e-3 * abs(le) + 1e-4, (lg, le)
-            tr._graph = None
+            tr.release_graph()   # the captured NCCL work is gone before the process group is torn down
         out.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         import traceback
         out.put((rank, traceback.format_exc()[-1500:]))
     finally:
-        if grad_sync == "flat":
-            out.close()
-            out.join_thread()
-            os._exit(0)  # a process that captured NCCL work in a CUDA graph must not run the NCCL teardown
+        dist.barrier()
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("loss,in_batch,inf_free,grad_sync", [("infonce", True, True, "ddp"), ("kldiv", False, False, "ddp"),
-                                                              ("infonce", True, True, "flat")])
-def test_two_gpu_global_loss_and_gradients(loss, in_batch, inf_free, grad_sync):
+@pytest.mark.parametrize("loss,in_batch,inf_free,grad_sync,rep_gather", [
+    ("infonce", True, True, "ddp", "nccl"), ("kldiv", False, False, "ddp", "nccl"), ("infonce", True, True, "flat", "nccl"),
+    ("infonce", True, True, "flat_overlap", "peer"),   # fused head all-gather + id exchange over NVLink peer memory
+    ("kldiv", True, False, "flat", "peer"),            # learned queries: q_rep and the teacher scores through copy sinks
+])
+def test_two_gpu_global_loss_and_gradients(loss, in_batch, inf_free, grad_sync, rep_gather):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, loss, in_batch, inf_free, out, grad_sync)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, loss, in_batch, inf_free, out, grad_sync, rep_gather))
+             for r in range(2)]
     for p in procs:
         p.start()
-    results = [out.get(timeout=120) for _ in procs]
+    results = [out.get(timeout=180) for _ in procs]
+    hung = []
     for p in procs:
         p.join(timeout=60)
+        if p.is_alive():     # a rank that does not exit after its result is a teardown hang
+            hung.append(p.pid)
+            p.kill()
     assert sorted(r for r, _ in results) == [0, 1]
     assert all(msg == "ok" for _, msg in results), "\n".join(f"rank {r}: {m}" for r, m in results)
+    assert not hung, f"ranks did not exit after finishing: {hung}"

@@ -54,7 +54,7 @@ def test_ctypes_prototypes_match_the_header():
 
 def test_argument_errors_are_reported_not_crashes():
     lib = _lib.load()
-    code = lib.sb200_head_fwd(0, 0, 0, 0, 8, 1, 1, 8, 1, 0, 0, 0, 0, 0, 0, 0)
+    code = lib.sb200_head_fwd(0, 0, 0, 0, 8, 1, 1, 8, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0)
     assert code == 1 and b"null" in lib.sb200_last_error()
     code = lib.sb200_rank_loss(7, 1, 0, 1, 1, 1, 0, 1.0, 1, 0, 0, 0, 0)
     assert code == 1 and b"mode" in lib.sb200_last_error()
