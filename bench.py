@@ -243,8 +243,12 @@ def dist_parity(trainer, wl, args, device, batch, world, rank):
                 solo.set_bi_encoder_teacher(models=trainer.bi_encoder_teacher.models)
             solo.model.eval()
             trainer._zero_grads()
+            if trainer._buckets is not None:
+                trainer._buckets.enabled = False     # this backward pass is rank 0's alone: no bucket all-reduces
             loss_1 = solo._forward_backward(global_batch)
-            a, b = float(loss_dp) / world, float(loss_1)
+            if trainer._buckets is not None:
+                trainer._buckets.enabled = True
+            a, b = float(loss_dp.detach()) / world, float(loss_1.detach())
             out = {"loss_dp_over_world": a, "loss_single_process_global_batch": b,
                    "loss_rel_err": abs(a - b) / max(abs(b), 1e-12), "tolerance": 1e-4}
             if g_dp is not None:

@@ -34,7 +34,9 @@ enum {
 
 /* flags for the sparse head */
 enum {
-    SB200_HEAD_L0 = 1          /* second log1p ("use_l0", sparse_encoders.py:113-114) */
+    SB200_HEAD_L0 = 1,         /* second log1p ("use_l0", sparse_encoders.py:113-114) */
+    SB200_HEAD_FP16 = 2        /* hidden and W are IEEE fp16 instead of bf16 (the reference configs train with fp16: true);
+                                  products are exact and accumulated in fp32 either way */
 };
 
 /* loss modes for sb200_score_loss_* (scripts/train/loss.py:110 LOSS_CLS_MAP) */
@@ -56,8 +58,8 @@ unsigned long long sb200_launch_count(void);
  *     self.backbone + `output * mask` + torch.max(dim=1) + log1p(relu) [+ log1p]) and
  *     bi_encoder_wrapper.py:29-33.
  *
- *   hidden  bf16 [B, L, H]   output of the MLM head transform (input of the vocab decoder)
- *   W       bf16 [V, H]      decoder weight (tied word embeddings)
+ *   hidden  bf16 [B, L, H]   output of the MLM head transform (input of the vocab decoder); fp16 with SB200_HEAD_FP16
+ *   W       bf16 [V, H]      decoder weight (tied word embeddings); fp16 with SB200_HEAD_FP16
  *   bias    f32  [V]         decoder bias (may be NULL)
  *   mask    [B, L] attention mask, element size mask_elem_bytes in {1, 4, 8}; non-zero = real token
  *   rep     f32  [B, V]  out: log1p(relu(max_l(logit*mask)))  (log1p applied twice with SB200_HEAD_L0)

@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libsparse_b200.so")
 
 SB200_OK = 0
 HEAD_L0 = 1
+HEAD_FP16 = 2
 LOSS_INFONCE, LOSS_KLDIV, LOSS_MARGINMSE = 0, 1, 2
 
 _c_int = ctypes.c_int

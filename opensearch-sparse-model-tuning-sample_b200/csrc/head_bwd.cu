@@ -10,6 +10,7 @@
 // B*V*H multiply-adds instead of 2*B*L*V*H, and entries with c == 0 (inactive vocabulary) cost nothing.
 // All three kernels are gather-bound on L2 (hidden and W are L2-resident: tens of MB).
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include "common.h"
@@ -32,11 +33,14 @@ __device__ __forceinline__ float head_coef(float g, float x, int l0) {
     return c / (1.f + x);
 }
 
-__device__ __forceinline__ void fma_bf16x8(float (&acc)[8], const uint4& raw, float c) {
-    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+// acc[0..8) += c * (8 half-precision values in `raw`): bf16 or, kFp16, IEEE fp16
+template <bool kFp16>
+__device__ __forceinline__ void fma_half8(float (&acc)[8], const uint4& raw, float c) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const float2 f = __bfloat1622float2(h2[i]);
+        float2 f;
+        if (kFp16) f = __half22float2(reinterpret_cast<const __half2*>(&raw)[i]);
+        else f = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(&raw)[i]);
         acc[2 * i] = fmaf(c, f.x, acc[2 * i]);
         acc[2 * i + 1] = fmaf(c, f.y, acc[2 * i + 1]);
     }
@@ -45,7 +49,7 @@ __device__ __forceinline__ void fma_bf16x8(float (&acc)[8], const uint4& raw, fl
 // ---------------------------------------------------------------- dW / dbias
 // Block = 32 consecutive vocab rows; (c, l*) for [Bc sequences x 32 rows] staged in smem (coalesced),
 // then each warp owns 4 rows and walks the sequences, gathering hidden rows with 16-byte loads.
-template <int NCHUNK>
+template <int NCHUNK, bool kFp16>
 __global__ void __launch_bounds__(kDwThreads)
 bwd_dw_kernel(const float* __restrict__ d_rep, const float* __restrict__ xmax, const int32_t* __restrict__ argmax,
               const __nv_bfloat16* __restrict__ hidden, int B, int L, int H, int V, int l0, int Bc,
@@ -93,7 +97,7 @@ bwd_dw_kernel(const float* __restrict__ d_rep, const float* __restrict__ xmax, c
                     const int ch = lane + 32 * k;
                     if (ch < n_chunks) {
                         const uint4 raw = __ldg(reinterpret_cast<const uint4*>(row) + ch);
-                        fma_bf16x8(acc[k], raw, e.x);
+                        fma_half8<kFp16>(acc[k], raw, e.x);
                     }
                 }
             }
@@ -199,7 +203,7 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 // ---------------------------------------------------------------- d_hidden
 // grid (ceil(V / 256), B). Each warp takes 32 consecutive bucketed entries, accumulates runs of equal l in
 // registers and flushes a run with vector reductions into the (pre-zeroed) fp32 d_hidden row.
-template <int NCHUNK>
+template <int NCHUNK, bool kFp16>
 __global__ void __launch_bounds__(256)
 bwd_dh_kernel(const uint2* __restrict__ entries, const int* __restrict__ nact, const __nv_bfloat16* __restrict__ W,
               int L, int H, int V, float* __restrict__ d_hidden) {
@@ -259,7 +263,7 @@ bwd_dh_kernel(const uint2* __restrict__ entries, const int* __restrict__ nact, c
                     cur_l = l;
                 }
 #pragma unroll
-                for (int k = 0; k < NCHUNK; ++k) fma_bf16x8(acc[k], raw[j][k], cf[j]);
+                for (int k = 0; k < NCHUNK; ++k) fma_half8<kFp16>(acc[k], raw[j][k], cf[j]);
             }
         }
     }
@@ -286,7 +290,7 @@ __global__ void __launch_bounds__(256) prune_rows_kernel(float* __restrict__ rep
     }
 }
 
-template <int NCHUNK>
+template <int NCHUNK, bool kFp16>
 int launch_bwd(const float* d_rep, const float* xmax, const int32_t* argmax, const __nv_bfloat16* hidden,
                const __nv_bfloat16* W, int B, int L, int H, int V, int l0, float* d_hidden, float* dW, float* dbias,
                uint2* entries, int* nact, cudaStream_t stream) {
@@ -296,9 +300,10 @@ int launch_bwd(const float* d_rep, const float* xmax, const int32_t* argmax, con
         const int max_smem = 96 * 1024;
         if (size_t(Bc) * kDwRows * sizeof(float2) > size_t(max_smem)) Bc = max_smem / int(kDwRows * sizeof(float2));
         const size_t smem = size_t(Bc) * kDwRows * sizeof(float2);
-        if (!device_flag_test_and_set(NCHUNK))
-            SB200_CUDA(cudaFuncSetAttribute(bwd_dw_kernel<NCHUNK>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        bwd_dw_kernel<NCHUNK><<<(V + kDwRows - 1) / kDwRows, kDwThreads, smem, stream>>>(
+        if (!device_flag_test_and_set(kFp16 ? 15 + NCHUNK : NCHUNK))
+            SB200_CUDA(cudaFuncSetAttribute(bwd_dw_kernel<NCHUNK, kFp16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            max_smem));
+        bwd_dw_kernel<NCHUNK, kFp16><<<(V + kDwRows - 1) / kDwRows, kDwThreads, smem, stream>>>(
             d_rep, xmax, argmax, hidden, B, L, H, V, l0, Bc, dW, dbias);
         SB200_CHECK_LAUNCH("bwd_dw_kernel");
     }
@@ -307,7 +312,7 @@ int launch_bwd(const float* d_rep, const float* xmax, const int32_t* argmax, con
     bwd_bucket_kernel<<<B, kBucketThreads, 0, stream>>>(d_rep, xmax, argmax, L, V, l0, entries, nact);
     SB200_CHECK_LAUNCH("bwd_bucket_kernel");
     dim3 grid((V + kDhEntriesPerBlock - 1) / kDhEntriesPerBlock, B);
-    bwd_dh_kernel<NCHUNK><<<grid, 256, 0, stream>>>(entries, nact, W, L, H, V, d_hidden);
+    bwd_dh_kernel<NCHUNK, kFp16><<<grid, 256, 0, stream>>>(entries, nact, W, L, H, V, d_hidden);
     SB200_CHECK_LAUNCH("bwd_dh_kernel");
     return SB200_OK;
 }
@@ -343,12 +348,22 @@ extern "C" int sb200_head_bwd(const float* d_rep, const float* xmax, const int32
     const __nv_bfloat16* h = static_cast<const __nv_bfloat16*>(hidden);
     const __nv_bfloat16* w = static_cast<const __nv_bfloat16*>(W);
     const int nchunk = (H / 8 + 31) / 32;
-    switch (nchunk) {
-        case 1: return launch_bwd<1>(d_rep, xmax, argmax, h, w, B, L, H, V, l0, d_hidden, dW, dbias, entries, nact, stream);
-        case 2: return launch_bwd<2>(d_rep, xmax, argmax, h, w, B, L, H, V, l0, d_hidden, dW, dbias, entries, nact, stream);
-        case 3: return launch_bwd<3>(d_rep, xmax, argmax, h, w, B, L, H, V, l0, d_hidden, dW, dbias, entries, nact, stream);
-        default: return launch_bwd<4>(d_rep, xmax, argmax, h, w, B, L, H, V, l0, d_hidden, dW, dbias, entries, nact, stream);
+#define SB200_BWD(N, F) launch_bwd<N, F>(d_rep, xmax, argmax, h, w, B, L, H, V, l0, d_hidden, dW, dbias, entries, nact, stream)
+    if (flags & SB200_HEAD_FP16) {   // the 16-bit payload is reinterpreted inside the kernels
+        switch (nchunk) {
+            case 1: return SB200_BWD(1, true);
+            case 2: return SB200_BWD(2, true);
+            case 3: return SB200_BWD(3, true);
+            default: return SB200_BWD(4, true);
+        }
     }
+    switch (nchunk) {
+        case 1: return SB200_BWD(1, false);
+        case 2: return SB200_BWD(2, false);
+        case 3: return SB200_BWD(3, false);
+        default: return SB200_BWD(4, false);
+    }
+#undef SB200_BWD
 }
 
 extern "C" int sb200_prune_rows(float* rep, int B, int V, float ratio, sb200_stream_t stream_) {

@@ -62,6 +62,7 @@ struct HeadFwdParams {
     int LC, S, NC, N;          // chunk length, sequences per tile, chunks per sequence, S*LC
     int n_vtiles, n_groups, kblocks;   // n_vtiles counts tiles of 128 * kCG vocab rows
     int l0;
+    int fp16;                  // operands are IEEE fp16 (else bf16)
     int n_peers;               // data-parallel all-gather fused into the epilogue: rep[b, v] is also stored into the
     float* peer_rep[7];        // gathered buffers of up to 7 other ranks (peer-mapped pointers to THIS rank's slot)
     int b_s_off;               // CTA pair, S >= 2: sequence offset of the second CTA's half of the token tile
@@ -213,7 +214,7 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
             int n_next = (u_begin < u_end) ? tile_columns(p, u_begin / p.n_vtiles, 0) : 16;
             for (int u = u_begin; u < u_end; ++u) {
                 for (int c = 0; c < p.NC; ++c, ++ci) {
-                    const uint32_t idesc = umma_idesc_bf16(kBlockM * kCG, n_next);
+                    const uint32_t idesc = umma_idesc_f16(kBlockM * kCG, n_next, p.fp16 != 0);
                     {
                         int un = u, cn = c + 1;
                         if (cn == p.NC) { cn = 0; ++un; }
@@ -524,12 +525,14 @@ extern "C" int sb200_head_fwd(const void* hidden, const void* W, const float* bi
         else          { box_l = t.LC / 2; }
     }
     CUtensorMap tmap_w, tmap_h;
+    const CUtensorMapDataType operand_type =
+        (flags & SB200_HEAD_FP16) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     {
         cuuint64_t dims[2] = {cuuint64_t(H), cuuint64_t(V)};
         cuuint64_t strides[1] = {cuuint64_t(H) * 2};
         cuuint32_t box[2] = {kBlockK, kBlockM};
         cuuint32_t estr[2] = {1, 1};
-        CUresult r = encode(&tmap_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(W), dims, strides, box, estr,
+        CUresult r = encode(&tmap_w, operand_type, 2, const_cast<void*>(W), dims, strides, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail(SB200_ERR_CUDA, "head_fwd: tensor map (W) encode failed: %d", int(r));
@@ -539,7 +542,7 @@ extern "C" int sb200_head_fwd(const void* hidden, const void* W, const float* bi
         cuuint64_t strides[2] = {cuuint64_t(H) * 2, cuuint64_t(L) * cuuint64_t(H) * 2};
         cuuint32_t box[3] = {kBlockK, cuuint32_t(box_l), cuuint32_t(box_s)};
         cuuint32_t estr[3] = {1, 1, 1};
-        CUresult r = encode(&tmap_h, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(hidden), dims, strides, box,
+        CUresult r = encode(&tmap_h, operand_type, 3, const_cast<void*>(hidden), dims, strides, box,
                             estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail(SB200_ERR_CUDA, "head_fwd: tensor map (hidden) encode failed: %d", int(r));
@@ -567,6 +570,7 @@ extern "C" int sb200_head_fwd(const void* hidden, const void* W, const float* bi
     p.n_groups = t.n_groups;
     p.kblocks = (H + kBlockK - 1) / kBlockK;
     p.l0 = (flags & SB200_HEAD_L0) ? 1 : 0;
+    p.fp16 = (flags & SB200_HEAD_FP16) ? 1 : 0;
     p.n_peers = n_peers;
     for (int k = 0; k < 7; ++k) p.peer_rep[k] = k < n_peers ? peer_rep[k] : nullptr;
     p.b_s_off = b_s_off;

@@ -121,12 +121,12 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     return d;
 }
 
-// Instruction descriptor for kind::f16: bf16 x bf16 -> fp32, both operands K-major.
-__host__ __device__ inline uint32_t umma_idesc_bf16(int M, int N) {
+// Instruction descriptor for kind::f16: (bf16 x bf16 | fp16 x fp16) -> fp32, both operands K-major.
+__host__ __device__ inline uint32_t umma_idesc_f16(int M, int N, bool fp16) {
     uint32_t d = 0;
     d |= 1u << 4;                    // D format F32
-    d |= 1u << 7;                    // A format BF16
-    d |= 1u << 10;                   // B format BF16
+    d |= (fp16 ? 0u : 1u) << 7;      // A format: 0 = F16, 1 = BF16
+    d |= (fp16 ? 0u : 1u) << 10;     // B format
     d |= static_cast<uint32_t>(N >> 3) << 17;
     d |= static_cast<uint32_t>(M >> 4) << 24;
     return d;

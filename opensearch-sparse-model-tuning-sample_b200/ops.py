@@ -74,8 +74,9 @@ def head_forward(hidden, weight, bias, attention_mask, use_l0=False, want_aux=Tr
     Returns (rep [B,V] fp32, xmax [B,V] fp32 | None, argmax [B,V] int32 | None).
     """
     _need_cuda(hidden, weight, bias, attention_mask)
-    if hidden.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16:
-        raise TypeError("head_forward expects bf16 hidden and weight")
+    if hidden.dtype != weight.dtype or hidden.dtype not in (torch.bfloat16, torch.float16):
+        raise TypeError("head_forward expects hidden and weight both bf16 or both fp16")
+    half_flag = _lib.HEAD_FP16 if hidden.dtype == torch.float16 else 0
     B, L, H = hidden.shape
     V = weight.shape[0]
     if weight.shape[1] != H:
@@ -108,15 +109,19 @@ def head_forward(hidden, weight, bias, attention_mask, use_l0=False, want_aux=Tr
     c_peers = (_lib.ctypes.c_void_p * max(1, len(peers)))(*peers) if peers else None
     with torch.cuda.device(dev), _timed("head_fwd"):
         code = lib.sb200_head_fwd(_ptr(hidden), _ptr(weight), _ptr(bias), _ptr(mask), mask.element_size(), B, L, H, V,
-                                  (_lib.HEAD_L0 if use_l0 else 0), _ptr(rep), _ptr(xmax), _ptr(argmax), c_peers,
+                                  (_lib.HEAD_L0 if use_l0 else 0) | half_flag, _ptr(rep), _ptr(xmax), _ptr(argmax), c_peers,
                                   len(peers), _ptr(ws), ws.numel(), _stream())
     _lib.check(code, "sb200_head_fwd")
     return rep, xmax, argmax
 
 
 def head_backward(d_rep, xmax, argmax, hidden, weight, use_l0=False, want_bias_grad=True):
-    """Sparse head backward -> (d_hidden [B,L,H] fp32, dW [V,H] fp32, dbias [V] fp32 | None)."""
+    """Sparse head backward -> (d_hidden [B,L,H] fp32, dW [V,H] fp32, dbias [V] fp32 | None). hidden / weight are the
+    half-precision operands of the forward call (both bf16 or both fp16)."""
     _need_cuda(d_rep, xmax, argmax, hidden, weight)
+    if hidden.dtype != weight.dtype or hidden.dtype not in (torch.bfloat16, torch.float16):
+        raise TypeError("head_backward expects hidden and weight both bf16 or both fp16")
+    half_flag = _lib.HEAD_FP16 if hidden.dtype == torch.float16 else 0
     B, L, H = hidden.shape
     V = weight.shape[0]
     lib = _lib.load()
@@ -128,7 +133,7 @@ def head_backward(d_rep, xmax, argmax, hidden, weight, use_l0=False, want_bias_g
     ws = _workspace(lib.sb200_head_bwd_workspace_bytes(B, L, H, V), dev)
     with torch.cuda.device(dev), _timed("head_bwd"):
         code = lib.sb200_head_bwd(_ptr(d_rep), _ptr(xmax), _ptr(argmax), _ptr(hidden), _ptr(weight), B, L, H, V,
-                                  _lib.HEAD_L0 if use_l0 else 0, _ptr(d_hidden), _ptr(dW), _ptr(dbias), _ptr(ws),
+                                  (_lib.HEAD_L0 if use_l0 else 0) | half_flag, _ptr(d_hidden), _ptr(dW), _ptr(dbias), _ptr(ws),
                                   ws.numel(), _stream())
     _lib.check(code, "sb200_head_bwd")
     return d_hidden, dW, dbias
@@ -146,12 +151,19 @@ def prune_rows_(rep, ratio):
 
 
 class SparseHeadFunction(torch.autograd.Function):
-    """rep = head(hidden, weight, bias, mask); gradients flow to hidden, weight and bias."""
+    """rep = head(hidden, weight, bias, mask); gradients flow to hidden, weight and bias.
+    Operand precision follows the reference's autocast: fp16 operands when the hidden states arrive in fp16 or fp16
+    autocast is active (configs with `fp16: true` -- the decoder Linear then multiplies fp16 x fp16 upstream too), bf16
+    otherwise (bf16 autocast, and fp32 callers: the tensor-core kernel has no fp32-operand mode; accumulation is fp32)."""
 
     @staticmethod
     def forward(ctx, hidden, weight, bias, attention_mask, use_l0, sink=None):
-        h16 = hidden.detach().to(torch.bfloat16).contiguous()
-        w16 = weight.detach().to(torch.bfloat16).contiguous()
+        half = torch.bfloat16
+        if hidden.dtype == torch.float16 or (hidden.is_cuda and torch.is_autocast_enabled("cuda")
+                                              and torch.get_autocast_dtype("cuda") == torch.float16):
+            half = torch.float16
+        h16 = hidden.detach().to(half).contiguous()
+        w16 = weight.detach().to(half).contiguous()
         needs_grad = any(t is not None and t.requires_grad for t in (hidden, weight, bias))
         out = peers = None
         if sink is not None and (sink.rows, sink.width) == (h16.shape[0], w16.shape[0]) and sink.world <= 8:

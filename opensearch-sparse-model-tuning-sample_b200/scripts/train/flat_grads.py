@@ -50,12 +50,15 @@ class FlatGradBuckets:
         self.comm_stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
         self._use_avg = dev.type == "cuda" and dist.is_initialized() and dist.get_backend(group) == "nccl"
         self._handles = []
+        self.enabled = True     # False: the hooks do nothing (a backward pass that is not part of a data-parallel step)
         if overlap:
             for idx, p in enumerate(self.params):
                 self._handles.append(p.register_post_accumulate_grad_hook(self._make_hook(idx)))
 
     def _make_hook(self, idx):
         def hook(param):
+            if not self.enabled:
+                return
             b = self.bucket_of[idx]
             self._left[b] -= 1
             if self._left[b] == 0:

@@ -91,6 +91,37 @@ def test_head_golden_reference_outputs(ops, golden):
             assert_close(rep, c["rep"][use_l0], 1e-4, 2e-5, "golden rep")
 
 
+@pytest.mark.parametrize("B,L,H,V", [(4, 128, 384, 3000), (3, 300, 768, 1200), (8, 64, 64, 500)])
+def test_head_fp16_operands_vs_oracle(ops, B, L, H, V):
+    """The reference configs train with `fp16: true`: the head then multiplies IEEE fp16 operands (SB200_HEAD_FP16), not
+    operands re-rounded to bf16. Oracle fed the same fp16-rounded values in fp32; forward and backward."""
+    g = torch.Generator().manual_seed(B + L)
+    hidden = torch.randn(B, L, H, generator=g).half()
+    W = (torch.randn(V, H, generator=g) * 0.1).half()
+    bias = torch.randn(V, generator=g) * 0.1 - 0.3
+    lens = torch.randint(L // 2, L + 1, (B,), generator=g)
+    mask = (torch.arange(L)[None, :] < lens[:, None]).long()
+    rep, xmax, amax = ops.head_forward(cuda(hidden), cuda(W), cuda(bias), cuda(mask), use_l0=True)
+    want, values, where = R.sparse_head(hidden.float(), W.float(), bias, mask, use_l0=True)
+    assert_close(rep, want, 1e-4, 2e-5, "rep (fp16 operands)")
+    check_argmax(hidden, W, bias, mask, values, amax)
+    # a bf16 re-rounding of the same operands would be off by ~1e-3: make sure the kernel really consumed fp16
+    rep_bf16, _, _ = ops.head_forward(cuda(hidden).bfloat16(), cuda(W).bfloat16(), cuda(bias), cuda(mask), use_l0=True)
+    assert float((rep_bf16.cpu() - want).abs().max()) > 10 * float((rep.cpu() - want).abs().max())
+    d_rep = torch.randn(B, V, generator=g)
+    dh, dw, db = ops.head_backward(cuda(d_rep), xmax, amax, cuda(hidden), cuda(W), use_l0=True)
+    gh, gw, gb = R.sparse_head_grads(hidden.float(), W.float(), bias, mask, d_rep, use_l0=True)
+    assert_close(dh, gh, 1e-4, 1e-5 * float(gh.abs().max()), "d_hidden (fp16 operands)")
+    assert_close(dw, gw, 1e-4, 1e-5 * float(gw.abs().max()), "dW (fp16 operands)")
+    assert_close(db, gb, 1e-4, 1e-5 * float(gb.abs().max()), "dbias (fp16 operands)")
+    # autograd entry point: fp16 autocast keeps fp16 operands
+    hc = cuda(hidden).float().requires_grad_(True)
+    wc = cuda(W).float().requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.float16):
+        out = ops.sparse_head(hc, wc, cuda(bias), cuda(mask), use_l0=True)
+    assert_close(out, want, 1e-4, 2e-5, "sparse_head under fp16 autocast")
+
+
 def test_head_is_deterministic_and_idempotent(ops):
     hidden, W, bias, mask = make_head_inputs(6, 200, 128, 4000, seed=11)
     a = ops.head_forward(cuda(hidden), cuda(W), cuda(bias), cuda(mask))
