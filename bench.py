@@ -242,6 +242,7 @@ def dist_parity(trainer, wl, args, device, batch, world, rank):
             if hasattr(trainer, "bi_encoder_teacher"):
                 solo.set_bi_encoder_teacher(models=trainer.bi_encoder_teacher.models)
             solo.model.eval()
+            solo.state.global_step = trainer.state.global_step     # same regulariser warm-up weight (get_lambda)
             trainer._zero_grads()
             if trainer._buckets is not None:
                 trainer._buckets.enabled = False     # this backward pass is rank 0's alone: no bucket all-reduces
