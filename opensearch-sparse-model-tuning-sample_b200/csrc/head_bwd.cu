@@ -270,6 +270,198 @@ bwd_dh_kernel(const uint2* __restrict__ entries, const int* __restrict__ nact, c
     flush(cur_l);
 }
 
+// ---------------------------------------------------------------- exact-fit variants (H * 2 bytes = VB * 32 * NCH)
+// The generic kernels above predicate every 16-byte chunk on `ch < n_chunks` (H = 384 leaves half of the warp idle on
+// the second chunk) and carry 64-bit address arithmetic and the run-flush control flow through every entry: ncu showed
+// them issue-bound (94 / 66 warp instructions per entry, IPC 2.1-2.5, L2 at 21-31 %). For the common widths each lane
+// instead owns NCH chunks of VB bytes that tile the row exactly, the run structure of a warp's 32 entries comes from
+// one ballot, and rows are fetched four entries ahead of their use.
+template <int VB> struct Chunk;
+template <> struct Chunk<16> { using type = uint4; static constexpr int kWords = 4; };
+template <> struct Chunk<8> { using type = uint2; static constexpr int kWords = 2; };
+template <> struct Chunk<4> { using type = uint32_t; static constexpr int kWords = 1; };
+
+template <bool kFp16>
+__device__ __forceinline__ void fma_word(float& a0, float& a1, uint32_t w, float c) {
+    float lo, hi;
+    if (kFp16) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w));
+        lo = f.x;
+        hi = f.y;
+    } else {
+        lo = __uint_as_float(w << 16);
+        hi = __uint_as_float(w & 0xffff0000u);
+    }
+    a0 = fmaf(c, lo, a0);
+    a1 = fmaf(c, hi, a1);
+}
+template <int VB, bool kFp16>
+__device__ __forceinline__ void fma_chunk(float* acc, const typename Chunk<VB>::type& raw, float c) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(&raw);
+#pragma unroll
+    for (int i = 0; i < Chunk<VB>::kWords; ++i) fma_word<kFp16>(acc[2 * i], acc[2 * i + 1], w[i], c);
+}
+// the lane's chunks of one row: chunk k lives at byte offset (lane + 32 k) * VB
+template <int VB, int NCH>
+__device__ __forceinline__ void load_row(typename Chunk<VB>::type (&dst)[NCH], const char* row_lane) {
+#pragma unroll
+    for (int k = 0; k < NCH; ++k)
+        dst[k] = __ldg(reinterpret_cast<const typename Chunk<VB>::type*>(row_lane + k * 32 * VB));
+}
+
+template <int VB, int NCH, bool kFp16>
+__global__ void __launch_bounds__(kDwThreads)
+bwd_dw_fit_kernel(const float* __restrict__ d_rep, const float* __restrict__ xmax, const int32_t* __restrict__ argmax,
+                  const char* __restrict__ hidden, int B, int L, int V, int l0, int Bc, float* __restrict__ dW,
+                  float* __restrict__ dbias) {
+    constexpr int kRowBytes = VB * 32 * NCH;       // = H * 2
+    constexpr int kPer = VB / 2;                    // fp32 accumulators per chunk
+    extern __shared__ float2 stage[];               // [32 vocab rows][Bc + 1] (c, row index as int bits)
+    const int v0 = blockIdx.x * kDwRows;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pitch = Bc + 1;                       // odd pitch: the transposed fill is at most 2-way bank conflicted
+    for (int b0 = 0; b0 < B; b0 += Bc) {
+        const int nb = min(Bc, B - b0);
+        __syncthreads();
+        for (int t = threadIdx.x; t < nb * kDwRows; t += kDwThreads) {
+            const int bo = t >> 5, vo = t & 31;
+            const int v = v0 + vo;
+            float c = 0.f;
+            int l = 0;
+            if (v < V) {
+                const size_t o = size_t(b0 + bo) * V + v;
+                c = head_coef(__ldg(d_rep + o), __ldg(xmax + o), l0);
+                l = min(max(__ldg(argmax + o), 0), L - 1);
+            }
+            stage[vo * pitch + bo] = make_float2(c, __int_as_float(bo * L + l));
+        }
+        __syncthreads();
+        const char* base = hidden + size_t(b0) * L * kRowBytes + lane * VB;
+        for (int r = 0; r < 4; ++r) {
+            const int vo = warp * 4 + r;
+            const int v = v0 + vo;
+            if (v >= V) break;  // warp-uniform
+            float acc[NCH][kPer];
+            float bsum = 0.f;
+#pragma unroll
+            for (int k = 0; k < NCH; ++k)
+#pragma unroll
+                for (int i = 0; i < kPer; ++i) acc[k][i] = 0.f;
+            for (int bo0 = 0; bo0 < nb; bo0 += 32) {
+                // 32 sequences at a time: lane i holds sequence bo0+i's (c, row); entries with c == 0 (inactive vocabulary
+                // in that sequence -- almost all of them once the model is trained) are skipped through the ballot
+                float2 mine = make_float2(0.f, 0.f);
+                if (bo0 + lane < nb) mine = stage[vo * pitch + bo0 + lane];
+                bsum += mine.x;
+                uint32_t live = __ballot_sync(0xffffffffu, mine.x != 0.f);
+                while (live != 0u) {
+                    int src[4];
+                    float cf[4];
+                    typename Chunk<VB>::type raw[4][NCH];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {       // up to four gathered rows in flight
+                        src[u] = live != 0u ? (__ffs(live) - 1) : -1;
+                        if (live != 0u) live &= live - 1;
+                        const int sl = src[u] < 0 ? 0 : src[u];
+                        cf[u] = src[u] < 0 ? 0.f : __shfl_sync(0xffffffffu, mine.x, sl);
+                        const int row = __float_as_int(__shfl_sync(0xffffffffu, mine.y, sl));
+                        if (src[u] >= 0) load_row<VB, NCH>(raw[u], base + size_t(row) * kRowBytes);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (src[u] >= 0) {
+#pragma unroll
+                            for (int k = 0; k < NCH; ++k) fma_chunk<VB, kFp16>(acc[k], raw[u][k], cf[u]);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) bsum += __shfl_xor_sync(0xffffffffu, bsum, o);
+            // this block is the only writer of rows v0..v0+31: first pass stores, later passes accumulate
+            float* out = dW + size_t(v) * (kRowBytes / 2) + lane * kPer;
+#pragma unroll
+            for (int k = 0; k < NCH; ++k) {
+#pragma unroll
+                for (int i = 0; i < kPer; ++i) {
+                    float* o = out + k * 32 * kPer + i;
+                    *o = (b0 > 0 ? *o : 0.f) + acc[k][i];
+                }
+            }
+            if (dbias != nullptr && lane == 0) dbias[v] = (b0 > 0 ? dbias[v] : 0.f) + bsum;
+        }
+    }
+}
+
+template <int VB, int NCH, bool kFp16>
+__global__ void __launch_bounds__(256)
+bwd_dh_fit_kernel(const uint2* __restrict__ entries, const int* __restrict__ nact, const char* __restrict__ W, int L,
+                  int V, float* __restrict__ d_hidden) {
+    constexpr int kRowBytes = VB * 32 * NCH;
+    constexpr int kPer = VB / 2;
+    const int b = blockIdx.y;
+    const int n = __ldg(nact + b);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int first = blockIdx.x * kDhEntriesPerBlock + warp * 32;
+    if (first >= n) return;
+    const int cnt = min(32, n - first);
+    uint2 mine = make_uint2(0xffffffffu, 0u);       // lanes past the end: a key that starts no run of its own
+    if (lane < cnt) mine = __ldg(entries + size_t(b) * V + first + lane);
+    const uint32_t my_l = mine.x >> 20;
+    // run structure of the (l-sorted) entries: bit e set <=> entry e starts a new run
+    const uint32_t prev_l = __shfl_up_sync(0xffffffffu, my_l, 1);
+    uint32_t starts = __ballot_sync(0xffffffffu, lane < cnt && (lane == 0 || my_l != prev_l));
+    const char* wl = W + lane * VB;
+    float* dh = d_hidden + size_t(b) * L * (kRowBytes / 2) + lane * kPer;
+    while (starts != 0u) {
+        const int s = __ffs(starts) - 1;
+        starts &= starts - 1;
+        const int e_end = starts != 0u ? (__ffs(starts) - 1) : cnt;
+        float acc[NCH][kPer];
+#pragma unroll
+        for (int k = 0; k < NCH; ++k)
+#pragma unroll
+            for (int i = 0; i < kPer; ++i) acc[k][i] = 0.f;
+        int e = s;
+        for (; e + 4 <= e_end; e += 4) {
+            typename Chunk<VB>::type raw[4][NCH];
+            float cf[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t key = __shfl_sync(0xffffffffu, mine.x, e + u);
+                cf[u] = __uint_as_float(__shfl_sync(0xffffffffu, mine.y, e + u));
+                load_row<VB, NCH>(raw[u], wl + size_t(key & 0xFFFFFu) * kRowBytes);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int k = 0; k < NCH; ++k) fma_chunk<VB, kFp16>(acc[k], raw[u][k], cf[u]);
+        }
+        for (; e < e_end; ++e) {
+            const uint32_t key = __shfl_sync(0xffffffffu, mine.x, e);
+            const float cf = __uint_as_float(__shfl_sync(0xffffffffu, mine.y, e));
+            typename Chunk<VB>::type raw[NCH];
+            load_row<VB, NCH>(raw, wl + size_t(key & 0xFFFFFu) * kRowBytes);
+#pragma unroll
+            for (int k = 0; k < NCH; ++k) fma_chunk<VB, kFp16>(acc[k], raw[k], cf);
+        }
+        const uint32_t l = __shfl_sync(0xffffffffu, my_l, s);
+        float* row = dh + size_t(l) * (kRowBytes / 2);
+#pragma unroll
+        for (int k = 0; k < NCH; ++k) {
+            float* o = row + k * 32 * kPer;
+            if (kPer == 8) {
+                red_add_v4(o, acc[k][0], acc[k][1], acc[k][2], acc[k][3]);
+                red_add_v4(o + 4, acc[k][4 % kPer], acc[k][5 % kPer], acc[k][6 % kPer], acc[k][7 % kPer]);
+            } else if (kPer == 4) {
+                red_add_v4(o, acc[k][0], acc[k][1], acc[k][2], acc[k][3]);
+            } else {
+                asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(o), "f"(acc[k][0]), "f"(acc[k][1]) : "memory");
+            }
+        }
+    }
+}
+
 // rep[b,v] *= (rep[b,v] > ratio * rowmax)   (sparse_encoders.py:118-119)
 __global__ void __launch_bounds__(256) prune_rows_kernel(float* __restrict__ rep, int V, float ratio) {
     __shared__ float red[8];
@@ -288,6 +480,52 @@ __global__ void __launch_bounds__(256) prune_rows_kernel(float* __restrict__ rep
         const float x = row[v];
         row[v] = (x > thr) ? x : x * 0.f;
     }
+}
+
+// exact-fit dispatch: returns false when H has no (VB, NCH) tiling
+template <bool kFp16>
+bool launch_bwd_fit(const float* d_rep, const float* xmax, const int32_t* argmax, const void* hidden, const void* W, int B,
+                    int L, int H, int V, int l0, float* d_hidden, float* dW, float* dbias, uint2* entries, int* nact,
+                    cudaStream_t stream, int* rc) {
+    int Bc = B;
+    const int max_smem = 96 * 1024;
+    if (size_t(Bc + 1) * kDwRows * sizeof(float2) > size_t(max_smem)) Bc = max_smem / int(kDwRows * sizeof(float2)) - 1;
+    const size_t smem = size_t(Bc + 1) * kDwRows * sizeof(float2);
+    const dim3 dh_grid((V + kDhEntriesPerBlock - 1) / kDhEntriesPerBlock, B);
+    const int dw_grid = (V + kDwRows - 1) / kDwRows;
+    const char* h = static_cast<const char*>(hidden);
+    const char* w = static_cast<const char*>(W);
+    *rc = SB200_OK;
+#define SB200_FIT(VB, NCH, SLOT)                                                                                        \
+    do {                                                                                                                \
+        if (smem > 48 * 1024 && !device_flag_test_and_set(SLOT + (kFp16 ? 1 : 0))) {                                    \
+            if (cudaFuncSetAttribute(bwd_dw_fit_kernel<VB, NCH, kFp16>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                     max_smem) != cudaSuccess) { *rc = fail(SB200_ERR_CUDA, "bwd_dw_fit: smem attribute"); return true; } \
+        }                                                                                                               \
+        bwd_dw_fit_kernel<VB, NCH, kFp16><<<dw_grid, kDwThreads, smem, stream>>>(d_rep, xmax, argmax, h, B, L, V, l0, Bc, \
+                                                                                 dW, dbias);                           \
+        if (cudaGetLastError() != cudaSuccess) { *rc = fail(SB200_ERR_CUDA, "bwd_dw_fit_kernel launch"); return true; } \
+        count_launch();                                                                                                 \
+        if (cudaMemsetAsync(d_hidden, 0, size_t(B) * L * H * sizeof(float), stream) != cudaSuccess) {                   \
+            *rc = fail(SB200_ERR_CUDA, "bwd: memset"); return true; }                                                   \
+        bwd_bucket_kernel<<<B, kBucketThreads, 0, stream>>>(d_rep, xmax, argmax, L, V, l0, entries, nact);             \
+        count_launch();                                                                                                 \
+        bwd_dh_fit_kernel<VB, NCH, kFp16><<<dh_grid, 256, 0, stream>>>(entries, nact, w, L, V, d_hidden);              \
+        if (cudaGetLastError() != cudaSuccess) { *rc = fail(SB200_ERR_CUDA, "bwd_dh_fit_kernel launch"); return true; } \
+        count_launch();                                                                                                 \
+        return true;                                                                                                    \
+    } while (0)
+    switch (H) {
+        case 64: SB200_FIT(4, 1, 20);
+        case 128: SB200_FIT(8, 1, 22);
+        case 256: SB200_FIT(16, 1, 24);
+        case 384: SB200_FIT(8, 3, 26);
+        case 512: SB200_FIT(16, 2, 28);
+        case 768: SB200_FIT(16, 3, 30);
+        default: break;
+    }
+#undef SB200_FIT
+    return false;
 }
 
 template <int NCHUNK, bool kFp16>
@@ -347,6 +585,13 @@ extern "C" int sb200_head_bwd(const float* d_rep, const float* xmax, const int32
     const int l0 = (flags & SB200_HEAD_L0) ? 1 : 0;
     const __nv_bfloat16* h = static_cast<const __nv_bfloat16*>(hidden);
     const __nv_bfloat16* w = static_cast<const __nv_bfloat16*>(W);
+    {
+        int rc = SB200_OK;
+        const bool done = (flags & SB200_HEAD_FP16)
+            ? launch_bwd_fit<true>(d_rep, xmax, argmax, hidden, W, B, L, H, V, l0, d_hidden, dW, dbias, entries, nact, stream, &rc)
+            : launch_bwd_fit<false>(d_rep, xmax, argmax, hidden, W, B, L, H, V, l0, d_hidden, dW, dbias, entries, nact, stream, &rc);
+        if (done) return rc;
+    }
     const int nchunk = (H / 8 + 31) / 32;
 #define SB200_BWD(N, F) launch_bwd<N, F>(d_rep, xmax, argmax, h, w, B, L, H, V, l0, d_hidden, dW, dbias, entries, nact, stream)
     if (flags & SB200_HEAD_FP16) {   // the 16-bit payload is reinterpreted inside the kernels
