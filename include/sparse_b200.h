@@ -93,6 +93,23 @@ int sb200_head_bwd(const float* d_rep, const float* xmax, const int32_t* argmax,
                    int B, int L, int H, int V, int flags, float* d_hidden, float* dW, float* dbias,
                    void* workspace, size_t workspace_bytes, sb200_stream_t stream);
 
+/* (1p)/(2p) The same head on PACKED hidden states (padding-free encoder body): hidden is [T, H], every row a real token,
+ * sequence b = rows [cu_seqlens[b], cu_seqlens[b+1]) (device i32 [B+1], lengths <= max_len). No padded [B, L, H] copy
+ * is made in either direction: the forward reads the runs through a 2-D tensor map (one sequence per tile, so
+ * max_len > 128), the backward gathers / scatters packed rows and returns d_hidden as [T, H] f32. A sequence shorter
+ * than max_len counts as having masked slots (their logit * mask = 0 takes part in the max, as in the reference);
+ * argmax is the token's rank inside its sequence. sb200_head_packed_supported(H, max_len) tells whether the pair of
+ * calls is available (H in {64, 128, 256, 384, 512, 768}, 128 < max_len <= 4096). Workspaces as for the padded calls
+ * with L = max_len. */
+int sb200_head_packed_supported(int H, int max_len);
+int sb200_head_fwd_packed(const void* hidden, const void* W, const float* bias, const int32_t* cu_seqlens, int T, int B,
+                          int max_len, int H, int V, int flags, float* rep, float* xmax, int32_t* argmax,
+                          float* const* peer_rep, int n_peers, void* workspace, size_t workspace_bytes,
+                          sb200_stream_t stream);
+int sb200_head_bwd_packed(const float* d_rep, const float* xmax, const int32_t* argmax, const void* hidden, const void* W,
+                          const int32_t* cu_seqlens, int T, int B, int max_len, int H, int V, int flags, float* d_hidden,
+                          float* dW, float* dbias, void* workspace, size_t workspace_bytes, sb200_stream_t stream);
+
 /* (2b) Row pruning, in place: rep[b,v] *= (rep[b,v] > ratio * max_v rep[b,:]).  sparse_encoders.py:115-119 */
 int sb200_prune_rows(float* rep, int B, int V, float ratio, sb200_stream_t stream);
 

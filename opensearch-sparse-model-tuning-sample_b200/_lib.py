@@ -30,6 +30,11 @@ _PROTOTYPES = {
     "sb200_head_bwd_workspace_bytes": (_sz, [_c_int, _c_int, _c_int, _c_int]),
     "sb200_head_bwd": (_c_int, [_vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp,
                                 _sz, _vp]),
+    "sb200_head_packed_supported": (_c_int, [_c_int, _c_int]),
+    "sb200_head_fwd_packed": (_c_int, [_vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp,
+                                       _vp, _c_int, _vp, _sz, _vp]),
+    "sb200_head_bwd_packed": (_c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _vp,
+                                       _vp, _vp, _vp, _sz, _vp]),
     "sb200_prune_rows": (_c_int, [_vp, _c_int, _c_int, _c_f, _vp]),
     "sb200_idf_query": (_c_int, [_vp, _c_int, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp]),
     "sb200_idf_query_bwd": (_c_int, [_vp, _vp, _c_int, _c_int, _vp, _vp]),

@@ -312,8 +312,8 @@ __device__ __forceinline__ void load_row(typename Chunk<VB>::type (&dst)[NCH], c
 template <int VB, int NCH, bool kFp16>
 __global__ void __launch_bounds__(kDwThreads)
 bwd_dw_fit_kernel(const float* __restrict__ d_rep, const float* __restrict__ xmax, const int32_t* __restrict__ argmax,
-                  const char* __restrict__ hidden, int B, int L, int V, int l0, int Bc, float* __restrict__ dW,
-                  float* __restrict__ dbias) {
+                  const char* __restrict__ hidden, const int32_t* __restrict__ cu, int B, int L, int V, int l0, int Bc,
+                  float* __restrict__ dW, float* __restrict__ dbias) {
     constexpr int kRowBytes = VB * 32 * NCH;       // = H * 2
     constexpr int kPer = VB / 2;                    // fp32 accumulators per chunk
     extern __shared__ float2 stage[];               // [32 vocab rows][Bc + 1] (c, row index as int bits)
@@ -333,10 +333,12 @@ bwd_dw_fit_kernel(const float* __restrict__ d_rep, const float* __restrict__ xma
                 c = head_coef(__ldg(d_rep + o), __ldg(xmax + o), l0);
                 l = min(max(__ldg(argmax + o), 0), L - 1);
             }
-            stage[vo * pitch + bo] = make_float2(c, __int_as_float(bo * L + l));
+            // absolute row of the gathered hidden state: padded [B, L, H] or packed [T, H] (cu = sequence starts)
+            const int row = (cu != nullptr) ? min(__ldg(cu + b0 + bo) + l, __ldg(cu + b0 + bo + 1) - 1) : (b0 + bo) * L + l;
+            stage[vo * pitch + bo] = make_float2(c, __int_as_float(max(row, 0)));
         }
         __syncthreads();
-        const char* base = hidden + size_t(b0) * L * kRowBytes + lane * VB;
+        const char* base = hidden + lane * VB;
         for (int r = 0; r < 4; ++r) {
             const int vo = warp * 4 + r;
             const int v = v0 + vo;
@@ -395,8 +397,8 @@ bwd_dw_fit_kernel(const float* __restrict__ d_rep, const float* __restrict__ xma
 
 template <int VB, int NCH, bool kFp16>
 __global__ void __launch_bounds__(256)
-bwd_dh_fit_kernel(const uint2* __restrict__ entries, const int* __restrict__ nact, const char* __restrict__ W, int L,
-                  int V, float* __restrict__ d_hidden) {
+bwd_dh_fit_kernel(const uint2* __restrict__ entries, const int* __restrict__ nact, const char* __restrict__ W,
+                  const int32_t* __restrict__ cu, int L, int V, float* __restrict__ d_hidden) {
     constexpr int kRowBytes = VB * 32 * NCH;
     constexpr int kPer = VB / 2;
     const int b = blockIdx.y;
@@ -412,7 +414,8 @@ bwd_dh_fit_kernel(const uint2* __restrict__ entries, const int* __restrict__ nac
     const uint32_t prev_l = __shfl_up_sync(0xffffffffu, my_l, 1);
     uint32_t starts = __ballot_sync(0xffffffffu, lane < cnt && (lane == 0 || my_l != prev_l));
     const char* wl = W + lane * VB;
-    float* dh = d_hidden + size_t(b) * L * (kRowBytes / 2) + lane * kPer;
+    const size_t row0 = (cu != nullptr) ? size_t(__ldg(cu + b)) : size_t(b) * L;   // packed [T, H] or padded [B, L, H]
+    float* dh = d_hidden + row0 * (kRowBytes / 2) + lane * kPer;
     while (starts != 0u) {
         const int s = __ffs(starts) - 1;
         starts &= starts - 1;
@@ -484,9 +487,9 @@ __global__ void __launch_bounds__(256) prune_rows_kernel(float* __restrict__ rep
 
 // exact-fit dispatch: returns false when H has no (VB, NCH) tiling
 template <bool kFp16>
-bool launch_bwd_fit(const float* d_rep, const float* xmax, const int32_t* argmax, const void* hidden, const void* W, int B,
-                    int L, int H, int V, int l0, float* d_hidden, float* dW, float* dbias, uint2* entries, int* nact,
-                    cudaStream_t stream, int* rc) {
+bool launch_bwd_fit(const float* d_rep, const float* xmax, const int32_t* argmax, const void* hidden, const void* W,
+                    const int32_t* cu, size_t total_rows, int B, int L, int H, int V, int l0, float* d_hidden, float* dW,
+                    float* dbias, uint2* entries, int* nact, cudaStream_t stream, int* rc) {
     int Bc = B;
     const int max_smem = 96 * 1024;
     if (size_t(Bc + 1) * kDwRows * sizeof(float2) > size_t(max_smem)) Bc = max_smem / int(kDwRows * sizeof(float2)) - 1;
@@ -502,15 +505,15 @@ bool launch_bwd_fit(const float* d_rep, const float* xmax, const int32_t* argmax
             if (cudaFuncSetAttribute(bwd_dw_fit_kernel<VB, NCH, kFp16>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
                                      max_smem) != cudaSuccess) { *rc = fail(SB200_ERR_CUDA, "bwd_dw_fit: smem attribute"); return true; } \
         }                                                                                                               \
-        bwd_dw_fit_kernel<VB, NCH, kFp16><<<dw_grid, kDwThreads, smem, stream>>>(d_rep, xmax, argmax, h, B, L, V, l0, Bc, \
-                                                                                 dW, dbias);                           \
+        bwd_dw_fit_kernel<VB, NCH, kFp16><<<dw_grid, kDwThreads, smem, stream>>>(d_rep, xmax, argmax, h, cu, B, L, V, l0, \
+                                                                                 Bc, dW, dbias);                       \
         if (cudaGetLastError() != cudaSuccess) { *rc = fail(SB200_ERR_CUDA, "bwd_dw_fit_kernel launch"); return true; } \
         count_launch();                                                                                                 \
-        if (cudaMemsetAsync(d_hidden, 0, size_t(B) * L * H * sizeof(float), stream) != cudaSuccess) {                   \
+        if (cudaMemsetAsync(d_hidden, 0, total_rows * H * sizeof(float), stream) != cudaSuccess) {                      \
             *rc = fail(SB200_ERR_CUDA, "bwd: memset"); return true; }                                                   \
         bwd_bucket_kernel<<<B, kBucketThreads, 0, stream>>>(d_rep, xmax, argmax, L, V, l0, entries, nact);             \
         count_launch();                                                                                                 \
-        bwd_dh_fit_kernel<VB, NCH, kFp16><<<dh_grid, 256, 0, stream>>>(entries, nact, w, L, V, d_hidden);              \
+        bwd_dh_fit_kernel<VB, NCH, kFp16><<<dh_grid, 256, 0, stream>>>(entries, nact, w, cu, L, V, d_hidden);          \
         if (cudaGetLastError() != cudaSuccess) { *rc = fail(SB200_ERR_CUDA, "bwd_dh_fit_kernel launch"); return true; } \
         count_launch();                                                                                                 \
         return true;                                                                                                    \
@@ -567,10 +570,11 @@ extern "C" size_t sb200_head_bwd_workspace_bytes(int B, int L, int H, int V) {
     return align_up(size_t(B) * V * sizeof(uint2), 256) + align_up(size_t(B) * sizeof(int), 256);
 }
 
-extern "C" int sb200_head_bwd(const float* d_rep, const float* xmax, const int32_t* argmax, const void* hidden,
-                              const void* W, int B, int L, int H, int V, int flags, float* d_hidden, float* dW,
-                              float* dbias, void* workspace, size_t workspace_bytes, sb200_stream_t stream_) {
+static int head_bwd_impl(const float* d_rep, const float* xmax, const int32_t* argmax, const void* hidden, const void* W,
+                         const int32_t* cu, int T, int B, int L, int H, int V, int flags, float* d_hidden, float* dW,
+                         float* dbias, void* workspace, size_t workspace_bytes, sb200_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const size_t total_rows = cu != nullptr ? size_t(T) : size_t(B) * L;
     SB200_REQUIRE(d_rep && xmax && argmax && hidden && W && d_hidden && dW, "head_bwd: null pointer");
     SB200_REQUIRE(B >= 1 && L >= 1 && L <= kMaxL && V >= 1 && V <= (1 << 20), "head_bwd: bad shape B=%d L=%d V=%d", B,
                   L, V);
@@ -588,9 +592,10 @@ extern "C" int sb200_head_bwd(const float* d_rep, const float* xmax, const int32
     {
         int rc = SB200_OK;
         const bool done = (flags & SB200_HEAD_FP16)
-            ? launch_bwd_fit<true>(d_rep, xmax, argmax, hidden, W, B, L, H, V, l0, d_hidden, dW, dbias, entries, nact, stream, &rc)
-            : launch_bwd_fit<false>(d_rep, xmax, argmax, hidden, W, B, L, H, V, l0, d_hidden, dW, dbias, entries, nact, stream, &rc);
+            ? launch_bwd_fit<true>(d_rep, xmax, argmax, hidden, W, cu, total_rows, B, L, H, V, l0, d_hidden, dW, dbias, entries, nact, stream, &rc)
+            : launch_bwd_fit<false>(d_rep, xmax, argmax, hidden, W, cu, total_rows, B, L, H, V, l0, d_hidden, dW, dbias, entries, nact, stream, &rc);
         if (done) return rc;
+        if (cu != nullptr) return fail(SB200_ERR_ARG, "head_bwd_packed: H=%d has no exact-fit kernel (64/128/256/384/512/768)", H);
     }
     const int nchunk = (H / 8 + 31) / 32;
 #define SB200_BWD(N, F) launch_bwd<N, F>(d_rep, xmax, argmax, h, w, B, L, H, V, l0, d_hidden, dW, dbias, entries, nact, stream)
@@ -609,6 +614,26 @@ extern "C" int sb200_head_bwd(const float* d_rep, const float* xmax, const int32
         default: return SB200_BWD(4, false);
     }
 #undef SB200_BWD
+}
+
+extern "C" int sb200_head_bwd(const float* d_rep, const float* xmax, const int32_t* argmax, const void* hidden,
+                              const void* W, int B, int L, int H, int V, int flags, float* d_hidden, float* dW,
+                              float* dbias, void* workspace, size_t workspace_bytes, sb200_stream_t stream) {
+    return head_bwd_impl(d_rep, xmax, argmax, hidden, W, nullptr, 0, B, L, H, V, flags, d_hidden, dW, dbias, workspace,
+                         workspace_bytes, stream);
+}
+
+extern "C" int sb200_head_bwd_packed(const float* d_rep, const float* xmax, const int32_t* argmax, const void* hidden,
+                                     const void* W, const int32_t* cu_seqlens, int T, int B, int max_len, int H, int V,
+                                     int flags, float* d_hidden, float* dW, float* dbias, void* workspace,
+                                     size_t workspace_bytes, sb200_stream_t stream) {
+    if (cu_seqlens == nullptr || T < 1) return fail(SB200_ERR_ARG, "head_bwd_packed: cu_seqlens / T");
+    return head_bwd_impl(d_rep, xmax, argmax, hidden, W, cu_seqlens, T, B, max_len, H, V, flags, d_hidden, dW, dbias,
+                         workspace, workspace_bytes, stream);
+}
+
+extern "C" int sb200_head_packed_supported(int H, int max_len) {
+    return (max_len > 128 && max_len <= 4096 && (H == 64 || H == 128 || H == 256 || H == 384 || H == 512 || H == 768)) ? 1 : 0;
 }
 
 extern "C" int sb200_prune_rows(float* rep, int B, int V, float ratio, sb200_stream_t stream_) {

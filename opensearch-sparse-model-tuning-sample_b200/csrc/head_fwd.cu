@@ -54,7 +54,8 @@ constexpr int kMaskWords = kMaxN / 32;                          // 8
 struct HeadFwdParams {
     const float* bias;
     const uint32_t* tilemask;  // [n_groups][NC][8] validity bits per tile column
-    const int4* seqinfo;       // [B] (number of masked slots, first masked slot, last real position + 1, 0)
+    const int4* seqinfo;       // [B] (number of masked slots, first masked slot, last real position + 1, packed start row)
+    int packed;                // hidden is [T, H] (real tokens only, sequence b = rows seqinfo[b].w ...): 2-D tensor map
     float* rep;
     float* xmax;
     int32_t* argmax;
@@ -106,6 +107,32 @@ __global__ void head_prep_kernel(const void* __restrict__ mask, int elem_bytes, 
             extent = max(extent, __shfl_xor_sync(0xffffffffu, extent, o));
         }
         if (lane == 0) seqinfo[b] = make_int4(L - count, first, extent, 0);
+    }
+}
+
+// Packed input (padding-free encoder body): sequence b is the run of rows [cu[b], cu[b+1]) of a [T, H] matrix, every
+// row a real token. One sequence per tile (S == 1): validity bits and padding info follow from the lengths alone.
+__global__ void head_prep_packed_kernel(const int32_t* __restrict__ cu, int B, int L, int LC, int NC,
+                                        uint32_t* __restrict__ tilemask, int4* __restrict__ seqinfo) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n_words = B * NC * kMaskWords;
+    if (t < n_words) {
+        const int word = t % kMaskWords;
+        const int c = (t / kMaskWords) % NC;
+        const int b = t / (kMaskWords * NC);
+        const int len = min(max(__ldg(cu + b + 1) - __ldg(cu + b), 0), L);
+        uint32_t bits = 0u;
+#pragma unroll 4
+        for (int i = 0; i < 32; ++i) {
+            const int j = word * 32 + i;
+            if (j < LC && c * LC + j < len) bits |= 1u << i;
+        }
+        tilemask[t] = bits;
+    } else if (t - n_words < B) {
+        const int b = t - n_words;
+        const int start = __ldg(cu + b);
+        const int len = min(max(__ldg(cu + b + 1) - start, 0), L);
+        seqinfo[b] = make_int4(L - len, len, len, start);
     }
 }
 
@@ -187,20 +214,26 @@ head_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
                 for (int c = 0; c < p.NC; ++c) {
                     // CTA pair, one sequence per tile: the second CTA's half starts where the first one's ends
                     const int l_off = (p.S == 1) ? tile_columns(p, g, c) / 2 : 0;
+                    const int row0 = p.packed ? __ldg(p.seqinfo + g).w + c * p.LC : 0;   // packed: first row of the chunk
                     for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
                         const uint32_t s = it % kStages, ph = (it / kStages) & 1;
                         mbar_wait(&empty_bar[s], ph ^ 1);
                         if (kCG == 1) {
                             mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
                             tma_load_2d(smem_a + s * kABytes, &tmap_w, &full_bar[s], kb * kBlockK, vt * kBlockM);
-                            tma_load_3d(smem_b + s * kBBytes, &tmap_h, &full_bar[s], kb * kBlockK, c * p.LC, g * p.S);
+                            if (p.packed) tma_load_2d(smem_b + s * kBBytes, &tmap_h, &full_bar[s], kb * kBlockK, row0);
+                            else tma_load_3d(smem_b + s * kBBytes, &tmap_h, &full_bar[s], kb * kBlockK, c * p.LC, g * p.S);
                         } else {
                             // each CTA loads its 128 vocab rows and its half of the token tile
                             if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
                             tma_load_2d_pair(smem_a + s * kABytes, &tmap_w, &full_bar[s], kb * kBlockK,
                                              (vt * 2 + int(rank)) * kBlockM);
-                            tma_load_3d_pair(smem_b + s * kBBytes, &tmap_h, &full_bar[s], kb * kBlockK,
-                                             c * p.LC + int(rank) * l_off, g * p.S + int(rank) * p.b_s_off);
+                            if (p.packed)
+                                tma_load_2d_pair(smem_b + s * kBBytes, &tmap_h, &full_bar[s], kb * kBlockK,
+                                                 row0 + int(rank) * l_off);
+                            else
+                                tma_load_3d_pair(smem_b + s * kBBytes, &tmap_h, &full_bar[s], kb * kBlockK,
+                                                 c * p.LC + int(rank) * l_off, g * p.S + int(rank) * p.b_s_off);
                         }
                     }
                 }
@@ -489,18 +522,22 @@ extern "C" size_t sb200_head_fwd_workspace_bytes(int B, int L) {
     return a > b ? a : b;
 }
 
-extern "C" int sb200_head_fwd(const void* hidden, const void* W, const float* bias, const void* mask,
-                              int mask_elem_bytes, int B, int L, int H, int V, int flags, float* rep, float* xmax,
-                              int32_t* argmax, float* const* peer_rep, int n_peers, void* workspace,
-                              size_t workspace_bytes, sb200_stream_t stream_) {
+// cu_seqlens == nullptr: hidden is the padded [B, L, H] tensor and `mask` the attention mask; otherwise hidden is the
+// packed [T, H] matrix of real tokens and sequence b its rows [cu_seqlens[b], cu_seqlens[b+1]) (one sequence per tile).
+static int head_fwd_impl(const void* hidden, const void* W, const float* bias, const void* mask, int mask_elem_bytes,
+                         const int32_t* cu_seqlens, int T, int B, int L, int H, int V, int flags, float* rep, float* xmax,
+                         int32_t* argmax, float* const* peer_rep, int n_peers, void* workspace, size_t workspace_bytes,
+                         sb200_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    SB200_REQUIRE(hidden && W && mask && rep, "head_fwd: null pointer");
+    const bool packed = cu_seqlens != nullptr;
+    SB200_REQUIRE(hidden && W && (mask || packed) && rep, "head_fwd: null pointer");
     SB200_REQUIRE(n_peers >= 0 && n_peers <= 7 && (n_peers == 0 || peer_rep != nullptr), "head_fwd: bad peer list (%d)",
                   n_peers);
     SB200_REQUIRE(B >= 1 && V >= 1 && L >= 1 && L <= 4096, "head_fwd: bad shape B=%d L=%d V=%d", B, L, V);
     SB200_REQUIRE(H >= 8 && H % 8 == 0, "head_fwd: H=%d must be a positive multiple of 8", H);
-    SB200_REQUIRE(mask_elem_bytes == 1 || mask_elem_bytes == 4 || mask_elem_bytes == 8, "head_fwd: mask_elem_bytes=%d",
-                  mask_elem_bytes);
+    SB200_REQUIRE(packed || mask_elem_bytes == 1 || mask_elem_bytes == 4 || mask_elem_bytes == 8,
+                  "head_fwd: mask_elem_bytes=%d", mask_elem_bytes);
+    SB200_REQUIRE(!packed || (L > 128 && T >= 1), "head_fwd_packed: needs max_len > 128 (one sequence per tile), T >= 1");
     SB200_REQUIRE((reinterpret_cast<uintptr_t>(hidden) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0,
                   "head_fwd: hidden/W must be 16-byte aligned");
     const size_t need = sb200_head_fwd_workspace_bytes(B, L);
@@ -537,7 +574,16 @@ extern "C" int sb200_head_fwd(const void* hidden, const void* W, const float* bi
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail(SB200_ERR_CUDA, "head_fwd: tensor map (W) encode failed: %d", int(r));
     }
-    {
+    if (packed) {
+        cuuint64_t dims[2] = {cuuint64_t(H), cuuint64_t(T)};
+        cuuint64_t strides[1] = {cuuint64_t(H) * 2};
+        cuuint32_t box[2] = {kBlockK, cuuint32_t(box_l)};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = encode(&tmap_h, operand_type, 2, const_cast<void*>(hidden), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(SB200_ERR_CUDA, "head_fwd: tensor map (packed hidden) encode failed: %d", int(r));
+    } else {
         cuuint64_t dims[3] = {cuuint64_t(H), cuuint64_t(L), cuuint64_t(B)};
         cuuint64_t strides[2] = {cuuint64_t(H) * 2, cuuint64_t(L) * cuuint64_t(H) * 2};
         cuuint32_t box[3] = {kBlockK, cuuint32_t(box_l), cuuint32_t(box_s)};
@@ -548,7 +594,12 @@ extern "C" int sb200_head_fwd(const void* hidden, const void* W, const float* bi
         if (r != CUDA_SUCCESS) return fail(SB200_ERR_CUDA, "head_fwd: tensor map (hidden) encode failed: %d", int(r));
     }
 
-    {
+    if (packed) {
+        if (t.S != 1) return fail(SB200_ERR_ARG, "head_fwd_packed: tiling holds %d sequences per tile", t.S);
+        const int n = B * t.NC * kMaskWords + B;
+        head_prep_packed_kernel<<<(n + 255) / 256, 256, 0, stream>>>(cu_seqlens, B, L, t.LC, t.NC, tilemask, seqinfo);
+        SB200_CHECK_LAUNCH("head_prep_packed_kernel");
+    } else {
         const int n_warps = t.n_groups * t.NC * kMaskWords + B;
         const int threads = 256;
         const int blocks = (n_warps * 32 + threads - 1) / threads;
@@ -561,6 +612,7 @@ extern "C" int sb200_head_fwd(const void* hidden, const void* W, const float* bi
     p.bias = bias;
     p.tilemask = tilemask;
     p.seqinfo = seqinfo;
+    p.packed = packed ? 1 : 0;
     p.rep = rep;
     p.xmax = xmax;
     p.argmax = argmax;
@@ -606,4 +658,21 @@ extern "C" int sb200_head_fwd(const void* hidden, const void* W, const float* bi
     }
     SB200_CHECK_LAUNCH("head_fwd_kernel");
     return SB200_OK;
+}
+
+extern "C" int sb200_head_fwd(const void* hidden, const void* W, const float* bias, const void* mask,
+                              int mask_elem_bytes, int B, int L, int H, int V, int flags, float* rep, float* xmax,
+                              int32_t* argmax, float* const* peer_rep, int n_peers, void* workspace,
+                              size_t workspace_bytes, sb200_stream_t stream) {
+    return head_fwd_impl(hidden, W, bias, mask, mask_elem_bytes, nullptr, 0, B, L, H, V, flags, rep, xmax, argmax, peer_rep,
+                         n_peers, workspace, workspace_bytes, stream);
+}
+
+extern "C" int sb200_head_fwd_packed(const void* hidden, const void* W, const float* bias, const int32_t* cu_seqlens, int T,
+                                     int B, int max_len, int H, int V, int flags, float* rep, float* xmax, int32_t* argmax,
+                                     float* const* peer_rep, int n_peers, void* workspace, size_t workspace_bytes,
+                                     sb200_stream_t stream) {
+    if (cu_seqlens == nullptr) return fail(SB200_ERR_ARG, "head_fwd_packed: cu_seqlens is null");
+    return head_fwd_impl(hidden, W, bias, nullptr, 0, cu_seqlens, T, B, max_len, H, V, flags, rep, xmax, argmax, peer_rep,
+                         n_peers, workspace, workspace_bytes, stream);
 }

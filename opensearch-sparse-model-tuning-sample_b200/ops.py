@@ -139,6 +139,114 @@ def head_backward(d_rep, xmax, argmax, hidden, weight, use_l0=False, want_bias_g
     return d_hidden, dW, dbias
 
 
+# --------------------------------------------------------------------------------------------- sparse head, packed input
+def head_packed_supported(hidden_size, max_len):
+    return bool(_lib.load().sb200_head_packed_supported(int(hidden_size), int(max_len)))
+
+
+def _half_flag(hidden, weight, what):
+    if hidden.dtype != weight.dtype or hidden.dtype not in (torch.bfloat16, torch.float16):
+        raise TypeError(f"{what} expects hidden and weight both bf16 or both fp16")
+    return _lib.HEAD_FP16 if hidden.dtype == torch.float16 else 0
+
+
+def head_forward_packed(hidden, cu_seqlens, max_len, weight, bias, use_l0=False, want_aux=True, out=None, peer_ptrs=None):
+    """The fused head on packed hidden states: hidden [T,H] (real tokens only), sequence b = rows
+    [cu_seqlens[b], cu_seqlens[b+1]) (int32 [B+1] on the device). -> (rep [B,V], xmax | None, argmax | None); argmax is
+    the token's rank inside its sequence."""
+    _need_cuda(hidden, weight, bias, cu_seqlens)
+    half = _half_flag(hidden, weight, "head_forward_packed")
+    T, H = hidden.shape
+    V = weight.shape[0]
+    B = cu_seqlens.numel() - 1
+    cu = cu_seqlens.to(torch.int32).contiguous()
+    hidden, weight = hidden.contiguous(), weight.contiguous()
+    if bias is not None:
+        bias = bias.detach().float().contiguous()
+    lib = _lib.load()
+    dev = hidden.device
+    if out is None:
+        rep = torch.empty(B, V, dtype=torch.float32, device=dev)
+    else:
+        if out.dtype != torch.float32 or tuple(out.shape) != (B, V) or not out.is_contiguous():
+            raise ValueError("head_forward_packed: `out` must be a contiguous fp32 [B, V] tensor")
+        rep = out
+    xmax = torch.empty(B, V, dtype=torch.float32, device=dev) if want_aux else None
+    argmax = torch.empty(B, V, dtype=torch.int32, device=dev) if want_aux else None
+    ws = _workspace(lib.sb200_head_fwd_workspace_bytes(B, int(max_len)), dev)
+    peers = list(peer_ptrs or [])
+    c_peers = (_lib.ctypes.c_void_p * max(1, len(peers)))(*peers) if peers else None
+    with torch.cuda.device(dev), _timed("head_fwd"):
+        code = lib.sb200_head_fwd_packed(_ptr(hidden), _ptr(weight), _ptr(bias), _ptr(cu), T, B, int(max_len), H, V,
+                                         (_lib.HEAD_L0 if use_l0 else 0) | half, _ptr(rep), _ptr(xmax), _ptr(argmax),
+                                         c_peers, len(peers), _ptr(ws), ws.numel(), _stream())
+    _lib.check(code, "sb200_head_fwd_packed")
+    return rep, xmax, argmax
+
+
+def head_backward_packed(d_rep, xmax, argmax, hidden, cu_seqlens, max_len, weight, use_l0=False, want_bias_grad=True):
+    """-> (d_hidden [T,H] fp32 packed, dW [V,H] fp32, dbias [V] fp32 | None)"""
+    _need_cuda(d_rep, xmax, argmax, hidden, weight, cu_seqlens)
+    half = _half_flag(hidden, weight, "head_backward_packed")
+    T, H = hidden.shape
+    V = weight.shape[0]
+    B = cu_seqlens.numel() - 1
+    lib = _lib.load()
+    dev = hidden.device
+    d_rep = d_rep.float().contiguous()
+    d_hidden = torch.empty(T, H, dtype=torch.float32, device=dev)
+    dW = torch.empty(V, H, dtype=torch.float32, device=dev)
+    dbias = torch.empty(V, dtype=torch.float32, device=dev) if want_bias_grad else None
+    ws = _workspace(lib.sb200_head_bwd_workspace_bytes(B, int(max_len), H, V), dev)
+    with torch.cuda.device(dev), _timed("head_bwd"):
+        code = lib.sb200_head_bwd_packed(_ptr(d_rep), _ptr(xmax), _ptr(argmax), _ptr(hidden), _ptr(weight),
+                                         _ptr(cu_seqlens), T, B, int(max_len), H, V, (_lib.HEAD_L0 if use_l0 else 0) | half,
+                                         _ptr(d_hidden), _ptr(dW), _ptr(dbias), _ptr(ws), ws.numel(), _stream())
+    _lib.check(code, "sb200_head_bwd_packed")
+    return d_hidden, dW, dbias
+
+
+class SparseHeadPackedFunction(torch.autograd.Function):
+    """SparseHeadFunction on the packed [T,H] activations of the padding-free body (no padded copy in either direction)."""
+
+    @staticmethod
+    def forward(ctx, hidden, cu_seqlens, max_len, weight, bias, use_l0, sink=None):
+        half = torch.bfloat16
+        if hidden.dtype == torch.float16 or (torch.is_autocast_enabled("cuda")
+                                              and torch.get_autocast_dtype("cuda") == torch.float16):
+            half = torch.float16
+        h16 = hidden.detach().to(half).contiguous()
+        w16 = weight.detach().to(half).contiguous()
+        cu = cu_seqlens.to(torch.int32).contiguous()
+        needs_grad = any(t is not None and t.requires_grad for t in (hidden, weight, bias))
+        out = peers = None
+        B = cu.numel() - 1
+        if sink is not None and (sink.rows, sink.width) == (B, w16.shape[0]) and sink.world <= 8:
+            out, peers = sink.slot(), sink.remote_slots()
+        rep, xmax, argmax = head_forward_packed(h16, cu, max_len, w16, bias, use_l0, want_aux=needs_grad, out=out,
+                                                peer_ptrs=peers)
+        if needs_grad:
+            ctx.save_for_backward(h16, w16, xmax, argmax, cu)
+        ctx.use_l0, ctx.max_len = bool(use_l0), int(max_len)
+        ctx.has_bias = bias is not None
+        ctx.in_dtypes = (hidden.dtype, weight.dtype, None if bias is None else bias.dtype)
+        return rep
+
+    @staticmethod
+    def backward(ctx, d_rep):
+        h16, w16, xmax, argmax, cu = ctx.saved_tensors
+        need_h, need_w, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[3], ctx.needs_input_grad[4]
+        d_hidden, dW, dbias = head_backward_packed(d_rep, xmax, argmax, h16, cu, ctx.max_len, w16, ctx.use_l0,
+                                                   want_bias_grad=ctx.has_bias)
+        hd, wd, bd = ctx.in_dtypes
+        return (d_hidden.to(hd) if need_h else None, None, None, dW.to(wd) if need_w else None,
+                dbias.to(bd) if (need_b and ctx.has_bias) else None, None, None)
+
+
+def sparse_head_packed(hidden, cu_seqlens, max_len, weight, bias, use_l0=False, sink=None):
+    return SparseHeadPackedFunction.apply(hidden, cu_seqlens, max_len, weight, bias, use_l0, sink)
+
+
 def prune_rows_(rep, ratio):
     """In-place row pruning (sparse_encoders.py:115-119)."""
     _need_cuda(rep)

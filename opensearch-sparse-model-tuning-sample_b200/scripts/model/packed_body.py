@@ -148,7 +148,7 @@ class PackedBertBody:
             y = self._dense_act(head_transform.dense, head_transform.transform_act_fn, x16)
             ln = head_transform.LayerNorm
             _, x16 = ops.add_layer_norm(y, None, ln.weight, ln.bias, ln.eps, want_f32=False)
-        return x16, (dest.clamp_max(t_cap - 1), src_of, row_valid, (B, L))
+        return x16, (dest.clamp_max(t_cap - 1), src_of, row_valid, (B, L), cu)
 
     @staticmethod
     def _dense_act(dense, act, x16):
@@ -162,5 +162,5 @@ class PackedBertBody:
 
     @staticmethod
     def repad(packed, plan):
-        dest, src_of, row_valid, (B, L) = plan
+        dest, src_of, row_valid, (B, L) = plan[:4]
         return _Repad.apply(packed, dest, src_of, row_valid).view(B, L, packed.shape[-1])

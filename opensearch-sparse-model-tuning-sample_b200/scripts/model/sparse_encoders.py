@@ -162,17 +162,20 @@ class SparseModel(torch.nn.Module):
             self._special_cache[key] = torch.tensor(list(self.special_token_ids), dtype=torch.int32, device=device)
         return self._special_cache[key]
 
+    def _use_packed(self, features):
+        packed = self.__dict__.get("_packed")
+        ids = features.get("input_ids")
+        return (packed is not None and ids is not None and ids.is_cuda and torch.is_autocast_enabled("cuda")
+                and torch.get_autocast_dtype("cuda") == torch.bfloat16)
+
     def head_inputs(self, **features):
         """Runs the backbone up to the decoder input: -> (hidden [B,L,H], decoder Linear)."""
         if self._split is None:
             self._split = _split_mlm_backbone(self.backbone)
-        packed = self.__dict__.get("_packed")
-        ids = features.get("input_ids")
-        if packed is not None and ids is not None and ids.is_cuda and torch.is_autocast_enabled("cuda") \
-                and torch.get_autocast_dtype("cuda") == torch.bfloat16:
+        if self._use_packed(features):
             from .packed_body import PackedBertBody
             # [T_cap, H] bf16, real tokens only, MLM head transform included
-            hidden, plan = packed(head_transform=self.backbone.cls.predictions.transform, **features)
+            hidden, plan = self.__dict__["_packed"](head_transform=self.backbone.cls.predictions.transform, **features)
             return PackedBertBody.repad(hidden, plan), self._split.decoder
         seq = self._split.body(**features)[0]
         return self._split.transform(seq), self._split.decoder
@@ -205,9 +208,20 @@ class SparseModel(torch.nn.Module):
     def _encode(self, _sink=None, **kwargs):
         """`_sink` (B200 extension, not a tokenizer feature): a scripts.peer.PeerSink -- the head kernel then stores its
         rows into every rank's gathered buffer as well (gather_rep fused into the GEMM epilogue)."""
-        hidden, decoder = self.head_inputs(**kwargs)
-        rep = ops.sparse_head(hidden, decoder.weight, decoder.bias, kwargs.get("attention_mask"), use_l0=self.use_l0,
-                              sink=_sink)
+        ids = kwargs.get("input_ids")
+        if self._use_packed(kwargs) and ops.head_packed_supported(self.backbone.config.hidden_size, ids.shape[1]):
+            # padding-free all the way: the head reads the packed [T, H] rows of the body through a 2-D tensor map and
+            # its backward writes packed rows -- no padded [B, L, H] copy in either direction
+            if self._split is None:
+                self._split = _split_mlm_backbone(self.backbone)
+            hidden, plan = self.__dict__["_packed"](head_transform=self.backbone.cls.predictions.transform, **kwargs)
+            decoder = self._split.decoder
+            rep = ops.sparse_head_packed(hidden, plan[4][:ids.shape[0] + 1], ids.shape[1], decoder.weight, decoder.bias,
+                                         use_l0=self.use_l0, sink=_sink)
+        else:
+            hidden, decoder = self.head_inputs(**kwargs)
+            rep = ops.sparse_head(hidden, decoder.weight, decoder.bias, kwargs.get("attention_mask"), use_l0=self.use_l0,
+                                  sink=_sink)
         if self.prune_ratio is None:
             return rep
         return _PruneFunction.apply(rep, float(self.prune_ratio))

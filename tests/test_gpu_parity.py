@@ -122,6 +122,48 @@ def test_head_fp16_operands_vs_oracle(ops, B, L, H, V):
     assert_close(out, want, 1e-4, 2e-5, "sparse_head under fp16 autocast")
 
 
+@pytest.mark.parametrize("B,L,H,V", [(5, 256, 384, 3000), (3, 512, 768, 1500), (4, 200, 64, 700), (2, 1000, 128, 600),
+                                     (6, 129, 256, 900)])
+def test_head_packed_input_matches_padded_and_oracle(ops, B, L, H, V):
+    """Padding-free head: hidden states packed as [T, H] + cu_seqlens give the same representations, arg-max and
+    gradients as the padded [B, L, H] call (and the oracle), with d_hidden returned in packed rows."""
+    hidden, W, bias, mask = make_head_inputs(B, L, H, V, seed=B * 31 + L, shift=-0.3)
+    mask[0] = 1                                   # one sequence without padding
+    lens = mask.sum(1)
+    cu = torch.zeros(B + 1, dtype=torch.int32)
+    cu[1:] = torch.cumsum(lens, 0)
+    filler = torch.randn(24, H).bfloat16()        # rows behind the last sequence (the packed body keeps such rows)
+    packed = torch.cat([hidden[b, :lens[b]] for b in range(B)] + [filler], 0)
+    assert ops.head_packed_supported(H, L)
+    rep_p, xmax_p, amax_p = ops.head_forward_packed(cuda(packed), cuda(cu), L, cuda(W), cuda(bias), use_l0=True)
+    rep, xmax, amax = ops.head_forward(cuda(hidden), cuda(W), cuda(bias), cuda(mask), use_l0=True)
+    assert torch.equal(rep_p, rep) and torch.equal(xmax_p, xmax) and torch.equal(amax_p, amax)
+    want, values, _ = R.sparse_head(hidden.float(), W.float(), bias, mask, use_l0=True)
+    assert_close(rep_p, want, 1e-4, 2e-5, "packed rep vs oracle")
+    g = torch.Generator().manual_seed(4)
+    d_rep = torch.randn(B, V, generator=g)
+    dh_p, dw_p, db_p = ops.head_backward_packed(cuda(d_rep), xmax_p, amax_p, cuda(packed), cuda(cu), L, cuda(W), use_l0=True)
+    dh, dw, db = ops.head_backward(cuda(d_rep), xmax, amax, cuda(hidden), cuda(W), use_l0=True)
+    gh, gw, gb = R.sparse_head_grads(hidden.float(), W.float(), bias, mask, d_rep, use_l0=True)
+    assert_close(dw_p, gw, 1e-4, 1e-5 * float(gw.abs().max()), "packed dW vs oracle")
+    assert_close(db_p, gb, 1e-4, 1e-5 * float(gb.abs().max()), "packed dbias vs oracle")
+    assert_close(dw_p, dw, 1e-5, 1e-6 * float(gw.abs().max()), "packed dW vs padded")
+    for b in range(B):
+        rows = dh_p[int(cu[b]):int(cu[b + 1])]
+        assert_close(rows, gh[b, :lens[b]], 1e-4, 1e-5 * float(gh.abs().max()), "packed d_hidden vs oracle")
+        assert float(dh[b, lens[b]:].abs().max() if lens[b] < L else 0.0) == 0.0
+    assert float(dh_p[int(cu[B]):].abs().max()) == 0.0          # filler rows receive no gradient
+    # autograd entry point
+    pc = cuda(packed).float().requires_grad_(True)
+    wc = cuda(W).float().requires_grad_(True)
+    bc = cuda(bias).requires_grad_(True)
+    out = ops.sparse_head_packed(pc, cuda(cu), L, wc, bc, use_l0=True)
+    (out * cuda(d_rep)).sum().backward()
+    assert_close(out, want, 1e-4, 2e-5, "sparse_head_packed")
+    assert_close(wc.grad, gw, 1e-4, 1e-5 * float(gw.abs().max()), "autograd dW")
+    assert_close(bc.grad, gb, 1e-4, 1e-5 * float(gb.abs().max()), "autograd dbias")
+
+
 def test_head_is_deterministic_and_idempotent(ops):
     hidden, W, bias, mask = make_head_inputs(6, 200, 128, 4000, seed=11)
     a = ops.head_forward(cuda(hidden), cuda(W), cuda(bias), cuda(mask))
