@@ -219,12 +219,17 @@ def dist_parity(trainer, wl, args, device, batch, world, rank):
     out = {}
     try:
         flat = trainer._flat_grads
+        params = [p for p in sm.parameters() if p.requires_grad]
+
+        def grads():
+            return torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).detach().float().flatten()
+                              for p in params])
         trainer._zero_grads()
         loss_dp = trainer._forward_backward(clone_inputs(batch))
         g_dp = None
         if flat is not None:
             trainer._sync_flat_grads()
-            g_dp = flat.clone()
+            g_dp = grads()
 
         def gather_tree(o):
             if torch.is_tensor(o):
@@ -253,7 +258,7 @@ def dist_parity(trainer, wl, args, device, batch, world, rank):
             out = {"loss_dp_over_world": a, "loss_single_process_global_batch": b,
                    "loss_rel_err": abs(a - b) / max(abs(b), 1e-12), "tolerance": 1e-4}
             if g_dp is not None:
-                g1 = flat if flat is not None else None
+                g1 = grads()
                 num = float((g_dp - g1).norm())
                 den = float(g1.norm())
                 out["grad_rel_l2_err"] = num / max(den, 1e-30)

@@ -63,6 +63,38 @@ class _timed:
             self.pair[1].record()
 
 
+# --------------------------------------------------------------------------------------------- half-precision weights
+# Under autocast every Linear re-casts its fp32 master weight to bf16 / fp16 in every forward pass (53 small cast kernels
+# per C2 step, the 23 MB decoder weight among them). refresh_half_weights() does all of them with one multi-tensor copy
+# at the start of a step; the ops below then pick the cached copy up as long as the parameter has not been modified
+# since (tensor version check), and fall back to a private cast otherwise.
+def refresh_half_weights(params, dtype=torch.bfloat16):
+    """params: list of fp32 parameters (any shapes). Creates (once) and refreshes their half-precision copies."""
+    params = [p for p in params if p.is_cuda and p.dtype == torch.float32]
+    if not params:
+        return
+    halves = []
+    for p in params:
+        c = p.__dict__.get("_sb200_half")
+        if c is None or c[0].dtype != dtype or c[0].shape != p.shape:
+            c = [torch.empty_like(p, dtype=dtype), -1]
+            p.__dict__["_sb200_half"] = c
+        halves.append(c[0])
+    torch._foreach_copy_(halves, [p.detach() for p in params])
+    for p in params:
+        p.__dict__["_sb200_half"][1] = p._version
+
+
+def half_weight(weight, dtype):
+    """weight in `dtype`: the cached copy when it is current, a fresh cast otherwise (no-op when already `dtype`)."""
+    if weight.dtype == dtype:
+        return weight.detach()
+    c = weight.__dict__.get("_sb200_half") if hasattr(weight, "__dict__") else None
+    if c is not None and c[0].dtype == dtype and c[1] == weight._version:
+        return c[0]
+    return weight.detach().to(dtype)
+
+
 # --------------------------------------------------------------------------------------------- sparse head
 def head_forward(hidden, weight, bias, attention_mask, use_l0=False, want_aux=True, out=None, peer_ptrs=None):
     """Fused MLM-decoder GEMM + mask + max-pool + log1p(relu) (sparse_encoders.py:108-114).
@@ -216,7 +248,7 @@ class SparseHeadPackedFunction(torch.autograd.Function):
                                               and torch.get_autocast_dtype("cuda") == torch.float16):
             half = torch.float16
         h16 = hidden.detach().to(half).contiguous()
-        w16 = weight.detach().to(half).contiguous()
+        w16 = half_weight(weight, half).contiguous()
         cu = cu_seqlens.to(torch.int32).contiguous()
         needs_grad = any(t is not None and t.requires_grad for t in (hidden, weight, bias))
         out = peers = None
@@ -271,7 +303,7 @@ class SparseHeadFunction(torch.autograd.Function):
                                               and torch.get_autocast_dtype("cuda") == torch.float16):
             half = torch.float16
         h16 = hidden.detach().to(half).contiguous()
-        w16 = weight.detach().to(half).contiguous()
+        w16 = half_weight(weight, half).contiguous()
         needs_grad = any(t is not None and t.requires_grad for t in (hidden, weight, bias))
         out = peers = None
         if sink is not None and (sink.rows, sink.width) == (h16.shape[0], w16.shape[0]) and sink.world <= 8:
@@ -826,7 +858,7 @@ class LinearFunction(torch.autograd.Function):
     def forward(ctx, x, weight, bias):
         # the fp32 master weight is the autograd input: its gradient leaves the weight-gradient GEMM in fp32
         # (bf16 operands, fp32 output) instead of being rounded to bf16 and cast back
-        w = weight if weight.dtype == x.dtype else weight.to(x.dtype)
+        w = half_weight(weight, x.dtype)
         ctx.save_for_backward(x, w)
         ctx.has_bias = bias is not None
         ctx.w_dtype = weight.dtype
@@ -885,7 +917,7 @@ class LinearGeluFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias):
-        w = weight if weight.dtype == x.dtype else weight.to(x.dtype)
+        w = half_weight(weight, x.dtype)
         pre = torch.nn.functional.linear(x, w, None if bias is None else bias.to(x.dtype))
         ctx.save_for_backward(x, w, pre)
         ctx.has_bias = bias is not None

@@ -1,10 +1,10 @@
 """Flat gradient buffer with bucketed all-reduce overlapped with the backward pass (data-parallel training, the
 gradient all-reduce of the reference's DDP wrapper: HF Trainer / accelerate around ``scripts/train/trainer.py``).
 
-All parameter gradients are views of one flat fp32 buffer (static addresses: CUDA-graph friendly). The buffer is cut
-into contiguous buckets; a post-accumulate hook per parameter counts a bucket down and, when its last gradient has
-been accumulated, issues the bucket's all-reduce on a side stream, so that the transfer runs while the backward pass
-of the earlier layers is still computing. ``finish()`` issues whatever is left and makes the compute stream wait for
+All parameter gradients end up as views of one flat fp32 buffer (static addresses: CUDA-graph friendly). The buffer is
+cut into contiguous buckets; a post-accumulate hook per parameter counts a bucket down and, when its last gradient has
+been produced, moves the bucket's gradients into the buffer with one multi-tensor copy and issues the bucket's
+all-reduce on a side stream, so that the transfer runs while the backward pass of the earlier layers is still computing. ``finish()`` issues whatever is left and makes the compute stream wait for
 the side stream. Inside a CUDA-graph capture the side stream is forked from and joined back into the capturing
 stream, so the collectives become nodes of the same graph. The mean over ranks is taken by NCCL (``ReduceOp.AVG``).
 
@@ -26,8 +26,9 @@ class FlatGradBuckets:
         total = sum(p.numel() for p in self.params)
         self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
         spans, off = [], 0
+        self.views = []
         for p in self.params:
-            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            self.views.append(self.flat[off:off + p.numel()].view_as(p))
             spans.append((off, off + p.numel()))
             off += p.numel()
         # buckets are cut from the END of the buffer: the gradients of the last layers are produced first
@@ -42,18 +43,21 @@ class FlatGradBuckets:
                 i -= 1
             self.bounds.append((lo, hi))
             hi = lo
-        self._count = [0] * len(self.bounds)
-        for b in self.bucket_of:
-            self._count[b] += 1
+        self.members = [[] for _ in self.bounds]
+        for idx, b in enumerate(self.bucket_of):
+            self.members[b].append(idx)
+        self._count = [len(m) for m in self.members]
         self._left = list(self._count)
         self._launched = [False] * len(self.bounds)
-        self.comm_stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
+        self.overlap = bool(overlap)
+        self.comm_stream = torch.cuda.Stream(device=dev) if (dev.type == "cuda" and overlap) else None
         self._use_avg = dev.type == "cuda" and dist.is_initialized() and dist.get_backend(group) == "nccl"
         self._handles = []
         self.enabled = True     # False: the hooks do nothing (a backward pass that is not part of a data-parallel step)
         if overlap:
             for idx, p in enumerate(self.params):
                 self._handles.append(p.register_post_accumulate_grad_hook(self._make_hook(idx)))
+        self.prepare()
 
     def _make_hook(self, idx):
         def hook(param):
@@ -74,32 +78,50 @@ class FlatGradBuckets:
             dist.all_reduce(t, group=self.group)
             t.div_(self.world)
 
+    def prepare(self):
+        """Start of a step: every .grad is dropped, so the backward pass WRITES fresh gradient tensors (autograd would
+        otherwise add into the flat views with one elementwise kernel per parameter: 107 launches / 0.28 ms per C2 step).
+        They are moved into the flat buffer bucket by bucket with one multi-tensor copy each (_launch)."""
+        for p in self.params:
+            p.grad = None
+        self._left = list(self._count)
+        self._launched = [False] * len(self.bounds)
+
+    zero = prepare
+
     def _launch(self, b):
         if self._launched[b]:
             return
         self._launched[b] = True
         lo, hi = self.bounds[b]
+        src, dst = [], []
+        for idx in self.members[b]:
+            p, view = self.params[idx], self.views[idx]
+            if p.grad is None:
+                view.zero_()                 # no gradient this step (same on every rank): contributes zeros
+            elif p.grad.data_ptr() != view.data_ptr():
+                src.append(p.grad)
+                dst.append(view)
+            p.grad = view
+        if src:
+            torch._foreach_copy_(dst, src)
         t = self.flat[lo:hi]
         if self.comm_stream is None:
             self._all_reduce(t)
             return
-        # the gradient was accumulated on the stream that is current inside the hook (the autograd engine sets it)
+        # the gradients were produced on the stream that is current inside the hook (the autograd engine sets it)
         self.comm_stream.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(self.comm_stream):
             self._all_reduce(t)
 
-    def zero(self):
-        self.flat.zero_()
-
     def finish(self):
-        """After backward: all-reduce the buckets whose hooks did not complete (parameters without a gradient in this
-        step), in bucket order on every rank, then make the current stream wait for the communication stream."""
+        """After backward: moves and all-reduces the buckets whose hooks did not complete (parameters without a
+        gradient in this step; every bucket when overlap is off), in bucket order on every rank, then makes the current
+        stream wait for the communication stream. Afterwards every .grad is its view of the flat buffer."""
         for b in range(len(self.bounds)):
             self._launch(b)
         if self.comm_stream is not None:
             torch.cuda.current_stream(self.device).wait_stream(self.comm_stream)
-        self._left = list(self._count)
-        self._launched = [False] * len(self.bounds)
 
     def remove_hooks(self):
         for h in self._handles:

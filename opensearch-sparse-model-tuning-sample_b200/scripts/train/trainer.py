@@ -95,12 +95,12 @@ class SparseModelTrainer:
             dev = next(wrapper.parameters()).device
             self.model = torch.nn.parallel.DistributedDataParallel(wrapper, device_ids=[dev.index],
                                                                    gradient_as_bucket_view=True)
-        elif self.grad_sync == "flat":
-            self._setup_flat_grads()
-        elif self.grad_sync == "flat_overlap":
+        elif self.grad_sync in ("flat", "flat_overlap"):
             from .flat_grads import FlatGradBuckets
+            overlap = self.grad_sync == "flat_overlap"
             self._buckets = FlatGradBuckets(self.model_wrapper.parameters(), self.accelerator.num_processes,
-                                            group=getattr(self.accelerator, "group", None))
+                                            group=getattr(self.accelerator, "group", None), overlap=overlap,
+                                            bucket_bytes=(24 << 20) if overlap else (1 << 62))
             self._flat_grads = self._buckets.flat
         self.scaler = None
         if args is not None and getattr(args, "fp16", False):
@@ -112,6 +112,7 @@ class SparseModelTrainer:
         self._step_t = None
         self._ovf_host = None
         self._ovf_event = None
+        self._half_params = None
 
     # ------------------------------------------------------------------ reference attribute, without a per-step sync
     @property
@@ -234,34 +235,16 @@ class SparseModelTrainer:
             return torch.autocast("cuda", dtype=torch.bfloat16)
         return contextlib.nullcontext()
 
-    def _setup_flat_grads(self):
-        """All parameter gradients become views of one flat fp32 buffer (one all-reduce, static addresses)."""
-        params = [p for p in self.model_wrapper.parameters() if p.requires_grad]
-        total = sum(p.numel() for p in params)
-        self._flat_grads = torch.zeros(total, dtype=torch.float32, device=params[0].device)
-        off = 0
-        for p in params:
-            p.grad = self._flat_grads[off:off + p.numel()].view_as(p)
-            off += p.numel()
-
     def _zero_grads(self):
-        if self._flat_grads is not None:
-            self._flat_grads.zero_()
+        if self._buckets is not None:
+            self._buckets.prepare()     # gradients are written (not accumulated) and moved into the flat buffer per bucket
         else:
             self.optimizer.zero_grad(set_to_none=True)
 
     def _sync_flat_grads(self):
-        """One NCCL all-reduce of the flat gradient buffer; mean over ranks like DDP (the loss carries x world)."""
-        if self._buckets is not None:   # "flat_overlap": most buckets are already in flight; issue the rest and join
-            self._buckets.finish()
-            return
-        import torch.distributed as dist
-        group = getattr(self.accelerator, "group", None)
-        if self._flat_grads.is_cuda and dist.get_backend(group) == "nccl":
-            dist.all_reduce(self._flat_grads, op=dist.ReduceOp.AVG, group=group)   # mean taken inside NCCL
-        else:
-            dist.all_reduce(self._flat_grads, group=group)
-            self._flat_grads.div_(self.accelerator.num_processes)
+        """Moves the remaining gradients into the flat buffer and all-reduces them (mean over ranks, like DDP; the loss
+        carries x world). "flat": one all-reduce; "flat_overlap": most buckets are already in flight."""
+        self._buckets.finish()
 
     def _forward_backward(self, inputs):
         """forward (autocast) + loss + backward; gradients are left in .grad (not yet synchronised in "flat" mode)."""
@@ -270,6 +253,7 @@ class SparseModelTrainer:
                 return self.model(student)
 
         self.model_wrapper.sparse_model.unpad_step_reset()
+        self._refresh_half_weights()
         if hasattr(self.accelerator, "begin_step"):
             self.accelerator.begin_step()      # peer-memory gather sites are numbered per step
         loss = self.compute_loss(run, inputs)
@@ -283,6 +267,22 @@ class SparseModelTrainer:
         if hasattr(self.accelerator, "end_step"):
             self.accelerator.end_step()
         return loss
+
+    def _refresh_half_weights(self):
+        """One multi-tensor cast of the matrix parameters to the autocast dtype at the start of the step instead of one
+        cast kernel per Linear per forward pass (ops.refresh_half_weights / ops.half_weight)."""
+        if self.args is None or not next(self.model_wrapper.parameters()).is_cuda:
+            return
+        if getattr(self.args, "fp16", False):
+            dtype = torch.float16
+        elif getattr(self.args, "bf16", False):
+            dtype = torch.bfloat16
+        else:
+            return
+        if self._half_params is None:
+            self._half_params = [p for p in self.model_wrapper.sparse_model.backbone.parameters()
+                                 if p.dim() == 2 and p.dtype == torch.float32]
+        ops.refresh_half_weights(self._half_params, dtype)
 
     def _optimizer_step(self):
         """optimizer.step(), skipped ON THE DEVICE for a batch that overflowed the packed-body capacity: the fused
@@ -414,7 +414,7 @@ class SparseModelTrainer:
         else:
             self.model.train()
             if self._flat_grads is not None:
-                self._flat_grads.zero_()
+                self._zero_grads()
             loss = self._eager_step_body(inputs).detach()
             if self._flat_grads is None:
                 self.optimizer.zero_grad(set_to_none=True)

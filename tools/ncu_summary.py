@@ -34,5 +34,35 @@ def main(path):
             print(f"    {a:70s} {b}")
 
 
+def traffic(path, key, out_json, pattern="head_fwd_kernel"):
+    """Records dram__bytes_read.sum + dram__bytes_write.sum of the first `pattern` launch of the capture under `key`
+    (e.g. mini_L256_B160) in out_json -- bench.py reads roofline.traffic from that file."""
+    import json
+    import os
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units = rows[0], rows[1]
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for r in rows[2:]:
+        if pattern in r[hdr.index("Kernel Name")]:
+            total = 0.0
+            for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                total += float(r[hdr.index(m)]) * scale[units[hdr.index(m)]]
+            table = {}
+            if os.path.exists(out_json):
+                with open(out_json) as f:
+                    table = json.load(f)
+            table[key] = {"dram_bytes": total, "source": f"ncu --set full capture {os.path.basename(path)} "
+                                                         f"(summary: profiles/r02_ncu_full_kernels_c2.txt), kernel {pattern}"}
+            with open(out_json, "w") as f:
+                json.dump(table, f, indent=1)
+            print(key, total)
+            return
+    raise SystemExit(f"no {pattern} launch in {path}")
+
+
 if __name__ == "__main__":
-    main(sys.argv[1])
+    if len(sys.argv) >= 5 and sys.argv[2] == "--traffic":
+        traffic(sys.argv[1], sys.argv[3], sys.argv[4])
+    else:
+        main(sys.argv[1])
