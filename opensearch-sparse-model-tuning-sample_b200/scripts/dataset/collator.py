@@ -32,8 +32,9 @@ class _TextCollator:
     def _encode_all(self, queries, docs):
         kw = dict(padding=True, truncation=True, max_length=self.max_length, return_tensors="pt",
                   return_token_type_ids=False)
-        return {"query": [tok(list(queries), **kw) for tok in self.tokenizers],
-                "docs": [tok(list(docs), **kw) for tok in self.tokenizers]}
+        queries, docs = list(queries), list(docs)      # every tokenizer sees the same texts (docs may be an iterator)
+        return {"query": [tok(queries, **kw) for tok in self.tokenizers],
+                "docs": [tok(docs, **kw) for tok in self.tokenizers]}
 
 
 class KnowledgeDistillDataCollator(_TextCollator):

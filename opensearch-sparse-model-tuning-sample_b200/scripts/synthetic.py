@@ -35,6 +35,25 @@ class SyntheticTokenizer:
     def _convert_token_to_id_with_added_voc(self, token):
         return self.vocab[token]
 
+    def __call__(self, texts, padding=True, truncation=True, max_length=512, return_tensors="pt",
+                 return_token_type_ids=False, **unused):
+        """Whitespace "tokenisation" with the HF call signature (offline stand-in): every word is hashed (crc32) to a
+        non-special id; [CLS] ... [SEP], right-padded with [PAD] to the longest text of the batch."""
+        import zlib
+        V = len(self.vocab)
+        low = min(1000, V // 2)
+        rows = []
+        for t in texts:
+            ids = [low + zlib.crc32(w.encode()) % (V - low) for w in t.split()][:max(0, max_length - 2)]
+            rows.append([min(101, V - 1)] + ids + [min(102, V - 1)])
+        width = max(len(r) for r in rows)
+        out_ids = torch.zeros(len(rows), width, dtype=torch.long)
+        mask = torch.zeros(len(rows), width, dtype=torch.long)
+        for i, r in enumerate(rows):
+            out_ids[i, :len(r)] = torch.tensor(r)
+            mask[i, :len(r)] = 1
+        return {"input_ids": out_ids, "attention_mask": mask}
+
     def _convert_id_to_token(self, idx):
         return self._inv[int(idx)]
 

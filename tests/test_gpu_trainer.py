@@ -240,8 +240,9 @@ def test_fp16_autocast_training_step_runs():
     assert all(torch.isfinite(p).all() for p in model.parameters())
 
 
-@pytest.mark.parametrize("capacity,mask_kind", [(1.0, "prefix"), (0.9, "prefix"), (1.0, "holes")])
-def test_padding_free_body_matches_padded_body(capacity, mask_kind):
+@pytest.mark.parametrize("capacity,mask_kind,L", [(1.0, "prefix", 96), (0.9, "prefix", 96), (1.0, "holes", 96),
+                                                    (0.9, "prefix", 192), (1.0, "holes", 192)])   # L > 128: packed head too
+def test_padding_free_body_matches_padded_body(capacity, mask_kind, L):
     """The packed (unpadded, flash-attn varlen) body gives the same sparse vectors and gradients as the padded
     transformers body on the real tokens."""
     import sparse_b200  # noqa: F401
@@ -254,7 +255,7 @@ def test_padding_free_body_matches_padded_body(capacity, mask_kind):
         pytest.skip("flash_attn varlen kernels unavailable")
     assert packed.state_dict().keys() == padded.state_dict().keys()
     padded.load_state_dict(packed.state_dict())
-    feats = synthetic.token_batch(12, 96, seed=2, vocab_size=V, device="cuda")
+    feats = synthetic.token_batch(12, L, seed=2, vocab_size=V, device="cuda")
     if mask_kind == "holes":
         feats["attention_mask"][:, 5::7] = 0
     g = torch.Generator(device="cuda").manual_seed(0)
@@ -277,3 +278,70 @@ def test_padding_free_body_matches_padded_body(capacity, mask_kind):
     with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
         tight(inf_free=False, **feats)
     assert tight.unpad_overflows() == 1
+
+
+def test_overflowed_packed_batch_never_reaches_the_weights():
+    """unpad_capacity too small for the batch: the step runs (no host sync inside it), but the fused optimizer skips the
+    update on the device flag -- weights, moments and step counts untouched -- and the trainer raises afterwards."""
+    import sparse_b200  # noqa: F401
+    from sparse_b200.scripts import synthetic
+    from sparse_b200.scripts.args import DataTrainingArguments, ModelArguments, TrainingArguments
+    from sparse_b200.scripts.train.loss import LOSS_CLS_MAP
+    from sparse_b200.scripts.train.trainer import SparseModelTrainer
+    V = 2000
+    model = synthetic.build_sparse_model("mini", vocab_size=V, bias_shift=-0.1, dropout=0.0, unpad_capacity=0.9).cuda()
+    if model.__dict__["_packed"] is None:
+        pytest.skip("flash_attn varlen kernels unavailable")
+    targs = TrainingArguments(bf16=True, learning_rate=1e-3, logging_steps=10 ** 9, max_grad_norm=None, max_steps=10)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, fused=True)
+    tr = SparseModelTrainer(ModelArguments(inf_free=True), DataTrainingArguments(loss_types=["infonce"], use_in_batch_negatives=True,
+                                                                                 flops_d_lambda=0.05, flops_d_T=10),
+                            [LOSS_CLS_MAP["infonce"](use_in_batch_negatives=True)], model=model, args=targs, optimizers=(opt, None))
+    ok = synthetic.train_batch(4, 3, 192, query_len=12, vocab_size=V, seed=300, device="cuda")      # lengths in [L/2, L]
+    full = synthetic.train_batch(4, 3, 192, query_len=12, vocab_size=V, seed=301, device="cuda")
+    full["docs"][0]["attention_mask"][:] = 1                                                         # 100 % real tokens > 0.9
+    before = [p.detach().clone() for p in model.parameters()]
+    tr.training_step(ok)
+    tr.check_unpad()
+    after_ok = [p.detach().clone() for p in model.parameters()]
+    assert any(not torch.equal(a, b) for a, b in zip(before, after_ok)), "a fitting batch must train"
+    tr.training_step(full)
+    torch.cuda.synchronize()
+    assert all(torch.equal(a, p.detach()) for a, p in zip(after_ok, model.parameters())), "overflowed batch leaked into the weights"
+    with pytest.raises(RuntimeError, match="unpad_capacity"):
+        tr.check_unpad()
+    with pytest.raises(RuntimeError, match="unpad_capacity"):
+        tr.training_step(ok)          # the asynchronous per-step poll has seen the counter by now
+
+
+def test_train_ir_on_text_rows_and_encode_texts(tmp_path):
+    """The reference's `data_type: posnegs` pipeline end to end (dataset -> collator -> prefetch -> training steps) with
+    the offline stand-in tokenizer, then SparseEncoder.encode on raw texts (tokenizer half included)."""
+    import json
+    import sparse_b200  # noqa: F401
+    from sparse_b200 import train_ir
+    from sparse_b200.scripts import synthetic
+    from sparse_b200.scripts.model.sparse_encoders import SparseEncoder
+    V = 1500
+    path = tmp_path / "train.jsonl"
+    with open(path, "w") as f:
+        for i in range(12):
+            f.write(json.dumps({"query": f"what is item {i}", "pos": f"item {i} is a thing with number {i}",
+                                "negs": [f"unrelated text {i} {k} about something else entirely" for k in range(4)]}) + "\n")
+    argv = ["--output_dir", str(tmp_path / "out"), "--data_type", "posnegs", "--train_file", str(path),
+            "--loss_types", "[infonce]", "--use_in_batch_negatives", "true", "--sample_num_one_query", "2",
+            "--max_seq_length", "24", "--per_device_train_batch_size", "4", "--max_steps", "4", "--bf16", "true",
+            "--logging_steps", "2", "--save_strategy", "no", "--flops_d_lambda", "0.01", "--flops_d_T", "10",
+            "--learning_rate", "1e-4", "--dataloader_drop_last", "true"]
+    trainer = train_ir.main(argv, backbone=synthetic.build_backbone("tiny", V, dropout=0.0),
+                            tokenizer=synthetic.SyntheticTokenizer(V))
+    assert trainer.state.global_step == 4
+    assert float(trainer.ranking_loss_moving_avg) > 0
+    model = trainer.model_wrapper.sparse_model.eval()
+    enc = SparseEncoder(model, max_length=24)
+    out = enc.encode(["item 3 is a thing", "unrelated text about something"])
+    assert len(out) == 2 and all(isinstance(d, dict) for d in out)
+    assert all(w > 0 for d in out for w in d.values())
+    q = enc.encode(["what is item 3"], inf_free=True)[0]
+    assert set(q) <= {"tok%d" % i for i in range(V)} and 1 <= len(q) <= 4      # 4 words (hash collisions may merge two)
+    assert all(w == 1.0 for w in q.values())                                     # default idf weight, specials dropped
