@@ -726,7 +726,7 @@ def cpu_baseline(wl, args, seconds=20.0):
 
 def run_reference(args):
     """The reference arm: the reference's CPU implementation of the same full-size step (same `config`) on the host
-    cores. --steps / --warmup are honoured up to a wall-clock cap (--ref-seconds, default 270 s for the whole run): if
+    cores. --steps / --warmup are honoured up to a wall-clock cap (--ref-seconds, default 400 s for the whole run): if
     the projected time exceeds it, first the warm-ups beyond one, then the timed steps are cut; the line states the
     numbers actually run."""
     rank = int(os.environ.get("RANK", "0"))
@@ -832,7 +832,7 @@ def main():
     ap.add_argument("--no-unfused", action="store_true", help="skip the unfused PyTorch GPU step in `extras`")
     ap.add_argument("--no-dist-parity", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
-    ap.add_argument("--ref-seconds", type=float, default=270.0)
+    ap.add_argument("--ref-seconds", type=float, default=400.0)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

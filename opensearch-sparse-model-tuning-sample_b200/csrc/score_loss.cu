@@ -144,6 +144,97 @@ scores_tile_kernel(const float* __restrict__ q, const float* __restrict__ d, int
     }
 }
 
+// Dense fallback on the legacy tensor-core path: the same 64x64 tile / split-K scheme, but the inner product runs as
+// mma.sync.m16n8k8 TF32 with the 3xTF32 split (x = hi + lo, both TF32; lo*hi + hi*lo + hi*hi, small terms first), which
+// keeps fp32-level accuracy (the reference multiplies in fp32 with TF32 off). 8 warps = 4 (query rows) x 2 (doc rows);
+// a warp owns a 16 x 32 patch = 4 MMA n-tiles. Shared-memory rows are padded to 36 floats: every fragment load of a warp
+// hits 32 different banks. Needs 8-byte aligned rows (V even); other shapes use the CUDA-core kernel above.
+constexpr int kMmaStride = kSK + 4;
+
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+    const float rest = x - __uint_as_float(hi);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(rest));
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+__global__ void __launch_bounds__(256)
+scores_tile_mma_kernel(const float* __restrict__ q, const float* __restrict__ d, int Nq, int Nd, int V, int kchunk,
+                       const int* __restrict__ dense_flag, float* __restrict__ S) {
+    __shared__ __align__(16) float qs[kST * kMmaStride];
+    __shared__ __align__(16) float ds[kST * kMmaStride];
+    if (dense_flag != nullptr && *dense_flag == 0) return;  // the sparse-query kernel produced S
+    const int i0 = blockIdx.y * kST, j0 = blockIdx.x * kST;
+    const int k_begin = blockIdx.z * kchunk;
+    const int k_end = min(V, k_begin + kchunk);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wr = warp >> 1, wc = warp & 1;        // 4 x 2 warps
+    const int g = lane >> 2, t = lane & 3;
+    float acc[4][4];
+#pragma unroll
+    for (int n = 0; n < 4; ++n)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[n][e] = 0.f;
+
+    for (int k0 = k_begin; k0 < k_end; k0 += kSK) {
+        float2 qv[4], dv[4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {               // 64 rows x 16 float2 per operand, 4 per thread
+            const int idx = threadIdx.x + 256 * p;
+            const int r = idx >> 4, k = k0 + 2 * (idx & 15);
+            const bool k_ok = k < k_end;            // k_end is even (V even, kchunk a multiple of 32)
+            qv[p] = (k_ok && i0 + r < Nq) ? __ldg(reinterpret_cast<const float2*>(q + size_t(i0 + r) * V + k))
+                                          : make_float2(0.f, 0.f);
+            dv[p] = (k_ok && j0 + r < Nd) ? __ldg(reinterpret_cast<const float2*>(d + size_t(j0 + r) * V + k))
+                                          : make_float2(0.f, 0.f);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const int idx = threadIdx.x + 256 * p;
+            const int r = idx >> 4, c = 2 * (idx & 15);
+            *reinterpret_cast<float2*>(&qs[r * kMmaStride + c]) = qv[p];
+            *reinterpret_cast<float2*>(&ds[r * kMmaStride + c]) = dv[p];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < kSK / 8; ++kk) {
+            uint32_t a_hi[4], a_lo[4];
+            const float* ap = qs + (wr * 16 + g) * kMmaStride + kk * 8 + t;
+            split_tf32(ap[0], a_hi[0], a_lo[0]);
+            split_tf32(ap[8 * kMmaStride], a_hi[1], a_lo[1]);
+            split_tf32(ap[4], a_hi[2], a_lo[2]);
+            split_tf32(ap[8 * kMmaStride + 4], a_hi[3], a_lo[3]);
+#pragma unroll
+            for (int n = 0; n < 4; ++n) {
+                uint32_t b_hi[2], b_lo[2];
+                const float* bp = ds + (wc * 32 + n * 8 + g) * kMmaStride + kk * 8 + t;
+                split_tf32(bp[0], b_hi[0], b_lo[0]);
+                split_tf32(bp[4], b_hi[1], b_lo[1]);
+                mma_tf32(acc[n], a_lo, b_hi);
+                mma_tf32(acc[n], a_hi, b_lo);
+                mma_tf32(acc[n], a_hi, b_hi);
+            }
+        }
+    }
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int i = i0 + wr * 16 + g + ((e & 2) ? 8 : 0);
+            const int j = j0 + wc * 32 + n * 8 + 2 * t + (e & 1);
+            if (i < Nq && j < Nd) {
+                if (gridDim.z == 1) S[size_t(i) * Nd + j] = acc[n][e];
+                else atomicAdd(S + size_t(i) * Nd + j, acc[n][e]);
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------ ranking-loss row
 // Loss contribution of query row i (already scaled by the batch mean) and, if g != nullptr, d loss / d S[i, :].
 // Result valid in thread 0. All THREADS threads of the block must call it. loss.py:33-42, 64-76, 94-106.
@@ -771,20 +862,44 @@ scores_group_bwd_q_kernel(const float* __restrict__ dS, const float* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------ CSR compaction
-// Three passes, all parallel over (row, 1024-column segment): count non-zeros per segment, scan the counts (one block),
-// ordered fill inside each segment (ballot/popc), so columns stay ascending inside a row (= torch.nonzero order).
-constexpr int kSeg = 1024;
+// Two streaming passes with one block per row (8-byte loads, 8 of them in flight per thread) around a one-block scan of
+// the row counts: count the non-zeros of every row; ordered fill (each thread owns 4 consecutive columns of a 4096-column
+// chunk, block scan of the per-thread counts), so columns stay ascending inside a row (= torch.nonzero order).
+constexpr int kSeg = 1024;            // legacy segment width, still used by the scan kernel's interface (nseg = 1 here)
+constexpr int kCsrThreads = 1024;
 
-__global__ void __launch_bounds__(256)
-compact_count_kernel(const float* __restrict__ rep, int V, int first_col, int nseg, int* __restrict__ segcnt) {
-    __shared__ float red[8];
-    const int b = blockIdx.y, sgm = blockIdx.x;
-    const float* row = rep + size_t(b) * V;
-    const int c0 = max(first_col, sgm * kSeg), c1 = min(V, (sgm + 1) * kSeg);
-    float c = 0.f;
-    for (int v = c0 + threadIdx.x; v < c1; v += 256) c += (__ldg(row + v) != 0.f) ? 1.f : 0.f;
-    c = block_sum<256>(c, red);
-    if (threadIdx.x == 0) segcnt[b * nseg + sgm] = int(c);
+// loads elements [c, c+4) of a row (c % 4 == 0), zero beyond V / below first handled by the caller
+__device__ __forceinline__ void load4(const float* __restrict__ row, int c, int V, bool vec2, float (&x)[4]) {
+    if (vec2 && c + 4 <= V) {
+        const float2 a = __ldg(reinterpret_cast<const float2*>(row + c));
+        const float2 b = __ldg(reinterpret_cast<const float2*>(row + c + 2));
+        x[0] = a.x; x[1] = a.y; x[2] = b.x; x[3] = b.y;
+    } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) x[e] = (c + e < V) ? __ldg(row + c + e) : 0.f;
+    }
+}
+
+__global__ void __launch_bounds__(kCsrThreads)
+compact_count_kernel(const float* __restrict__ rep, int V, int first_col, int* __restrict__ rowcnt) {
+    __shared__ float red[kCsrThreads / 32];
+    const float* row = rep + size_t(blockIdx.x) * V;
+    const bool vec2 = (reinterpret_cast<uintptr_t>(row) & 7) == 0;
+    int cnt = 0;
+    for (int c0 = 0; c0 < V; c0 += kCsrThreads * 4 * 2) {       // two chunks (8 eight-byte loads) in flight per thread
+        float x[2][4];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) load4(row, c0 + u * kCsrThreads * 4 + threadIdx.x * 4, V, vec2, x[u]);
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int v = c0 + u * kCsrThreads * 4 + threadIdx.x * 4 + e;
+                cnt += (v >= first_col && x[u][e] != 0.f) ? 1 : 0;
+            }
+    }
+    const float total = block_sum<kCsrThreads>(float(cnt), red);   // exact: counts < 2^24
+    if (threadIdx.x == 0) rowcnt[blockIdx.x] = int(total);
 }
 
 // exclusive scan of n counts -> offsets; row_ptr[b] = offset of the row's first segment; row_ptr[B] = total
@@ -830,38 +945,56 @@ compact_scan_kernel(const int* __restrict__ counts, int n, int nseg, int B, int*
     if (threadIdx.x == 0) row_ptr[B] = carry_s;
 }
 
-__global__ void __launch_bounds__(256)
-compact_fill_kernel(const float* __restrict__ rep, int V, int first_col, int nseg, const int* __restrict__ offsets,
+__global__ void __launch_bounds__(kCsrThreads)
+compact_fill_kernel(const float* __restrict__ rep, int V, int first_col, const int* __restrict__ offsets,
                     int32_t* __restrict__ cols, float* __restrict__ vals, int capacity,
                     unsigned long long* __restrict__ df_count) {
-    __shared__ int warp_cnt[8];
-    const int b = blockIdx.y, sgm = blockIdx.x;
+    __shared__ int warp_tot[kCsrThreads / 32];
+    const int b = blockIdx.x;
     const float* row = rep + size_t(b) * V;
+    const bool vec2 = (reinterpret_cast<uintptr_t>(row) & 7) == 0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int base = offsets[b * nseg + sgm];
-    const int c1 = min(V, (sgm + 1) * kSeg);
-    for (int v0 = sgm * kSeg; v0 < c1; v0 += 256) {
-        const int v = v0 + threadIdx.x;
-        const float x = (v < c1) ? __ldg(row + v) : 0.f;
-        // document frequency counts every column; only columns >= first_col are compacted
-        if (df_count != nullptr && x > 0.f) atomicAdd(df_count + v, 1ull);
-        const bool nz = (v >= first_col) && x != 0.f;
-        const uint32_t bal = __ballot_sync(0xffffffffu, nz);
-        __syncthreads();
-        if (lane == 0) warp_cnt[warp] = __popc(bal);
-        __syncthreads();
-        int off = base, tot = 0;
+    int base = offsets[b];
+    for (int c0 = 0; c0 < V; c0 += kCsrThreads * 4) {
+        const int c = c0 + threadIdx.x * 4;
+        float x[4];
+        load4(row, c, V, vec2, x);
+        int mine = 0;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) {
-            if (w < warp) off += warp_cnt[w];
-            tot += warp_cnt[w];
+        for (int e = 0; e < 4; ++e) {
+            // document frequency counts every column; only columns >= first_col are compacted
+            if (df_count != nullptr && x[e] > 0.f) atomicAdd(df_count + c + e, 1ull);
+            mine += (c + e >= first_col && x[e] != 0.f) ? 1 : 0;
         }
-        off += __popc(bal & ((1u << lane) - 1u));
-        if (nz && off < capacity) {
-            cols[off] = v;
-            vals[off] = x;
+        int incl = mine;                                        // block-exclusive scan of the per-thread counts
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
         }
-        base += tot;
+        __syncthreads();
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        const int wv = warp_tot[lane];                          // 32 warps: lane w holds warp w's total
+        int winc = wv;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += t;
+        }
+        const int chunk_total = __shfl_sync(0xffffffffu, winc, 31);
+        int off = base + __shfl_sync(0xffffffffu, winc - wv, warp) + incl - mine;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            if (c + e >= first_col && x[e] != 0.f) {
+                if (off < capacity) {
+                    cols[off] = c + e;
+                    vals[off] = x[e];
+                }
+                ++off;
+            }
+        }
+        base += chunk_total;
     }
 }
 
@@ -997,7 +1130,9 @@ static int launch_dense_scores(const float* q, const float* d, int Nq, int Nd, i
             SB200_CUDA(cudaMemsetAsync(S, 0, size_t(Nq) * Nd * sizeof(float), stream));
         }
     }
-    scores_tile_kernel<<<dim3(tj, ti, ks), 256, 0, stream>>>(q, d, Nq, Nd, V, kchunk, dense_flag, S);
+    const bool mma_ok = (V % 2 == 0) && ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(d)) & 7) == 0;
+    if (mma_ok) scores_tile_mma_kernel<<<dim3(tj, ti, ks), 256, 0, stream>>>(q, d, Nq, Nd, V, kchunk, dense_flag, S);
+    else scores_tile_kernel<<<dim3(tj, ti, ks), 256, 0, stream>>>(q, d, Nq, Nd, V, kchunk, dense_flag, S);
     SB200_CHECK_LAUNCH("scores_tile_kernel");
     return SB200_OK;
 }
@@ -1188,8 +1323,7 @@ extern "C" int sb200_rank_loss(int mode, const float* S, const float* teacher, i
 
 extern "C" size_t sb200_compact_workspace_bytes(int B, int V) {
     if (B <= 0 || V <= 0) return 0;
-    const size_t nseg = size_t((V + kSeg - 1) / kSeg);
-    return 2 * align_up(size_t(B) * nseg * sizeof(int), 256);
+    return 2 * align_up(size_t(B) * sizeof(int), 256);     // row counts, row offsets
 }
 
 extern "C" int sb200_compact_rows(const float* rep, int B, int V, int first_col, int32_t* row_ptr, int32_t* cols,
@@ -1197,18 +1331,17 @@ extern "C" int sb200_compact_rows(const float* rep, int B, int V, int first_col,
                                   sb200_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     SB200_REQUIRE(rep && row_ptr && cols && vals, "compact_rows: null pointer");
-    SB200_REQUIRE(B >= 1 && B <= 65535 && V >= 1 && first_col >= 0 && capacity >= 0, "compact_rows: bad shape");
+    SB200_REQUIRE(B >= 1 && V >= 1 && first_col >= 0 && capacity >= 0, "compact_rows: bad shape");
     if (workspace == nullptr || workspace_bytes < sb200_compact_workspace_bytes(B, V))
         return fail(SB200_ERR_WORKSPACE, "compact_rows: workspace too small");
-    const int nseg = (V + kSeg - 1) / kSeg;
-    int* segcnt = static_cast<int*>(workspace);
-    int* segoff = reinterpret_cast<int*>(static_cast<uint8_t*>(workspace) + align_up(size_t(B) * nseg * sizeof(int), 256));
-    compact_count_kernel<<<dim3(nseg, B), 256, 0, stream>>>(rep, V, first_col, nseg, segcnt);
+    int* rowcnt = static_cast<int*>(workspace);
+    int* rowoff = reinterpret_cast<int*>(static_cast<uint8_t*>(workspace) + align_up(size_t(B) * sizeof(int), 256));
+    compact_count_kernel<<<B, kCsrThreads, 0, stream>>>(rep, V, first_col, rowcnt);
     SB200_CHECK_LAUNCH("compact_count_kernel");
-    compact_scan_kernel<<<1, 1024, 0, stream>>>(segcnt, B * nseg, nseg, B, segoff, row_ptr);
+    compact_scan_kernel<<<1, 1024, 0, stream>>>(rowcnt, B, 1, B, rowoff, row_ptr);
     SB200_CHECK_LAUNCH("compact_scan_kernel");
-    compact_fill_kernel<<<dim3(nseg, B), 256, 0, stream>>>(rep, V, first_col, nseg, segoff, cols, vals, capacity,
-                                                           reinterpret_cast<unsigned long long*>(df_count));
+    compact_fill_kernel<<<B, kCsrThreads, 0, stream>>>(rep, V, first_col, rowoff, cols, vals, capacity,
+                                                       reinterpret_cast<unsigned long long*>(df_count));
     SB200_CHECK_LAUNCH("compact_fill_kernel");
     return SB200_OK;
 }

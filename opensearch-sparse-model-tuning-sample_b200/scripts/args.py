@@ -104,11 +104,26 @@ class TrainingArguments:
     save_safetensors: bool = True
 
 
+def _coerce(field, value):
+    """YAML 1.1 reads `1e-4` (no dot) as a string: numeric fields accept such strings, like HfArgumentParser does."""
+    if isinstance(value, str):
+        kind = str(field.type)
+        try:
+            if "float" in kind:
+                return float(value)
+            if "int" in kind and "Union" not in kind:
+                return int(value)
+        except ValueError:
+            pass
+    return value
+
+
 def _split_config(cfg, classes):
     out, used = [], set()
     for cls in classes:
-        names = {f.name for f in dataclasses.fields(cls)}
-        out.append(cls(**{k: v for k, v in cfg.items() if k in names}))
+        fields = {f.name: f for f in dataclasses.fields(cls)}
+        names = set(fields)
+        out.append(cls(**{k: _coerce(fields[k], v) for k, v in cfg.items() if k in names}))
         used |= names & set(cfg)
     unknown = sorted(set(cfg) - used)
     return out, unknown

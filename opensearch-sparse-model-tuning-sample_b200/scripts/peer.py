@@ -35,6 +35,11 @@ class _RawCuda:
         self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
 
 
+class PeerUnavailable(RuntimeError):
+    """Raised on EVERY rank when any rank could not allocate / export / import a sink (no CUDA IPC between the
+    processes, no peer access between two devices): the caller then stays with the NCCL gather."""
+
+
 class PeerSink:
     """One gather site. Collective constructor: every rank must create its sinks in the same order."""
 
@@ -52,24 +57,42 @@ class PeerSink:
         total = _CTRL_BYTES + self.data_bytes
         lib = _lib.load()
         local = ctypes.c_void_p()
+        group = getattr(env, "group", None)
+        self.ptrs, error = [], None
         with torch.cuda.device(device):
-            _lib.check(lib.sb200_peer_alloc(total, ctypes.byref(local)), "sb200_peer_alloc")
             handle = (ctypes.c_ubyte * 64)()
-            _lib.check(lib.sb200_peer_export(local, handle), "sb200_peer_export")
+            try:
+                _lib.check(lib.sb200_peer_alloc(total, ctypes.byref(local)), "sb200_peer_alloc")
+                _lib.check(lib.sb200_peer_export(local, handle), "sb200_peer_export")
+            except _lib.SparseB200Error as exc:
+                error = exc
             mine = torch.tensor(list(handle), dtype=torch.uint8, device=device)
             everyone = torch.empty(self.world * 64, dtype=torch.uint8, device=device)
-            dist.all_gather_into_tensor(everyone, mine, group=getattr(env, "group", None))
+            dist.all_gather_into_tensor(everyone, mine, group=group)
             handles = everyone.cpu().view(self.world, 64)
-            self.ptrs = []
             for r in range(self.world):
+                if error is not None:
+                    break
                 if r == self.rank:
                     self.ptrs.append(int(local.value))
                     continue
                 raw = (ctypes.c_ubyte * 64)(*handles[r].tolist())
                 p = ctypes.c_void_p()
-                _lib.check(lib.sb200_peer_import(raw, ctypes.byref(p)), "sb200_peer_import")
-                self.ptrs.append(int(p.value))
-            dist.barrier(group=getattr(env, "group", None))   # everyone has imported before anyone starts writing
+                try:
+                    _lib.check(lib.sb200_peer_import(raw, ctypes.byref(p)), "sb200_peer_import")
+                    self.ptrs.append(int(p.value))
+                except _lib.SparseB200Error as exc:
+                    error = exc
+            # every rank learns whether ALL ranks succeeded (also the barrier: everyone has imported before anyone writes)
+            ok = torch.tensor([0 if error is not None else 1], dtype=torch.int32, device=device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if int(ok) == 0:
+                for r, p in enumerate(self.ptrs):
+                    if r != self.rank:
+                        lib.sb200_peer_close(ctypes.c_void_p(p))
+                if local.value:
+                    lib.sb200_peer_free(local)
+                raise PeerUnavailable(f"symmetric peer memory unavailable (rank {self.rank}: {error})")
         self._local = int(local.value)
         self._holder = _RawCuda(self._local, total)
         self._bytes = torch.as_tensor(self._holder, device=device)

@@ -88,7 +88,8 @@ class SparseModelTrainer:
         if (rep_gather == "peer" and 1 < self.accelerator.num_processes <= 8 and model is not None
                 and next(model.parameters()).is_cuda and hasattr(self.accelerator, "enable_peer_sinks")):
             wrapper.__dict__["peer_sinks"] = self.accelerator.enable_peer_sinks(next(model.parameters()).device)
-            self.rep_gather = "peer"
+            if wrapper.__dict__["peer_sinks"] is not None:      # None: no CUDA IPC / peer access here -> NCCL gather
+                self.rep_gather = "peer"
         self._flat_grads = None
         self._buckets = None
         if self.grad_sync == "ddp" and next(wrapper.parameters()).is_cuda:

@@ -66,9 +66,31 @@ class DistEnv:
 
     # ------------------------------------------------------------------ symmetric peer memory (rep_gather="peer")
     def enable_peer_sinks(self, device):
-        from .peer import PeerSinks
+        """-> PeerSinks, or None (on every rank alike) when CUDA IPC / peer access is not available between the ranks:
+        a one-element probe sink is created, written, signalled and read back before anything depends on it."""
+        from .peer import PeerSinks, PeerUnavailable
         if self.peer_sinks is None:
-            self.peer_sinks = PeerSinks(self, device)
+            sinks = PeerSinks(self, device)
+            try:
+                probe = sinks.get("probe", 1, 4, torch.float32)
+                self._in_step = True
+                mine = torch.full((1, 4), float(self.process_index + 1), device=device)
+                probe.fan_out(mine)
+                probe.publish()
+                probe.wait()
+                want = torch.arange(1, self.num_processes + 1, device=device, dtype=torch.float32)
+                good = bool((probe.gathered[:, 0] == want).all())
+                flag = torch.tensor([1 if good else 0], dtype=torch.int32, device=device)
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+                if int(flag) == 0:
+                    raise PeerUnavailable("peer probe read back wrong data")
+            except PeerUnavailable as exc:
+                logging.getLogger(__name__).warning("rep_gather='peer' is not available here, using NCCL: %s", exc)
+                sinks.close()
+                return None
+            finally:
+                self._in_step = False
+            self.peer_sinks = sinks
         return self.peer_sinks
 
     def begin_step(self):
