@@ -135,13 +135,19 @@ bwd_bucket_kernel(const float* __restrict__ d_rep, const float* __restrict__ xma
     for (int l = tid; l < L; l += kBucketThreads) cnt[l] = 0;
     __syncthreads();
     const size_t base = size_t(b) * V;
-    for (int v = tid; v < V; v += kBucketThreads) {
-        const float c = head_coef(__ldg(d_rep + base + v), __ldg(xmax + base + v), l0);
-        if (c != 0.f) {
-            int l = __ldg(argmax + base + v);
-            l = min(max(l, 0), L - 1);
-            atomicAdd(&cnt[l], 1);
+    // pass 1: entries per position. Only "is the coefficient non-zero" matters here (x > 0 and g != 0, see head_coef);
+    // lanes of a warp that hit the same counter are aggregated into one shared-memory atomic (dense regime: ~120
+    // entries per counter).
+    for (int v0 = 0; v0 < V; v0 += kBucketThreads) {
+        const int v = v0 + tid;
+        bool active = false;
+        int l = 0;
+        if (v < V) {
+            active = (__ldg(xmax + base + v) > 0.f) && (__ldg(d_rep + base + v) != 0.f);
+            if (active) l = min(max(__ldg(argmax + base + v), 0), L - 1);
         }
+        const unsigned int peers = __match_any_sync(0xffffffffu, active ? l : -1);
+        if (active && lane == __ffs(peers) - 1) atomicAdd(&cnt[l], __popc(peers));
     }
     __syncthreads();
     // exclusive scan of cnt[0..L) in place; each thread owns a contiguous run of 4 counters
@@ -185,14 +191,25 @@ bwd_bucket_kernel(const float* __restrict__ d_rep, const float* __restrict__ xma
     }
     __syncthreads();
     uint2* out = entries + base;
-    for (int v = tid; v < V; v += kBucketThreads) {
-        const float c = head_coef(__ldg(d_rep + base + v), __ldg(xmax + base + v), l0);
-        if (c != 0.f) {
-            int l = __ldg(argmax + base + v);
-            l = min(max(l, 0), L - 1);
-            const int pos = atomicAdd(&cnt[l], 1);
-            out[pos] = make_uint2((uint32_t(l) << 20) | uint32_t(v), __float_as_uint(c));
+    for (int v0 = 0; v0 < V; v0 += kBucketThreads) {
+        const int v = v0 + tid;
+        float c = 0.f;
+        int l = 0;
+        bool active = false;
+        if (v < V) {
+            const float gv = __ldg(d_rep + base + v), xv = __ldg(xmax + base + v);
+            active = (xv > 0.f) && (gv != 0.f);        // the same predicate as pass 1 (a coefficient that underflows to
+            if (active) {                              // zero keeps its slot and contributes nothing)
+                c = head_coef(gv, xv, l0);
+                l = min(max(__ldg(argmax + base + v), 0), L - 1);
+            }
         }
+        const unsigned int peers = __match_any_sync(0xffffffffu, active ? l : -1);
+        const int leader = __ffs(peers) - 1;
+        int slot = 0;
+        if (active && lane == leader) slot = atomicAdd(&cnt[l], __popc(peers));
+        slot = __shfl_sync(0xffffffffu, slot, leader);
+        if (active) out[slot + __popc(peers & ((1u << lane) - 1u))] = make_uint2((uint32_t(l) << 20) | uint32_t(v), __float_as_uint(c));
     }
 }
 
