@@ -564,7 +564,7 @@ def extras(trainer, wl, args, device, peaks, hosts):
         add("torch_sum_read_only_yardstick", lambda: d_rep.sum(), nd * V * 4)
         add("flops_fwd", lambda: ops.flops_forward(d_rep, G, None), nd * V * 4)
         add("flops_fwd_l0_threshold", lambda: ops.flops_forward(d_rep, G, 150), 2 * nd * V * 4)
-        add("scores_fwd_in_batch", lambda: ops.scores_forward(q_rep, d_rep, True), (nq + nd) * V * 4)
+        add("scores_fwd_in_batch", lambda: ops.scores_forward(q_rep, d_rep, True, q_nnz_bound=lq), (nq + nd) * V * 4)
         add("scores_fwd_in_batch_dense_queries", lambda: ops.scores_forward(q_dense, d_rep, True), (nq + nd) * V * 4)
         # scores + infoNCE loss + dS in one call (2 launches: query lists, persistent cooperative row kernel)
         add("score_loss_fwd_infonce_in_batch",

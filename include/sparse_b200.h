@@ -159,9 +159,10 @@ size_t sb200_scores_workspace_bytes(int Nq, int Nd, int V, int in_batch);
  * any V) and gathered by all query lists: one HBM pass over d, no atomics, deterministic. Lists of up to 1024 entries
  * per query are supported (short ones live in registers, longer ones are streamed from L2); beyond that a device-side
  * flag routes the work to the dense fp32 tile kernel (no host sync). Without a workspace only the dense kernel runs.
- * in_batch == 0: one cluster of CTAs per query (DSMEM reduction), no workspace needed. */
-int sb200_scores_fwd(const float* q, const float* d, int Nq, int Nd, int V, int in_batch, float* S, void* workspace,
-                     size_t workspace_bytes, sb200_stream_t stream);
+ * q_nnz_bound > 0 promises that no query row has more non-zeros than that (0 = unknown): the dense fallback kernels are
+ * then not even enqueued. in_batch == 0: one cluster of CTAs per query (DSMEM reduction). */
+int sb200_scores_fwd(const float* q, const float* d, int Nq, int Nd, int V, int in_batch, int q_nnz_bound, float* S,
+                     void* workspace, size_t workspace_bytes, sb200_stream_t stream);
 /* d_q[i,:] = gs * sum_j dS[i,j] d[j,:] (rows q_begin..q_end) ; d_d[j,:] = gs * sum_i dS[i,j] q[i,:] (rows
  * d_begin..d_end); gs = *gscale (device scalar, nullable = 1): the upstream gradient of a scalar loss, so that no
  * separate dS * g pass is needed. Either output may be NULL. accumulate != 0 adds into the outputs. Outputs are

@@ -42,7 +42,7 @@ _PROTOTYPES = {
     "sb200_flops_fwd": (_c_int, [_vp, _c_int, _c_int, _c_int, _c_f, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "sb200_flops_bwd": (_c_int, [_vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp]),
     "sb200_scores_workspace_bytes": (_sz, [_c_int, _c_int, _c_int, _c_int]),
-    "sb200_scores_fwd": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp, _vp, _sz, _vp]),
+    "sb200_scores_fwd": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp, _sz, _vp]),
     "sb200_scores_bwd": (_c_int, [_vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
                                   _c_int, _vp, _vp, _vp, _sz, _vp]),
     "sb200_rank_loss_workspace_bytes": (_sz, [_c_int]),

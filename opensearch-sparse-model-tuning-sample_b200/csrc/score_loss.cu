@@ -385,9 +385,8 @@ score_group_kernel(const float* __restrict__ q, const float* __restrict__ d, int
 //
 // The row kernel is persistent (one CTA per SM, rows round-robin) and keeps the memory pipe busy with a ring of
 // shared-memory stages, each holding one PART of a row (a row is cut into n_parts equal column ranges so that any
-// vocabulary size fits): all 512 threads fetch a part with 16-byte cp.async copies (no registers held, two parts in
-// flight per SM while the current one is consumed -- measured: LSU-issued copies stream HBM at 5+ TB/s where one bulk
-// (TMA) request per part reached 3.2 TB/s).
+// vocabulary size fits): a part is fetched with one bulk async copy (TMA engine, mbarrier completion), two parts in
+// flight per SM while the current one is consumed.
 // Two gather modes, chosen on the device from the list lengths (block-uniform):
 //   (A) registers: tpq = 512/Nq threads share a query, each keeps <= 32 entries in registers for the whole kernel;
 //   (B) streamed lists: warps walk the queries, lanes the (ascending) entries of the current part, from L2.
@@ -419,34 +418,38 @@ inline QLists qlists_carve(void* ws, int Nq) {
     return q;
 }
 
-// One block per query row: ordered stream compaction (ballot + block scan), no atomics, no pre-zeroed counters.
+// Ordered stream compaction of one row by one block (ballots + block scan), no atomics, no pre-zeroed counters. A
+// thread owns 2 adjacent columns per load (rows are 8-byte aligned when V is even) and keeps kCompactBatch loads in
+// flight, so a 30522-column row is one (1024 threads) or two (512 threads) round trips to memory.
+// store(offset, column, value) is called for every non-zero in ascending column order; returns the row's count.
 constexpr int kCompactThreads = 1024;
-constexpr int kCompactBatch = 16;  // independent loads in flight per thread
+constexpr int kCompactBatch = 16;  // independent 8-byte loads in flight per thread
 
-__global__ void __launch_bounds__(kCompactThreads)
-q_compact_kernel(const float* __restrict__ q, int V, QLists L) {
-    __shared__ int warp_cnt[kCompactBatch][32];
-    const int i = blockIdx.x;
-    const float* row = q + size_t(i) * V;
+template <int THREADS, typename Store>
+__device__ __forceinline__ int compact_row(const float* __restrict__ row, int V, int (*warp_cnt)[32], Store store) {
+    constexpr int kWarps = THREADS / 32;
+    const bool vec2 = (reinterpret_cast<uintptr_t>(row) & 7) == 0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int base = 0;
-    for (int v0 = 0; v0 < V; v0 += kCompactThreads * kCompactBatch) {
-        float x[kCompactBatch];
-        uint32_t bal[kCompactBatch];
+    for (int v0 = 0; v0 < V; v0 += THREADS * kCompactBatch * 2) {
+        float2 x[kCompactBatch];
+        uint32_t b0[kCompactBatch], b1[kCompactBatch];
 #pragma unroll
         for (int b = 0; b < kCompactBatch; ++b) {
-            const int v = v0 + b * kCompactThreads + threadIdx.x;
-            x[b] = (v < V) ? __ldg(row + v) : 0.f;
+            const int v = v0 + (b * THREADS + threadIdx.x) * 2;
+            if (vec2 && v + 1 < V) x[b] = __ldg(reinterpret_cast<const float2*>(row + v));
+            else x[b] = make_float2(v < V ? __ldg(row + v) : 0.f, v + 1 < V ? __ldg(row + v + 1) : 0.f);
         }
 #pragma unroll
         for (int b = 0; b < kCompactBatch; ++b) {
-            bal[b] = __ballot_sync(0xffffffffu, x[b] != 0.f);
-            if (lane == 0) warp_cnt[b][warp] = __popc(bal[b]);
+            b0[b] = __ballot_sync(0xffffffffu, x[b].x != 0.f);
+            b1[b] = __ballot_sync(0xffffffffu, x[b].y != 0.f);
+            if (lane == 0) warp_cnt[b][warp] = __popc(b0[b]) + __popc(b1[b]);
         }
         __syncthreads();
 #pragma unroll
         for (int b = 0; b < kCompactBatch; ++b) {
-            const int c = warp_cnt[b][lane];                 // lane w holds the count of warp w
+            const int c = (lane < kWarps) ? warp_cnt[b][lane] : 0;     // lane w holds the count of warp w
             int incl = c;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -455,16 +458,29 @@ q_compact_kernel(const float* __restrict__ q, int V, QLists L) {
             }
             const int total = __shfl_sync(0xffffffffu, incl, 31);
             const int before = __shfl_sync(0xffffffffu, incl - c, warp);   // entries of lower warps
-            const int off = base + before + __popc(bal[b] & ((1u << lane) - 1u));
-            if (x[b] != 0.f && off < kQCap) {
-                L.cols[size_t(i) * kQCap + off] = v0 + b * kCompactThreads + threadIdx.x;
-                L.vals[size_t(i) * kQCap + off] = x[b];
-            }
+            const uint32_t lt = (1u << lane) - 1u;
+            int off = base + before + __popc(b0[b] & lt) + __popc(b1[b] & lt);   // both columns of lower lanes first
+            const int v = v0 + (b * THREADS + threadIdx.x) * 2;
+            if (x[b].x != 0.f) store(off++, v, x[b].x);
+            if (x[b].y != 0.f) store(off, v + 1, x[b].y);
             base += total;
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) L.nnz[i] = base;
+    return base;
+}
+
+__global__ void __launch_bounds__(kCompactThreads)
+q_compact_kernel(const float* __restrict__ q, int V, QLists L) {
+    __shared__ int warp_cnt[kCompactBatch][32];
+    const int i = blockIdx.x;
+    const int n = compact_row<kCompactThreads>(q + size_t(i) * V, V, warp_cnt, [&](int off, int v, float x) {
+        if (off < kQCap) {
+            L.cols[size_t(i) * kQCap + off] = v;
+            L.vals[size_t(i) * kQCap + off] = x;
+        }
+    });
+    if (threadIdx.x == 0) L.nnz[i] = n;
 }
 
 struct LossArgs {
@@ -477,39 +493,43 @@ struct LossArgs {
     float* rowloss;           // [Nq] scratch
 };
 
-// Issues the asynchronous fetch of part `p` of document row `j` into `stage` (all threads): 16-byte cp.async for the
-// aligned interior, 4-byte cp.async for the <= 3 floats in front of / behind it. The stage keeps the source's phase
-// inside a 16-byte line (element x of the part lives at stage[a + x]), so source and destination are co-aligned.
-__device__ __forceinline__ void row_part_issue(const float* __restrict__ d, int V, int j, int p, int part_len,
-                                               float* stage) {
+// Fetches part `p` of document row `j` into `stage` with ONE bulk async copy (TMA engine, mbarrier completion): called
+// by warp 0; lane 0 drives the copy of the 16-byte aligned interior, lanes 1-6 move the <= 3 floats in front of / behind
+// it with ordinary loads. The stage keeps the source's phase inside a 16-byte line (element x of the part lives at
+// stage[a + x]), so source and destination are co-aligned. No LSU issue slots are spent on the transfer: an A/B run with
+// 16-byte cp.async issued by all threads (same ring) measured 78.6 us against 59.3 us for this version at the large
+// shape -- the copies' issue and shared-memory write slots compete with the gather's shared-memory loads.
+__device__ __forceinline__ void row_part_issue_bulk(const float* __restrict__ d, int V, int j, int p, int part_len,
+                                                    float* stage, uint64_t* bar, int lane) {
     const int c0 = p * part_len;
     const int len = min(V, c0 + part_len) - c0;
     const float* src = d + size_t(j) * V + c0;
     const int a = int(reinterpret_cast<uintptr_t>(src) & 15) >> 2;
     const int head = min(len, (4 - a) & 3);
-    const int n16 = (len - head) >> 2;
-    const uint32_t dst0 = smem_u32(stage + a + head);
-    const float* s0 = src + head;
-    for (int t = threadIdx.x; t < n16; t += kRowThreads)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + uint32_t(t) * 16u), "l"(s0 + 4 * t) : "memory");
-    const int tail0 = head + 4 * n16;
-    if (int(threadIdx.x) < head)
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(stage + a + threadIdx.x)), "l"(src + threadIdx.x)
-                     : "memory");
-    else if (threadIdx.x >= 32 && int(threadIdx.x) - 32 < len - tail0)
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;"
-                     ::"r"(smem_u32(stage + a + tail0 + threadIdx.x - 32)), "l"(src + tail0 + threadIdx.x - 32)
-                     : "memory");
+    const int nbulk = ((len - head) >> 2) << 2;
+    const int tail0 = head + nbulk;
+    if (lane == 0) {
+        if (nbulk > 0) {
+            mbar_arrive_expect_tx(bar, uint32_t(nbulk) * 4u);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_u32(stage + head + a)), "l"(src + head), "r"(uint32_t(nbulk) * 4u), "r"(smem_u32(bar))
+                         : "memory");
+        } else {
+            mbar_arrive(bar);
+        }
+    } else if (lane <= 3) {
+        if (lane - 1 < head) stage[a + lane - 1] = __ldg(src + lane - 1);
+    } else if (lane <= 6) {
+        const int t = tail0 + lane - 4;
+        if (t < len) stage[a + t] = __ldg(src + t);
+    }
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
 template <bool kFused>
 __global__ void __launch_bounds__(kRowThreads, 1)
 scores_docrow_kernel(const float* __restrict__ d, int Nq, int Nd, int V, int n_parts, int part_len, QLists L,
                      float* __restrict__ S, LossArgs la) {
     extern __shared__ __align__(128) float stages[];            // [kRowStages][part_len + 8]
+    __shared__ __align__(8) uint64_t full_bar[kRowStages];      // completion barriers of the stages
     __shared__ int cursor_s[kRowMaxQ];                          // mode (B)
     __shared__ float acc_s[kRowMaxQ];
     __shared__ float red[kRowThreads / 32];
@@ -545,12 +565,17 @@ scores_docrow_kernel(const float* __restrict__ d, int Nq, int Nd, int V, int n_p
         }
         const int my_rows = (Nd - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
         const int total = my_rows * n_parts;
-        // prologue: parts 0 .. kRowStages-2 in flight (one commit group per part, empty groups past the end)
-        for (int t = 0; t < kRowStages - 1; ++t) {
-            if (t < total)
-                row_part_issue(d, V, blockIdx.x + (t / n_parts) * gridDim.x, t % n_parts, part_len, stages + t * stage_floats);
-            cp_async_commit();
+        if (threadIdx.x == 0) {
+            for (int s = 0; s < kRowStages; ++s) mbar_init(&full_bar[s], 1);
+            fence_mbar_init();
         }
+        __syncthreads();
+        auto issue = [&](int t) {
+            if (warp == 0)
+                row_part_issue_bulk(d, V, blockIdx.x + (t / n_parts) * gridDim.x, t % n_parts, part_len,
+                                    stages + (t % kRowStages) * stage_floats, &full_bar[t % kRowStages], lane);
+        };
+        for (int t = 0; t < kRowStages - 1 && t < total; ++t) issue(t);   // prologue: kRowStages-1 parts in flight
         float acc = 0.f;
         for (int t = 0; t < total; ++t) {
             const int s = t % kRowStages;
@@ -560,15 +585,9 @@ scores_docrow_kernel(const float* __restrict__ d, int Nq, int Nd, int V, int n_p
             const int plen = min(V, c0 + part_len) - c0;
             const float* st = stages + s * stage_floats +
                               (int(reinterpret_cast<uintptr_t>(d + size_t(j) * V + c0) & 15) >> 2);
-            cp_async_wait<kRowStages - 2>();   // this thread's copies of part t have landed ...
-            __syncthreads();                   // ... and everybody's; everybody is also done gathering part t-1
-            {   // refill the stage part t-1 lived in with part t + kRowStages - 1
-                const int tn = t + kRowStages - 1;
-                if (tn < total)
-                    row_part_issue(d, V, blockIdx.x + (tn / n_parts) * gridDim.x, tn % n_parts, part_len,
-                                   stages + (tn % kRowStages) * stage_floats);
-                cp_async_commit();
-            }
+            mbar_wait(&full_bar[s], uint32_t(t / kRowStages) & 1u);   // the bulk copy of part t has landed
+            __syncthreads();     // its scalar head / tail floats are visible; everybody is done gathering part t-1
+            if (t + kRowStages - 1 < total) issue(t + kRowStages - 1);   // refill the stage part t-1 lived in
             if (mode_a) {
 #pragma unroll
                 for (int e = 0; e < kEPT; ++e) {
@@ -605,7 +624,6 @@ scores_docrow_kernel(const float* __restrict__ d, int Nq, int Nd, int V, int n_p
                 }
             }
         }
-        cp_async_wait<0>();
     }
     if constexpr (kFused) {
         // ---- ranking loss on the finished score matrix: grid-wide barrier (cooperative launch), rows over blocks
@@ -642,60 +660,28 @@ score_gather_kernel(const float* __restrict__ q, const float* __restrict__ d, in
                     float* __restrict__ S, LossArgs la) {
     __shared__ int col_s[kGatherCap];
     __shared__ float val_s[kGatherCap];
-    __shared__ int warp_cnt[kCompactBatch][kGatherThreads / 32];
+    __shared__ int warp_cnt[kCompactBatch][32];
     __shared__ float red[kGatherThreads / 32];
     extern __shared__ float srow[];     // [Nd]
     const int i = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int kWarps = kGatherThreads / 32;
     // ---- (1) ordered compaction
-    const float* row = q + size_t(i) * V;
-    int base = 0;
-    for (int v0 = 0; v0 < V; v0 += kGatherThreads * kCompactBatch) {
-        float x[kCompactBatch];
-        uint32_t bal[kCompactBatch];
-#pragma unroll
-        for (int b = 0; b < kCompactBatch; ++b) {
-            const int v = v0 + b * kGatherThreads + threadIdx.x;
-            x[b] = (v < V) ? __ldg(row + v) : 0.f;
+    const int base = compact_row<kGatherThreads>(q + size_t(i) * V, V, warp_cnt, [&](int off, int v, float x) {
+        if (off < kGatherCap) {
+            col_s[off] = v;
+            val_s[off] = x;
         }
-#pragma unroll
-        for (int b = 0; b < kCompactBatch; ++b) {
-            bal[b] = __ballot_sync(0xffffffffu, x[b] != 0.f);
-            if (lane == 0) warp_cnt[b][warp] = __popc(bal[b]);
+        if (off < kQCap) {
+            L.cols[size_t(i) * kQCap + off] = v;
+            L.vals[size_t(i) * kQCap + off] = x;
         }
-        __syncthreads();
-#pragma unroll
-        for (int b = 0; b < kCompactBatch; ++b) {
-            const int c = (lane < kWarps) ? warp_cnt[b][lane] : 0;
-            int incl = c;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += t;
-            }
-            const int total = __shfl_sync(0xffffffffu, incl, 31);
-            const int before = __shfl_sync(0xffffffffu, incl - c, warp);
-            const int off = base + before + __popc(bal[b] & ((1u << lane) - 1u));
-            if (x[b] != 0.f) {
-                const int v = v0 + b * kGatherThreads + threadIdx.x;
-                if (off < kGatherCap) {
-                    col_s[off] = v;
-                    val_s[off] = x[b];
-                }
-                if (off < kQCap) {
-                    L.cols[size_t(i) * kQCap + off] = v;
-                    L.vals[size_t(i) * kQCap + off] = x[b];
-                }
-            }
-            base += total;
-        }
-        __syncthreads();
-    }
+    });
     if (threadIdx.x == 0) {
         L.nnz[i] = base;
         if (i == 0) *L.flag = 0;
     }
+    __syncthreads();
     const int n = min(base, kGatherCap);   // the host only picks this kernel when the caller's bound fits
     // ---- (2) gather
     for (int j0 = warp * 4; j0 < Nd; j0 += kWarps * 4) {
@@ -1166,8 +1152,8 @@ static float* rowloss_of(void* workspace, int Nq, int in_batch) {
     return reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + (in_batch ? qlists_bytes(Nq) : 0));
 }
 
-extern "C" int sb200_scores_fwd(const float* q, const float* d, int Nq, int Nd, int V, int in_batch, float* S,
-                                void* workspace, size_t workspace_bytes, sb200_stream_t stream_) {
+extern "C" int sb200_scores_fwd(const float* q, const float* d, int Nq, int Nd, int V, int in_batch, int q_nnz_bound,
+                                float* S, void* workspace, size_t workspace_bytes, sb200_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     SB200_REQUIRE(q && d && S, "scores_fwd: null pointer");
     SB200_REQUIRE(Nq >= 1 && Nd >= 1 && V >= 1, "scores_fwd: bad shape");
@@ -1183,6 +1169,8 @@ extern "C" int sb200_scores_fwd(const float* q, const float* d, int Nq, int Nd, 
             rc = launch_docrow(d, Nq, Nd, V, L, S, la, false, stream);
             if (rc != SB200_OK) return rc;
             dense_flag = L.flag;
+            // a promised bound on the non-zeros per query row: the sparse kernel always does the work
+            if (q_nnz_bound > 0 && q_nnz_bound <= kQCap && Nq <= kRowMaxQ) return SB200_OK;
         }
         return launch_dense_scores(q, d, Nq, Nd, V, dense_flag, S, stream);
     }

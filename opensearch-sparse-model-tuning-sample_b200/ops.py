@@ -459,15 +459,18 @@ def _check_qd(q, d, in_batch):
     return q, d, Nq, Nd, V
 
 
-def scores_forward(q, d, in_batch, return_workspace=False):
+def scores_forward(q, d, in_batch, return_workspace=False, q_nnz_bound=None):
+    """q . d^T. q_nnz_bound: promised maximum of non-zeros per query row (default: what ops.idf_query recorded on q)."""
+    if q_nnz_bound is None:
+        q_nnz_bound = int(getattr(q, "_sb200_nnz_bound", 0) or 0)
     q, d, Nq, Nd, V = _check_qd(q, d, in_batch)
     C = Nd if in_batch else Nd // Nq
     S = torch.empty(Nq, C, dtype=torch.float32, device=q.device)
     lib = _lib.load()
     ws = _workspace(lib.sb200_scores_workspace_bytes(Nq, Nd, V, 1 if in_batch else 0), q.device)
     with torch.cuda.device(q.device):
-        code = lib.sb200_scores_fwd(_ptr(q), _ptr(d), Nq, Nd, V, 1 if in_batch else 0, _ptr(S), _ptr(ws), ws.numel(),
-                                    _stream())
+        code = lib.sb200_scores_fwd(_ptr(q), _ptr(d), Nq, Nd, V, 1 if in_batch else 0, int(q_nnz_bound), _ptr(S), _ptr(ws),
+                                    ws.numel(), _stream())
     _lib.check(code, "sb200_scores_fwd")
     return (S, ws) if return_workspace else S
 
@@ -493,7 +496,8 @@ class ScoresFunction(torch.autograd.Function):
     def forward(ctx, q, d, in_batch):
         q32 = q.detach().float().contiguous()
         d32 = d.detach().float().contiguous()
-        S, ws = scores_forward(q32, d32, in_batch, return_workspace=True)
+        S, ws = scores_forward(q32, d32, in_batch, return_workspace=True,
+                               q_nnz_bound=int(getattr(q, "_sb200_nnz_bound", 0) or 0))
         ctx.save_for_backward(q32, d32)
         ctx.ws = ws if in_batch else None  # thresholded query lists, reused by the backward kernels
         ctx.q_rows = getattr(q, "_sb200_grad_rows", None)  # set by gather_rep: only these rows carry grad
