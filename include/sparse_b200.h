@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SB200_ABI_VERSION 2
+#define SB200_ABI_VERSION 3
 
 enum {
     SB200_OK = 0,
@@ -280,6 +280,37 @@ int sb200_colsum_supported(int N);
 size_t sb200_colsum_workspace_bytes(int R, int N);
 int sb200_colsum(const void* dy, int elem_bytes, int R, int N, float* out, void* workspace, size_t workspace_bytes,
                  sb200_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Variable-length multi-head self-attention of the body on packed token rows, forward and backward:
+ *   replaces transformers BertSelfAttention.forward (scores = Q K^T / sqrt(d), softmax, attention-probs dropout,
+ *   probs V) inside the backbone call at scripts/model/sparse_encoders.py:108 and its autograd chain; the padding the
+ *   reference multiplies (collator.py:34-41 pads to the longest text) is never touched: sequence i is token rows
+ *   [cu_seqlens[i], cu_seqlens[i + 1]) and attends only to itself (non-causal, no further mask).
+ *   q, k, v     bf16, element [t, head, :] at ptr + t * in_stride + head * d (a fused [T, 3, h, d] projection output:
+ *               q = base, k = base + h * d, v = base + 2 * h * d, in_stride = 3 * h * d); in_stride % 8 == 0
+ *   cu_seqlens  int32 [nseq + 1] on the device, non-decreasing, cu_seqlens[nseq] <= T; empty sequences allowed
+ *   max_len     host upper bound of every sequence length (<= 1024); d = 32 or 64
+ *   out         bf16 [T, h * d];  lse f32 [h, T] = log sum_j exp(scale * q . k_j)
+ *   drop_p / drop_seed / salt: dropout on the probabilities. The keep mask is a pure function of (the 64-bit value at
+ *               drop_seed, salt, sequence, head, query, key); keep probability is round(256 * (1 - drop_p)) / 256 and
+ *               the kept entries are rescaled by its inverse. Pass the same three values to the backward call.
+ *               drop_p == 0: no dropout (drop_seed may be NULL).
+ * Backward: dout bf16 [T, h * d]; writes dq / dk / dv (bf16, element [t, head, :] at ptr + t * d_stride + head * d,
+ * every row of every sequence exactly once; rows outside all sequences are left untouched); dsum f32 [h, T] is
+ * scratch (rowsum(dout * out)). Deterministic (no atomics).
+ * sb200_attn_dropout_mask (test hook): mask u8 [h, T, max_len], mask[head, t, j] = 1 iff query t keeps key j of its
+ * own sequence. */
+int sb200_attn_supported(int head_dim, int max_len);
+int sb200_attn_fwd(const void* q, const void* k, const void* v, size_t in_stride, const int* cu_seqlens, int nseq,
+                   int max_len, int T, int h, int d, float scale, float drop_p, const void* drop_seed, int salt,
+                   void* out, float* lse, sb200_stream_t stream);
+int sb200_attn_bwd(const void* q, const void* k, const void* v, size_t in_stride, const void* out, const void* dout,
+                   const float* lse, const int* cu_seqlens, int nseq, int max_len, int T, int h, int d, float scale,
+                   float drop_p, const void* drop_seed, int salt, void* dq, void* dk, void* dv,
+                   size_t d_stride, float* dsum, sb200_stream_t stream);
+int sb200_attn_dropout_mask(const int* cu_seqlens, int nseq, int max_len, int T, int h, float drop_p,
+                            const void* drop_seed, int salt, unsigned char* mask, sb200_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Symmetric peer memory over NVLink (CUDA IPC), one process per GPU: the exchange steps of data-parallel training

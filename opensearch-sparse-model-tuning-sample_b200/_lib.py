@@ -67,6 +67,11 @@ _PROTOTYPES = {
     "sb200_colsum_supported": (_c_int, [_c_int]),
     "sb200_colsum_workspace_bytes": (_sz, [_c_int, _c_int]),
     "sb200_colsum": (_c_int, [_vp, _c_int, _c_int, _c_int, _vp, _vp, _sz, _vp]),
+    "sb200_attn_supported": (_c_int, [_c_int, _c_int]),
+    "sb200_attn_fwd": (_c_int, [_vp] * 3 + [_sz, _vp] + [_c_int] * 5 + [_c_f, _c_f, _vp, _c_int, _vp, _vp, _vp]),
+    "sb200_attn_bwd": (_c_int, [_vp] * 3 + [_sz] + [_vp] * 4 + [_c_int] * 5 + [_c_f, _c_f, _vp, _c_int] + [_vp] * 3
+                       + [_sz, _vp, _vp]),
+    "sb200_attn_dropout_mask": (_c_int, [_vp] + [_c_int] * 4 + [_c_f, _vp, _c_int, _vp, _vp]),
     "sb200_peer_alloc": (_c_int, [_sz, _vp]),
     "sb200_peer_free": (_c_int, [_vp]),
     "sb200_peer_export": (_c_int, [_vp, _vp]),
@@ -104,7 +109,7 @@ def load():
             raise SparseB200Error(f"{LIB_PATH} does not export {name}; rebuild the library") from None
         fn.restype = res
         fn.argtypes = args
-    if lib.sb200_abi_version() != 2:
+    if lib.sb200_abi_version() != 3:
         raise SparseB200Error("libsparse_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -1,0 +1,767 @@
+// Variable-length (padding-free) multi-head self-attention of the BERT body, forward and backward, for head_dim 32 / 64:
+//   P = softmax(Q K^T * scale) per (sequence, head), O = dropout(P) V
+// (transformers BertSelfAttention.forward inside the backbone call at scripts/model/sparse_encoders.py:108, and its
+// autograd chain). Sequences are packed back to back in one [T, .] token matrix and delimited by cu_seqlens, so no
+// padding row is ever multiplied.
+//
+// Why warp-level mma.sync and not tcgen05 here: at head_dim 32 a score element costs 4 tensor flops per exp2 / max /
+// sum / convert / dropout decision -- the kernel is bound by the FP32 + MUFU pipes and (through TMEM) by the same
+// 64 B/clk read port that bounds the head epilogue, not by the tensor pipe. With mma.sync the score fragment IS the
+// A fragment of the following P V product, so S and P never leave the register file. See DESIGN.md 4.6.
+//
+// Work split: one CTA = one (sequence, head, tile of 64 rows); 4 warps x 16 rows; the other operand streams through a
+// 2-stage cp.async ring of 64-row blocks (XOR-swizzled, conflict-free for ldmatrix).
+//   forward   warp owns 16 queries: S = Q K^T (64 keys) -> online softmax -> dropout -> O += P V.   Saves LSE.
+//   backward  two CTA roles in ONE launch, no atomics, no cross-warp reduction, every output written exactly once:
+//     role dQ     warp owns 16 queries, streams K/V:  S, P, dP = dO V^T, dS = P (dP - D)  ->  dQ += dS K
+//     role dK/dV  warp owns 16 keys, streams Q/dO (transposed problem S^T = K Q^T): dV += P^T dO, dK += dS^T Q
+//   D = rowsum(dO * O) comes from a small pre-pass.
+// Dropout: the keep mask is a pure function of (seed, salt, sequence, head, query, key): one 32-bit hash per 2x2 patch
+// {r, r+8} x {c, c+8} of a 16x16 score block, a byte per element. That patch is exactly what one thread holds in the
+// m16n8k16 accumulator layout in BOTH orientations (queries x keys and keys x queries), so the forward and both
+// backward roles regenerate identical masks from registers. Keep probability is quantised to thr/256 and the
+// rescale uses the quantised value (unbiased).
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace sb200 {
+namespace {
+
+constexpr int kAttThreads = 128;
+constexpr int kAttTile = 64;
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+struct AttnParams {
+    const __nv_bfloat16* q;   // [T, .] row stride in_stride, this head at + head * D
+    const __nv_bfloat16* k;
+    const __nv_bfloat16* v;
+    long long in_stride;
+    __nv_bfloat16* out;       // [T, h * D]
+    float* lse;               // [h, T] natural-log LSE of the scaled scores
+    const int* cu;            // [nseq + 1]
+    int T, h, nseq, ntile;
+    float scale, scale_log2;
+    uint32_t keep_thr;        // keep iff byte < keep_thr  (256 = keep everything)
+    float inv_keep;
+    const unsigned long long* seed;
+    uint32_t salt;
+    // backward
+    const __nv_bfloat16* dout;  // [T, h * D]
+    const float* dsum;          // [h, T]
+    __nv_bfloat16* dq;          // same layout as q / k / v (row stride d_stride)
+    __nv_bfloat16* dk;
+    __nv_bfloat16* dv;
+    long long d_stride;
+    unsigned char* mask_out;    // test hook (dropout mask dump)
+};
+
+// ---------------------------------------------------------------------------------------------------------- PTX
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src, int src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t (&r)[4]) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+        "{%0, %1, %2, %3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+    x ^= x >> 16;
+    x *= 0x7feb352dU;
+    x ^= x >> 15;
+    x *= 0x846ca68bU;
+    x ^= x >> 16;
+    return x;
+}
+
+// ---------------------------------------------------------------------------------------------------------- tiles
+// A [64][D] bf16 tile in shared memory; 16-byte chunks XOR-swizzled so that the 8 row addresses of every ldmatrix
+// 8x8 matrix fall into 8 different bank groups (D = 32: rows are 64 B, two rows per 128 B line).
+template <int D>
+__device__ __forceinline__ uint32_t tile_off(int row, int chunk) {
+    if (D == 32) return uint32_t(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
+    return uint32_t(row * 128 + ((chunk ^ (row & 7)) << 4));
+}
+
+// Stages rows [row0, row0 + 64) of one sequence (rows >= len zero-filled) into a tile. src points at row 0 of the sequence.
+template <int D>
+__device__ __forceinline__ void load_tile(uint32_t dst, const __nv_bfloat16* src, int row0, int len, long long stride,
+                                          int tid) {
+    constexpr int CPR = D / 8;
+#pragma unroll
+    for (int i = 0; i < kAttTile * CPR / kAttThreads; ++i) {
+        const int idx = tid + i * kAttThreads;
+        const int r = idx / CPR, c = idx % CPR;
+        const int gr = row0 + r;
+        const bool ok = gr < len;
+        cp_async16(dst + tile_off<D>(r, c), src + (long long)(ok ? gr : 0) * stride + c * 8, ok ? 16 : 0);
+    }
+}
+
+// 64 floats of a per-row statistic (rows >= len -> 0).
+__device__ __forceinline__ void load_stat(uint32_t dst, const float* src, int row0, int len, int tid) {
+    if (tid < kAttTile) {
+        const int gr = row0 + tid;
+        const bool ok = gr < len;
+        cp_async4(dst + tid * 4, src + (ok ? gr : 0), ok ? 4 : 0);
+    }
+}
+
+// "A pattern": the 16 x 16 region at (row0, 16 * kc): r0 = rows 0-7 / cols 0-7, r1 = rows 8-15 / cols 0-7,
+// r2 = rows 0-7 / cols 8-15, r3 = rows 8-15 / cols 8-15. Plain: the A fragment. Transposed (stored rows = k index):
+// {r0, r1} = B fragment of n-tile 2 * kc, {r2, r3} = B fragment of n-tile 2 * kc + 1.
+template <int D>
+__device__ __forceinline__ uint32_t addr_a(uint32_t tile, int row0, int kc, int lane) {
+    return tile + tile_off<D>(row0 + (lane & 7) + ((lane >> 3) & 1) * 8, 2 * kc + (lane >> 4));
+}
+// "B pattern": 8 stored rows (n index) x 32 columns (k index) starting at chunk c0: r[2j], r[2j+1] = B fragment of
+// k-step (c0 / 2 + j).
+template <int D>
+__device__ __forceinline__ uint32_t addr_b(uint32_t tile, int row0, int c0, int lane) {
+    return tile + tile_off<D>(row0 + (lane & 7), c0 + (lane >> 3));
+}
+
+// Loads the A fragments (all k-steps) of the warp's 16 rows.
+template <int D>
+__device__ __forceinline__ void load_a_frags(uint32_t tile, int row0, int lane, uint32_t (&a)[D / 16][4]) {
+#pragma unroll
+    for (int ks = 0; ks < D / 16; ++ks) ldsm_x4(addr_a<D>(tile, row0, ks, lane), a[ks]);
+}
+
+// acc[nt] (16 x 8) += A[16 x D] * B^T where B = 8 stored rows starting at brow0 of `tile`
+template <int D>
+__device__ __forceinline__ void mma_rows(float (&acc)[4], const uint32_t (&a)[D / 16][4], uint32_t tile, int brow0,
+                                         int lane) {
+#pragma unroll
+    for (int gi = 0; gi < D / 32; ++gi) {
+        uint32_t b[4];
+        ldsm_x4(addr_b<D>(tile, brow0, 4 * gi, lane), b);
+        mma_bf16(acc, a[2 * gi], b[0], b[1]);
+        mma_bf16(acc, a[2 * gi + 1], b[2], b[3]);
+    }
+}
+
+// acc[D / 8] (16 x D) += A (16 x 16, registers) * tile rows [krow0, krow0 + 16) (stored rows = k index)
+template <int D>
+__device__ __forceinline__ void mma_cols(float (&acc)[D / 8][4], const uint32_t (&a)[4], uint32_t tile, int krow0,
+                                         int lane) {
+#pragma unroll
+    for (int np = 0; np < D / 16; ++np) {
+        uint32_t b[4];
+        ldsm_x4_t(addr_a<D>(tile, krow0, np, lane), b);
+        mma_bf16(acc[2 * np], a, b[0], b[1]);
+        mma_bf16(acc[2 * np + 1], a, b[2], b[3]);
+    }
+}
+
+// Writes the warp's 16 x D accumulator (scaled) as bf16 through its own 16 rows of `tile` to global rows.
+template <int D>
+__device__ __forceinline__ void store_rows(const float (&acc)[D / 8][4], float s0, float s1, uint32_t tile,
+                                           unsigned char* tile_ptr, int wrow0, __nv_bfloat16* dst, long long stride,
+                                           int grow0, int len, int lane) {
+    constexpr int CPR = D / 8;
+    const int g = lane >> 2, t = lane & 3;
+    __syncwarp();
+#pragma unroll
+    for (int nt = 0; nt < D / 8; ++nt) {
+        *reinterpret_cast<uint32_t*>(tile_ptr + tile_off<D>(wrow0 + g, nt) + t * 4) =
+            pack_bf16(acc[nt][0] * s0, acc[nt][1] * s0);
+        *reinterpret_cast<uint32_t*>(tile_ptr + tile_off<D>(wrow0 + g + 8, nt) + t * 4) =
+            pack_bf16(acc[nt][2] * s1, acc[nt][3] * s1);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 16 * CPR / 32; ++i) {
+        const int idx = lane + i * 32;
+        const int r = idx / CPR, c = idx % CPR;
+        const int gr = grow0 + wrow0 + r;
+        if (gr < len) {
+            const uint4 val = *reinterpret_cast<const uint4*>(tile_ptr + tile_off<D>(wrow0 + r, c));
+            *reinterpret_cast<uint4*>(dst + (long long)gr * stride + c * 8) = val;
+        }
+    }
+    (void)tile;
+}
+
+__device__ __forceinline__ uint32_t seq_key(const AttnParams& p, int seq, int head) {
+    const unsigned long long s = *p.seed;
+    return mix32(uint32_t(s) ^ mix32(uint32_t(s >> 32) + 0x9E3779B9u * uint32_t(seq * p.h + head + 1)) ^
+                 (p.salt * 0x85EBCA6Bu));
+}
+// One hash per 2x2 patch {r, r+8} x {c, c+8} of the 16 x 16 block (qblk, kblk); byte 0: (r, c), 1: (r, c+8),
+// 2: (r+8, c), 3: (r+8, c+8).
+__device__ __forceinline__ uint32_t patch_hash(uint32_t key, int qblk, int kblk, int r, int c) {
+    const uint32_t idx = uint32_t(((qblk * 64 + kblk) * 64) + r * 8 + c);
+    return mix32(key ^ (idx * 0x9E3779B1u));
+}
+__device__ __forceinline__ bool keep_byte(uint32_t h, int i, uint32_t thr) { return ((h >> (8 * i)) & 0xFFu) < thr; }
+
+// ---------------------------------------------------------------------------------------------------------- forward
+template <int D, bool kDrop>
+__global__ void __launch_bounds__(kAttThreads) attn_fwd_kernel(const AttnParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int kTileBytes = kAttTile * D * 2;
+    const int seq = blockIdx.z, head = blockIdx.y, qt = blockIdx.x;
+    const int s0 = __ldg(p.cu + seq);
+    const int len = __ldg(p.cu + seq + 1) - s0;
+    if (qt * kAttTile >= len) return;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const uint32_t sQ = smem_u32(smem), sK = sQ + kTileBytes, sV = sK + 2 * kTileBytes;
+    const __nv_bfloat16* qs = p.q + (long long)s0 * p.in_stride + head * D;
+    const __nv_bfloat16* ks = p.k + (long long)s0 * p.in_stride + head * D;
+    const __nv_bfloat16* vs = p.v + (long long)s0 * p.in_stride + head * D;
+    const int nb = (len + kAttTile - 1) / kAttTile;
+
+    load_tile<D>(sQ, qs, qt * kAttTile, len, p.in_stride, tid);
+    load_tile<D>(sK, ks, 0, len, p.in_stride, tid);
+    load_tile<D>(sV, vs, 0, len, p.in_stride, tid);
+    cp_async_commit();
+
+    uint32_t qa[D / 16][4];
+    float o[D / 8][4];
+#pragma unroll
+    for (int i = 0; i < D / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+    uint32_t key = 0;
+    if (kDrop) key = seq_key(p, seq, head);
+    const int qblk = qt * 4 + warp;
+
+    for (int kb = 0; kb < nb; ++kb) {
+        const int st = kb & 1;
+        if (kb + 1 < nb) {
+            load_tile<D>(sK + (st ^ 1) * kTileBytes, ks, (kb + 1) * kAttTile, len, p.in_stride, tid);
+            load_tile<D>(sV + (st ^ 1) * kTileBytes, vs, (kb + 1) * kAttTile, len, p.in_stride, tid);
+        }
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+        if (kb == 0) load_a_frags<D>(sQ, warp * 16, lane, qa);
+        const uint32_t tK = sK + st * kTileBytes, tV = sV + st * kTileBytes;
+
+        float s[8][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+            mma_rows<D>(s[nt], qa, tK, nt * 8, lane);
+        }
+        if (kb == nb - 1) {
+            const int lim = len - kb * kAttTile;
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                const int c = nt * 8 + 2 * t;
+                if (c >= lim) s[nt][0] = s[nt][2] = -INFINITY;
+                if (c + 1 >= lim) s[nt][1] = s[nt][3] = -INFINITY;
+            }
+        }
+        float mx0 = s[0][0], mx1 = s[0][2];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+            mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+        const float c0 = ex2((m0 - mn0) * p.scale_log2), c1 = ex2((m1 - mn1) * p.scale_log2);
+        m0 = mn0;
+        m1 = mn1;
+        const float b0 = mn0 * p.scale_log2, b1 = mn1 * p.scale_log2;
+        float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            s[nt][0] = ex2(fmaf(s[nt][0], p.scale_log2, -b0));
+            s[nt][1] = ex2(fmaf(s[nt][1], p.scale_log2, -b0));
+            s[nt][2] = ex2(fmaf(s[nt][2], p.scale_log2, -b1));
+            s[nt][3] = ex2(fmaf(s[nt][3], p.scale_log2, -b1));
+            sum0 += s[nt][0] + s[nt][1];
+            sum1 += s[nt][2] + s[nt][3];
+        }
+        l0 = l0 * c0 + sum0;
+        l1 = l1 * c1 + sum1;
+#pragma unroll
+        for (int i = 0; i < D / 8; ++i) {
+            o[i][0] *= c0;
+            o[i][1] *= c0;
+            o[i][2] *= c1;
+            o[i][3] *= c1;
+        }
+        if (kDrop) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                for (int jj = 0; jj < 2; ++jj) {
+                    const uint32_t hsh = patch_hash(key, qblk, kb * 4 + j, g, 2 * t + jj);
+                    if (!keep_byte(hsh, 0, p.keep_thr)) s[2 * j][jj] = 0.f;
+                    if (!keep_byte(hsh, 1, p.keep_thr)) s[2 * j + 1][jj] = 0.f;
+                    if (!keep_byte(hsh, 2, p.keep_thr)) s[2 * j][2 + jj] = 0.f;
+                    if (!keep_byte(hsh, 3, p.keep_thr)) s[2 * j + 1][2 + jj] = 0.f;
+                }
+            }
+        }
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            uint32_t a[4];
+            a[0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
+            a[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
+            a[2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+            a[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+            mma_cols<D>(o, a, tV, kk * 16, lane);
+        }
+        __syncthreads();
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float i0 = p.inv_keep / l0, i1 = p.inv_keep / l1;
+    store_rows<D>(o, i0, i1, sQ, smem, warp * 16, p.out + (long long)s0 * (p.h * D) + head * D, (long long)p.h * D,
+                  qt * kAttTile, len, lane);
+    if (t == 0) {
+        const int r0 = qt * kAttTile + warp * 16 + g;
+        float* lse = p.lse + (long long)head * p.T + s0;
+        if (r0 < len) lse[r0] = (m0 * p.scale_log2 + log2f(l0)) * kLn2;
+        if (r0 + 8 < len) lse[r0 + 8] = (m1 * p.scale_log2 + log2f(l1)) * kLn2;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------- D pre-pass
+// dsum[head, t] = sum_d dout[t, head, d] * out[t, head, d]; one warp per token row.
+template <int D>
+__global__ void __launch_bounds__(256) attn_dsum_kernel(const __nv_bfloat16* __restrict__ dout,
+                                                        const __nv_bfloat16* __restrict__ out, int T, int h,
+                                                        float* __restrict__ dsum) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= T) return;
+    const int H = h * D;
+    for (int c0 = 0; c0 < H; c0 += 256) {   // uniform trip count: the shuffles below need the whole warp
+        const int c = c0 + lane * 8;
+        float acc = 0.f;
+        if (c < H) {
+            const uint4 a = __ldg(reinterpret_cast<const uint4*>(dout + (long long)row * H + c));
+            const uint4 b = __ldg(reinterpret_cast<const uint4*>(out + (long long)row * H + c));
+            const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+            const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 fa = __bfloat1622float2(pa[i]), fb = __bfloat1622float2(pb[i]);
+                acc = fmaf(fa.x, fb.x, acc);
+                acc = fmaf(fa.y, fb.y, acc);
+            }
+        }
+#pragma unroll
+        for (int off = 1; off < D / 8; off <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+        if (c < H && (lane & (D / 8 - 1)) == 0) dsum[(long long)(c / D) * T + row] = acc;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------- backward
+// Role dQ: the warp owns 16 queries (Q and dO fragments in registers) and streams K / V.
+template <int D, bool kDrop>
+__device__ __forceinline__ void attn_bwd_dq(const AttnParams& p, unsigned char* smem, int seq, int head, int qt, int s0,
+                                            int len) {
+    constexpr int kTileBytes = kAttTile * D * 2;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const uint32_t sQ = smem_u32(smem), sDO = sQ + kTileBytes, sK = sDO + kTileBytes, sV = sK + 2 * kTileBytes;
+    const __nv_bfloat16* qs = p.q + (long long)s0 * p.in_stride + head * D;
+    const __nv_bfloat16* ks = p.k + (long long)s0 * p.in_stride + head * D;
+    const __nv_bfloat16* vs = p.v + (long long)s0 * p.in_stride + head * D;
+    const __nv_bfloat16* dos = p.dout + (long long)s0 * (p.h * D) + head * D;
+    const int nb = (len + kAttTile - 1) / kAttTile;
+
+    load_tile<D>(sQ, qs, qt * kAttTile, len, p.in_stride, tid);
+    load_tile<D>(sDO, dos, qt * kAttTile, len, (long long)p.h * D, tid);
+    load_tile<D>(sK, ks, 0, len, p.in_stride, tid);
+    load_tile<D>(sV, vs, 0, len, p.in_stride, tid);
+    cp_async_commit();
+
+    const int r0 = qt * kAttTile + warp * 16 + g;
+    const float* lse = p.lse + (long long)head * p.T + s0;
+    const float* dsm = p.dsum + (long long)head * p.T + s0;
+    const float l2_0 = (r0 < len ? __ldg(lse + r0) : 0.f) * kLog2e, l2_1 = (r0 + 8 < len ? __ldg(lse + r0 + 8) : 0.f) * kLog2e;
+    const float d_0 = r0 < len ? __ldg(dsm + r0) : 0.f, d_1 = r0 + 8 < len ? __ldg(dsm + r0 + 8) : 0.f;
+
+    uint32_t qa[D / 16][4], da[D / 16][4];
+    float dq[D / 8][4];
+#pragma unroll
+    for (int i = 0; i < D / 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
+    uint32_t key = 0;
+    if (kDrop) key = seq_key(p, seq, head);
+    const int qblk = qt * 4 + warp;
+
+    for (int kb = 0; kb < nb; ++kb) {
+        const int st = kb & 1;
+        if (kb + 1 < nb) {
+            load_tile<D>(sK + (st ^ 1) * kTileBytes, ks, (kb + 1) * kAttTile, len, p.in_stride, tid);
+            load_tile<D>(sV + (st ^ 1) * kTileBytes, vs, (kb + 1) * kAttTile, len, p.in_stride, tid);
+        }
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+        if (kb == 0) {
+            load_a_frags<D>(sQ, warp * 16, lane, qa);
+            load_a_frags<D>(sDO, warp * 16, lane, da);
+        }
+        const uint32_t tK = sK + st * kTileBytes, tV = sV + st * kTileBytes;
+        const int lim = len - kb * kAttTile;
+#pragma unroll
+        for (int kc = 0; kc < 4; ++kc) {
+            float s[2][4], dp[2][4];
+#pragma unroll
+            for (int n2 = 0; n2 < 2; ++n2) {
+                s[n2][0] = s[n2][1] = s[n2][2] = s[n2][3] = 0.f;
+                dp[n2][0] = dp[n2][1] = dp[n2][2] = dp[n2][3] = 0.f;
+                mma_rows<D>(s[n2], qa, tK, kc * 16 + n2 * 8, lane);
+                mma_rows<D>(dp[n2], da, tV, kc * 16 + n2 * 8, lane);
+            }
+            uint32_t h0 = 0, h1 = 0;
+            if (kDrop) {
+                h0 = patch_hash(key, qblk, kb * 4 + kc, g, 2 * t);
+                h1 = patch_hash(key, qblk, kb * 4 + kc, g, 2 * t + 1);
+            }
+#pragma unroll
+            for (int n2 = 0; n2 < 2; ++n2) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int col = kc * 16 + n2 * 8 + 2 * t + (j & 1);
+                    float pr = ex2(fmaf(s[n2][j], p.scale_log2, -((j & 2) ? l2_1 : l2_0)));
+                    if (col >= lim) pr = 0.f;
+                    float dpe = dp[n2][j];
+                    if (kDrop) {
+                        const bool keep = keep_byte((j & 1) ? h1 : h0, n2 + (j & 2), p.keep_thr);
+                        dpe = keep ? dpe * p.inv_keep : 0.f;
+                    }
+                    s[n2][j] = pr * (dpe - ((j & 2) ? d_1 : d_0));
+                }
+            }
+            uint32_t a[4];
+            a[0] = pack_bf16(s[0][0], s[0][1]);
+            a[1] = pack_bf16(s[0][2], s[0][3]);
+            a[2] = pack_bf16(s[1][0], s[1][1]);
+            a[3] = pack_bf16(s[1][2], s[1][3]);
+            mma_cols<D>(dq, a, tK, kc * 16, lane);
+        }
+        __syncthreads();
+    }
+    store_rows<D>(dq, p.scale, p.scale, sQ, smem, warp * 16, p.dq + (long long)s0 * p.d_stride + head * D, p.d_stride,
+                  qt * kAttTile, len, lane);
+}
+
+// Role dK/dV: the warp owns 16 keys (K and V fragments in registers) and streams Q / dO / LSE / D.
+template <int D, bool kDrop>
+__device__ __forceinline__ void attn_bwd_dkv(const AttnParams& p, unsigned char* smem, int seq, int head, int kt, int s0,
+                                             int len) {
+    constexpr int kTileBytes = kAttTile * D * 2;
+    constexpr int kStatBytes = kAttTile * 4;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const uint32_t sK = smem_u32(smem), sV = sK + kTileBytes, sQ = sV + kTileBytes, sDO = sQ + 2 * kTileBytes,
+                   sL = sDO + 2 * kTileBytes, sD = sL + 2 * kStatBytes;
+    unsigned char* pL = smem + 6 * kTileBytes;
+    unsigned char* pD = pL + 2 * kStatBytes;
+    const __nv_bfloat16* qs = p.q + (long long)s0 * p.in_stride + head * D;
+    const __nv_bfloat16* ks = p.k + (long long)s0 * p.in_stride + head * D;
+    const __nv_bfloat16* vs = p.v + (long long)s0 * p.in_stride + head * D;
+    const __nv_bfloat16* dos = p.dout + (long long)s0 * (p.h * D) + head * D;
+    const float* lse = p.lse + (long long)head * p.T + s0;
+    const float* dsm = p.dsum + (long long)head * p.T + s0;
+    const int nb = (len + kAttTile - 1) / kAttTile;
+
+    load_tile<D>(sK, ks, kt * kAttTile, len, p.in_stride, tid);
+    load_tile<D>(sV, vs, kt * kAttTile, len, p.in_stride, tid);
+    load_tile<D>(sQ, qs, 0, len, p.in_stride, tid);
+    load_tile<D>(sDO, dos, 0, len, (long long)p.h * D, tid);
+    load_stat(sL, lse, 0, len, tid);
+    load_stat(sD, dsm, 0, len, tid);
+    cp_async_commit();
+
+    uint32_t ka[D / 16][4], va[D / 16][4];
+    float dk[D / 8][4], dv[D / 8][4];
+#pragma unroll
+    for (int i = 0; i < D / 8; ++i) {
+        dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f;
+        dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f;
+    }
+    uint32_t key = 0;
+    if (kDrop) key = seq_key(p, seq, head);
+    const int kblk = kt * 4 + warp;
+
+    for (int qb = 0; qb < nb; ++qb) {
+        const int st = qb & 1;
+        if (qb + 1 < nb) {
+            load_tile<D>(sQ + (st ^ 1) * kTileBytes, qs, (qb + 1) * kAttTile, len, p.in_stride, tid);
+            load_tile<D>(sDO + (st ^ 1) * kTileBytes, dos, (qb + 1) * kAttTile, len, (long long)p.h * D, tid);
+            load_stat(sL + (st ^ 1) * kStatBytes, lse, (qb + 1) * kAttTile, len, tid);
+            load_stat(sD + (st ^ 1) * kStatBytes, dsm, (qb + 1) * kAttTile, len, tid);
+        }
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+        if (qb == 0) {
+            load_a_frags<D>(sK, warp * 16, lane, ka);
+            load_a_frags<D>(sV, warp * 16, lane, va);
+        }
+        const uint32_t tQ = sQ + st * kTileBytes, tDO = sDO + st * kTileBytes;
+        const float* Ls = reinterpret_cast<const float*>(pL + st * kStatBytes);
+        const float* Ds = reinterpret_cast<const float*>(pD + st * kStatBytes);
+        const int lim = len - qb * kAttTile;
+#pragma unroll
+        for (int qc = 0; qc < 4; ++qc) {
+            float s[2][4], dp[2][4];
+#pragma unroll
+            for (int n2 = 0; n2 < 2; ++n2) {
+                s[n2][0] = s[n2][1] = s[n2][2] = s[n2][3] = 0.f;
+                dp[n2][0] = dp[n2][1] = dp[n2][2] = dp[n2][3] = 0.f;
+                mma_rows<D>(s[n2], ka, tQ, qc * 16 + n2 * 8, lane);
+                mma_rows<D>(dp[n2], va, tDO, qc * 16 + n2 * 8, lane);
+            }
+            uint32_t h0 = 0, h1 = 0;
+            if (kDrop) {
+                h0 = patch_hash(key, qb * 4 + qc, kblk, 2 * t, g);
+                h1 = patch_hash(key, qb * 4 + qc, kblk, 2 * t + 1, g);
+            }
+            float pd[2][4];
+#pragma unroll
+            for (int n2 = 0; n2 < 2; ++n2) {
+                const int col = qc * 16 + n2 * 8 + 2 * t;
+                const float2 l2 = *reinterpret_cast<const float2*>(Ls + col);
+                const float2 dd = *reinterpret_cast<const float2*>(Ds + col);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float pr = ex2(fmaf(s[n2][j], p.scale_log2, -((j & 1) ? l2.y : l2.x) * kLog2e));
+                    if (col + (j & 1) >= lim) pr = 0.f;
+                    float dpe = dp[n2][j];
+                    float pk = pr;
+                    if (kDrop) {
+                        // element (key g + 8 * (j >> 1), query n2 * 8 + 2t + (j & 1)): byte = 2 * n2 + (j >> 1)
+                        const bool keep = keep_byte((j & 1) ? h1 : h0, 2 * n2 + (j >> 1), p.keep_thr);
+                        dpe = keep ? dpe * p.inv_keep : 0.f;
+                        pk = keep ? pr * p.inv_keep : 0.f;
+                    }
+                    pd[n2][j] = pk;
+                    s[n2][j] = pr * (dpe - ((j & 1) ? dd.y : dd.x));
+                }
+            }
+            uint32_t a[4];
+            a[0] = pack_bf16(pd[0][0], pd[0][1]);
+            a[1] = pack_bf16(pd[0][2], pd[0][3]);
+            a[2] = pack_bf16(pd[1][0], pd[1][1]);
+            a[3] = pack_bf16(pd[1][2], pd[1][3]);
+            mma_cols<D>(dv, a, tDO, qc * 16, lane);
+            a[0] = pack_bf16(s[0][0], s[0][1]);
+            a[1] = pack_bf16(s[0][2], s[0][3]);
+            a[2] = pack_bf16(s[1][0], s[1][1]);
+            a[3] = pack_bf16(s[1][2], s[1][3]);
+            mma_cols<D>(dk, a, tQ, qc * 16, lane);
+        }
+        __syncthreads();
+    }
+    store_rows<D>(dk, p.scale, p.scale, sK, smem, warp * 16, p.dk + (long long)s0 * p.d_stride + head * D, p.d_stride,
+                  kt * kAttTile, len, lane);
+    store_rows<D>(dv, 1.f, 1.f, sV, smem + kTileBytes, warp * 16, p.dv + (long long)s0 * p.d_stride + head * D,
+                  p.d_stride, kt * kAttTile, len, lane);
+}
+
+template <int D, bool kDrop>
+__global__ void __launch_bounds__(kAttThreads) attn_bwd_kernel(const AttnParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int seq = blockIdx.z, head = blockIdx.y;
+    const bool dkv = int(blockIdx.x) < p.ntile;   // the longer role is scheduled first
+    const int tile = dkv ? blockIdx.x : blockIdx.x - p.ntile;
+    const int s0 = __ldg(p.cu + seq);
+    const int len = __ldg(p.cu + seq + 1) - s0;
+    if (tile * kAttTile >= len) return;
+    if (dkv)
+        attn_bwd_dkv<D, kDrop>(p, smem, seq, head, tile, s0, len);
+    else
+        attn_bwd_dq<D, kDrop>(p, smem, seq, head, tile, s0, len);
+}
+
+// Test hook: mask[head, t, j] = 1 iff key j of token t's sequence is kept for query t (j < max_len).
+__global__ void attn_mask_kernel(const AttnParams p, int max_len) {
+    const int seq = blockIdx.z, head = blockIdx.y;
+    const int s0 = p.cu[seq], len = p.cu[seq + 1] - s0;
+    const uint32_t key = seq_key(p, seq, head);
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < len * len; idx += gridDim.x * blockDim.x) {
+        const int q = idx / len, k = idx % len;
+        const int r = q & 15, c = k & 15;
+        const uint32_t hsh = patch_hash(key, q >> 4, k >> 4, r & 7, c & 7);
+        const int byte = (r >> 3) * 2 + (c >> 3);
+        p.mask_out[((long long)head * p.T + s0 + q) * max_len + k] = keep_byte(hsh, byte, p.keep_thr) ? 1 : 0;
+    }
+}
+
+size_t fwd_smem(int D) { return size_t(5) * kAttTile * D * 2; }
+size_t bwd_smem(int D) { return size_t(6) * kAttTile * D * 2 + 4 * kAttTile * 4; }
+
+int fill_dropout(AttnParams& p, float drop_p, const void* seed, int salt) {
+    p.keep_thr = 256;
+    p.inv_keep = 1.f;
+    p.seed = nullptr;
+    p.salt = uint32_t(salt);
+    if (drop_p > 0.f) {
+        SB200_REQUIRE(seed != nullptr, "attention: dropout needs a seed pointer");
+        SB200_REQUIRE(drop_p < 1.f, "attention: drop_p must be < 1");
+        int thr = int((1.f - drop_p) * 256.f + 0.5f);
+        thr = thr < 1 ? 1 : (thr > 256 ? 256 : thr);
+        p.keep_thr = uint32_t(thr);
+        p.inv_keep = 256.f / float(thr);
+        p.seed = static_cast<const unsigned long long*>(seed);
+    }
+    return SB200_OK;
+}
+
+template <typename K>
+int opt_in_smem(K kernel, size_t bytes, int slot) {
+    if (bytes > 48 * 1024 && slot >= 0 && !device_flag_test_and_set(slot))
+        SB200_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes)));
+    return SB200_OK;
+}
+
+int check_common(int T, int h, int d, int nseq, int max_len) {
+    SB200_REQUIRE(d == 32 || d == 64, "attention: head_dim %d unsupported (32 or 64)", d);
+    SB200_REQUIRE(T > 0 && h > 0 && h <= 65535 && nseq > 0 && nseq <= 65535, "attention: bad T / heads / nseq");
+    SB200_REQUIRE(max_len > 0 && max_len <= 1024, "attention: max_len %d unsupported (1..1024)", max_len);
+    return SB200_OK;
+}
+
+}  // namespace
+}  // namespace sb200
+
+using namespace sb200;
+
+extern "C" int sb200_attn_supported(int head_dim, int max_len) {
+    return (head_dim == 32 || head_dim == 64) && max_len > 0 && max_len <= 1024;
+}
+
+extern "C" int sb200_attn_fwd(const void* q, const void* k, const void* v, size_t in_stride, const int* cu_seqlens,
+                              int nseq, int max_len, int T, int h, int d, float scale, float drop_p,
+                              const void* drop_seed, int salt, void* out, float* lse, sb200_stream_t stream) {
+    if (int rc = check_common(T, h, d, nseq, max_len)) return rc;
+    SB200_REQUIRE(q && k && v && cu_seqlens && out && lse, "attn_fwd: null pointer");
+    SB200_REQUIRE(in_stride % 8 == 0, "attn_fwd: row stride must be a multiple of 8 elements");
+    AttnParams p{};
+    p.q = static_cast<const __nv_bfloat16*>(q);
+    p.k = static_cast<const __nv_bfloat16*>(k);
+    p.v = static_cast<const __nv_bfloat16*>(v);
+    p.in_stride = (long long)in_stride;
+    p.out = static_cast<__nv_bfloat16*>(out);
+    p.lse = lse;
+    p.cu = cu_seqlens;
+    p.T = T; p.h = h; p.nseq = nseq;
+    p.ntile = (max_len + kAttTile - 1) / kAttTile;
+    p.scale = scale;
+    p.scale_log2 = scale * kLog2e;
+    if (int rc = fill_dropout(p, drop_p, drop_seed, salt)) return rc;
+    const dim3 grid(p.ntile, h, nseq);
+    const size_t sm = fwd_smem(d);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const bool drop = p.keep_thr < 256;
+#define SB200_ATT_FWD(DD, DR, SLOT)                                                            \
+    do {                                                                                       \
+        if (int rc = opt_in_smem(attn_fwd_kernel<DD, DR>, sm, SLOT)) return rc;                \
+        attn_fwd_kernel<DD, DR><<<grid, kAttThreads, sm, s>>>(p);                              \
+    } while (0)
+    if (d == 32) { if (drop) SB200_ATT_FWD(32, true, -1); else SB200_ATT_FWD(32, false, -1); }   // <= 40 KB: no opt-in
+    else { if (drop) SB200_ATT_FWD(64, true, -1); else SB200_ATT_FWD(64, false, -1); }
+#undef SB200_ATT_FWD
+    SB200_CHECK_LAUNCH("attn_fwd_kernel");
+    return SB200_OK;
+}
+
+extern "C" int sb200_attn_bwd(const void* q, const void* k, const void* v, size_t in_stride, const void* out,
+                              const void* dout, const float* lse, const int* cu_seqlens, int nseq, int max_len, int T,
+                              int h, int d, float scale, float drop_p, const void* drop_seed, int salt, void* dq,
+                              void* dk, void* dv, size_t d_stride, float* dsum, sb200_stream_t stream) {
+    if (int rc = check_common(T, h, d, nseq, max_len)) return rc;
+    SB200_REQUIRE(q && k && v && out && dout && lse && cu_seqlens && dq && dk && dv && dsum, "attn_bwd: null pointer");
+    SB200_REQUIRE(in_stride % 8 == 0 && d_stride % 8 == 0, "attn_bwd: row strides must be multiples of 8 elements");
+    AttnParams p{};
+    p.q = static_cast<const __nv_bfloat16*>(q);
+    p.k = static_cast<const __nv_bfloat16*>(k);
+    p.v = static_cast<const __nv_bfloat16*>(v);
+    p.in_stride = (long long)in_stride;
+    p.lse = const_cast<float*>(lse);
+    p.cu = cu_seqlens;
+    p.T = T; p.h = h; p.nseq = nseq;
+    p.ntile = (max_len + kAttTile - 1) / kAttTile;
+    p.scale = scale;
+    p.scale_log2 = scale * kLog2e;
+    p.dout = static_cast<const __nv_bfloat16*>(dout);
+    p.dsum = dsum;
+    p.dq = static_cast<__nv_bfloat16*>(dq);
+    p.dk = static_cast<__nv_bfloat16*>(dk);
+    p.dv = static_cast<__nv_bfloat16*>(dv);
+    p.d_stride = (long long)d_stride;
+    if (int rc = fill_dropout(p, drop_p, drop_seed, salt)) return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int dsum_blocks = (T + 7) / 8;
+    if (d == 32)
+        attn_dsum_kernel<32><<<dsum_blocks, 256, 0, s>>>(p.dout, static_cast<const __nv_bfloat16*>(out), T, h, dsum);
+    else
+        attn_dsum_kernel<64><<<dsum_blocks, 256, 0, s>>>(p.dout, static_cast<const __nv_bfloat16*>(out), T, h, dsum);
+    SB200_CHECK_LAUNCH("attn_dsum_kernel");
+    const dim3 grid(2 * p.ntile, h, nseq);
+    const size_t sm = bwd_smem(d);
+    const bool drop = p.keep_thr < 256;
+#define SB200_ATT_BWD(DD, DR, SLOT)                                                            \
+    do {                                                                                       \
+        if (int rc = opt_in_smem(attn_bwd_kernel<DD, DR>, sm, SLOT)) return rc;                \
+        attn_bwd_kernel<DD, DR><<<grid, kAttThreads, sm, s>>>(p);                              \
+    } while (0)
+    if (d == 32) { if (drop) SB200_ATT_BWD(32, true, -1); else SB200_ATT_BWD(32, false, -1); }
+    else { if (drop) SB200_ATT_BWD(64, true, 14); else SB200_ATT_BWD(64, false, 15); }   // 49 KB: opt-in slots 14 / 15
+#undef SB200_ATT_BWD
+    SB200_CHECK_LAUNCH("attn_bwd_kernel");
+    return SB200_OK;
+}
+
+extern "C" int sb200_attn_dropout_mask(const int* cu_seqlens, int nseq, int max_len, int T, int h, float drop_p,
+                                       const void* drop_seed, int salt, unsigned char* mask,
+                                       sb200_stream_t stream) {
+    SB200_REQUIRE(cu_seqlens && mask && drop_seed, "attn_dropout_mask: null pointer");
+    SB200_REQUIRE(drop_p > 0.f, "attn_dropout_mask: drop_p must be > 0");
+    AttnParams p{};
+    p.cu = cu_seqlens;
+    p.T = T; p.h = h; p.nseq = nseq;
+    if (int rc = fill_dropout(p, drop_p, drop_seed, salt)) return rc;
+    p.mask_out = mask;
+    attn_mask_kernel<<<dim3(8, h, nseq), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, max_len);
+    SB200_CHECK_LAUNCH("attn_mask_kernel");
+    return SB200_OK;
+}

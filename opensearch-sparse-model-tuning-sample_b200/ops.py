@@ -824,6 +824,103 @@ def embed_sum(ids, pos, typ, word_table, pos_table, type_table, padding_idx=None
     return EmbedSumFunction.apply(ids, pos, typ, word_table, pos_table, type_table, padding_idx)
 
 
+# --------------------------------------------------------------------------------------------- encoder body: attention
+def attn_supported(head_dim, max_len):
+    return bool(_lib.load().sb200_attn_supported(int(head_dim), int(max_len)))
+
+
+def _attn_views(qkv):
+    """qkv bf16 [T, 3, h, d] (the fused projection output) -> (T, h, d, row stride in elements)."""
+    if qkv.dtype != torch.bfloat16 or qkv.dim() != 4 or qkv.shape[1] != 3:
+        raise TypeError("varlen_attention: qkv must be bf16 [T, 3, heads, head_dim]")
+    T, _, h, d = qkv.shape
+    return T, h, d, 3 * h * d
+
+
+def attn_forward(qkv, cu_seqlens, max_len, scale, drop_p=0.0, seed=None, salt=0):
+    """Raw forward: returns (out bf16 [T, h, d], lse f32 [h, T])."""
+    _need_cuda(qkv, cu_seqlens, seed)
+    T, h, d, stride = _attn_views(qkv)
+    if cu_seqlens.dtype != torch.int32:
+        raise TypeError("varlen_attention: cu_seqlens must be int32")
+    qkv = qkv.contiguous()
+    out = torch.empty(T, h, d, dtype=torch.bfloat16, device=qkv.device)
+    lse = torch.empty(h, T, dtype=torch.float32, device=qkv.device)
+    base, e = qkv.data_ptr(), 2 * h * d
+    with torch.cuda.device(qkv.device):
+        code = _lib.load().sb200_attn_fwd(base, base + e, base + 2 * e, stride, _ptr(cu_seqlens),
+                                          cu_seqlens.numel() - 1, int(max_len), T, h, d, float(scale), float(drop_p),
+                                          _ptr(seed), int(salt), _ptr(out), _ptr(lse), _stream())
+    _lib.check(code, "sb200_attn_fwd")
+    return out, lse
+
+
+def attn_backward(qkv, out, dout, lse, cu_seqlens, max_len, scale, drop_p=0.0, seed=None, salt=0, zero_fill=False):
+    """Raw backward: returns dqkv bf16 [T, 3, h, d]. Rows outside every sequence are only defined with zero_fill."""
+    T, h, d, stride = _attn_views(qkv)
+    dout = dout.contiguous()
+    if dout.dtype != torch.bfloat16:
+        dout = dout.to(torch.bfloat16)
+    dqkv = (torch.zeros if zero_fill else torch.empty)(T, 3, h, d, dtype=torch.bfloat16, device=qkv.device)
+    dsum = torch.empty(h, T, dtype=torch.float32, device=qkv.device)
+    base, dbase, e = qkv.data_ptr(), dqkv.data_ptr(), 2 * h * d
+    with torch.cuda.device(qkv.device):
+        code = _lib.load().sb200_attn_bwd(base, base + e, base + 2 * e, stride, _ptr(out), _ptr(dout), _ptr(lse),
+                                          _ptr(cu_seqlens), cu_seqlens.numel() - 1, int(max_len), T, h, d,
+                                          float(scale), float(drop_p), _ptr(seed), int(salt), dbase, dbase + e,
+                                          dbase + 2 * e, stride, _ptr(dsum), _stream())
+    _lib.check(code, "sb200_attn_bwd")
+    return dqkv
+
+
+def attn_dropout_mask(cu_seqlens, max_len, T, h, drop_p, seed, salt=0):
+    """Test hook: bool [h, T, max_len], entry [head, t, j] = query t keeps key j of its own sequence."""
+    _need_cuda(cu_seqlens, seed)
+    mask = torch.zeros(h, T, int(max_len), dtype=torch.uint8, device=cu_seqlens.device)
+    with torch.cuda.device(cu_seqlens.device):
+        code = _lib.load().sb200_attn_dropout_mask(_ptr(cu_seqlens), cu_seqlens.numel() - 1, int(max_len), T, h,
+                                                   float(drop_p), _ptr(seed), int(salt), _ptr(mask), _stream())
+    _lib.check(code, "sb200_attn_dropout_mask")
+    return mask.bool()
+
+
+class VarlenAttentionFunction(torch.autograd.Function):
+    """softmax(Q K^T * scale) -> dropout -> V per packed sequence (transformers BertSelfAttention under bf16 autocast)."""
+
+    @staticmethod
+    def forward(ctx, qkv, cu_seqlens, max_len, scale, drop_p, seed, salt, covers_all_rows):
+        qc = qkv.detach().contiguous()
+        out, lse = attn_forward(qc, cu_seqlens, max_len, scale, drop_p, seed, salt)
+        ctx.save_for_backward(qc, out, lse, cu_seqlens, seed)
+        ctx.cfg = (int(max_len), float(scale), float(drop_p), int(salt), bool(covers_all_rows))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        qc, out, lse, cu, seed = ctx.saved_tensors
+        max_len, scale, drop_p, salt, covers = ctx.cfg
+        dqkv = attn_backward(qc, out, dout, lse, cu, max_len, scale, drop_p, seed, salt, zero_fill=not covers)
+        return dqkv, None, None, None, None, None, None, None
+
+
+def varlen_attention(qkv, cu_seqlens, max_len, scale=None, drop_p=0.0, training=False, seed=None, salt=0,
+                     covers_all_rows=False):
+    """Self-attention over packed sequences. qkv bf16 [T, 3, h, d]; cu_seqlens int32 [nseq + 1] (device); returns bf16
+    [T, h, d] (rows outside every sequence are undefined). Dropout only when training and drop_p > 0; `seed` is a
+    1-element int64 device tensor (drawn from torch's CUDA generator when None: CUDA-graph safe), `salt` separates
+    calls that share a seed (the layer index). covers_all_rows: cu_seqlens[-1] == T, so the gradient needs no
+    zero fill."""
+    d = qkv.shape[-1]
+    if scale is None:
+        scale = 1.0 / (d ** 0.5)
+    p = float(drop_p) if training else 0.0
+    if p > 0.0 and seed is None:
+        seed = torch.randint(-2 ** 62, 2 ** 62, (1,), dtype=torch.int64, device=qkv.device)
+    if p == 0.0:
+        seed = None
+    return VarlenAttentionFunction.apply(qkv, cu_seqlens, max_len, scale, p, seed, salt, covers_all_rows)
+
+
 # --------------------------------------------------------------------------------------------- encoder body: Linear
 def colsum_supported(n):
     return bool(_lib.load().sb200_colsum_supported(int(n)))

@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.EXPORTED_SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.sb200_abi_version() == 2
+    assert lib.sb200_abi_version() == 3
     assert lib.sb200_head_fwd_workspace_bytes(160, 256) > 0
     assert lib.sb200_head_bwd_workspace_bytes(160, 256, 384, 30522) >= 160 * 30522 * 8
 
