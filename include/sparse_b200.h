@@ -297,8 +297,8 @@ int sb200_colsum(const void* dy, int elem_bytes, int R, int N, float* out, void*
  *               the kept entries are rescaled by its inverse. Pass the same three values to the backward call.
  *               drop_p == 0: no dropout (drop_seed may be NULL).
  * Backward: dout bf16 [T, h * d]; writes dq / dk / dv (bf16, element [t, head, :] at ptr + t * d_stride + head * d,
- * every row of every sequence exactly once; rows outside all sequences are left untouched); dsum f32 [h, T] is
- * scratch (rowsum(dout * out)). Deterministic (no atomics).
+ * every row of every sequence exactly once; rows outside all sequences are left untouched); dsum f32 [2, h, T] is
+ * scratch (per-row constants of the pass). Deterministic (no atomics). drop_p <= 0.5.
  * sb200_attn_dropout_mask (test hook): mask u8 [h, T, max_len], mask[head, t, j] = 1 iff query t keeps key j of its
  * own sequence. */
 int sb200_attn_supported(int head_dim, int max_len);

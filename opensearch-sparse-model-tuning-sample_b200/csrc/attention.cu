@@ -47,13 +47,14 @@ struct AttnParams {
     const int* cu;            // [nseq + 1]
     int T, h, nseq, ntile;
     float scale, scale_log2;
-    uint32_t keep_thr;        // keep iff byte < keep_thr  (256 = keep everything)
+    uint32_t keep_thr;        // keep probability = keep_thr / 256  (256 = keep everything)
+    uint32_t keep_add;        // (128 - (256 - keep_thr)) in every byte: SWAR compare byte >= 256 - keep_thr
     float inv_keep;
     const unsigned long long* seed;
     uint32_t salt;
     // backward
     const __nv_bfloat16* dout;  // [T, h * D]
-    const float* dsum;          // [h, T]
+    const float* stat;          // [2, h, T]: lse * log2e - log2(inv_keep), rowsum(dout * out) / inv_keep
     __nv_bfloat16* dq;          // same layout as q / k / v (row stride d_stride)
     __nv_bfloat16* dk;
     __nv_bfloat16* dv;
@@ -191,7 +192,7 @@ __device__ __forceinline__ void mma_cols(float (&acc)[D / 8][4], const uint32_t 
 
 // Writes the warp's 16 x D accumulator (scaled) as bf16 through its own 16 rows of `tile` to global rows.
 template <int D>
-__device__ __forceinline__ void store_rows(const float (&acc)[D / 8][4], float s0, float s1, uint32_t tile,
+__device__ __forceinline__ void store_rows(const float (&acc)[D / 8][4], float s0, float s1,
                                            unsigned char* tile_ptr, int wrow0, __nv_bfloat16* dst, long long stride,
                                            int grow0, int len, int lane) {
     constexpr int CPR = D / 8;
@@ -215,7 +216,6 @@ __device__ __forceinline__ void store_rows(const float (&acc)[D / 8][4], float s
             *reinterpret_cast<uint4*>(dst + (long long)gr * stride + c * 8) = val;
         }
     }
-    (void)tile;
 }
 
 __device__ __forceinline__ uint32_t seq_key(const AttnParams& p, int seq, int head) {
@@ -223,15 +223,114 @@ __device__ __forceinline__ uint32_t seq_key(const AttnParams& p, int seq, int he
     return mix32(uint32_t(s) ^ mix32(uint32_t(s >> 32) + 0x9E3779B9u * uint32_t(seq * p.h + head + 1)) ^
                  (p.salt * 0x85EBCA6Bu));
 }
-// One hash per 2x2 patch {r, r+8} x {c, c+8} of the 16 x 16 block (qblk, kblk); byte 0: (r, c), 1: (r, c+8),
-// 2: (r+8, c), 3: (r+8, c+8).
-__device__ __forceinline__ uint32_t patch_hash(uint32_t key, int qblk, int kblk, int r, int c) {
-    const uint32_t idx = uint32_t(((qblk * 64 + kblk) * 64) + r * 8 + c);
-    return mix32(key ^ (idx * 0x9E3779B1u));
+// Dropout decisions of one 2x2 patch {r, r+8} x {c, c+8} of the 16 x 16 score block (qblk, kblk): a 32-bit hash, one
+// byte per element (byte 0: (r, c), 1: (r, c+8), 2: (r+8, c), 3: (r+8, c+8)); an element is kept iff its byte is
+// >= 256 - thr. Returned as flags: bit 7 of byte i set <=> element i kept (SWAR compare; needs 256 - thr <= 128).
+constexpr uint32_t kGolden = 0x9E3779B1u;
+__device__ __forceinline__ uint32_t patch_index(int qblk, int kblk, int r, int c) {
+    return uint32_t(((qblk * 64 + kblk) * 64) + r * 8 + c);
 }
-__device__ __forceinline__ bool keep_byte(uint32_t h, int i, uint32_t thr) { return ((h >> (8 * i)) & 0xFFu) < thr; }
+__device__ __forceinline__ uint32_t patch_flags(uint32_t key, uint32_t idx_times_golden, uint32_t addc) {
+    const uint32_t h = mix32(key ^ idx_times_golden);
+    return ((h & 0x7F7F7F7Fu) + addc) | h;
+}
+template <uint32_t kSel>
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "n"(kSel));
+    return d;
+}
+// bf16x2 mask of byte I of two patches: low half from f0, high half from f1 (selector bit 3 = replicate the byte's msb)
+template <int I>
+__device__ __forceinline__ uint32_t pair_mask(uint32_t f0, uint32_t f1) {
+    return prmt<0xCC88u + 0x1111u * I>(f0, f1);
+}
+template <int I>
+__device__ __forceinline__ float mask_f32(float x, uint32_t f) {
+    return __uint_as_float(__float_as_uint(x) & prmt<0x8888u + 0x1111u * I>(f, f));
+}
 
 // ---------------------------------------------------------------------------------------------------------- forward
+// One 64-key block of the forward pass for the warp's 16 queries. kTail: the block holds fewer than 64 valid keys
+// (n-tiles beyond the sequence are skipped, the straddling one is masked).
+template <int D, bool kDrop, bool kTail>
+__device__ __forceinline__ void fwd_block(const AttnParams& p, const uint32_t (&qa)[D / 16][4], float (&o)[D / 8][4],
+                                          float& m0, float& m1, float& l0, float& l1, uint32_t tK, uint32_t tV, int lim,
+                                          uint32_t key, uint32_t ig, int lane) {
+    const int t = lane & 3;
+    float s[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+        if (!kTail || nt * 8 < lim) {
+            s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+            mma_rows<D>(s[nt], qa, tK, nt * 8, lane);
+        } else {
+            s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = -INFINITY;
+        }
+    }
+    if (kTail) {
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            const int c = nt * 8 + 2 * t;
+            if (c >= lim) s[nt][0] = s[nt][2] = -INFINITY;
+            if (c + 1 >= lim) s[nt][1] = s[nt][3] = -INFINITY;
+        }
+    }
+    float mx0 = s[0][0], mx1 = s[0][2];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+        mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+        mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+    const float c0 = ex2((m0 - mn0) * p.scale_log2), c1 = ex2((m1 - mn1) * p.scale_log2);
+    m0 = mn0;
+    m1 = mn1;
+    const float b0 = mn0 * p.scale_log2, b1 = mn1 * p.scale_log2;
+    float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+        s[nt][0] = ex2(fmaf(s[nt][0], p.scale_log2, -b0));
+        s[nt][1] = ex2(fmaf(s[nt][1], p.scale_log2, -b0));
+        s[nt][2] = ex2(fmaf(s[nt][2], p.scale_log2, -b1));
+        s[nt][3] = ex2(fmaf(s[nt][3], p.scale_log2, -b1));
+        sum0 += s[nt][0] + s[nt][1];
+        sum1 += s[nt][2] + s[nt][3];
+    }
+    l0 = l0 * c0 + sum0;
+    l1 = l1 * c1 + sum1;
+#pragma unroll
+    for (int i = 0; i < D / 8; ++i) {
+        o[i][0] *= c0;
+        o[i][1] *= c0;
+        o[i][2] *= c1;
+        o[i][3] *= c1;
+    }
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+        if (!kTail || kk * 16 < lim) {
+            uint32_t a[4];
+            a[0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
+            a[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
+            a[2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+            a[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+            if (kDrop) {
+                const uint32_t igk = ig + uint32_t(kk * 64) * kGolden;
+                const uint32_t f0 = patch_flags(key, igk, p.keep_add), f1 = patch_flags(key, igk + kGolden, p.keep_add);
+                a[0] &= pair_mask<0>(f0, f1);
+                a[1] &= pair_mask<2>(f0, f1);
+                a[2] &= pair_mask<1>(f0, f1);
+                a[3] &= pair_mask<3>(f0, f1);
+            }
+            mma_cols<D>(o, a, tV, kk * 16, lane);
+        }
+    }
+}
+
 template <int D, bool kDrop>
 __global__ void __launch_bounds__(kAttThreads) attn_fwd_kernel(const AttnParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -246,6 +345,7 @@ __global__ void __launch_bounds__(kAttThreads) attn_fwd_kernel(const AttnParams 
     const __nv_bfloat16* ks = p.k + (long long)s0 * p.in_stride + head * D;
     const __nv_bfloat16* vs = p.v + (long long)s0 * p.in_stride + head * D;
     const int nb = (len + kAttTile - 1) / kAttTile;
+    const bool active = qt * kAttTile + warp * 16 < len;   // warps whose 16 rows are all padding only load and sync
 
     load_tile<D>(sQ, qs, qt * kAttTile, len, p.in_stride, tid);
     load_tile<D>(sK, ks, 0, len, p.in_stride, tid);
@@ -259,7 +359,7 @@ __global__ void __launch_bounds__(kAttThreads) attn_fwd_kernel(const AttnParams 
     float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
     uint32_t key = 0;
     if (kDrop) key = seq_key(p, seq, head);
-    const int qblk = qt * 4 + warp;
+    const uint32_t ig0 = patch_index(qt * 4 + warp, 0, g, 2 * t) * kGolden;
 
     for (int kb = 0; kb < nb; ++kb) {
         const int st = kb & 1;
@@ -270,88 +370,25 @@ __global__ void __launch_bounds__(kAttThreads) attn_fwd_kernel(const AttnParams 
         cp_async_commit();
         cp_async_wait<1>();
         __syncthreads();
-        if (kb == 0) load_a_frags<D>(sQ, warp * 16, lane, qa);
-        const uint32_t tK = sK + st * kTileBytes, tV = sV + st * kTileBytes;
-
-        float s[8][4];
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-            s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-            mma_rows<D>(s[nt], qa, tK, nt * 8, lane);
-        }
-        if (kb == nb - 1) {
-            const int lim = len - kb * kAttTile;
-#pragma unroll
-            for (int nt = 0; nt < 8; ++nt) {
-                const int c = nt * 8 + 2 * t;
-                if (c >= lim) s[nt][0] = s[nt][2] = -INFINITY;
-                if (c + 1 >= lim) s[nt][1] = s[nt][3] = -INFINITY;
-            }
-        }
-        float mx0 = s[0][0], mx1 = s[0][2];
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-            mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
-            mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
-        }
-        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
-        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
-        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-        const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
-        const float c0 = ex2((m0 - mn0) * p.scale_log2), c1 = ex2((m1 - mn1) * p.scale_log2);
-        m0 = mn0;
-        m1 = mn1;
-        const float b0 = mn0 * p.scale_log2, b1 = mn1 * p.scale_log2;
-        float sum0 = 0.f, sum1 = 0.f;
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-            s[nt][0] = ex2(fmaf(s[nt][0], p.scale_log2, -b0));
-            s[nt][1] = ex2(fmaf(s[nt][1], p.scale_log2, -b0));
-            s[nt][2] = ex2(fmaf(s[nt][2], p.scale_log2, -b1));
-            s[nt][3] = ex2(fmaf(s[nt][3], p.scale_log2, -b1));
-            sum0 += s[nt][0] + s[nt][1];
-            sum1 += s[nt][2] + s[nt][3];
-        }
-        l0 = l0 * c0 + sum0;
-        l1 = l1 * c1 + sum1;
-#pragma unroll
-        for (int i = 0; i < D / 8; ++i) {
-            o[i][0] *= c0;
-            o[i][1] *= c0;
-            o[i][2] *= c1;
-            o[i][3] *= c1;
-        }
-        if (kDrop) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-#pragma unroll
-                for (int jj = 0; jj < 2; ++jj) {
-                    const uint32_t hsh = patch_hash(key, qblk, kb * 4 + j, g, 2 * t + jj);
-                    if (!keep_byte(hsh, 0, p.keep_thr)) s[2 * j][jj] = 0.f;
-                    if (!keep_byte(hsh, 1, p.keep_thr)) s[2 * j + 1][jj] = 0.f;
-                    if (!keep_byte(hsh, 2, p.keep_thr)) s[2 * j][2 + jj] = 0.f;
-                    if (!keep_byte(hsh, 3, p.keep_thr)) s[2 * j + 1][2 + jj] = 0.f;
-                }
-            }
-        }
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-            uint32_t a[4];
-            a[0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
-            a[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
-            a[2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
-            a[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
-            mma_cols<D>(o, a, tV, kk * 16, lane);
+        if (active) {
+            if (kb == 0) load_a_frags<D>(sQ, warp * 16, lane, qa);
+            const uint32_t tK = sK + st * kTileBytes, tV = sV + st * kTileBytes;
+            const int lim = len - kb * kAttTile;     // valid keys in this block
+            const uint32_t ig = ig0 + uint32_t(kb * 4 * 64) * kGolden;
+            if (lim >= kAttTile)
+                fwd_block<D, kDrop, false>(p, qa, o, m0, m1, l0, l1, tK, tV, lim, key, ig, lane);
+            else
+                fwd_block<D, kDrop, true>(p, qa, o, m0, m1, l0, l1, tK, tV, lim, key, ig, lane);
         }
         __syncthreads();
     }
+    if (!active) return;
     l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
     l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
     l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
     l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
     const float i0 = p.inv_keep / l0, i1 = p.inv_keep / l1;
-    store_rows<D>(o, i0, i1, sQ, smem, warp * 16, p.out + (long long)s0 * (p.h * D) + head * D, (long long)p.h * D,
+    store_rows<D>(o, i0, i1, smem, warp * 16, p.out + (long long)s0 * (p.h * D) + head * D, (long long)p.h * D,
                   qt * kAttTile, len, lane);
     if (t == 0) {
         const int r0 = qt * kAttTile + warp * 16 + g;
@@ -361,15 +398,19 @@ __global__ void __launch_bounds__(kAttThreads) attn_fwd_kernel(const AttnParams 
     }
 }
 
-// ---------------------------------------------------------------------------------------------------------- D pre-pass
-// dsum[head, t] = sum_d dout[t, head, d] * out[t, head, d]; one warp per token row.
+// ---------------------------------------------------------------------------------------------------------- pre-pass
+// Per (head, token) constants of the backward pass; one warp per token row:
+//   stat[0][head, t] = lse * log2(e) - log2(inv_keep)        (so that exp2(s * scale_log2 - .) = P * inv_keep)
+//   stat[1][head, t] = rowsum(dout * out) / inv_keep          (D / inv_keep)
 template <int D>
-__global__ void __launch_bounds__(256) attn_dsum_kernel(const __nv_bfloat16* __restrict__ dout,
-                                                        const __nv_bfloat16* __restrict__ out, int T, int h,
-                                                        float* __restrict__ dsum) {
+__global__ void __launch_bounds__(256) attn_prep_kernel(const __nv_bfloat16* __restrict__ dout,
+                                                        const __nv_bfloat16* __restrict__ out,
+                                                        const float* __restrict__ lse, int T, int h, float inv_keep,
+                                                        float* __restrict__ stat) {
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= T) return;
     const int H = h * D;
+    const float lg = log2f(inv_keep), rk = 1.f / inv_keep;
     for (int c0 = 0; c0 < H; c0 += 256) {   // uniform trip count: the shuffles below need the whole warp
         const int c = c0 + lane * 8;
         float acc = 0.f;
@@ -387,11 +428,80 @@ __global__ void __launch_bounds__(256) attn_dsum_kernel(const __nv_bfloat16* __r
         }
 #pragma unroll
         for (int off = 1; off < D / 8; off <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-        if (c < H && (lane & (D / 8 - 1)) == 0) dsum[(long long)(c / D) * T + row] = acc;
+        if (c < H && (lane & (D / 8 - 1)) == 0) {
+            const long long at = (long long)(c / D) * T + row;
+            stat[at] = fmaf(__ldg(lse + at), kLog2e, -lg);
+            stat[(long long)h * T + at] = acc * rk;
+        }
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------- backward
+// ds = P' * (mask * dp - D') for one accumulator fragment pair (16 x 16 chunk), with P' = exp2(s * scale_log2 - l2').
+// Role dQ: rows = queries (l2 / dd per row: x = row g, y = row g + 8). Role dK/dV: rows = keys, columns = queries
+// (l2 / dd per column).
+template <bool kDrop, bool kRowStats, int N2>
+__device__ __forceinline__ void bwd_chunk_math(float (&s)[4], float (&dp)[4], float sl2, float2 l2, float2 dd, uint32_t f0,
+                                               uint32_t f1) {
+    // element j: accumulator row half (j >> 1), column parity (j & 1); dropout byte: role dQ -> N2 + (j & 2),
+    // role dK/dV -> 2 * N2 + (j >> 1); hash f0 for even columns, f1 for odd ones
+#define SB200_ATT_ELEM(J)                                                                              \
+    {                                                                                                  \
+        const float l = kRowStats ? ((J & 2) ? l2.y : l2.x) : ((J & 1) ? l2.y : l2.x);                 \
+        const float d = kRowStats ? ((J & 2) ? dd.y : dd.x) : ((J & 1) ? dd.y : dd.x);                 \
+        const float pr = ex2(fmaf(s[J], sl2, -l));                                                     \
+        float dpe = dp[J];                                                                             \
+        if (kDrop) dpe = mask_f32<kRowStats ? (N2 + (J & 2)) : (2 * N2 + (J >> 1))>(dpe, (J & 1) ? f1 : f0); \
+        dp[J] = pr;                                                                                    \
+        s[J] = pr * (dpe - d);                                                                         \
+    }
+    SB200_ATT_ELEM(0) SB200_ATT_ELEM(1) SB200_ATT_ELEM(2) SB200_ATT_ELEM(3)
+#undef SB200_ATT_ELEM
+}
+
+// One 64-key block of role dQ (see attn_bwd_dq) in chunks of 16 keys.
+template <int D, bool kDrop, bool kTail>
+__device__ __forceinline__ void bwd_dq_block(const AttnParams& p, const uint32_t (&qa)[D / 16][4],
+                                             const uint32_t (&da)[D / 16][4], float (&dq)[D / 8][4], float2 l2, float2 dd,
+                                             uint32_t tK, uint32_t tV, int lim, uint32_t key, uint32_t ig, int lane) {
+    const int t = lane & 3;
+#pragma unroll
+    for (int kc = 0; kc < 4; ++kc) {
+        if (!kTail || kc * 16 < lim) {
+            float s[2][4], dp[2][4];
+#pragma unroll
+            for (int n2 = 0; n2 < 2; ++n2) {
+                s[n2][0] = s[n2][1] = s[n2][2] = s[n2][3] = 0.f;
+                dp[n2][0] = dp[n2][1] = dp[n2][2] = dp[n2][3] = 0.f;
+                mma_rows<D>(s[n2], qa, tK, kc * 16 + n2 * 8, lane);
+                mma_rows<D>(dp[n2], da, tV, kc * 16 + n2 * 8, lane);
+            }
+            if (kTail && kc * 16 + 16 > lim) {   // the chunk straddles the end of the sequence: P = 0 beyond it
+#pragma unroll
+                for (int n2 = 0; n2 < 2; ++n2) {
+                    const int c = kc * 16 + n2 * 8 + 2 * t;
+                    if (c >= lim) s[n2][0] = s[n2][2] = -INFINITY;
+                    if (c + 1 >= lim) s[n2][1] = s[n2][3] = -INFINITY;
+                }
+            }
+            uint32_t f0 = 0, f1 = 0;
+            if (kDrop) {
+                const uint32_t igk = ig + uint32_t(kc * 64) * kGolden;
+                f0 = patch_flags(key, igk, p.keep_add);
+                f1 = patch_flags(key, igk + kGolden, p.keep_add);
+            }
+            bwd_chunk_math<kDrop, true, 0>(s[0], dp[0], p.scale_log2, l2, dd, f0, f1);
+            bwd_chunk_math<kDrop, true, 1>(s[1], dp[1], p.scale_log2, l2, dd, f0, f1);
+            uint32_t a[4];
+            a[0] = pack_bf16(s[0][0], s[0][1]);
+            a[1] = pack_bf16(s[0][2], s[0][3]);
+            a[2] = pack_bf16(s[1][0], s[1][1]);
+            a[3] = pack_bf16(s[1][2], s[1][3]);
+            mma_cols<D>(dq, a, tK, kc * 16, lane);
+        }
+    }
+}
+
 // Role dQ: the warp owns 16 queries (Q and dO fragments in registers) and streams K / V.
 template <int D, bool kDrop>
 __device__ __forceinline__ void attn_bwd_dq(const AttnParams& p, unsigned char* smem, int seq, int head, int qt, int s0,
@@ -404,6 +514,7 @@ __device__ __forceinline__ void attn_bwd_dq(const AttnParams& p, unsigned char* 
     const __nv_bfloat16* vs = p.v + (long long)s0 * p.in_stride + head * D;
     const __nv_bfloat16* dos = p.dout + (long long)s0 * (p.h * D) + head * D;
     const int nb = (len + kAttTile - 1) / kAttTile;
+    const bool active = qt * kAttTile + warp * 16 < len;
 
     load_tile<D>(sQ, qs, qt * kAttTile, len, p.in_stride, tid);
     load_tile<D>(sDO, dos, qt * kAttTile, len, (long long)p.h * D, tid);
@@ -412,10 +523,13 @@ __device__ __forceinline__ void attn_bwd_dq(const AttnParams& p, unsigned char* 
     cp_async_commit();
 
     const int r0 = qt * kAttTile + warp * 16 + g;
-    const float* lse = p.lse + (long long)head * p.T + s0;
-    const float* dsm = p.dsum + (long long)head * p.T + s0;
-    const float l2_0 = (r0 < len ? __ldg(lse + r0) : 0.f) * kLog2e, l2_1 = (r0 + 8 < len ? __ldg(lse + r0 + 8) : 0.f) * kLog2e;
-    const float d_0 = r0 < len ? __ldg(dsm + r0) : 0.f, d_1 = r0 + 8 < len ? __ldg(dsm + r0 + 8) : 0.f;
+    const float* st_l = p.stat + (long long)head * p.T + s0;
+    const float* st_d = st_l + (long long)p.h * p.T;
+    float2 l2, dd;
+    l2.x = r0 < len ? __ldg(st_l + r0) : 0.f;
+    l2.y = r0 + 8 < len ? __ldg(st_l + r0 + 8) : 0.f;
+    dd.x = r0 < len ? __ldg(st_d + r0) : 0.f;
+    dd.y = r0 + 8 < len ? __ldg(st_d + r0 + 8) : 0.f;
 
     uint32_t qa[D / 16][4], da[D / 16][4];
     float dq[D / 8][4];
@@ -423,7 +537,7 @@ __device__ __forceinline__ void attn_bwd_dq(const AttnParams& p, unsigned char* 
     for (int i = 0; i < D / 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
     uint32_t key = 0;
     if (kDrop) key = seq_key(p, seq, head);
-    const int qblk = qt * 4 + warp;
+    const uint32_t ig0 = patch_index(qt * 4 + warp, 0, g, 2 * t) * kGolden;
 
     for (int kb = 0; kb < nb; ++kb) {
         const int st = kb & 1;
@@ -434,56 +548,86 @@ __device__ __forceinline__ void attn_bwd_dq(const AttnParams& p, unsigned char* 
         cp_async_commit();
         cp_async_wait<1>();
         __syncthreads();
-        if (kb == 0) {
-            load_a_frags<D>(sQ, warp * 16, lane, qa);
-            load_a_frags<D>(sDO, warp * 16, lane, da);
+        if (active) {
+            if (kb == 0) {
+                load_a_frags<D>(sQ, warp * 16, lane, qa);
+                load_a_frags<D>(sDO, warp * 16, lane, da);
+            }
+            const uint32_t tK = sK + st * kTileBytes, tV = sV + st * kTileBytes;
+            const int lim = len - kb * kAttTile;
+            const uint32_t ig = ig0 + uint32_t(kb * 4 * 64) * kGolden;
+            if (lim >= kAttTile)
+                bwd_dq_block<D, kDrop, false>(p, qa, da, dq, l2, dd, tK, tV, lim, key, ig, lane);
+            else
+                bwd_dq_block<D, kDrop, true>(p, qa, da, dq, l2, dd, tK, tV, lim, key, ig, lane);
         }
-        const uint32_t tK = sK + st * kTileBytes, tV = sV + st * kTileBytes;
-        const int lim = len - kb * kAttTile;
+        __syncthreads();
+    }
+    if (!active) return;
+    store_rows<D>(dq, p.scale, p.scale, smem, warp * 16, p.dq + (long long)s0 * p.d_stride + head * D, p.d_stride,
+                  qt * kAttTile, len, lane);
+}
+
+// One 64-query block of role dK/dV (see attn_bwd_dkv) in chunks of 16 queries.
+template <int D, bool kDrop, bool kTail>
+__device__ __forceinline__ void bwd_dkv_block(const AttnParams& p, const uint32_t (&ka)[D / 16][4],
+                                              const uint32_t (&va)[D / 16][4], float (&dk)[D / 8][4],
+                                              float (&dv)[D / 8][4], const float* Ls, const float* Ds, uint32_t tQ,
+                                              uint32_t tDO, int lim, uint32_t key, uint32_t ig, int lane) {
+    const int t = lane & 3;
 #pragma unroll
-        for (int kc = 0; kc < 4; ++kc) {
+    for (int qc = 0; qc < 4; ++qc) {
+        if (!kTail || qc * 16 < lim) {
             float s[2][4], dp[2][4];
 #pragma unroll
             for (int n2 = 0; n2 < 2; ++n2) {
                 s[n2][0] = s[n2][1] = s[n2][2] = s[n2][3] = 0.f;
                 dp[n2][0] = dp[n2][1] = dp[n2][2] = dp[n2][3] = 0.f;
-                mma_rows<D>(s[n2], qa, tK, kc * 16 + n2 * 8, lane);
-                mma_rows<D>(dp[n2], da, tV, kc * 16 + n2 * 8, lane);
+                mma_rows<D>(s[n2], ka, tQ, qc * 16 + n2 * 8, lane);
+                mma_rows<D>(dp[n2], va, tDO, qc * 16 + n2 * 8, lane);
             }
-            uint32_t h0 = 0, h1 = 0;
-            if (kDrop) {
-                h0 = patch_hash(key, qblk, kb * 4 + kc, g, 2 * t);
-                h1 = patch_hash(key, qblk, kb * 4 + kc, g, 2 * t + 1);
-            }
+            if (kTail && qc * 16 + 16 > lim) {   // queries beyond the sequence contribute nothing
 #pragma unroll
-            for (int n2 = 0; n2 < 2; ++n2) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int col = kc * 16 + n2 * 8 + 2 * t + (j & 1);
-                    float pr = ex2(fmaf(s[n2][j], p.scale_log2, -((j & 2) ? l2_1 : l2_0)));
-                    if (col >= lim) pr = 0.f;
-                    float dpe = dp[n2][j];
-                    if (kDrop) {
-                        const bool keep = keep_byte((j & 1) ? h1 : h0, n2 + (j & 2), p.keep_thr);
-                        dpe = keep ? dpe * p.inv_keep : 0.f;
-                    }
-                    s[n2][j] = pr * (dpe - ((j & 2) ? d_1 : d_0));
+                for (int n2 = 0; n2 < 2; ++n2) {
+                    const int c = qc * 16 + n2 * 8 + 2 * t;
+                    if (c >= lim) s[n2][0] = s[n2][2] = -INFINITY;
+                    if (c + 1 >= lim) s[n2][1] = s[n2][3] = -INFINITY;
                 }
             }
+            uint32_t f0 = 0, f1 = 0;
+            if (kDrop) {
+                const uint32_t igk = ig + uint32_t(qc * 64 * 64) * kGolden;
+                f0 = patch_flags(key, igk, p.keep_add);
+                f1 = patch_flags(key, igk + 8u * kGolden, p.keep_add);
+            }
+            const int col = qc * 16 + 2 * t;
+            bwd_chunk_math<kDrop, false, 0>(s[0], dp[0], p.scale_log2, *reinterpret_cast<const float2*>(Ls + col),
+                                            *reinterpret_cast<const float2*>(Ds + col), f0, f1);
+            bwd_chunk_math<kDrop, false, 1>(s[1], dp[1], p.scale_log2, *reinterpret_cast<const float2*>(Ls + col + 8),
+                                            *reinterpret_cast<const float2*>(Ds + col + 8), f0, f1);
+            // dp now holds P' = P * inv_keep; the dropped entries leave dV through the packed mask
             uint32_t a[4];
+            a[0] = pack_bf16(dp[0][0], dp[0][1]);
+            a[1] = pack_bf16(dp[0][2], dp[0][3]);
+            a[2] = pack_bf16(dp[1][0], dp[1][1]);
+            a[3] = pack_bf16(dp[1][2], dp[1][3]);
+            if (kDrop) {
+                a[0] &= pair_mask<0>(f0, f1);
+                a[1] &= pair_mask<1>(f0, f1);
+                a[2] &= pair_mask<2>(f0, f1);
+                a[3] &= pair_mask<3>(f0, f1);
+            }
+            mma_cols<D>(dv, a, tDO, qc * 16, lane);
             a[0] = pack_bf16(s[0][0], s[0][1]);
             a[1] = pack_bf16(s[0][2], s[0][3]);
             a[2] = pack_bf16(s[1][0], s[1][1]);
             a[3] = pack_bf16(s[1][2], s[1][3]);
-            mma_cols<D>(dq, a, tK, kc * 16, lane);
+            mma_cols<D>(dk, a, tQ, qc * 16, lane);
         }
-        __syncthreads();
     }
-    store_rows<D>(dq, p.scale, p.scale, sQ, smem, warp * 16, p.dq + (long long)s0 * p.d_stride + head * D, p.d_stride,
-                  qt * kAttTile, len, lane);
 }
 
-// Role dK/dV: the warp owns 16 keys (K and V fragments in registers) and streams Q / dO / LSE / D.
+// Role dK/dV: the warp owns 16 keys (K and V fragments in registers) and streams Q / dO / the two row statistics.
 template <int D, bool kDrop>
 __device__ __forceinline__ void attn_bwd_dkv(const AttnParams& p, unsigned char* smem, int seq, int head, int kt, int s0,
                                              int len) {
@@ -498,16 +642,17 @@ __device__ __forceinline__ void attn_bwd_dkv(const AttnParams& p, unsigned char*
     const __nv_bfloat16* ks = p.k + (long long)s0 * p.in_stride + head * D;
     const __nv_bfloat16* vs = p.v + (long long)s0 * p.in_stride + head * D;
     const __nv_bfloat16* dos = p.dout + (long long)s0 * (p.h * D) + head * D;
-    const float* lse = p.lse + (long long)head * p.T + s0;
-    const float* dsm = p.dsum + (long long)head * p.T + s0;
+    const float* st_l = p.stat + (long long)head * p.T + s0;
+    const float* st_d = st_l + (long long)p.h * p.T;
     const int nb = (len + kAttTile - 1) / kAttTile;
+    const bool active = kt * kAttTile + warp * 16 < len;
 
     load_tile<D>(sK, ks, kt * kAttTile, len, p.in_stride, tid);
     load_tile<D>(sV, vs, kt * kAttTile, len, p.in_stride, tid);
     load_tile<D>(sQ, qs, 0, len, p.in_stride, tid);
     load_tile<D>(sDO, dos, 0, len, (long long)p.h * D, tid);
-    load_stat(sL, lse, 0, len, tid);
-    load_stat(sD, dsm, 0, len, tid);
+    load_stat(sL, st_l, 0, len, tid);
+    load_stat(sD, st_d, 0, len, tid);
     cp_async_commit();
 
     uint32_t ka[D / 16][4], va[D / 16][4];
@@ -519,82 +664,41 @@ __device__ __forceinline__ void attn_bwd_dkv(const AttnParams& p, unsigned char*
     }
     uint32_t key = 0;
     if (kDrop) key = seq_key(p, seq, head);
-    const int kblk = kt * 4 + warp;
+    const uint32_t ig0 = patch_index(0, kt * 4 + warp, 2 * t, g) * kGolden;
 
     for (int qb = 0; qb < nb; ++qb) {
         const int st = qb & 1;
         if (qb + 1 < nb) {
             load_tile<D>(sQ + (st ^ 1) * kTileBytes, qs, (qb + 1) * kAttTile, len, p.in_stride, tid);
             load_tile<D>(sDO + (st ^ 1) * kTileBytes, dos, (qb + 1) * kAttTile, len, (long long)p.h * D, tid);
-            load_stat(sL + (st ^ 1) * kStatBytes, lse, (qb + 1) * kAttTile, len, tid);
-            load_stat(sD + (st ^ 1) * kStatBytes, dsm, (qb + 1) * kAttTile, len, tid);
+            load_stat(sL + (st ^ 1) * kStatBytes, st_l, (qb + 1) * kAttTile, len, tid);
+            load_stat(sD + (st ^ 1) * kStatBytes, st_d, (qb + 1) * kAttTile, len, tid);
         }
         cp_async_commit();
         cp_async_wait<1>();
         __syncthreads();
-        if (qb == 0) {
-            load_a_frags<D>(sK, warp * 16, lane, ka);
-            load_a_frags<D>(sV, warp * 16, lane, va);
-        }
-        const uint32_t tQ = sQ + st * kTileBytes, tDO = sDO + st * kTileBytes;
-        const float* Ls = reinterpret_cast<const float*>(pL + st * kStatBytes);
-        const float* Ds = reinterpret_cast<const float*>(pD + st * kStatBytes);
-        const int lim = len - qb * kAttTile;
-#pragma unroll
-        for (int qc = 0; qc < 4; ++qc) {
-            float s[2][4], dp[2][4];
-#pragma unroll
-            for (int n2 = 0; n2 < 2; ++n2) {
-                s[n2][0] = s[n2][1] = s[n2][2] = s[n2][3] = 0.f;
-                dp[n2][0] = dp[n2][1] = dp[n2][2] = dp[n2][3] = 0.f;
-                mma_rows<D>(s[n2], ka, tQ, qc * 16 + n2 * 8, lane);
-                mma_rows<D>(dp[n2], va, tDO, qc * 16 + n2 * 8, lane);
+        if (active) {
+            if (qb == 0) {
+                load_a_frags<D>(sK, warp * 16, lane, ka);
+                load_a_frags<D>(sV, warp * 16, lane, va);
             }
-            uint32_t h0 = 0, h1 = 0;
-            if (kDrop) {
-                h0 = patch_hash(key, qb * 4 + qc, kblk, 2 * t, g);
-                h1 = patch_hash(key, qb * 4 + qc, kblk, 2 * t + 1, g);
-            }
-            float pd[2][4];
-#pragma unroll
-            for (int n2 = 0; n2 < 2; ++n2) {
-                const int col = qc * 16 + n2 * 8 + 2 * t;
-                const float2 l2 = *reinterpret_cast<const float2*>(Ls + col);
-                const float2 dd = *reinterpret_cast<const float2*>(Ds + col);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float pr = ex2(fmaf(s[n2][j], p.scale_log2, -((j & 1) ? l2.y : l2.x) * kLog2e));
-                    if (col + (j & 1) >= lim) pr = 0.f;
-                    float dpe = dp[n2][j];
-                    float pk = pr;
-                    if (kDrop) {
-                        // element (key g + 8 * (j >> 1), query n2 * 8 + 2t + (j & 1)): byte = 2 * n2 + (j >> 1)
-                        const bool keep = keep_byte((j & 1) ? h1 : h0, 2 * n2 + (j >> 1), p.keep_thr);
-                        dpe = keep ? dpe * p.inv_keep : 0.f;
-                        pk = keep ? pr * p.inv_keep : 0.f;
-                    }
-                    pd[n2][j] = pk;
-                    s[n2][j] = pr * (dpe - ((j & 1) ? dd.y : dd.x));
-                }
-            }
-            uint32_t a[4];
-            a[0] = pack_bf16(pd[0][0], pd[0][1]);
-            a[1] = pack_bf16(pd[0][2], pd[0][3]);
-            a[2] = pack_bf16(pd[1][0], pd[1][1]);
-            a[3] = pack_bf16(pd[1][2], pd[1][3]);
-            mma_cols<D>(dv, a, tDO, qc * 16, lane);
-            a[0] = pack_bf16(s[0][0], s[0][1]);
-            a[1] = pack_bf16(s[0][2], s[0][3]);
-            a[2] = pack_bf16(s[1][0], s[1][1]);
-            a[3] = pack_bf16(s[1][2], s[1][3]);
-            mma_cols<D>(dk, a, tQ, qc * 16, lane);
+            const uint32_t tQ = sQ + st * kTileBytes, tDO = sDO + st * kTileBytes;
+            const float* Ls = reinterpret_cast<const float*>(pL + st * kStatBytes);
+            const float* Ds = reinterpret_cast<const float*>(pD + st * kStatBytes);
+            const int lim = len - qb * kAttTile;
+            const uint32_t ig = ig0 + uint32_t(qb * 4 * 64 * 64) * kGolden;
+            if (lim >= kAttTile)
+                bwd_dkv_block<D, kDrop, false>(p, ka, va, dk, dv, Ls, Ds, tQ, tDO, lim, key, ig, lane);
+            else
+                bwd_dkv_block<D, kDrop, true>(p, ka, va, dk, dv, Ls, Ds, tQ, tDO, lim, key, ig, lane);
         }
         __syncthreads();
     }
-    store_rows<D>(dk, p.scale, p.scale, sK, smem, warp * 16, p.dk + (long long)s0 * p.d_stride + head * D, p.d_stride,
+    if (!active) return;
+    store_rows<D>(dk, p.scale, p.scale, smem, warp * 16, p.dk + (long long)s0 * p.d_stride + head * D, p.d_stride,
                   kt * kAttTile, len, lane);
-    store_rows<D>(dv, 1.f, 1.f, sV, smem + kTileBytes, warp * 16, p.dv + (long long)s0 * p.d_stride + head * D,
-                  p.d_stride, kt * kAttTile, len, lane);
+    store_rows<D>(dv, 1.f, 1.f, smem + kTileBytes, warp * 16, p.dv + (long long)s0 * p.d_stride + head * D, p.d_stride,
+                  kt * kAttTile, len, lane);
 }
 
 template <int D, bool kDrop>
@@ -620,9 +724,9 @@ __global__ void attn_mask_kernel(const AttnParams p, int max_len) {
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < len * len; idx += gridDim.x * blockDim.x) {
         const int q = idx / len, k = idx % len;
         const int r = q & 15, c = k & 15;
-        const uint32_t hsh = patch_hash(key, q >> 4, k >> 4, r & 7, c & 7);
+        const uint32_t f = patch_flags(key, patch_index(q >> 4, k >> 4, r & 7, c & 7) * kGolden, p.keep_add);
         const int byte = (r >> 3) * 2 + (c >> 3);
-        p.mask_out[((long long)head * p.T + s0 + q) * max_len + k] = keep_byte(hsh, byte, p.keep_thr) ? 1 : 0;
+        p.mask_out[((long long)head * p.T + s0 + q) * max_len + k] = (f >> (8 * byte + 7)) & 1u;
     }
 }
 
@@ -631,15 +735,17 @@ size_t bwd_smem(int D) { return size_t(6) * kAttTile * D * 2 + 4 * kAttTile * 4;
 
 int fill_dropout(AttnParams& p, float drop_p, const void* seed, int salt) {
     p.keep_thr = 256;
+    p.keep_add = 0;
     p.inv_keep = 1.f;
     p.seed = nullptr;
     p.salt = uint32_t(salt);
     if (drop_p > 0.f) {
         SB200_REQUIRE(seed != nullptr, "attention: dropout needs a seed pointer");
-        SB200_REQUIRE(drop_p < 1.f, "attention: drop_p must be < 1");
+        SB200_REQUIRE(drop_p <= 0.5f, "attention: drop_p must be <= 0.5");
         int thr = int((1.f - drop_p) * 256.f + 0.5f);
-        thr = thr < 1 ? 1 : (thr > 256 ? 256 : thr);
+        thr = thr < 128 ? 128 : (thr > 256 ? 256 : thr);
         p.keep_thr = uint32_t(thr);
+        p.keep_add = uint32_t(128 - (256 - thr)) * 0x01010101u;
         p.inv_keep = 256.f / float(thr);
         p.seed = static_cast<const unsigned long long*>(seed);
     }
@@ -723,19 +829,20 @@ extern "C" int sb200_attn_bwd(const void* q, const void* k, const void* v, size_
     p.scale = scale;
     p.scale_log2 = scale * kLog2e;
     p.dout = static_cast<const __nv_bfloat16*>(dout);
-    p.dsum = dsum;
+    p.stat = dsum;
     p.dq = static_cast<__nv_bfloat16*>(dq);
     p.dk = static_cast<__nv_bfloat16*>(dk);
     p.dv = static_cast<__nv_bfloat16*>(dv);
     p.d_stride = (long long)d_stride;
     if (int rc = fill_dropout(p, drop_p, drop_seed, salt)) return rc;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const int dsum_blocks = (T + 7) / 8;
+    const int prep_blocks = (T + 7) / 8;
+    const __nv_bfloat16* o = static_cast<const __nv_bfloat16*>(out);
     if (d == 32)
-        attn_dsum_kernel<32><<<dsum_blocks, 256, 0, s>>>(p.dout, static_cast<const __nv_bfloat16*>(out), T, h, dsum);
+        attn_prep_kernel<32><<<prep_blocks, 256, 0, s>>>(p.dout, o, lse, T, h, p.inv_keep, dsum);
     else
-        attn_dsum_kernel<64><<<dsum_blocks, 256, 0, s>>>(p.dout, static_cast<const __nv_bfloat16*>(out), T, h, dsum);
-    SB200_CHECK_LAUNCH("attn_dsum_kernel");
+        attn_prep_kernel<64><<<prep_blocks, 256, 0, s>>>(p.dout, o, lse, T, h, p.inv_keep, dsum);
+    SB200_CHECK_LAUNCH("attn_prep_kernel");
     const dim3 grid(2 * p.ntile, h, nseq);
     const size_t sm = bwd_smem(d);
     const bool drop = p.keep_thr < 256;

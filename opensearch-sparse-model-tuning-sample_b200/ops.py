@@ -862,7 +862,7 @@ def attn_backward(qkv, out, dout, lse, cu_seqlens, max_len, scale, drop_p=0.0, s
     if dout.dtype != torch.bfloat16:
         dout = dout.to(torch.bfloat16)
     dqkv = (torch.zeros if zero_fill else torch.empty)(T, 3, h, d, dtype=torch.bfloat16, device=qkv.device)
-    dsum = torch.empty(h, T, dtype=torch.float32, device=qkv.device)
+    dsum = torch.empty(2, h, T, dtype=torch.float32, device=qkv.device)
     base, dbase, e = qkv.data_ptr(), dqkv.data_ptr(), 2 * h * d
     with torch.cuda.device(qkv.device):
         code = _lib.load().sb200_attn_bwd(base, base + e, base + 2 * e, stride, _ptr(out), _ptr(dout), _ptr(lse),
