@@ -33,7 +33,18 @@ namespace sb200 {
 namespace {
 
 constexpr int kAttThreads = 128;
+// resident CTAs per SM the register allocation is capped for (head_dim 32 / 64)
+#ifndef SB200_ATT_FWD_CTAS32
+#define SB200_ATT_FWD_CTAS32 4
+#define SB200_ATT_FWD_CTAS64 3
+#define SB200_ATT_BWD_CTAS32 4
+#define SB200_ATT_BWD_CTAS64 2
+#endif
 constexpr int kAttTile = 64;
+// Stages of the operand ring: 4 x 64 rows cover sequences up to 256 tokens without ever reusing a stage (no block-wide
+// barrier in the loop at all); longer sequences refill a stage behind one __syncthreads.
+template <int D>
+constexpr int att_stages() { return D == 32 ? 4 : 3; }
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
@@ -73,6 +84,11 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+// Makes `bar` track the completion of every cp.async this thread has issued so far (counted in the barrier's
+// initial arrival count: one such arrival per thread and phase).
+__device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
@@ -119,29 +135,59 @@ __device__ __forceinline__ uint32_t tile_off(int row, int chunk) {
     return uint32_t(row * 128 + ((chunk ^ (row & 7)) << 4));
 }
 
-// Stages rows [row0, row0 + 64) of one sequence (rows >= len zero-filled) into a tile. src points at row 0 of the sequence.
+// Per-thread state of a stream of 64-row blocks of one [rows, D] operand of one sequence (rows >= len zero-filled):
+// everything that does not change from block to block (row / chunk of the thread, swizzled offset, strides) is
+// computed once, so that staging a block costs a handful of instructions per thread.
 template <int D>
-__device__ __forceinline__ void load_tile(uint32_t dst, const __nv_bfloat16* src, int row0, int len, long long stride,
-                                          int tid) {
-    constexpr int CPR = D / 8;
+struct TileStream {
+    static constexpr int CPR = D / 8;                   // 16-byte chunks per row
+    static constexpr int RPP = kAttThreads / CPR;       // rows per pass (the swizzle repeats every 8 rows)
+    const __nv_bfloat16* base;                          // a valid address for the zero-fill form
+    const __nv_bfloat16* next;
+    long long step, sub;
+    int row;
+    uint32_t dst_off;
+    __device__ __forceinline__ void init(const __nv_bfloat16* seq_base, long long stride, int row0, int tid) {
+        const int r = tid / CPR, c = tid % CPR;
+        base = seq_base;
+        step = kAttTile * stride;
+        sub = RPP * stride;
+        row = row0 + r;
+        next = seq_base + (long long)row * stride + c * 8;
+        dst_off = tile_off<D>(r, c);
+    }
+    __device__ __forceinline__ void load(uint32_t tile, int len) {   // stages the next block and advances
 #pragma unroll
-    for (int i = 0; i < kAttTile * CPR / kAttThreads; ++i) {
-        const int idx = tid + i * kAttThreads;
-        const int r = idx / CPR, c = idx % CPR;
-        const int gr = row0 + r;
-        const bool ok = gr < len;
-        cp_async16(dst + tile_off<D>(r, c), src + (long long)(ok ? gr : 0) * stride + c * 8, ok ? 16 : 0);
+        for (int i = 0; i < kAttTile / RPP; ++i) {
+            const bool ok = row + i * RPP < len;
+            cp_async16(tile + dst_off + i * RPP * D * 2, ok ? next + i * sub : base, ok ? 16 : 0);
+        }
+        next += step;
+        row += kAttTile;
     }
-}
+};
 
-// 64 floats of a per-row statistic (rows >= len -> 0).
-__device__ __forceinline__ void load_stat(uint32_t dst, const float* src, int row0, int len, int tid) {
-    if (tid < kAttTile) {
-        const int gr = row0 + tid;
-        const bool ok = gr < len;
-        cp_async4(dst + tid * 4, src + (ok ? gr : 0), ok ? 4 : 0);
+// Same for a per-row fp32 statistic (threads 0..63, one float each; rows >= len -> 0).
+struct StatStream {
+    const float* base;
+    const float* next;
+    int row;
+    uint32_t dst_off;
+    __device__ __forceinline__ void init(const float* seq_base, int tid) {
+        base = seq_base;
+        row = tid;
+        next = seq_base + tid;
+        dst_off = uint32_t(tid) * 4u;
     }
-}
+    __device__ __forceinline__ void load(uint32_t dst, int len) {
+        if (dst_off < kAttTile * 4u) {
+            const bool ok = row < len;
+            cp_async4(dst + dst_off, ok ? next : base, ok ? 4 : 0);
+        }
+        next += kAttTile;
+        row += kAttTile;
+    }
+};
 
 // "A pattern": the 16 x 16 region at (row0, 16 * kc): r0 = rows 0-7 / cols 0-7, r1 = rows 8-15 / cols 0-7,
 // r2 = rows 0-7 / cols 8-15, r3 = rows 8-15 / cols 8-15. Plain: the A fragment. Transposed (stored rows = k index):
@@ -231,7 +277,9 @@ __device__ __forceinline__ uint32_t patch_index(int qblk, int kblk, int r, int c
     return uint32_t(((qblk * 64 + kblk) * 64) + r * 8 + c);
 }
 __device__ __forceinline__ uint32_t patch_flags(uint32_t key, uint32_t idx_times_golden, uint32_t addc) {
-    const uint32_t h = mix32(key ^ idx_times_golden);
+    // multiply-fold ("mum") of the keyed, golden-ratio-scrambled patch index: high ^ low word of a 32 x 32 -> 64 product
+    const unsigned long long m = (unsigned long long)(key ^ idx_times_golden) * 0xD6E8FEB9u;
+    const uint32_t h = uint32_t(m >> 32) ^ uint32_t(m);
     return ((h & 0x7F7F7F7Fu) + addc) | h;
 }
 template <uint32_t kSel>
@@ -332,7 +380,7 @@ __device__ __forceinline__ void fwd_block(const AttnParams& p, const uint32_t (&
 }
 
 template <int D, bool kDrop>
-__global__ void __launch_bounds__(kAttThreads) attn_fwd_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(kAttThreads, D == 32 ? SB200_ATT_FWD_CTAS32 : SB200_ATT_FWD_CTAS64) attn_fwd_kernel(const AttnParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int kTileBytes = kAttTile * D * 2;
     const int seq = blockIdx.z, head = blockIdx.y, qt = blockIdx.x;
@@ -340,17 +388,34 @@ __global__ void __launch_bounds__(kAttThreads) attn_fwd_kernel(const AttnParams 
     const int len = __ldg(p.cu + seq + 1) - s0;
     if (qt * kAttTile >= len) return;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-    const uint32_t sQ = smem_u32(smem), sK = sQ + kTileBytes, sV = sK + 2 * kTileBytes;
+    constexpr int NS = att_stages<D>();
+    const uint32_t sQ = smem_u32(smem), sK = sQ + kTileBytes, sV = sK + NS * kTileBytes;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (1 + 2 * NS) * kTileBytes);
     const __nv_bfloat16* qs = p.q + (long long)s0 * p.in_stride + head * D;
     const __nv_bfloat16* ks = p.k + (long long)s0 * p.in_stride + head * D;
     const __nv_bfloat16* vs = p.v + (long long)s0 * p.in_stride + head * D;
     const int nb = (len + kAttTile - 1) / kAttTile;
-    const bool active = qt * kAttTile + warp * 16 < len;   // warps whose 16 rows are all padding only load and sync
+    const bool active = qt * kAttTile + warp * 16 < len;   // warps whose 16 rows are all padding only load
 
-    load_tile<D>(sQ, qs, qt * kAttTile, len, p.in_stride, tid);
-    load_tile<D>(sK, ks, 0, len, p.in_stride, tid);
-    load_tile<D>(sV, vs, 0, len, p.in_stride, tid);
-    cp_async_commit();
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < NS; ++i) mbar_init(full + i, kAttThreads);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    TileStream<D> tq, tk, tv;
+    tq.init(qs, p.in_stride, qt * kAttTile, tid);
+    tk.init(ks, p.in_stride, 0, tid);
+    tv.init(vs, p.in_stride, 0, tid);
+    tq.load(sQ, len);
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+        if (i < nb) {
+            tk.load(sK + i * kTileBytes, len);
+            tv.load(sV + i * kTileBytes, len);
+            cp_async_arrive(full + i);
+        }
+    }
 
     uint32_t qa[D / 16][4];
     float o[D / 8][4];
@@ -362,15 +427,9 @@ __global__ void __launch_bounds__(kAttThreads) attn_fwd_kernel(const AttnParams 
     const uint32_t ig0 = patch_index(qt * 4 + warp, 0, g, 2 * t) * kGolden;
 
     for (int kb = 0; kb < nb; ++kb) {
-        const int st = kb & 1;
-        if (kb + 1 < nb) {
-            load_tile<D>(sK + (st ^ 1) * kTileBytes, ks, (kb + 1) * kAttTile, len, p.in_stride, tid);
-            load_tile<D>(sV + (st ^ 1) * kTileBytes, vs, (kb + 1) * kAttTile, len, p.in_stride, tid);
-        }
-        cp_async_commit();
-        cp_async_wait<1>();
-        __syncthreads();
+        const int st = kb % NS;
         if (active) {
+            mbar_wait(full + st, (kb / NS) & 1);
             if (kb == 0) load_a_frags<D>(sQ, warp * 16, lane, qa);
             const uint32_t tK = sK + st * kTileBytes, tV = sV + st * kTileBytes;
             const int lim = len - kb * kAttTile;     // valid keys in this block
@@ -380,7 +439,12 @@ __global__ void __launch_bounds__(kAttThreads) attn_fwd_kernel(const AttnParams 
             else
                 fwd_block<D, kDrop, true>(p, qa, o, m0, m1, l0, l1, tK, tV, lim, key, ig, lane);
         }
-        __syncthreads();
+        if (kb + NS < nb) {     // long sequence: the stage is reused once every warp is done with it
+            __syncthreads();
+            tk.load(sK + st * kTileBytes, len);
+            tv.load(sV + st * kTileBytes, len);
+            cp_async_arrive(full + st);
+        }
     }
     if (!active) return;
     l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
@@ -508,7 +572,9 @@ __device__ __forceinline__ void attn_bwd_dq(const AttnParams& p, unsigned char* 
                                             int len) {
     constexpr int kTileBytes = kAttTile * D * 2;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-    const uint32_t sQ = smem_u32(smem), sDO = sQ + kTileBytes, sK = sDO + kTileBytes, sV = sK + 2 * kTileBytes;
+    constexpr int NS = att_stages<D>();
+    const uint32_t sQ = smem_u32(smem), sDO = sQ + kTileBytes, sK = sDO + kTileBytes, sV = sK + NS * kTileBytes;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (2 + 2 * NS) * kTileBytes + 2 * NS * kAttTile * 4);
     const __nv_bfloat16* qs = p.q + (long long)s0 * p.in_stride + head * D;
     const __nv_bfloat16* ks = p.k + (long long)s0 * p.in_stride + head * D;
     const __nv_bfloat16* vs = p.v + (long long)s0 * p.in_stride + head * D;
@@ -516,11 +582,27 @@ __device__ __forceinline__ void attn_bwd_dq(const AttnParams& p, unsigned char* 
     const int nb = (len + kAttTile - 1) / kAttTile;
     const bool active = qt * kAttTile + warp * 16 < len;
 
-    load_tile<D>(sQ, qs, qt * kAttTile, len, p.in_stride, tid);
-    load_tile<D>(sDO, dos, qt * kAttTile, len, (long long)p.h * D, tid);
-    load_tile<D>(sK, ks, 0, len, p.in_stride, tid);
-    load_tile<D>(sV, vs, 0, len, p.in_stride, tid);
-    cp_async_commit();
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < NS; ++i) mbar_init(full + i, kAttThreads);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    TileStream<D> tq, tk, tv;
+    tq.init(qs, p.in_stride, qt * kAttTile, tid);
+    tq.load(sQ, len);
+    tq.init(dos, (long long)p.h * D, qt * kAttTile, tid);
+    tq.load(sDO, len);
+    tk.init(ks, p.in_stride, 0, tid);
+    tv.init(vs, p.in_stride, 0, tid);
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+        if (i < nb) {
+            tk.load(sK + i * kTileBytes, len);
+            tv.load(sV + i * kTileBytes, len);
+            cp_async_arrive(full + i);
+        }
+    }
 
     const int r0 = qt * kAttTile + warp * 16 + g;
     const float* st_l = p.stat + (long long)head * p.T + s0;
@@ -540,15 +622,9 @@ __device__ __forceinline__ void attn_bwd_dq(const AttnParams& p, unsigned char* 
     const uint32_t ig0 = patch_index(qt * 4 + warp, 0, g, 2 * t) * kGolden;
 
     for (int kb = 0; kb < nb; ++kb) {
-        const int st = kb & 1;
-        if (kb + 1 < nb) {
-            load_tile<D>(sK + (st ^ 1) * kTileBytes, ks, (kb + 1) * kAttTile, len, p.in_stride, tid);
-            load_tile<D>(sV + (st ^ 1) * kTileBytes, vs, (kb + 1) * kAttTile, len, p.in_stride, tid);
-        }
-        cp_async_commit();
-        cp_async_wait<1>();
-        __syncthreads();
+        const int st = kb % NS;
         if (active) {
+            mbar_wait(full + st, (kb / NS) & 1);
             if (kb == 0) {
                 load_a_frags<D>(sQ, warp * 16, lane, qa);
                 load_a_frags<D>(sDO, warp * 16, lane, da);
@@ -561,7 +637,12 @@ __device__ __forceinline__ void attn_bwd_dq(const AttnParams& p, unsigned char* 
             else
                 bwd_dq_block<D, kDrop, true>(p, qa, da, dq, l2, dd, tK, tV, lim, key, ig, lane);
         }
-        __syncthreads();
+        if (kb + NS < nb) {
+            __syncthreads();
+            tk.load(sK + st * kTileBytes, len);
+            tv.load(sV + st * kTileBytes, len);
+            cp_async_arrive(full + st);
+        }
     }
     if (!active) return;
     store_rows<D>(dq, p.scale, p.scale, smem, warp * 16, p.dq + (long long)s0 * p.d_stride + head * D, p.d_stride,
@@ -634,10 +715,12 @@ __device__ __forceinline__ void attn_bwd_dkv(const AttnParams& p, unsigned char*
     constexpr int kTileBytes = kAttTile * D * 2;
     constexpr int kStatBytes = kAttTile * 4;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-    const uint32_t sK = smem_u32(smem), sV = sK + kTileBytes, sQ = sV + kTileBytes, sDO = sQ + 2 * kTileBytes,
-                   sL = sDO + 2 * kTileBytes, sD = sL + 2 * kStatBytes;
-    unsigned char* pL = smem + 6 * kTileBytes;
-    unsigned char* pD = pL + 2 * kStatBytes;
+    constexpr int NS = att_stages<D>();
+    const uint32_t sK = smem_u32(smem), sV = sK + kTileBytes, sQ = sV + kTileBytes, sDO = sQ + NS * kTileBytes,
+                   sL = sDO + NS * kTileBytes, sD = sL + NS * kStatBytes;
+    unsigned char* pL = smem + (2 + 2 * NS) * kTileBytes;
+    unsigned char* pD = pL + NS * kStatBytes;
+    uint64_t* full = reinterpret_cast<uint64_t*>(pD + NS * kStatBytes);
     const __nv_bfloat16* qs = p.q + (long long)s0 * p.in_stride + head * D;
     const __nv_bfloat16* ks = p.k + (long long)s0 * p.in_stride + head * D;
     const __nv_bfloat16* vs = p.v + (long long)s0 * p.in_stride + head * D;
@@ -647,13 +730,32 @@ __device__ __forceinline__ void attn_bwd_dkv(const AttnParams& p, unsigned char*
     const int nb = (len + kAttTile - 1) / kAttTile;
     const bool active = kt * kAttTile + warp * 16 < len;
 
-    load_tile<D>(sK, ks, kt * kAttTile, len, p.in_stride, tid);
-    load_tile<D>(sV, vs, kt * kAttTile, len, p.in_stride, tid);
-    load_tile<D>(sQ, qs, 0, len, p.in_stride, tid);
-    load_tile<D>(sDO, dos, 0, len, (long long)p.h * D, tid);
-    load_stat(sL, st_l, 0, len, tid);
-    load_stat(sD, st_d, 0, len, tid);
-    cp_async_commit();
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < NS; ++i) mbar_init(full + i, kAttThreads);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    TileStream<D> tq, tdo;
+    StatStream tl, td;
+    tq.init(ks, p.in_stride, kt * kAttTile, tid);
+    tq.load(sK, len);
+    tq.init(vs, p.in_stride, kt * kAttTile, tid);
+    tq.load(sV, len);
+    tq.init(qs, p.in_stride, 0, tid);
+    tdo.init(dos, (long long)p.h * D, 0, tid);
+    tl.init(st_l, tid);
+    td.init(st_d, tid);
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+        if (i < nb) {
+            tq.load(sQ + i * kTileBytes, len);
+            tdo.load(sDO + i * kTileBytes, len);
+            tl.load(sL + i * kStatBytes, len);
+            td.load(sD + i * kStatBytes, len);
+            cp_async_arrive(full + i);
+        }
+    }
 
     uint32_t ka[D / 16][4], va[D / 16][4];
     float dk[D / 8][4], dv[D / 8][4];
@@ -667,17 +769,9 @@ __device__ __forceinline__ void attn_bwd_dkv(const AttnParams& p, unsigned char*
     const uint32_t ig0 = patch_index(0, kt * 4 + warp, 2 * t, g) * kGolden;
 
     for (int qb = 0; qb < nb; ++qb) {
-        const int st = qb & 1;
-        if (qb + 1 < nb) {
-            load_tile<D>(sQ + (st ^ 1) * kTileBytes, qs, (qb + 1) * kAttTile, len, p.in_stride, tid);
-            load_tile<D>(sDO + (st ^ 1) * kTileBytes, dos, (qb + 1) * kAttTile, len, (long long)p.h * D, tid);
-            load_stat(sL + (st ^ 1) * kStatBytes, st_l, (qb + 1) * kAttTile, len, tid);
-            load_stat(sD + (st ^ 1) * kStatBytes, st_d, (qb + 1) * kAttTile, len, tid);
-        }
-        cp_async_commit();
-        cp_async_wait<1>();
-        __syncthreads();
+        const int st = qb % NS;
         if (active) {
+            mbar_wait(full + st, (qb / NS) & 1);
             if (qb == 0) {
                 load_a_frags<D>(sK, warp * 16, lane, ka);
                 load_a_frags<D>(sV, warp * 16, lane, va);
@@ -692,7 +786,14 @@ __device__ __forceinline__ void attn_bwd_dkv(const AttnParams& p, unsigned char*
             else
                 bwd_dkv_block<D, kDrop, true>(p, ka, va, dk, dv, Ls, Ds, tQ, tDO, lim, key, ig, lane);
         }
-        __syncthreads();
+        if (qb + NS < nb) {
+            __syncthreads();
+            tq.load(sQ + st * kTileBytes, len);
+            tdo.load(sDO + st * kTileBytes, len);
+            tl.load(sL + st * kStatBytes, len);
+            td.load(sD + st * kStatBytes, len);
+            cp_async_arrive(full + st);
+        }
     }
     if (!active) return;
     store_rows<D>(dk, p.scale, p.scale, smem, warp * 16, p.dk + (long long)s0 * p.d_stride + head * D, p.d_stride,
@@ -702,7 +803,7 @@ __device__ __forceinline__ void attn_bwd_dkv(const AttnParams& p, unsigned char*
 }
 
 template <int D, bool kDrop>
-__global__ void __launch_bounds__(kAttThreads) attn_bwd_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(kAttThreads, D == 32 ? SB200_ATT_BWD_CTAS32 : SB200_ATT_BWD_CTAS64) attn_bwd_kernel(const AttnParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int seq = blockIdx.z, head = blockIdx.y;
     const bool dkv = int(blockIdx.x) < p.ntile;   // the longer role is scheduled first
@@ -730,8 +831,9 @@ __global__ void attn_mask_kernel(const AttnParams p, int max_len) {
     }
 }
 
-size_t fwd_smem(int D) { return size_t(5) * kAttTile * D * 2; }
-size_t bwd_smem(int D) { return size_t(6) * kAttTile * D * 2 + 4 * kAttTile * 4; }
+int stages(int D) { return D == 32 ? att_stages<32>() : att_stages<64>(); }
+size_t fwd_smem(int D) { return size_t(1 + 2 * stages(D)) * kAttTile * D * 2 + 64; }
+size_t bwd_smem(int D) { return size_t(2 + 2 * stages(D)) * kAttTile * D * 2 + 2 * stages(D) * kAttTile * 4 + 64; }
 
 int fill_dropout(AttnParams& p, float drop_p, const void* seed, int salt) {
     p.keep_thr = 256;
@@ -803,8 +905,8 @@ extern "C" int sb200_attn_fwd(const void* q, const void* k, const void* v, size_
         if (int rc = opt_in_smem(attn_fwd_kernel<DD, DR>, sm, SLOT)) return rc;                \
         attn_fwd_kernel<DD, DR><<<grid, kAttThreads, sm, s>>>(p);                              \
     } while (0)
-    if (d == 32) { if (drop) SB200_ATT_FWD(32, true, -1); else SB200_ATT_FWD(32, false, -1); }   // <= 40 KB: no opt-in
-    else { if (drop) SB200_ATT_FWD(64, true, -1); else SB200_ATT_FWD(64, false, -1); }
+    if (d == 32) { if (drop) SB200_ATT_FWD(32, true, -1); else SB200_ATT_FWD(32, false, -1); }   // 37 KB: no opt-in
+    else { if (drop) SB200_ATT_FWD(64, true, 32); else SB200_ATT_FWD(64, false, 33); }          // 57 KB: opt-in slots 32 / 33
 #undef SB200_ATT_FWD
     SB200_CHECK_LAUNCH("attn_fwd_kernel");
     return SB200_OK;
@@ -852,7 +954,7 @@ extern "C" int sb200_attn_bwd(const void* q, const void* k, const void* v, size_
         attn_bwd_kernel<DD, DR><<<grid, kAttThreads, sm, s>>>(p);                              \
     } while (0)
     if (d == 32) { if (drop) SB200_ATT_BWD(32, true, -1); else SB200_ATT_BWD(32, false, -1); }
-    else { if (drop) SB200_ATT_BWD(64, true, 14); else SB200_ATT_BWD(64, false, 15); }   // 49 KB: opt-in slots 14 / 15
+    else { if (drop) SB200_ATT_BWD(64, true, 14); else SB200_ATT_BWD(64, false, 15); }   // 67 KB: opt-in slots 14 / 15
 #undef SB200_ATT_BWD
     SB200_CHECK_LAUNCH("attn_bwd_kernel");
     return SB200_OK;

@@ -25,10 +25,10 @@ int num_sms() {
 }
 
 bool device_flag_test_and_set(int slot) {
-    static std::atomic<unsigned> flags[64];
+    static std::atomic<unsigned long long> flags[64];
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return false;
-    const unsigned bit = 1u << (slot & 31);
+    const unsigned long long bit = 1ull << (slot & 63);
     return (flags[dev].fetch_or(bit) & bit) != 0;
 }
 

@@ -45,9 +45,9 @@ inline void count_launch(unsigned n = 1) { g_launches.fetch_add(n, std::memory_o
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 int num_sms();  // SM count of the current device (cached per device)
-// Per-device one-shot flags (slot in [0, 32)): returns the previous value and sets the flag.
+// Per-device one-shot flags (slot in [0, 64)): returns the previous value and sets the flag.
 // Slots: 0/5 head_fwd<1/2>, 1-4 bwd_dw<NCHUNK, bf16>, 16-19 bwd_dw<NCHUNK, fp16>, 6/7 score row kernels, 8-13 colsum<T, NV> instances
-// that need > 48 KB of shared memory, 14/15 attn_bwd<64, drop/no drop>, 20-31 bwd_dw_fit<VB, NCH, bf16|fp16>.
+// that need > 48 KB of shared memory, 14/15 attn_bwd<64, drop/no drop>, 32/33 attn_fwd<64, drop/no drop>, 20-31 bwd_dw_fit<VB, NCH, bf16|fp16>.
 bool device_flag_test_and_set(int slot);
 
 }  // namespace sb200

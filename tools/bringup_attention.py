@@ -11,7 +11,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
 import sparse_b200  # noqa: E402,F401
-from sparse_b200 import ops  # noqa: E402
+from sparse_b200 import _lib, ops  # noqa: E402
+
+if "--lib" in sys.argv:      # A/B builds of the library (tools/probes/build_variants.sh); must precede the first call
+    _lib.LIB_PATH = os.path.abspath(sys.argv[sys.argv.index("--lib") + 1])
 
 try:
     from flash_attn import flash_attn_varlen_qkvpacked_func
@@ -138,19 +141,44 @@ def bench(nseq, lo, hi, h, d, p_drop, tag):
     print(line)
 
 
+def mask_stats():
+    """Keep rate and lag correlations of the positional dropout mask (one long sequence per head)."""
+    L, h, p_drop = 512, 8, 0.1
+    cu = torch.tensor([0, L, 2 * L], dtype=torch.int32, device="cuda")
+    seed = torch.tensor([20260101], dtype=torch.int64, device="cuda")
+    m = ops.attn_dropout_mask(cu, L, 2 * L, h, p_drop, seed, salt=1).float()      # [h, 2L, L]
+    x = m - m.mean()
+    var = float((x * x).mean())
+    out = [f"keep {float(m.mean()):.4f}"]
+    for name, a, b in (("q+1", x[:, 1:], x[:, :-1]), ("k+1", x[:, :, 1:], x[:, :, :-1]), ("q+8", x[:, 8:], x[:, :-8]),
+                       ("k+8", x[:, :, 8:], x[:, :, :-8]), ("q+16", x[:, 16:], x[:, :-16]),
+                       ("k+16", x[:, :, 16:], x[:, :, :-16]), ("head+1", x[1:], x[:-1]),
+                       ("seq+1", x[:, L:], x[:, :L])):
+        out.append(f"{name} {float((a * b).mean()) / var:+.4f}")
+    rows = m.mean(2)
+    cols = m[:, :L].mean(1)
+    out.append(f"row-rate sd {float(rows.std()):.4f} col-rate sd {float(cols.std()):.4f} (binomial {math.sqrt(0.09 / L):.4f})")
+    m2 = ops.attn_dropout_mask(cu, L, 2 * L, h, p_drop, seed + 1, salt=1).float()
+    out.append(f"other seed agreement {float((m == m2).float().mean()):.4f} (independent: {0.8984 ** 2 + 0.1016 ** 2:.4f})")
+    print("mask statistics: " + "  ".join(out))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--no-time", action="store_true")
+    ap.add_argument("--no-check", action="store_true")
+    ap.add_argument("--lib", default=None)
     args = ap.parse_args()
     torch.manual_seed(0)
     ok = True
     ragged = [256, 128, 1, 63, 64, 65, 200, 0, 37, 16, 15, 17]
-    for p in (0.0, 0.1):
+    for p in (() if args.no_check else (0.0, 0.1)):
         ok &= check([64], 1, 32, p, "one tile")
         ok &= check([128, 80], 2, 32, p, "two blocks")
         ok &= check(ragged, 12, 32, p, "ragged d32")
         ok &= check([512, 300, 17, 129, 0, 64], 4, 64, p, "ragged d64")
     print("ALL OK" if ok else "FAILURES")
+    mask_stats()
     if not args.no_time:
         for p in (0.0, 0.1):
             bench(160, 128, 256, 12, 32, p, f"C2 body layer (160 seqs 128..256, h12 d32, p={p})")
