@@ -151,7 +151,8 @@ def build_trainer(wl, args, device, accelerator=None, model=None, grad_sync=None
         shift = TRAINED_BIAS_SHIFT[wl["shape"]] if args.regime == "trained" else 0.0
         model = synthetic.build_sparse_model(wl["shape"], idf_vector=idf_vector(), use_l0=wl["use_l0"], bias_shift=shift,
                                              fuse_body=not args.no_fused_body,
-                                             unpad_capacity=args.unpad_capacity if args.unpad_capacity > 0 else None)
+                                             unpad_capacity=args.unpad_capacity if args.unpad_capacity > 0 else None,
+                                             attention=getattr(args, "attention", "auto"))
         model.to(device)
     model_args = ModelArguments(inf_free=True, use_l0=wl["use_l0"])
     teacher_kw = {}
@@ -428,9 +429,10 @@ def run_ours(args):
             "steps": args.steps, "warmup": n_warm, "ms_per_step": round(ms_resident / args.steps, 4),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": shared_config(wl, args, world),
-            "engine": {"body": ("padding-free packed body: cuBLAS GEMMs + flash_attn varlen (library); embeddings, block "
-                                "tails (dropout+residual+LayerNorm), GELU, bias gradients on this repo's sm_100a kernels; "
-                                "the fused head reads the packed [T,H] rows directly" if packed else
+            "engine": {"body": (f"padding-free packed body: cuBLAS GEMMs (library); varlen attention "
+                                f"({'this repo' if getattr(sm._packed, 'attention', 'auto') != 'flash' else 'flash_attn library'}), "
+                                "embeddings, block tails (dropout+residual+LayerNorm), GELU, bias gradients on this "
+                                "repo's sm_100a kernels; the fused head reads the packed [T,H] rows directly" if packed else
                                 f"padded transformers body, {sm.fused_layers} LayerNorm/Linear modules on this repo's kernels"),
                        "unpad_capacity": args.unpad_capacity if packed else None,
                        "launch": ("CUDA graph replay (whole step incl. NCCL collectives and optimizer)" if graphed
@@ -820,6 +822,9 @@ def main():
                     help="exchange of the representations between ranks: peer = symmetric NVLink peer memory (the head "
                          "kernel stores the document vectors into every rank's gathered buffer from its epilogue, flag "
                          "barrier instead of a collective); nccl = all_gather_into_tensor. auto = peer on 2..8 GPUs")
+    ap.add_argument("--attention", default="auto", choices=["auto", "own", "flash"],
+                    help="attention kernels of the padding-free body: own = csrc/attention.cu (head_dim 32 / 64), flash = the "
+                         "flash_attn library's varlen kernel (A/B); auto = own where supported")
     ap.add_argument("--unpad-capacity", type=float, default=0.85,
                     help="padding-free encoder body: real tokens are packed into ceil(capacity * B * L) rows (the synthetic "
                          "lengths are uniform in [L/2, L], mean 0.75; an overflowing batch skips its optimizer step on the "

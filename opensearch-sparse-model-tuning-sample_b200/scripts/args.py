@@ -61,6 +61,7 @@ class ModelArguments:
     # B200 extensions (absent from the reference's ModelArguments; defaults keep its behaviour)
     fuse_body: bool = True                    # backbone LayerNorm / Linear modules on the fused sm_100a kernels
     unpad_capacity: Optional[float] = None    # padding-free BERT body: rows = ceil(capacity * B * L); 1.0 never overflows
+    attention: str = "auto"                   # attention kernels of the padding-free body: auto / own / flash
 
     def __post_init__(self):
         if self.tokenizer_name is None:

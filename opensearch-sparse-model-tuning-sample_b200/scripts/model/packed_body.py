@@ -3,8 +3,9 @@
 The reference pads every batch to its longest text and runs the whole encoder on the padding (``collator.py:34-41``,
 ``sparse_encoders.py:108``). Here the real tokens are packed into one ``[T_cap, H]`` matrix, every row-wise op
 (Linear / GELU / LayerNorm / dropout, incl. the fused sm_100a kernels of ``fused_layers``) runs on packed rows only,
-and attention runs per sequence with the variable-length FlashAttention kernel of the ``flash_attn`` library (library
-code for this task, like cuBLAS). Each block tail (dropout + residual add + LayerNorm + the bf16 cast for the next GEMM) is one sm_100a kernel
+and attention runs per sequence on this repo's variable-length attention kernels (``ops.varlen_attention``,
+csrc/attention.cu: head_dim 32 / 64, dropout on the probabilities; ``attention="flash"`` selects the ``flash_attn``
+library kernel instead, for A/B runs and for head sizes the own kernels do not cover). Each block tail (dropout + residual add + LayerNorm + the bf16 cast for the next GEMM) is one sm_100a kernel
 (``ops.add_layer_norm``). The packed result is scattered back to ``[B, L, H]`` for the fused sparse head.
 The module re-uses the backbone's own sub-modules and parameters: nothing is copied, ``state_dict`` is unchanged.
 
@@ -21,7 +22,7 @@ import torch
 
 from ... import ops
 
-try:  # library kernel, optional: without it the padded path of transformers is used
+try:  # library kernel, optional (A/B runs, head sizes outside the own kernels)
     from flash_attn import flash_attn_varlen_qkvpacked_func
 except Exception:  # pragma: no cover
     flash_attn_varlen_qkvpacked_func = None
@@ -45,22 +46,33 @@ class PackedBertBody:
     """Callable like ``backbone.bert(input_ids=..., attention_mask=...)[0]`` but padding-free inside. A plain object
     (not an nn.Module) so that the backbone's parameters are not registered twice."""
 
-    def __init__(self, bert, capacity=1.0):
+    def __init__(self, bert, capacity=1.0, attention="auto"):
         self.bert = bert
         self.capacity = float(capacity)
         cfg = bert.config
         self.num_heads = cfg.num_attention_heads
         self.head_dim = cfg.hidden_size // cfg.num_attention_heads
         self.attn_dropout = float(cfg.attention_probs_dropout_prob)
+        if attention not in ("auto", "own", "flash"):
+            raise ValueError(f"attention must be auto / own / flash, got {attention!r}")
+        if attention == "flash" and flash_attn_varlen_qkvpacked_func is None:
+            raise RuntimeError("attention='flash' needs the flash_attn package")
+        if attention == "own" and (not ops.attn_supported(self.head_dim, 1) or self.attn_dropout > 0.5):
+            raise RuntimeError(f"own attention kernels: head_dim {self.head_dim} / dropout {self.attn_dropout} unsupported")
+        self.attention = attention
         self.overflow_count = None  # device int64 counter, created on first use
         self.step_overflow = None   # fp32 scalar device flag of the current step (the trainer resets and consumes it)
 
     @staticmethod
     def supported(backbone):
         bert = getattr(backbone, "bert", None)
-        if flash_attn_varlen_qkvpacked_func is None or bert is None:
+        if bert is None:
             return False
         cfg = bert.config
+        d = cfg.hidden_size // cfg.num_attention_heads
+        own = ops.attn_supported(d, 1) and float(cfg.attention_probs_dropout_prob) <= 0.5
+        if not own and flash_attn_varlen_qkvpacked_func is None:
+            return False
         ok_cfg = getattr(cfg, "position_embedding_type", "absolute") == "absolute" and not getattr(cfg, "is_decoder", False)
         layer = bert.encoder.layer[0]
         return ok_cfg and hasattr(layer.attention, "self") and hasattr(layer.attention.self, "query") \
@@ -101,7 +113,7 @@ class PackedBertBody:
         """Returns (bf16 [T_cap, H] packed activations, plan). With `head_transform` (transformers
         BertPredictionHeadTransform) the MLM head transform (dense + activation + LayerNorm) is applied as well.
         Must run under bf16 autocast. Per block: one QKV GEMM on the concatenated projection weights, varlen
-        FlashAttention on the packed qkv, and the fused dropout + residual + LayerNorm tail of `ops.add_layer_norm`
+        attention on the packed qkv, and the fused dropout + residual + LayerNorm tail of `ops.add_layer_norm`
         that hands the next GEMM its bf16 operand (no separate cast / add / dropout kernels)."""
         B, L = input_ids.shape
         if attention_mask is None:
@@ -130,12 +142,21 @@ class PackedBertBody:
         p_att = self.attn_dropout if training else 0.0
         scale = 1.0 / math.sqrt(d)
         layers = self.bert.encoder.layer
+        own = self.attention == "own" or (self.attention == "auto" and ops.attn_supported(d, L)
+                                          and self.attn_dropout <= 0.5)
+        att_seed = None
+        if own and p_att > 0.0:   # one seed per call from torch's generator (graph safe); the layer index is the salt
+            att_seed = torch.randint(-2 ** 62, 2 ** 62, (1,), dtype=torch.int64, device=x16.device)
         for li, layer in enumerate(layers):
             att, sa = layer.attention, layer.attention.self
             w_qkv = torch.cat([sa.query.weight, sa.key.weight, sa.value.weight], 0)
             b_qkv = torch.cat([sa.query.bias, sa.key.bias, sa.value.bias], 0)
             qkv = ops.linear(x16, w_qkv, b_qkv).view(t_cap, 3, h, d)
-            ctx = flash_attn_varlen_qkvpacked_func(qkv, cu, L, dropout_p=p_att, softmax_scale=scale, causal=False)
+            if own:      # cu covers all t_cap rows (real sequences + filler sequences): no zero fill in the backward
+                ctx = ops.varlen_attention(qkv, cu, L, scale, p_att, training, seed=att_seed, salt=li,
+                                           covers_all_rows=True)
+            else:
+                ctx = flash_attn_varlen_qkvpacked_func(qkv, cu, L, dropout_p=p_att, softmax_scale=scale, causal=False)
             y = att.output.dense(ctx.reshape(t_cap, h * d))
             ln = att.output.LayerNorm
             x32, x16 = ops.add_layer_norm(y, x32, ln.weight, ln.bias, ln.eps, p=att.output.dropout.p, training=training)

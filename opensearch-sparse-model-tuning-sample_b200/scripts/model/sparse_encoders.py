@@ -102,12 +102,14 @@ class _PruneFunction(torch.autograd.Function):
 
 class SparseModel(torch.nn.Module):
     def __init__(self, model_id, idf=None, tokenizer_id=None, idf_requires_grad=False, prune_ratio=None,
-                 preprocess_func=None, use_l0=True, backbone=None, tokenizer=None, fuse_body=True, unpad_capacity=None):
+                 preprocess_func=None, use_l0=True, backbone=None, tokenizer=None, fuse_body=True, unpad_capacity=None,
+                 attention="auto"):
         """Arguments as in the reference (:43-52). ``backbone``/``tokenizer`` may be passed pre-built (offline use:
         random-init architectures, tests, benchmarks); otherwise they are loaded with transformers as upstream.
         ``fuse_body`` swaps the backbone's LayerNorm / Linear modules for the fused sm_100a kernels (same parameters).
         ``unpad_capacity`` (None = off) runs a BERT body padding-free under autocast: real tokens are packed into
-        ceil(capacity * B * L) rows (see packed_body.py; 1.0 never overflows, smaller values must cover the data)."""
+        ceil(capacity * B * L) rows (see packed_body.py; 1.0 never overflows, smaller values must cover the data);
+        ``attention`` picks its attention kernels (auto / own / flash)."""
         super().__init__()
         import transformers
         if backbone is None:
@@ -123,7 +125,7 @@ class SparseModel(torch.nn.Module):
         if unpad_capacity is not None:
             from .packed_body import PackedBertBody
             if PackedBertBody.supported(self.backbone):
-                self.__dict__["_packed"] = PackedBertBody(self.backbone.bert, unpad_capacity)
+                self.__dict__["_packed"] = PackedBertBody(self.backbone.bert, unpad_capacity, attention)
         self.tokenizer = tokenizer
         if preprocess_func is not None:
             func = getattr(TextPreProcessors, preprocess_func)

@@ -74,13 +74,14 @@ def build_backbone(shape="mini", vocab_size=VOCAB_SIZE, seed=0, max_position_emb
 
 
 def build_sparse_model(shape="mini", idf_vector=None, use_l0=False, vocab_size=VOCAB_SIZE, seed=0, bias_shift=0.0,
-                       prune_ratio=None, idf_requires_grad=False, dropout=0.1, fuse_body=True, unpad_capacity=None):
+                       prune_ratio=None, idf_requires_grad=False, dropout=0.1, fuse_body=True, unpad_capacity=None,
+                       attention="auto"):
     """SparseModel over a random-init backbone. bias_shift < 0 gives the "trained-like" activation regime."""
     from .model.sparse_encoders import SparseModel
     backbone = build_backbone(shape, vocab_size, seed, dropout=dropout)
     model = SparseModel(None, backbone=backbone, tokenizer=SyntheticTokenizer(vocab_size), use_l0=use_l0,
                         prune_ratio=prune_ratio, idf_requires_grad=idf_requires_grad, fuse_body=fuse_body,
-                        unpad_capacity=unpad_capacity)
+                        unpad_capacity=unpad_capacity, attention=attention)
     if idf_vector is not None:
         with torch.no_grad():
             model.idf_vector.copy_(idf_vector)

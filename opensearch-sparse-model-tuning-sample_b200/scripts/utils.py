@@ -166,4 +166,5 @@ def get_model(model_args, backbone=None, tokenizer=None):
                        idf_requires_grad=model_args.idf_requires_grad, prune_ratio=model_args.prune_ratio,
                        preprocess_func=model_args.preprocess_func, use_l0=model_args.use_l0, backbone=backbone,
                        tokenizer=tokenizer, fuse_body=getattr(model_args, "fuse_body", True),
-                       unpad_capacity=getattr(model_args, "unpad_capacity", None))
+                       unpad_capacity=getattr(model_args, "unpad_capacity", None),
+                       attention=getattr(model_args, "attention", "auto"))

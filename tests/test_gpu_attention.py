@@ -1,0 +1,172 @@
+"""Variable-length attention kernels (csrc/attention.cu) against an fp32 torch restatement of
+transformers BertSelfAttention (softmax(Q K^T / sqrt(d)) -> dropout -> V per sequence; the backbone call at
+/root/reference/scripts/model/sparse_encoders.py:108). Floating-point kernel: bf16 operands, fp32 accumulation; the
+tolerance is 1.5e-2 of the largest reference magnitude (bf16 has 8 mantissa bits; the probabilities and the score
+gradients are rounded to bf16 before their second product, as in every flash-attention implementation)."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+TOL = 1.5e-2
+
+
+def _ops():
+    import sparse_b200  # noqa: F401
+    from sparse_b200 import ops
+    return ops
+
+
+def _make(lens, h, d, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    T = sum(lens)
+    qkv = (torch.randn(T, 3, h, d, generator=g) * 1.5).to(torch.bfloat16).cuda()
+    dout = torch.randn(T, h, d, generator=g).to(torch.bfloat16).cuda()
+    cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32).cuda()
+    return qkv, dout, cu
+
+
+def _reference(qkv, lens, scale, dout, mask=None, inv_keep=1.0):
+    x = qkv.float().detach().requires_grad_(True)
+    outs, lses, t0 = [], [], 0
+    for n in lens:
+        if n == 0:
+            continue
+        q, k, v = (x[t0:t0 + n, i].transpose(0, 1) for i in range(3))
+        s = q @ k.transpose(1, 2) * scale
+        p = torch.softmax(s, -1)
+        lses.append(torch.logsumexp(s, -1).detach())
+        if mask is not None:
+            p = p * mask[:, t0:t0 + n, :n].float() * inv_keep
+        outs.append((p @ v).transpose(0, 1))
+        t0 += n
+    out = torch.cat(outs, 0)
+    out.backward(dout.float())
+    return out.detach(), torch.cat(lses, 1), x.grad
+
+
+def _close(got, want, what):
+    err = float((got.float() - want.float()).abs().max())
+    ref = float(want.float().abs().max())
+    assert math.isfinite(err) and err <= TOL * ref, f"{what}: max err {err:.3e} vs reference magnitude {ref:.3e}"
+
+
+RAGGED = [256, 128, 1, 63, 64, 65, 200, 0, 37, 16, 15, 17]
+
+
+@pytest.mark.parametrize("lens,h,d", [([64], 1, 32), ([128, 80], 2, 32), (RAGGED, 12, 32), ([512, 300, 17, 129, 0, 64], 4, 64),
+                                      ([257, 255, 448], 2, 64), ([1, 1, 2, 3], 3, 32)])
+def test_forward_backward_match_fp32_reference(lens, h, d):
+    ops = _ops()
+    qkv, dout, cu = _make(lens, h, d)
+    scale = 1.0 / math.sqrt(d)
+    L = max(lens)
+    out, lse = ops.attn_forward(qkv, cu, L, scale)
+    dqkv = ops.attn_backward(qkv, out, dout, lse, cu, L, scale)
+    want, want_lse, wgrad = _reference(qkv, lens, scale, dout)
+    _close(out, want, "out")
+    assert float((lse - want_lse).abs().max()) < 1e-4
+    for i, name in enumerate(("dq", "dk", "dv")):
+        _close(dqkv[:, i], wgrad[:, i], name)
+
+
+@pytest.mark.parametrize("lens,h,d", [(RAGGED, 12, 32), ([512, 300, 17, 129, 0, 64], 4, 64)])
+def test_dropout_mask_is_the_same_in_forward_and_both_backward_roles(lens, h, d):
+    """The forward, the dQ role and the dK/dV role each regenerate the keep mask from registers in their own
+    accumulator orientation; the mask hook materialises it once more. All four must agree: the reference run with the
+    hook's mask reproduces out, dq, dk and dv."""
+    ops = _ops()
+    qkv, dout, cu = _make(lens, h, d, seed=3)
+    T, L, scale, p = qkv.shape[0], max(lens), 1.0 / math.sqrt(d), 0.1
+    seed = torch.tensor([987654321], dtype=torch.int64).cuda()
+    out, lse = ops.attn_forward(qkv, cu, L, scale, p, seed, salt=5)
+    dqkv = ops.attn_backward(qkv, out, dout, lse, cu, L, scale, p, seed, salt=5)
+    mask = ops.attn_dropout_mask(cu, L, T, h, p, seed, salt=5)
+    thr = int((1 - p) * 256 + 0.5)
+    want, _, wgrad = _reference(qkv, lens, scale, dout, mask, 256.0 / thr)
+    _close(out, want, "out")
+    for i, name in enumerate(("dq", "dk", "dv")):
+        _close(dqkv[:, i], wgrad[:, i], name)
+    valid = torch.zeros(T, L, dtype=torch.bool).cuda()
+    t0 = 0
+    for n in lens:
+        valid[t0:t0 + n, :n] = True
+        t0 += n
+    rate = float(mask[:, valid].float().mean())
+    assert abs(rate - thr / 256) < 4e-3, rate
+    # deterministic in (seed, salt); another salt or seed gives another mask
+    out2, _ = ops.attn_forward(qkv, cu, L, scale, p, seed, salt=5)
+    assert torch.equal(out, out2)
+    assert not torch.equal(mask, ops.attn_dropout_mask(cu, L, T, h, p, seed, salt=6))
+    assert not torch.equal(mask, ops.attn_dropout_mask(cu, L, T, h, p, seed + 1, salt=5))
+
+
+def test_dropout_mask_statistics():
+    """Positional hash: keep rate per row / column is binomial, neighbouring decisions are uncorrelated."""
+    ops = _ops()
+    L, h = 512, 8
+    cu = torch.tensor([0, L, 2 * L], dtype=torch.int32).cuda()
+    seed = torch.tensor([20260101], dtype=torch.int64).cuda()
+    m = ops.attn_dropout_mask(cu, L, 2 * L, h, 0.1, seed, salt=1).float()
+    x = m - m.mean()
+    var = float((x * x).mean())
+    for a, b in ((x[:, 1:], x[:, :-1]), (x[:, :, 1:], x[:, :, :-1]), (x[:, 8:], x[:, :-8]), (x[:, :, 8:], x[:, :, :-8]),
+                 (x[:, 16:], x[:, :-16]), (x[:, :, 16:], x[:, :, :-16]), (x[1:], x[:-1]), (x[:, L:], x[:, :L])):
+        assert abs(float((a * b).mean()) / var) < 0.02
+    binom = math.sqrt(0.8984 * 0.1016 / L)
+    assert float(m.mean(2).std()) < 1.2 * binom and float(m[:, :L].mean(1).std()) < 1.2 * binom
+
+
+def test_autograd_function_and_rows_outside_the_sequences():
+    ops = _ops()
+    lens, h, d = [100, 60], 4, 32
+    qkv, dout, cu = _make(lens + [40], h, d)            # 40 trailing rows belong to no sequence
+    cu = cu[:3].contiguous()
+    x = qkv.clone().requires_grad_(True)
+    out = ops.varlen_attention(x, cu, 128)
+    out[:160].backward(dout[:160])
+    assert torch.all(x.grad[160:] == 0)
+    want, _, wgrad = _reference(qkv[:160], lens, 1.0 / math.sqrt(d), dout[:160])
+    _close(out[:160], want, "out")
+    _close(x.grad[:160], wgrad, "dqkv")
+    # eval mode: dropout off even when drop_p is given
+    o2 = ops.varlen_attention(qkv, cu, 128, drop_p=0.1, training=False)
+    assert torch.equal(o2[:160], out[:160].detach())
+
+
+def test_argument_errors():
+    import sparse_b200  # noqa: F401
+    from sparse_b200 import _lib
+    ops = _ops()
+    qkv, dout, cu = _make([8], 2, 48)
+    with pytest.raises(_lib.SparseB200Error):
+        ops.attn_forward(qkv, cu, 8, 0.1)
+    qkv, dout, cu = _make([8], 2, 32)
+    with pytest.raises(_lib.SparseB200Error):
+        ops.attn_forward(qkv, cu, 8, 0.1, 0.7, torch.zeros(1, dtype=torch.int64).cuda())
+    with pytest.raises(TypeError):
+        ops.attn_forward(qkv.float(), cu, 8, 0.1)
+
+
+def test_packed_body_own_attention_matches_the_library_kernel():
+    """Same packed body, attention='own' vs attention='flash' (eval mode: no dropout): hidden states agree to bf16
+    rounding, and the training-mode step with dropout runs and gives finite gradients."""
+    pytest.importorskip("flash_attn")
+    import sparse_b200  # noqa: F401
+    from sparse_b200.scripts import synthetic
+    from sparse_b200.scripts.model.packed_body import PackedBertBody
+    backbone = synthetic.build_backbone("mini", 30522, 0).cuda()
+    batch = synthetic.train_batch(4, 2, 96, query_len=8, device="cuda")["docs"][0]
+    bodies = {k: PackedBertBody(backbone.bert, 1.0, attention=k) for k in ("own", "flash")}
+    backbone.eval()
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        hid = {k: b(**batch)[0].float() for k, b in bodies.items()}
+    err = float((hid["own"] - hid["flash"]).abs().max())
+    assert err <= 0.06 * float(hid["flash"].abs().max()), err
+    backbone.train()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        x, _ = bodies["own"](**batch)
+    x.float().square().mean().backward()
+    grads = [p.grad for p in backbone.bert.parameters() if p.grad is not None]
+    assert grads and all(torch.isfinite(g).all() for g in grads)

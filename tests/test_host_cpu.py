@@ -69,6 +69,8 @@ def test_no_cpu_fallback():
         ops.flops_value(torch.zeros(4, 8), 1)
     with pytest.raises(_lib.SparseB200Error):
         ops.scores(torch.zeros(2, 8), torch.zeros(4, 8), True)
+    with pytest.raises(_lib.SparseB200Error):
+        ops.varlen_attention(torch.zeros(4, 3, 2, 32, dtype=torch.bfloat16), torch.tensor([0, 4], dtype=torch.int32), 4)
 
 
 def test_product_package_does_not_import_the_oracle():
