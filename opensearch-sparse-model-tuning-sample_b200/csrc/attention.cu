@@ -38,7 +38,7 @@ constexpr int kAttThreads = 128;
 #define SB200_ATT_FWD_CTAS32 4
 #define SB200_ATT_FWD_CTAS64 3
 #define SB200_ATT_BWD_CTAS32 4
-#define SB200_ATT_BWD_CTAS64 2
+#define SB200_ATT_BWD_CTAS64 3
 #endif
 constexpr int kAttTile = 64;
 // Stages of the operand ring: 4 x 64 rows cover sequences up to 256 tokens without ever reusing a stage (no block-wide
@@ -299,26 +299,23 @@ __device__ __forceinline__ float mask_f32(float x, uint32_t f) {
 }
 
 // ---------------------------------------------------------------------------------------------------------- forward
-// One 64-key block of the forward pass for the warp's 16 queries. kTail: the block holds fewer than 64 valid keys
-// (n-tiles beyond the sequence are skipped, the straddling one is masked).
-template <int D, bool kDrop, bool kTail>
+// One block of the forward pass for the warp's 16 queries: NC chunks of 16 keys (NC = 4: a full 64-key block).
+// kMask: the last chunk may reach beyond the sequence (keys >= lim are masked); blocks are specialised by their
+// number of valid chunks so that a short tail block costs what its keys cost.
+template <int D, bool kDrop, int NC, bool kMask>
 __device__ __forceinline__ void fwd_block(const AttnParams& p, const uint32_t (&qa)[D / 16][4], float (&o)[D / 8][4],
                                           float& m0, float& m1, float& l0, float& l1, uint32_t tK, uint32_t tV, int lim,
                                           uint32_t key, uint32_t ig, int lane) {
     const int t = lane & 3;
-    float s[8][4];
+    float s[2 * NC][4];
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-        if (!kTail || nt * 8 < lim) {
-            s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-            mma_rows<D>(s[nt], qa, tK, nt * 8, lane);
-        } else {
-            s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = -INFINITY;
-        }
+    for (int nt = 0; nt < 2 * NC; ++nt) {
+        s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+        mma_rows<D>(s[nt], qa, tK, nt * 8, lane);
     }
-    if (kTail) {
+    if (kMask) {
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
+        for (int nt = 2 * NC - 2; nt < 2 * NC; ++nt) {
             const int c = nt * 8 + 2 * t;
             if (c >= lim) s[nt][0] = s[nt][2] = -INFINITY;
             if (c + 1 >= lim) s[nt][1] = s[nt][3] = -INFINITY;
@@ -326,7 +323,7 @@ __device__ __forceinline__ void fwd_block(const AttnParams& p, const uint32_t (&
     }
     float mx0 = s[0][0], mx1 = s[0][2];
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
+    for (int nt = 0; nt < 2 * NC; ++nt) {
         mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
         mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
     }
@@ -341,7 +338,7 @@ __device__ __forceinline__ void fwd_block(const AttnParams& p, const uint32_t (&
     const float b0 = mn0 * p.scale_log2, b1 = mn1 * p.scale_log2;
     float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
+    for (int nt = 0; nt < 2 * NC; ++nt) {
         s[nt][0] = ex2(fmaf(s[nt][0], p.scale_log2, -b0));
         s[nt][1] = ex2(fmaf(s[nt][1], p.scale_log2, -b0));
         s[nt][2] = ex2(fmaf(s[nt][2], p.scale_log2, -b1));
@@ -359,23 +356,21 @@ __device__ __forceinline__ void fwd_block(const AttnParams& p, const uint32_t (&
         o[i][3] *= c1;
     }
 #pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-        if (!kTail || kk * 16 < lim) {
-            uint32_t a[4];
-            a[0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
-            a[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
-            a[2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
-            a[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
-            if (kDrop) {
-                const uint32_t igk = ig + uint32_t(kk * 64) * kGolden;
-                const uint32_t f0 = patch_flags(key, igk, p.keep_add), f1 = patch_flags(key, igk + kGolden, p.keep_add);
-                a[0] &= pair_mask<0>(f0, f1);
-                a[1] &= pair_mask<2>(f0, f1);
-                a[2] &= pair_mask<1>(f0, f1);
-                a[3] &= pair_mask<3>(f0, f1);
-            }
-            mma_cols<D>(o, a, tV, kk * 16, lane);
+    for (int kk = 0; kk < NC; ++kk) {
+        uint32_t a[4];
+        a[0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
+        a[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
+        a[2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+        a[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+        if (kDrop) {
+            const uint32_t igk = ig + uint32_t(kk * 64) * kGolden;
+            const uint32_t f0 = patch_flags(key, igk, p.keep_add), f1 = patch_flags(key, igk + kGolden, p.keep_add);
+            a[0] &= pair_mask<0>(f0, f1);
+            a[1] &= pair_mask<2>(f0, f1);
+            a[2] &= pair_mask<1>(f0, f1);
+            a[3] &= pair_mask<3>(f0, f1);
         }
+        mma_cols<D>(o, a, tV, kk * 16, lane);
     }
 }
 
@@ -435,9 +430,15 @@ __global__ void __launch_bounds__(kAttThreads, D == 32 ? SB200_ATT_FWD_CTAS32 : 
             const int lim = len - kb * kAttTile;     // valid keys in this block
             const uint32_t ig = ig0 + uint32_t(kb * 4 * 64) * kGolden;
             if (lim >= kAttTile)
-                fwd_block<D, kDrop, false>(p, qa, o, m0, m1, l0, l1, tK, tV, lim, key, ig, lane);
+                fwd_block<D, kDrop, 4, false>(p, qa, o, m0, m1, l0, l1, tK, tV, lim, key, ig, lane);
+            else if (lim > 48)
+                fwd_block<D, kDrop, 4, true>(p, qa, o, m0, m1, l0, l1, tK, tV, lim, key, ig, lane);
+            else if (lim > 32)
+                fwd_block<D, kDrop, 3, true>(p, qa, o, m0, m1, l0, l1, tK, tV, lim, key, ig, lane);
+            else if (lim > 16)
+                fwd_block<D, kDrop, 2, true>(p, qa, o, m0, m1, l0, l1, tK, tV, lim, key, ig, lane);
             else
-                fwd_block<D, kDrop, true>(p, qa, o, m0, m1, l0, l1, tK, tV, lim, key, ig, lane);
+                fwd_block<D, kDrop, 1, true>(p, qa, o, m0, m1, l0, l1, tK, tV, lim, key, ig, lane);
         }
         if (kb + NS < nb) {     // long sequence: the stage is reused once every warp is done with it
             __syncthreads();
