@@ -40,6 +40,10 @@ constexpr int kAttThreads = 128;
 #define SB200_ATT_BWD_CTAS32 4
 #define SB200_ATT_BWD_CTAS64 3
 #endif
+// 1: separate code for full 64-row blocks and tail blocks in the backward roles; 0: one (tail-capable) path, half the code
+#ifndef SB200_ATT_BWD_SPLIT
+#define SB200_ATT_BWD_SPLIT 1
+#endif
 constexpr int kAttTile = 64;
 // Stages of the operand ring: 4 x 64 rows cover sequences up to 256 tokens without ever reusing a stage (no block-wide
 // barrier in the loop at all); longer sequences refill a stage behind one __syncthreads.
@@ -633,7 +637,7 @@ __device__ __forceinline__ void attn_bwd_dq(const AttnParams& p, unsigned char* 
             const uint32_t tK = sK + st * kTileBytes, tV = sV + st * kTileBytes;
             const int lim = len - kb * kAttTile;
             const uint32_t ig = ig0 + uint32_t(kb * 4 * 64) * kGolden;
-            if (lim >= kAttTile)
+            if (SB200_ATT_BWD_SPLIT && lim >= kAttTile)
                 bwd_dq_block<D, kDrop, false>(p, qa, da, dq, l2, dd, tK, tV, lim, key, ig, lane);
             else
                 bwd_dq_block<D, kDrop, true>(p, qa, da, dq, l2, dd, tK, tV, lim, key, ig, lane);
@@ -782,7 +786,7 @@ __device__ __forceinline__ void attn_bwd_dkv(const AttnParams& p, unsigned char*
             const float* Ds = reinterpret_cast<const float*>(pD + st * kStatBytes);
             const int lim = len - qb * kAttTile;
             const uint32_t ig = ig0 + uint32_t(qb * 4 * 64 * 64) * kGolden;
-            if (lim >= kAttTile)
+            if (SB200_ATT_BWD_SPLIT && lim >= kAttTile)
                 bwd_dkv_block<D, kDrop, false>(p, ka, va, dk, dv, Ls, Ds, tQ, tDO, lim, key, ig, lane);
             else
                 bwd_dkv_block<D, kDrop, true>(p, ka, va, dk, dv, Ls, Ds, tQ, tDO, lim, key, ig, lane);
