@@ -44,6 +44,10 @@ constexpr int kAttThreads = 128;
 #ifndef SB200_ATT_BWD_SPLIT
 #define SB200_ATT_BWD_SPLIT 1
 #endif
+// 1: the two backward roles as two launches (half the code per kernel); 0: one launch
+#ifndef SB200_ATT_BWD_TWO_LAUNCHES
+#define SB200_ATT_BWD_TWO_LAUNCHES 0
+#endif
 constexpr int kAttTile = 64;
 // Stages of the operand ring: 4 x 64 rows cover sequences up to 256 tokens without ever reusing a stage (no block-wide
 // barrier in the loop at all); longer sequences refill a stage behind one __syncthreads.
@@ -807,19 +811,19 @@ __device__ __forceinline__ void attn_bwd_dkv(const AttnParams& p, unsigned char*
                   kt * kAttTile, len, lane);
 }
 
-template <int D, bool kDrop>
+// kRole 0: both roles in one launch (blockIdx.x < ntile: dK/dV, the longer role, is scheduled first);
+// 1 / 2: dK/dV only / dQ only (two launches: half the code per kernel).
+template <int D, bool kDrop, int kRole>
 __global__ void __launch_bounds__(kAttThreads, D == 32 ? SB200_ATT_BWD_CTAS32 : SB200_ATT_BWD_CTAS64) attn_bwd_kernel(const AttnParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int seq = blockIdx.z, head = blockIdx.y;
-    const bool dkv = int(blockIdx.x) < p.ntile;   // the longer role is scheduled first
-    const int tile = dkv ? blockIdx.x : blockIdx.x - p.ntile;
+    const bool dkv = kRole == 1 || (kRole == 0 && int(blockIdx.x) < p.ntile);
+    const int tile = (kRole == 0 && !dkv) ? blockIdx.x - p.ntile : blockIdx.x;
     const int s0 = __ldg(p.cu + seq);
     const int len = __ldg(p.cu + seq + 1) - s0;
     if (tile * kAttTile >= len) return;
-    if (dkv)
-        attn_bwd_dkv<D, kDrop>(p, smem, seq, head, tile, s0, len);
-    else
-        attn_bwd_dq<D, kDrop>(p, smem, seq, head, tile, s0, len);
+    if (kRole != 2 && dkv) attn_bwd_dkv<D, kDrop>(p, smem, seq, head, tile, s0, len);
+    if (kRole != 1 && !dkv) attn_bwd_dq<D, kDrop>(p, smem, seq, head, tile, s0, len);
 }
 
 // Test hook: mask[head, t, j] = 1 iff key j of token t's sequence is kept for query t (j < max_len).
@@ -950,16 +954,25 @@ extern "C" int sb200_attn_bwd(const void* q, const void* k, const void* v, size_
     else
         attn_prep_kernel<64><<<prep_blocks, 256, 0, s>>>(p.dout, o, lse, T, h, p.inv_keep, dsum);
     SB200_CHECK_LAUNCH("attn_prep_kernel");
-    const dim3 grid(2 * p.ntile, h, nseq);
     const size_t sm = bwd_smem(d);
     const bool drop = p.keep_thr < 256;
-#define SB200_ATT_BWD(DD, DR, SLOT)                                                            \
+#define SB200_ATT_BWD(DD, DR, ROLE, SLOT)                                                      \
     do {                                                                                       \
-        if (int rc = opt_in_smem(attn_bwd_kernel<DD, DR>, sm, SLOT)) return rc;                \
-        attn_bwd_kernel<DD, DR><<<grid, kAttThreads, sm, s>>>(p);                              \
+        if (int rc = opt_in_smem(attn_bwd_kernel<DD, DR, ROLE>, sm, SLOT)) return rc;          \
+        attn_bwd_kernel<DD, DR, ROLE><<<grid, kAttThreads, sm, s>>>(p);                        \
     } while (0)
-    if (d == 32) { if (drop) SB200_ATT_BWD(32, true, -1); else SB200_ATT_BWD(32, false, -1); }
-    else { if (drop) SB200_ATT_BWD(64, true, 14); else SB200_ATT_BWD(64, false, 15); }   // 67 KB: opt-in slots 14 / 15
+#if SB200_ATT_BWD_TWO_LAUNCHES
+    const dim3 grid(p.ntile, h, nseq);
+    if (d == 32) { if (drop) SB200_ATT_BWD(32, true, 1, -1); else SB200_ATT_BWD(32, false, 1, -1); }
+    else { if (drop) SB200_ATT_BWD(64, true, 1, 14); else SB200_ATT_BWD(64, false, 1, 15); }
+    SB200_CHECK_LAUNCH("attn_bwd_kernel");
+    if (d == 32) { if (drop) SB200_ATT_BWD(32, true, 2, -1); else SB200_ATT_BWD(32, false, 2, -1); }
+    else { if (drop) SB200_ATT_BWD(64, true, 2, 34); else SB200_ATT_BWD(64, false, 2, 35); }
+#else
+    const dim3 grid(2 * p.ntile, h, nseq);
+    if (d == 32) { if (drop) SB200_ATT_BWD(32, true, 0, -1); else SB200_ATT_BWD(32, false, 0, -1); }
+    else { if (drop) SB200_ATT_BWD(64, true, 0, 14); else SB200_ATT_BWD(64, false, 0, 15); }   // 67 KB: opt-in slots 14 / 15
+#endif
 #undef SB200_ATT_BWD
     SB200_CHECK_LAUNCH("attn_bwd_kernel");
     return SB200_OK;
