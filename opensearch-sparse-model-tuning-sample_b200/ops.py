@@ -964,7 +964,7 @@ class LinearFunction(torch.autograd.Function):
         ctx.has_bias = bias is not None
         ctx.w_dtype = weight.dtype
         # the bias keeps its own (fp32) dtype as an autograd input so that its gradient stays the fp32 column sum
-        return torch.nn.functional.linear(x, w, None if bias is None else bias.to(x.dtype))
+        return torch.nn.functional.linear(x, w, None if bias is None else half_weight(bias, x.dtype))
 
     @staticmethod
     def backward(ctx, dy):
@@ -978,6 +978,43 @@ class LinearFunction(torch.autograd.Function):
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = colsum(dy2)
         return dx, dw, db
+
+
+class FusedQKVFunction(torch.autograd.Function):
+    """[q | k | v] = x [Wq; Wk; Wv]^T + [bq; bk; bv] as ONE GEMM (transformers BertSelfAttention.query / key / value on
+    the same activation). The concatenation happens on the cached half-precision copies (half the bytes of the fp32
+    concatenation + cast it replaces); the fp32 master parameters are the autograd inputs and receive slices of one
+    fp32 weight-gradient GEMM and of one column-sum."""
+
+    @staticmethod
+    def forward(ctx, x, wq, wk, wv, bq, bk, bv):
+        dt = x.dtype
+        w = torch.cat([half_weight(wq, dt), half_weight(wk, dt), half_weight(wv, dt)], 0)
+        b = torch.cat([half_weight(bq, dt), half_weight(bk, dt), half_weight(bv, dt)], 0)
+        ctx.save_for_backward(x, w)
+        ctx.sizes = (wq.shape[0], wk.shape[0], wv.shape[0])
+        ctx.w_dtype = wq.dtype
+        return torch.nn.functional.linear(x, w, b)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dy2 = dy.reshape(-1, dy.shape[-1])
+        if dy2.dtype != x.dtype:
+            dy2 = dy2.to(x.dtype)
+        dx = (dy2 @ w).view(x.shape) if ctx.needs_input_grad[0] else None
+        dw = _weight_grad(dy2, x.reshape(-1, x.shape[-1]), ctx.w_dtype).split(ctx.sizes, 0)
+        db = colsum(dy2).split(ctx.sizes, 0)
+        return (dx,) + tuple(dw) + tuple(db)
+
+
+def fused_qkv(x, wq, wk, wv, bq, bk, bv):
+    """The three attention projections of one activation as one GEMM; autocast semantics as `linear`."""
+    if torch.is_autocast_enabled("cuda"):
+        dt = torch.get_autocast_dtype("cuda")
+        with torch.autocast("cuda", enabled=False):
+            return FusedQKVFunction.apply(x.to(dt), wq, wk, wv, bq, bk, bv)
+    return FusedQKVFunction.apply(x, wq, wk, wv, bq, bk, bv)
 
 
 def gelu_forward(x):
@@ -1019,7 +1056,7 @@ class LinearGeluFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias):
         w = half_weight(weight, x.dtype)
-        pre = torch.nn.functional.linear(x, w, None if bias is None else bias.to(x.dtype))
+        pre = torch.nn.functional.linear(x, w, None if bias is None else half_weight(bias, x.dtype))
         ctx.save_for_backward(x, w, pre)
         ctx.has_bias = bias is not None
         ctx.w_dtype = weight.dtype

@@ -149,9 +149,8 @@ class PackedBertBody:
             att_seed = torch.randint(-2 ** 62, 2 ** 62, (1,), dtype=torch.int64, device=x16.device)
         for li, layer in enumerate(layers):
             att, sa = layer.attention, layer.attention.self
-            w_qkv = torch.cat([sa.query.weight, sa.key.weight, sa.value.weight], 0)
-            b_qkv = torch.cat([sa.query.bias, sa.key.bias, sa.value.bias], 0)
-            qkv = ops.linear(x16, w_qkv, b_qkv).view(t_cap, 3, h, d)
+            qkv = ops.fused_qkv(x16, sa.query.weight, sa.key.weight, sa.value.weight, sa.query.bias, sa.key.bias,
+                                sa.value.bias).view(t_cap, 3, h, d)
             if own:      # cu covers all t_cap rows (real sequences + filler sequences): no zero fill in the backward
                 ctx = ops.varlen_attention(qkv, cu, L, scale, p_att, training, seed=att_seed, salt=li,
                                            covers_all_rows=True)

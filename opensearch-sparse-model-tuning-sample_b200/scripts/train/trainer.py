@@ -280,9 +280,14 @@ class SparseModelTrainer:
             dtype = torch.bfloat16
         else:
             return
-        if self._half_params is None:
-            self._half_params = [p for p in self.model_wrapper.sparse_model.backbone.parameters()
-                                 if p.dim() == 2 and p.dtype == torch.float32]
+        if self._half_params is None:   # every matrix parameter + the biases of the Linear layers (not the LayerNorm affines)
+            backbone = self.model_wrapper.sparse_model.backbone
+            chosen = {id(p): p for p in backbone.parameters() if p.dim() == 2 and p.dtype == torch.float32}
+            for m in backbone.modules():
+                b = getattr(m, "bias", None)
+                if isinstance(m, torch.nn.Linear) and b is not None and b.dtype == torch.float32:
+                    chosen[id(b)] = b
+            self._half_params = list(chosen.values())
         ops.refresh_half_weights(self._half_params, dtype)
 
     def _optimizer_step(self):
