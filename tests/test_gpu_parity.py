@@ -672,6 +672,41 @@ def test_fused_linear_matches_torch(ops):
     torch.testing.assert_close(outs[0][3], dy.bfloat16().float().sum((0, 1)), rtol=1e-4, atol=1e-3)
 
 
+def test_fused_qkv_matches_three_linears(ops):
+    """One GEMM on the concatenated (cached) half weights = the three projections of transformers BertSelfAttention;
+    the fp32 master parameters receive fp32 gradients (slices of one weight-gradient GEMM / one column sum)."""
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(300, 384, generator=g)
+    ws = [torch.randn(384, 384, generator=g) * 0.05 for _ in range(3)]
+    bs = [torch.randn(384, generator=g) for _ in range(3)]
+    dy = torch.randn(300, 1152, generator=g)
+    xc = cuda(x).requires_grad_(True)
+    wc = [cuda(w).requires_grad_(True) for w in ws]
+    bc = [cuda(b).requires_grad_(True) for b in bs]
+    ops.refresh_half_weights(wc + bc)                      # the cached copies are what the op must pick up
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y = ops.fused_qkv(xc, *wc, *bc)
+    assert y.dtype == torch.bfloat16 and y.shape == (300, 1152)
+    y.backward(cuda(dy).bfloat16())
+    xr = cuda(x).requires_grad_(True)
+    wr = [cuda(w).requires_grad_(True) for w in ws]
+    br = [cuda(b).requires_grad_(True) for b in bs]
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        yr = torch.cat([torch.nn.functional.linear(xr, w, b) for w, b in zip(wr, br)], 1)
+    yr.backward(cuda(dy).bfloat16())
+    torch.testing.assert_close(y.float(), yr.float(), rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(xc.grad, xr.grad, rtol=2e-2, atol=2e-2)
+    for a, r in zip(wc + bc, wr + br):
+        assert a.grad.dtype == torch.float32
+        torch.testing.assert_close(a.grad, r.grad, rtol=2e-2, atol=2e-2 * float(r.grad.abs().max()))
+    # a parameter modified after the refresh must not be served from the stale cache
+    with torch.no_grad():
+        wc[0].mul_(2.0)
+        y2 = ops.fused_qkv(xc.detach().bfloat16(), *wc, *bc)
+    torch.testing.assert_close(y2[:, :384].float(), (2 * (y[:, :384].float() - bc[0].bfloat16().float())
+                                                     + bc[0].bfloat16().float()), rtol=3e-2, atol=3e-2)
+
+
 @pytest.mark.parametrize("in_batch", [False, True])
 def test_local_row_backward_matches_full_backward(ops, in_batch):
     """After gather_rep only the local slice of the gathered reps carries gradient; the loss/regulariser backward
