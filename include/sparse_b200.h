@@ -290,6 +290,8 @@ int sb200_colsum(const void* dy, int elem_bytes, int R, int N, float* out, void*
  *   q, k, v     bf16, element [t, head, :] at ptr + t * in_stride + head * d (a fused [T, 3, h, d] projection output:
  *               q = base, k = base + h * d, v = base + 2 * h * d, in_stride = 3 * h * d); in_stride % 8 == 0
  *   cu_seqlens  int32 [nseq + 1] on the device, non-decreasing, cu_seqlens[nseq] <= T; empty sequences allowed
+ *   nseq_live   sequences [nseq_live, nseq) are filler (the unused capacity of a packed batch): their rows of out /
+ *               dq / dk / dv are zero-filled (lse = 0) and no attention is computed for them
  *   max_len     host upper bound of every sequence length (<= 1024); d = 32 or 64
  *   out         bf16 [T, h * d];  lse f32 [h, T] = log sum_j exp(scale * q . k_j)
  *   drop_p / drop_seed / salt: dropout on the probabilities. The keep mask is a pure function of (the 64-bit value at
@@ -303,10 +305,11 @@ int sb200_colsum(const void* dy, int elem_bytes, int R, int N, float* out, void*
  * own sequence. */
 int sb200_attn_supported(int head_dim, int max_len);
 int sb200_attn_fwd(const void* q, const void* k, const void* v, size_t in_stride, const int* cu_seqlens, int nseq,
-                   int max_len, int T, int h, int d, float scale, float drop_p, const void* drop_seed, int salt,
+                   int nseq_live, int max_len, int T, int h, int d, float scale, float drop_p, const void* drop_seed, int salt,
                    void* out, float* lse, sb200_stream_t stream);
 int sb200_attn_bwd(const void* q, const void* k, const void* v, size_t in_stride, const void* out, const void* dout,
-                   const float* lse, const int* cu_seqlens, int nseq, int max_len, int T, int h, int d, float scale,
+                   const float* lse, const int* cu_seqlens, int nseq, int nseq_live, int max_len, int T, int h, int d,
+                   float scale,
                    float drop_p, const void* drop_seed, int salt, void* dq, void* dk, void* dv,
                    size_t d_stride, float* dsum, sb200_stream_t stream);
 int sb200_attn_dropout_mask(const int* cu_seqlens, int nseq, int max_len, int T, int h, float drop_p,

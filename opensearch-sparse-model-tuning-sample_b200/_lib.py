@@ -68,8 +68,8 @@ _PROTOTYPES = {
     "sb200_colsum_workspace_bytes": (_sz, [_c_int, _c_int]),
     "sb200_colsum": (_c_int, [_vp, _c_int, _c_int, _c_int, _vp, _vp, _sz, _vp]),
     "sb200_attn_supported": (_c_int, [_c_int, _c_int]),
-    "sb200_attn_fwd": (_c_int, [_vp] * 3 + [_sz, _vp] + [_c_int] * 5 + [_c_f, _c_f, _vp, _c_int, _vp, _vp, _vp]),
-    "sb200_attn_bwd": (_c_int, [_vp] * 3 + [_sz] + [_vp] * 4 + [_c_int] * 5 + [_c_f, _c_f, _vp, _c_int] + [_vp] * 3
+    "sb200_attn_fwd": (_c_int, [_vp] * 3 + [_sz, _vp] + [_c_int] * 6 + [_c_f, _c_f, _vp, _c_int, _vp, _vp, _vp]),
+    "sb200_attn_bwd": (_c_int, [_vp] * 3 + [_sz] + [_vp] * 4 + [_c_int] * 6 + [_c_f, _c_f, _vp, _c_int] + [_vp] * 3
                        + [_sz, _vp, _vp]),
     "sb200_attn_dropout_mask": (_c_int, [_vp] + [_c_int] * 4 + [_c_f, _vp, _c_int, _vp, _vp]),
     "sb200_peer_alloc": (_c_int, [_sz, _vp]),

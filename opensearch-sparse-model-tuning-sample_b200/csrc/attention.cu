@@ -65,6 +65,7 @@ struct AttnParams {
     float* lse;               // [h, T] natural-log LSE of the scaled scores
     const int* cu;            // [nseq + 1]
     int T, h, nseq, ntile;
+    int nseq_live;            // sequences [nseq_live, nseq) are filler: their output rows are zero-filled, nothing is computed
     float scale, scale_log2;
     uint32_t keep_thr;        // keep probability = keep_thr / 256  (256 = keep everything)
     uint32_t keep_add;        // (128 - (256 - keep_thr)) in every byte: SWAR compare byte >= 256 - keep_thr
@@ -272,6 +273,18 @@ __device__ __forceinline__ void store_rows(const float (&acc)[D / 8][4], float s
     }
 }
 
+// Zero-fills the D columns of one head in rows [row0, row0 + 64) of a sequence (filler sequences of a packed batch).
+template <int D>
+__device__ __forceinline__ void zero_rows(__nv_bfloat16* dst, long long stride, int row0, int len, int tid) {
+    constexpr int CPR = D / 8;
+#pragma unroll
+    for (int i = 0; i < kAttTile * CPR / kAttThreads; ++i) {
+        const int idx = tid + i * kAttThreads;
+        const int r = row0 + idx / CPR, c = idx % CPR;
+        if (r < len) *reinterpret_cast<uint4*>(dst + (long long)r * stride + c * 8) = make_uint4(0u, 0u, 0u, 0u);
+    }
+}
+
 __device__ __forceinline__ uint32_t seq_key(const AttnParams& p, int seq, int head) {
     const unsigned long long s = *p.seed;
     return mix32(uint32_t(s) ^ mix32(uint32_t(s >> 32) + 0x9E3779B9u * uint32_t(seq * p.h + head + 1)) ^
@@ -391,6 +404,11 @@ __global__ void __launch_bounds__(kAttThreads, D == 32 ? SB200_ATT_FWD_CTAS32 : 
     const int len = __ldg(p.cu + seq + 1) - s0;
     if (qt * kAttTile >= len) return;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    if (seq >= p.nseq_live) {
+        zero_rows<D>(p.out + (long long)s0 * (p.h * D) + head * D, (long long)p.h * D, qt * kAttTile, len, tid);
+        if (tid < kAttTile && qt * kAttTile + tid < len) p.lse[(long long)head * p.T + s0 + qt * kAttTile + tid] = 0.f;
+        return;
+    }
     constexpr int NS = att_stages<D>();
     const uint32_t sQ = smem_u32(smem), sK = sQ + kTileBytes, sV = sK + NS * kTileBytes;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + (1 + 2 * NS) * kTileBytes);
@@ -822,6 +840,15 @@ __global__ void __launch_bounds__(kAttThreads, D == 32 ? SB200_ATT_BWD_CTAS32 : 
     const int s0 = __ldg(p.cu + seq);
     const int len = __ldg(p.cu + seq + 1) - s0;
     if (tile * kAttTile >= len) return;
+    if (seq >= p.nseq_live) {
+        if (dkv) {
+            zero_rows<D>(p.dk + (long long)s0 * p.d_stride + head * D, p.d_stride, tile * kAttTile, len, threadIdx.x);
+            zero_rows<D>(p.dv + (long long)s0 * p.d_stride + head * D, p.d_stride, tile * kAttTile, len, threadIdx.x);
+        } else {
+            zero_rows<D>(p.dq + (long long)s0 * p.d_stride + head * D, p.d_stride, tile * kAttTile, len, threadIdx.x);
+        }
+        return;
+    }
     if (kRole != 2 && dkv) attn_bwd_dkv<D, kDrop>(p, smem, seq, head, tile, s0, len);
     if (kRole != 1 && !dkv) attn_bwd_dq<D, kDrop>(p, smem, seq, head, tile, s0, len);
 }
@@ -887,10 +914,11 @@ extern "C" int sb200_attn_supported(int head_dim, int max_len) {
 }
 
 extern "C" int sb200_attn_fwd(const void* q, const void* k, const void* v, size_t in_stride, const int* cu_seqlens,
-                              int nseq, int max_len, int T, int h, int d, float scale, float drop_p,
+                              int nseq, int nseq_live, int max_len, int T, int h, int d, float scale, float drop_p,
                               const void* drop_seed, int salt, void* out, float* lse, sb200_stream_t stream) {
     if (int rc = check_common(T, h, d, nseq, max_len)) return rc;
     SB200_REQUIRE(q && k && v && cu_seqlens && out && lse, "attn_fwd: null pointer");
+    SB200_REQUIRE(nseq_live >= 0 && nseq_live <= nseq, "attn_fwd: nseq_live out of range");
     SB200_REQUIRE(in_stride % 8 == 0, "attn_fwd: row stride must be a multiple of 8 elements");
     AttnParams p{};
     p.q = static_cast<const __nv_bfloat16*>(q);
@@ -901,6 +929,7 @@ extern "C" int sb200_attn_fwd(const void* q, const void* k, const void* v, size_
     p.lse = lse;
     p.cu = cu_seqlens;
     p.T = T; p.h = h; p.nseq = nseq;
+    p.nseq_live = nseq_live;
     p.ntile = (max_len + kAttTile - 1) / kAttTile;
     p.scale = scale;
     p.scale_log2 = scale * kLog2e;
@@ -922,11 +951,13 @@ extern "C" int sb200_attn_fwd(const void* q, const void* k, const void* v, size_
 }
 
 extern "C" int sb200_attn_bwd(const void* q, const void* k, const void* v, size_t in_stride, const void* out,
-                              const void* dout, const float* lse, const int* cu_seqlens, int nseq, int max_len, int T,
+                              const void* dout, const float* lse, const int* cu_seqlens, int nseq, int nseq_live,
+                              int max_len, int T,
                               int h, int d, float scale, float drop_p, const void* drop_seed, int salt, void* dq,
                               void* dk, void* dv, size_t d_stride, float* dsum, sb200_stream_t stream) {
     if (int rc = check_common(T, h, d, nseq, max_len)) return rc;
     SB200_REQUIRE(q && k && v && out && dout && lse && cu_seqlens && dq && dk && dv && dsum, "attn_bwd: null pointer");
+    SB200_REQUIRE(nseq_live >= 0 && nseq_live <= nseq, "attn_bwd: nseq_live out of range");
     SB200_REQUIRE(in_stride % 8 == 0 && d_stride % 8 == 0, "attn_bwd: row strides must be multiples of 8 elements");
     AttnParams p{};
     p.q = static_cast<const __nv_bfloat16*>(q);
@@ -936,6 +967,7 @@ extern "C" int sb200_attn_bwd(const void* q, const void* k, const void* v, size_
     p.lse = const_cast<float*>(lse);
     p.cu = cu_seqlens;
     p.T = T; p.h = h; p.nseq = nseq;
+    p.nseq_live = nseq_live;
     p.ntile = (max_len + kAttTile - 1) / kAttTile;
     p.scale = scale;
     p.scale_log2 = scale * kLog2e;

@@ -837,8 +837,9 @@ def _attn_views(qkv):
     return T, h, d, 3 * h * d
 
 
-def attn_forward(qkv, cu_seqlens, max_len, scale, drop_p=0.0, seed=None, salt=0):
-    """Raw forward: returns (out bf16 [T, h, d], lse f32 [h, T])."""
+def attn_forward(qkv, cu_seqlens, max_len, scale, drop_p=0.0, seed=None, salt=0, live=None):
+    """Raw forward: returns (out bf16 [T, h, d], lse f32 [h, T]). live: number of leading real sequences (the rest
+    are filler: zero output rows, nothing computed); None = all."""
     _need_cuda(qkv, cu_seqlens, seed)
     T, h, d, stride = _attn_views(qkv)
     if cu_seqlens.dtype != torch.int32:
@@ -848,14 +849,16 @@ def attn_forward(qkv, cu_seqlens, max_len, scale, drop_p=0.0, seed=None, salt=0)
     lse = torch.empty(h, T, dtype=torch.float32, device=qkv.device)
     base, e = qkv.data_ptr(), 2 * h * d
     with torch.cuda.device(qkv.device):
-        code = _lib.load().sb200_attn_fwd(base, base + e, base + 2 * e, stride, _ptr(cu_seqlens),
-                                          cu_seqlens.numel() - 1, int(max_len), T, h, d, float(scale), float(drop_p),
+        nseq = cu_seqlens.numel() - 1
+        code = _lib.load().sb200_attn_fwd(base, base + e, base + 2 * e, stride, _ptr(cu_seqlens), nseq,
+                                          nseq if live is None else int(live), int(max_len), T, h, d, float(scale), float(drop_p),
                                           _ptr(seed), int(salt), _ptr(out), _ptr(lse), _stream())
     _lib.check(code, "sb200_attn_fwd")
     return out, lse
 
 
-def attn_backward(qkv, out, dout, lse, cu_seqlens, max_len, scale, drop_p=0.0, seed=None, salt=0, zero_fill=False):
+def attn_backward(qkv, out, dout, lse, cu_seqlens, max_len, scale, drop_p=0.0, seed=None, salt=0, zero_fill=False,
+                  live=None):
     """Raw backward: returns dqkv bf16 [T, 3, h, d]. Rows outside every sequence are only defined with zero_fill."""
     T, h, d, stride = _attn_views(qkv)
     dout = dout.contiguous()
@@ -865,8 +868,9 @@ def attn_backward(qkv, out, dout, lse, cu_seqlens, max_len, scale, drop_p=0.0, s
     dsum = torch.empty(2, h, T, dtype=torch.float32, device=qkv.device)
     base, dbase, e = qkv.data_ptr(), dqkv.data_ptr(), 2 * h * d
     with torch.cuda.device(qkv.device):
+        nseq = cu_seqlens.numel() - 1
         code = _lib.load().sb200_attn_bwd(base, base + e, base + 2 * e, stride, _ptr(out), _ptr(dout), _ptr(lse),
-                                          _ptr(cu_seqlens), cu_seqlens.numel() - 1, int(max_len), T, h, d,
+                                          _ptr(cu_seqlens), nseq, nseq if live is None else int(live), int(max_len), T, h, d,
                                           float(scale), float(drop_p), _ptr(seed), int(salt), dbase, dbase + e,
                                           dbase + 2 * e, stride, _ptr(dsum), _stream())
     _lib.check(code, "sb200_attn_bwd")
@@ -888,28 +892,29 @@ class VarlenAttentionFunction(torch.autograd.Function):
     """softmax(Q K^T * scale) -> dropout -> V per packed sequence (transformers BertSelfAttention under bf16 autocast)."""
 
     @staticmethod
-    def forward(ctx, qkv, cu_seqlens, max_len, scale, drop_p, seed, salt, covers_all_rows):
+    def forward(ctx, qkv, cu_seqlens, max_len, scale, drop_p, seed, salt, covers_all_rows, live):
         qc = qkv.detach().contiguous()
-        out, lse = attn_forward(qc, cu_seqlens, max_len, scale, drop_p, seed, salt)
+        out, lse = attn_forward(qc, cu_seqlens, max_len, scale, drop_p, seed, salt, live)
         ctx.save_for_backward(qc, out, lse, cu_seqlens, seed)
-        ctx.cfg = (int(max_len), float(scale), float(drop_p), int(salt), bool(covers_all_rows))
+        ctx.cfg = (int(max_len), float(scale), float(drop_p), int(salt), bool(covers_all_rows), live)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         qc, out, lse, cu, seed = ctx.saved_tensors
-        max_len, scale, drop_p, salt, covers = ctx.cfg
-        dqkv = attn_backward(qc, out, dout, lse, cu, max_len, scale, drop_p, seed, salt, zero_fill=not covers)
-        return dqkv, None, None, None, None, None, None, None
+        max_len, scale, drop_p, salt, covers, live = ctx.cfg
+        dqkv = attn_backward(qc, out, dout, lse, cu, max_len, scale, drop_p, seed, salt, zero_fill=not covers, live=live)
+        return dqkv, None, None, None, None, None, None, None, None
 
 
 def varlen_attention(qkv, cu_seqlens, max_len, scale=None, drop_p=0.0, training=False, seed=None, salt=0,
-                     covers_all_rows=False):
+                     covers_all_rows=False, live_sequences=None):
     """Self-attention over packed sequences. qkv bf16 [T, 3, h, d]; cu_seqlens int32 [nseq + 1] (device); returns bf16
     [T, h, d] (rows outside every sequence are undefined). Dropout only when training and drop_p > 0; `seed` is a
     1-element int64 device tensor (drawn from torch's CUDA generator when None: CUDA-graph safe), `salt` separates
     calls that share a seed (the layer index). covers_all_rows: cu_seqlens[-1] == T, so the gradient needs no
-    zero fill."""
+    zero fill. live_sequences: only the first that many sequences are real; the others (filler rows of a packed
+    batch) get zero output / gradient rows without any attention being computed."""
     d = qkv.shape[-1]
     if scale is None:
         scale = 1.0 / (d ** 0.5)
@@ -918,7 +923,7 @@ def varlen_attention(qkv, cu_seqlens, max_len, scale=None, drop_p=0.0, training=
         seed = torch.randint(-2 ** 62, 2 ** 62, (1,), dtype=torch.int64, device=qkv.device)
     if p == 0.0:
         seed = None
-    return VarlenAttentionFunction.apply(qkv, cu_seqlens, max_len, scale, p, seed, salt, covers_all_rows)
+    return VarlenAttentionFunction.apply(qkv, cu_seqlens, max_len, scale, p, seed, salt, covers_all_rows, live_sequences)
 
 
 # --------------------------------------------------------------------------------------------- encoder body: Linear

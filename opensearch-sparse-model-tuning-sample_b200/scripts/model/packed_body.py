@@ -151,9 +151,9 @@ class PackedBertBody:
             att, sa = layer.attention, layer.attention.self
             qkv = ops.fused_qkv(x16, sa.query.weight, sa.key.weight, sa.value.weight, sa.query.bias, sa.key.bias,
                                 sa.value.bias).view(t_cap, 3, h, d)
-            if own:      # cu covers all t_cap rows (real sequences + filler sequences): no zero fill in the backward
+            if own:      # cu covers all t_cap rows (B real sequences, then the filler sequences, which are only zero-filled)
                 ctx = ops.varlen_attention(qkv, cu, L, scale, p_att, training, seed=att_seed, salt=li,
-                                           covers_all_rows=True)
+                                           covers_all_rows=True, live_sequences=B)
             else:
                 ctx = flash_attn_varlen_qkvpacked_func(qkv, cu, L, dropout_p=p_att, softmax_scale=scale, causal=False)
             y = att.output.dense(ctx.reshape(t_cap, h * d))

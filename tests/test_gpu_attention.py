@@ -135,6 +135,26 @@ def test_autograd_function_and_rows_outside_the_sequences():
     assert torch.equal(o2[:160], out[:160].detach())
 
 
+def test_filler_sequences_are_zero_filled_not_computed():
+    """live_sequences: the trailing (filler) sequences of a packed batch get zero output and gradient rows; the real
+    ones are unaffected."""
+    ops = _ops()
+    lens, h, d = [100, 60, 64, 37], 4, 32
+    qkv, dout, cu = _make(lens, h, d, seed=9)
+    scale = 1.0 / math.sqrt(d)
+    full_out, full_lse = ops.attn_forward(qkv, cu, 128, scale)
+    out, lse = ops.attn_forward(qkv, cu, 128, scale, live=2)
+    assert torch.equal(out[:160], full_out[:160]) and torch.equal(lse[:, :160], full_lse[:, :160])
+    assert torch.all(out[160:] == 0) and torch.all(lse[:, 160:] == 0)
+    full_grad = ops.attn_backward(qkv, full_out, dout, full_lse, cu, 128, scale)
+    grad = ops.attn_backward(qkv, out, dout, lse, cu, 128, scale, live=2)
+    assert torch.equal(grad[:160], full_grad[:160]) and torch.all(grad[160:] == 0)
+    x = qkv.clone().requires_grad_(True)
+    y = ops.varlen_attention(x, cu, 128, covers_all_rows=True, live_sequences=2)
+    y.backward(dout)
+    assert torch.equal(x.grad, grad)
+
+
 def test_argument_errors():
     import sparse_b200  # noqa: F401
     from sparse_b200 import _lib
@@ -161,7 +181,10 @@ def test_packed_body_own_attention_matches_the_library_kernel():
     bodies = {k: PackedBertBody(backbone.bert, 1.0, attention=k) for k in ("own", "flash")}
     backbone.eval()
     with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
-        hid = {k: b(**batch)[0].float() for k, b in bodies.items()}
+        res = {k: b(**batch) for k, b in bodies.items()}
+    valid = res["own"][1][2]                       # rows of real tokens (the filler rows are zero-filled by the own kernels)
+    hid = {k: r[0].float()[valid] for k, r in res.items()}
+    assert torch.isfinite(res["own"][0].float()).all()
     err = float((hid["own"] - hid["flash"]).abs().max())
     assert err <= 0.06 * float(hid["flash"].abs().max()), err
     backbone.train()
