@@ -150,6 +150,27 @@ def test_packed_body_plan_and_repad_cpu():
     assert int(body.overflow_count) == 1                                  # 6 tokens fit the 8 rows: counter unchanged
 
 
+def test_attention_selection_of_the_packed_body():
+    """`attention` (auto / own / flash) is validated when the body is built, is a ModelArguments key, and the packed
+    body hands the number of real sequences to the attention op (the filler sequences behind them are only
+    zero-filled)."""
+    import inspect
+    from sparse_b200.scripts import synthetic
+    from sparse_b200.scripts.args import ModelArguments, parse_dict
+    from sparse_b200.scripts.model.packed_body import PackedBertBody
+    bert = synthetic.build_backbone("tiny", 200, 0).bert                 # 4 heads x 16: outside the own kernels
+    with pytest.raises(ValueError):
+        PackedBertBody(bert, 1.0, attention="bogus")
+    with pytest.raises(RuntimeError):
+        PackedBertBody(bert, 1.0, attention="own")
+    assert ops.attn_supported(32, 256) and ops.attn_supported(64, 512)
+    assert not ops.attn_supported(16, 64) and not ops.attn_supported(32, 2048)
+    assert ModelArguments().attention == "auto"
+    m, _, _ = parse_dict({"attention": "flash", "unpad_capacity": 0.9})
+    assert m.attention == "flash" and m.unpad_capacity == 0.9
+    assert "live_sequences=B" in inspect.getsource(PackedBertBody.__call__)
+
+
 def test_trainer_refuses_overflowed_packed_batches():
     """A batch that did not fit unpad_capacity is reported at logging cadence, never trained on silently."""
     from types import SimpleNamespace
