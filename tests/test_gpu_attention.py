@@ -102,6 +102,60 @@ def test_dropout_mask_is_the_same_in_forward_and_both_backward_roles(lens, h, d)
     assert not torch.equal(mask, ops.attn_dropout_mask(cu, L, T, h, p, seed + 1, salt=5))
 
 
+_M32 = 0xFFFFFFFF
+
+
+def _mix32(x):
+    x = x ^ (x >> 16)
+    x = (x * 0x7FEB352D) & _M32
+    x = x ^ (x >> 15)
+    x = (x * 0x846CA68B) & _M32
+    return x ^ (x >> 16)
+
+
+def _mask_numpy(lens, heads, max_len, drop_p, seed, salt):
+    """Integer restatement (numpy, uint64 arithmetic masked to 32 bits) of the positional dropout hash of
+    csrc/attention.cu: seq_key -> patch_flags -> byte of the 2x2 patch {r, r+8} x {c, c+8}."""
+    import numpy as np
+    thr = min(256, max(128, int((1.0 - drop_p) * 256.0 + 0.5)))
+    addc = ((128 - (256 - thr)) * 0x01010101) & _M32
+    s = seed & 0xFFFFFFFFFFFFFFFF
+    lo, hi = s & _M32, s >> 32
+    T = sum(lens)
+    out = np.zeros((heads, T, max_len), dtype=bool)
+    t0 = 0
+    for seq, n in enumerate(lens):
+        if n == 0:
+            continue
+        q = np.arange(n, dtype=np.uint64)[:, None]
+        k = np.arange(n, dtype=np.uint64)[None, :]
+        idx = ((q >> 4) * 64 + (k >> 4)) * 64 + (q & 7) * 8 + (k & 7)
+        ig = (idx * 0x9E3779B1) & _M32
+        byte = ((q & 15) >> 3) * 2 + ((k & 15) >> 3)
+        for head in range(heads):
+            inner = _mix32((hi + 0x9E3779B9 * (seq * heads + head + 1)) & _M32)
+            key = _mix32(lo ^ inner ^ ((salt * 0x85EBCA6B) & _M32))
+            m = (np.uint64(key) ^ ig) * np.uint64(0xD6E8FEB9)                # 32 x 32 -> 64 bit product (no overflow)
+            h = (m >> 32) ^ (m & _M32)
+            flags = (((h & 0x7F7F7F7F) + addc) & _M32) | h
+            out[head, t0:t0 + n, :n] = ((flags >> (8 * byte + 7)) & 1).astype(bool)
+        t0 += n
+    return out
+
+
+def test_dropout_mask_is_bit_exact_against_the_integer_restatement():
+    """Integer work: the keep mask of the kernels (through the mask hook, which the forward / backward tests tie to
+    the kernels' own register-level masks) equals the numpy restatement bit for bit."""
+    ops = _ops()
+    lens, heads, L = [70, 0, 33, 128, 5], 3, 128
+    cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32).cuda()
+    for seed_val, salt, p in ((987654321, 5, 0.1), (-1234567890123, 0, 0.25), (2 ** 62 + 12345, 11, 0.5)):
+        seed = torch.tensor([seed_val], dtype=torch.int64).cuda()
+        got = ops.attn_dropout_mask(cu, L, sum(lens), heads, p, seed, salt=salt).cpu().numpy()
+        want = _mask_numpy(lens, heads, L, p, seed_val, salt)
+        assert (got == want).all(), (seed_val, salt, p, int((got != want).sum()))
+
+
 def test_dropout_mask_statistics():
     """Positional hash: keep rate per row / column is binomial, neighbouring decisions are uncorrelated."""
     ops = _ops()
